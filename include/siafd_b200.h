@@ -1,0 +1,247 @@
+/*
+ * siafd_b200.h -- C ABI of the B200-native SIAFD hot path.
+ *
+ * Drop-in boundary for PISM v1.2.1's `stressbalance::SIAFD` (an `SSB_Modifier`):
+ * a C++ subclass in the host model marshals `SIAFD::update()` to these entry points
+ * (INTEGRATION.md shows the shim).  Plain pointers and sizes only; no C++ or torch types.
+ * All reference citations are file:line in the juliusgarbe/pism tree (v1.2.1).
+ *
+ *   reference interface                                       replaced by
+ *   -------------------------------------------------------   ----------------------------------
+ *   SIAFD::SIAFD(grid)        sia/SIAFD.cc:42-91               siafd_b200_create
+ *   SIAFD::~SIAFD             sia/SIAFD.cc:93-95               siafd_b200_destroy
+ *   SIAFD::init               sia/SIAFD.cc:98-118              siafd_b200_create (no separate state)
+ *   BedSmoother::preprocess_bed  sia/BedSmoother.cc:99-153     siafd_b200_preprocess_bed /
+ *                                                              siafd_b200_set_smoothed_bed
+ *   SIAFD::update             sia/SIAFD.cc:122-155             siafd_b200_update  (one call), or the
+ *                                                              split form  _upload / _compute_gradient /
+ *                                                              _compute_flux_velocity / _download
+ *   SSB_Modifier::max_diffusivity  SSB_Modifier.cc:69-71       siafd_b200_max_diffusivity
+ *   SSB_Modifier::diffusive_flux / velocity_u / velocity_v     output pointers of siafd_b200_update
+ *   SIAFD::surface_gradient_x/y, diffusivity  SIAFD.cc:963-973 output pointers (h_x, h_y, D)
+ *   GeometryCalculator::compute  util/Mask.hh:96-133           siafd_b200_geometry_compute
+ *
+ * Array layout is PISM's DMDA local (ghosted) layout, unchanged: [j][i][dof] with dof
+ * fastest (util/IceModelVec_inline.hh:28-40); a 3D field is dof = Mz (util/iceModelVec3.cc:85);
+ * IceModelVec2Stag is dof = 2 (offset o); IceModelVec2V is dof = 2 {u, v}.  The array for a
+ * field with ghost width w covers i in [xs-w, xs+xm+w), j in [ys-w, ys+ym+w).
+ * The cell-type mask is the reference's double-stored integer (IceModelVec_inline.hh:95-101).
+ *
+ * Threading: one host thread per handle; calls on a handle are stream-ordered and, unless
+ * stated otherwise, synchronous at return.  No exception crosses this ABI: every entry
+ * point returns a status code, and siafd_b200_last_error() has the message.
+ */
+#ifndef SIAFD_B200_H
+#define SIAFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIAFD_B200_ABI_VERSION 1
+
+/* stress_balance.sia.flow_law keywords (pism_config.cdl:2093-2094, rheology/FlowLawFactory.cc:71-87) */
+enum {
+  SIAFD_B200_FLOW_ISOTHERMAL_GLEN = 0,
+  SIAFD_B200_FLOW_PB = 1,
+  SIAFD_B200_FLOW_GPBLD = 2,
+  SIAFD_B200_FLOW_HOOKE = 3,
+  SIAFD_B200_FLOW_ARR = 4,
+  SIAFD_B200_FLOW_ARRWARM = 5,
+  SIAFD_B200_FLOW_GK = 6
+};
+
+/* stress_balance.sia.surface_gradient_method (pism_config.cdl:2114-2115, sia/SIAFD.cc:197-220) */
+enum { SIAFD_B200_GRAD_HASELOFF = 0, SIAFD_B200_GRAD_MAHAFFY = 1, SIAFD_B200_GRAD_ETA = 2 };
+
+/* Status codes.  1..5 are the reference's RuntimeError conditions on this path. */
+enum {
+  SIAFD_B200_OK = 0,
+  SIAFD_B200_ERR_NEGATIVE_THICKNESS = 1, /* sia/BedSmoother.cc:303-305 */
+  SIAFD_B200_ERR_OMEGA_NEGATIVE = 2,     /* sia/BedSmoother.cc:383-387 */
+  SIAFD_B200_ERR_HEIGHT_BELOW_BASE = 3,  /* util/IceGrid.cc:429-432 */
+  SIAFD_B200_ERR_HEIGHT_ABOVE_TOP = 4,   /* util/IceGrid.cc:434-437 */
+  SIAFD_B200_ERR_DIFFUSIVITY = 5,        /* sia/SIAFD.cc:752-760 */
+  SIAFD_B200_ERR_BAD_CONFIG = 6,         /* sia/SIAFD.cc:69-86,216-219; BedSmoother.cc:134-137 */
+  SIAFD_B200_ERR_CUDA = 7,               /* any CUDA runtime failure, incl. "no device" */
+  SIAFD_B200_ERR_BAD_ARGUMENT = 8
+};
+
+/* Field ids for upload / download / bind / device_ptr / wrap_ghosts / halo pack. */
+enum {
+  SIAFD_B200_F_SURFACE = 0,   /* h,    2D, w_geom   (Geometry::ice_surface_elevation) */
+  SIAFD_B200_F_THICKNESS = 1, /* H,    2D, w_geom */
+  SIAFD_B200_F_MASK = 2,      /* cell_type as double, 2D, w_geom */
+  SIAFD_B200_F_BED = 3,       /* bed_elevation, 2D, w_geom */
+  SIAFD_B200_F_ENTHALPY = 4,  /* 3D, w_3d_in */
+  SIAFD_B200_F_AGE = 5,       /* 3D, w_3d_in (only with age coupling) */
+  SIAFD_B200_F_SLIDING = 6,   /* Vector2, w_sliding */
+  SIAFD_B200_F_TOPGSMOOTH = 7,
+  SIAFD_B200_F_MAXTL = 8,
+  SIAFD_B200_F_C2 = 9,
+  SIAFD_B200_F_C3 = 10,
+  SIAFD_B200_F_C4 = 11, /* 7..11: BedSmoother state, 2D, w_geom */
+  SIAFD_B200_F_H_X = 12,
+  SIAFD_B200_F_H_Y = 13, /* Stag, w_stag */
+  SIAFD_B200_F_D = 14,   /* Stag, w_stag: diffusivity */
+  SIAFD_B200_F_FLUX = 15, /* Stag, w_stag: diffusive_flux */
+  SIAFD_B200_F_U = 16,
+  SIAFD_B200_F_V = 17,          /* 3D, w_uv */
+  SIAFD_B200_F_THK_SMOOTH = 18, /* scratch 2D, w_geom (m_work_2d_0 in compute_diffusivity) */
+  SIAFD_B200_F_THETA = 19,      /* scratch 2D, w_geom (m_work_2d_1) */
+  SIAFD_B200_F_W_I = 20,
+  SIAFD_B200_F_W_J = 21, /* scratch 2D, w_geom: haseloff weights / eta */
+  SIAFD_B200_F_COUNT = 22
+};
+
+/* Everything SIAFD's constructor and update() read from Config/IceGrid
+ * (defaults: siafd_b200_default_config, values from src/pism_config.cdl). */
+typedef struct siafd_b200_config {
+  /* IceGrid (util/IceGrid.hh): global sizes, this rank's owned patch, spacing, levels */
+  int32_t Mx, My, Mz;
+  int32_t xs, xm, ys, ym;
+  double dx, dy;
+  const double *z; /* Mz levels; copied by create */
+  /* ghost widths of the caller's arrays */
+  int32_t w_geom;    /* 2 (geometry/Geometry.cc:33-42) */
+  int32_t w_3d_in;   /* >= 2 (sia/SIAFD.cc:587,602) */
+  int32_t w_stag;    /* 1 */
+  int32_t w_uv;      /* 1 */
+  int32_t w_sliding; /* >= 0 */
+  int32_t pad0;
+  /* EnthalpyConverter (util/EnthalpyConverter.cc:55-69; cold mode :287-296 = T_melting 1e6, beta 0) */
+  double ec_p_air, ec_g, ec_beta, ec_rho_i, ec_c_i, ec_c_w, ec_L, ec_T_melting, ec_T_0;
+  /* FlowLaw (rheology/FlowLaw.cc:33-58) */
+  int32_t flow_law;
+  int32_t pad1;
+  double fl_n, fl_e, fl_e_interglacial;
+  double fl_A_cold, fl_A_warm, fl_Q_cold, fl_Q_warm, fl_T_crit;
+  double fl_R, fl_rho, fl_g, fl_beta, fl_T_melting;
+  double gpbld_T_0, gpbld_water_frac_coeff, gpbld_water_frac_limit;
+  double iso_softness_A;
+  double hooke_Q, hooke_A, hooke_C, hooke_K, hooke_Tr;
+  double grain_size; /* m */
+  /* SIAFD (sia/SIAFD.cc:555-570) */
+  int32_t gradient_method;
+  int32_t limit_diffusivity;
+  int32_t grain_size_age_coupling;
+  int32_t e_age_coupling;
+  double D_limit;
+  double eemian_start, eemian_end, holocene_start; /* s */
+  double years_per_second;
+  /* BedSmoother (sia/BedSmoother.cc:74-75,370) */
+  double smoother_range, theta_min;
+  /* GeometryCalculator (util/Mask.hh:71-79) */
+  double sea_water_density, ice_free_thickness;
+  int32_t dry_simulation;
+  int32_t pad2;
+} siafd_b200_config;
+
+/* Host (or device, see memory_space) arrays of one update() call. NULL = not provided. */
+typedef struct siafd_b200_inputs {
+  const double *surface, *thickness, *mask, *bed; /* Inputs::geometry, StressBalance.hh:45 */
+  const double *enthalpy;                         /* Inputs::enthalpy */
+  const double *age;                              /* Inputs::age (may be NULL) */
+  const double *sliding;                          /* sliding_velocity argument of update() */
+  double current_time;                            /* grid->ctx()->time()->current(), SIAFD.cc:564 */
+  int32_t memory_space;                           /* 0 = host pointers, 1 = device pointers */
+  int32_t ghosts_valid;                           /* 1: caller filled ghosts (PISM always does);
+                                                     0: single-rank whole-domain patch, library
+                                                     wraps the input ghosts periodically itself */
+} siafd_b200_inputs;
+
+typedef struct siafd_b200_outputs {
+  double *h_x, *h_y; /* SIAFD::surface_gradient_x/y */
+  double *D;         /* SIAFD::diffusivity */
+  double *flux;      /* SSB_Modifier::diffusive_flux */
+  double *u, *v;     /* SSB_Modifier::velocity_u/v (full_update only) */
+  int32_t memory_space;
+  int32_t pad;
+} siafd_b200_outputs;
+
+typedef struct siafd_b200_handle siafd_b200_handle;
+
+int siafd_b200_abi_version(void);
+void siafd_b200_default_config(siafd_b200_config *cfg);
+const char *siafd_b200_status_string(int status);
+
+/* device < 0: use the current CUDA device.  Fails with SIAFD_B200_ERR_CUDA when no GPU. */
+int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handle **out);
+void siafd_b200_destroy(siafd_b200_handle *h);
+const char *siafd_b200_last_error(const siafd_b200_handle *h);
+
+/* Local array size (in doubles) and ghost width of a field for this handle's patch. */
+int64_t siafd_b200_field_size(const siafd_b200_handle *h, int field);
+int siafd_b200_field_width(const siafd_b200_handle *h, int field);
+int siafd_b200_field_dof(const siafd_b200_handle *h, int field);
+
+/* Device storage.  By default the handle owns one device buffer per field (allocated on
+ * first use).  bind() makes the handle use caller-owned device memory (e.g. a torch tensor's
+ * data_ptr) for that field instead; it must stay valid until re-bound or destroy. */
+int siafd_b200_bind(siafd_b200_handle *h, int field, void *device_ptr);
+void *siafd_b200_device_ptr(siafd_b200_handle *h, int field);
+/* CUDA stream (cudaStream_t as void*) all work of this handle is enqueued on; NULL resets
+ * to the handle's own stream. */
+int siafd_b200_set_stream(siafd_b200_handle *h, void *cuda_stream);
+
+int siafd_b200_upload(siafd_b200_handle *h, int field, const double *host);
+int siafd_b200_download(siafd_b200_handle *h, int field, double *host);
+
+/* Periodic self-wrap of a field's ghosts on device (single rank owning the whole domain in
+ * the wrapped direction; util/IceGrid.cc:870-872: the DMDA is always periodic). */
+int siafd_b200_wrap_ghosts(siafd_b200_handle *h, int field);
+/* Multi-rank halo exchange support: pack the owned strip that a neighbour needs into a
+ * contiguous device buffer / unpack a received strip into the ghost region.
+ * dir_x, dir_y in {-1,0,1} name the neighbour; width = ghost width to exchange (<= field
+ * width).  `stage` 0 exchanges in x only (rows = owned rows), stage 1 exchanges in y
+ * including the x ghosts, so that two stages fill BOX-stencil corners. */
+int64_t siafd_b200_halo_count(const siafd_b200_handle *h, int field, int dir_x, int dir_y, int width);
+int siafd_b200_halo_pack(siafd_b200_handle *h, int field, int dir_x, int dir_y, int width, double *device_buf);
+int siafd_b200_halo_unpack(siafd_b200_handle *h, int field, int dir_x, int dir_y, int width, const double *device_buf);
+
+/* BedSmoother::preprocess_bed on the GLOBAL bed (Mx*My doubles, [j][i], no ghosts; host
+ * pointer).  Every rank passes the same array and gets its own patch (+ghosts) of
+ * topgsmooth, maxtl, C2, C3, C4 on device.  Call when Inputs::new_bed_elevation. */
+int siafd_b200_preprocess_bed(siafd_b200_handle *h, const double *global_bed_host);
+/* Alternative: hand over the five local ghosted arrays PISM's own BedSmoother computed. */
+int siafd_b200_set_smoothed_bed(siafd_b200_handle *h, const double *topgsmooth, const double *maxtl,
+                                const double *C2, const double *C3, const double *C4, int smoother_active);
+
+/* The update, split at the reference's two communication points (SIAFD.cc:498-499, :946-947)
+ * so that a multi-rank caller can exchange ghosts in between.  All asynchronous on the
+ * handle's stream. */
+int siafd_b200_compute_gradient(siafd_b200_handle *h);                 /* SIAFD.cc:137 */
+int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update,
+                                     double current_time);             /* SIAFD.cc:141-153 */
+/* Waits for the stream, then evaluates the reference's error conditions; returns the status
+ * (collective callers reduce it over ranks before acting on it, cf. ParallelSection). */
+int siafd_b200_finish(siafd_b200_handle *h);
+/* Local maximum of D over owned+ghost staggered points of the last update (SIAFD.cc:729);
+ * multi-rank callers take the max over ranks (SIAFD.cc:748).  Synchronises the stream. */
+double siafd_b200_max_diffusivity(siafd_b200_handle *h);
+int siafd_b200_high_diffusivity_count(siafd_b200_handle *h);
+
+/* One-call drop-in form: upload inputs (if host), gradient, [wrap h_x,h_y], flux+velocity,
+ * [wrap u,v], download outputs (if host), finish.  With ghosts_valid = 1 and more than one
+ * rank the caller must use the split form instead (the wraps become exchanges). */
+int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out, int full_update);
+
+/* GeometryCalculator::compute (util/Mask.hh:96-133) for n points, on device memory. */
+int siafd_b200_geometry_compute(siafd_b200_handle *h, int64_t n, const double *sea_level_dev, const double *bed_dev,
+                                const double *thickness_dev, double *mask_out_dev, double *surface_out_dev);
+
+/* FlowLaw::flow for n points on device (rheology/FlowLaw.cc:97-105); known-answer tests. */
+int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev, const double *enthalpy_dev,
+                      const double *pressure_dev, const double *grainsize_dev, double *result_dev);
+
+/* Kernel tuning knobs (tile rows per CTA etc.); 0 keeps the default.  For benchmarking. */
+int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_copy, int skip_ice_free_rows);
+/* Number of kernel launches issued by this handle since create (bench.py's gpu_launches). */
+int64_t siafd_b200_launch_count(const siafd_b200_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIAFD_B200_H */

@@ -1,0 +1,840 @@
+// siafd_capi.cu -- the C ABI declared in include/siafd_b200.h.
+//
+// Host-side orchestration of SIAFD::update (sia/SIAFD.cc:122-155): device buffers in PISM's
+// local ghosted layout, one CUDA stream per handle, error flags and D_max reduced on device and
+// read back once per update.  No CPU fallback: without a CUDA device every entry point that
+// needs one fails with SIAFD_B200_ERR_CUDA.
+#include "../../include/siafd_b200.h"
+#include "siafd_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace siafd;
+
+struct siafd_b200_handle {
+  siafd_b200_config cfg;
+  std::vector<double> z;
+  DP P;
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  void *buf[SIAFD_B200_F_COUNT];
+  bool owned[SIAFD_B200_F_COUNT];
+  double *d_z = nullptr;
+  unsigned *d_err = nullptr;
+  unsigned long long *d_dmax = nullptr;
+  int *d_hdc = nullptr;
+  // pinned host mirror of {err, hdc, dmax}
+  struct Result {
+    unsigned long long dmax;
+    unsigned err;
+    int hdc;
+  } *h_res = nullptr;
+  bool result_pending = false;
+  bool smoother_set = false;
+  int bedNx = -1, bedNy = -1;
+  double *d_global_bed = nullptr;
+  Tuning tuning;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(siafd_b200_handle *h, int code, const char *fmt, ...) {
+  char msg[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof(msg), fmt, ap);
+  va_end(ap);
+  if (h) {
+    h->err = msg;
+  } else {
+    g_create_error = msg;
+  }
+  return code;
+}
+
+#define CU(h, call)                                                                                                    \
+  do {                                                                                                                 \
+    cudaError_t e_ = (call);                                                                                           \
+    if (e_ != cudaSuccess) {                                                                                           \
+      return fail((h), SIAFD_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,          \
+                  __LINE__);                                                                                           \
+    }                                                                                                                  \
+  } while (0)
+
+struct FieldMeta {
+  int width;
+  int dof;
+};
+
+FieldMeta meta(const siafd_b200_config &c, int f) {
+  switch (f) {
+  case SIAFD_B200_F_SURFACE:
+  case SIAFD_B200_F_THICKNESS:
+  case SIAFD_B200_F_MASK:
+  case SIAFD_B200_F_BED:
+  case SIAFD_B200_F_TOPGSMOOTH:
+  case SIAFD_B200_F_MAXTL:
+  case SIAFD_B200_F_C2:
+  case SIAFD_B200_F_C3:
+  case SIAFD_B200_F_C4:
+  case SIAFD_B200_F_THK_SMOOTH:
+  case SIAFD_B200_F_THETA:
+  case SIAFD_B200_F_W_I:
+  case SIAFD_B200_F_W_J:
+    return {c.w_geom, 1};
+  case SIAFD_B200_F_ENTHALPY:
+  case SIAFD_B200_F_AGE:
+    return {c.w_3d_in, c.Mz};
+  case SIAFD_B200_F_SLIDING:
+    return {c.w_sliding, 2};
+  case SIAFD_B200_F_H_X:
+  case SIAFD_B200_F_H_Y:
+  case SIAFD_B200_F_D:
+  case SIAFD_B200_F_FLUX:
+    return {c.w_stag, 2};
+  case SIAFD_B200_F_U:
+  case SIAFD_B200_F_V:
+    return {c.w_uv, c.Mz};
+  default:
+    return {-1, 0};
+  }
+}
+
+int64_t field_cells(const siafd_b200_config &c, int w) { return (int64_t)(c.xm + 2 * w) * (c.ym + 2 * w); }
+
+int ensure(siafd_b200_handle *h, int f) {
+  if (f < 0 || f >= SIAFD_B200_F_COUNT) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad field id %d", f);
+  }
+  if (h->buf[f]) {
+    return SIAFD_B200_OK;
+  }
+  const FieldMeta m = meta(h->cfg, f);
+  // +2 doubles of slack: bulk row copies are issued on 16-byte boundaries and may touch one
+  // double past the last element (pism_b200/csrc/siafd_kernels.cu, issue_row)
+  const size_t bytes = (size_t)(field_cells(h->cfg, m.width) * m.dof + 2) * sizeof(double);
+  CU(h, cudaMalloc(&h->buf[f], bytes));
+  // PETSc Vecs start zeroed and the reference relies on it (maxtl with the smoother off, G4)
+  CU(h, cudaMemsetAsync(h->buf[f], 0, bytes, h->stream));
+  h->owned[f] = true;
+  return SIAFD_B200_OK;
+}
+
+Fields fields_of(siafd_b200_handle *h) {
+  Fields F;
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  F.h = D(SIAFD_B200_F_SURFACE);
+  F.H = D(SIAFD_B200_F_THICKNESS);
+  F.mask = D(SIAFD_B200_F_MASK);
+  F.bed = D(SIAFD_B200_F_BED);
+  F.E = D(SIAFD_B200_F_ENTHALPY);
+  F.age = D(SIAFD_B200_F_AGE);
+  F.sliding = D(SIAFD_B200_F_SLIDING);
+  F.topgsmooth = D(SIAFD_B200_F_TOPGSMOOTH);
+  F.maxtl = D(SIAFD_B200_F_MAXTL);
+  F.C2 = D(SIAFD_B200_F_C2);
+  F.C3 = D(SIAFD_B200_F_C3);
+  F.C4 = D(SIAFD_B200_F_C4);
+  F.thk_smooth = D(SIAFD_B200_F_THK_SMOOTH);
+  F.theta = D(SIAFD_B200_F_THETA);
+  F.w_i = D(SIAFD_B200_F_W_I);
+  F.w_j = D(SIAFD_B200_F_W_J);
+  F.h_x = D(SIAFD_B200_F_H_X);
+  F.h_y = D(SIAFD_B200_F_H_Y);
+  F.D = D(SIAFD_B200_F_D);
+  F.Q = D(SIAFD_B200_F_FLUX);
+  F.u = D(SIAFD_B200_F_U);
+  F.v = D(SIAFD_B200_F_V);
+  F.z = h->d_z;
+  F.err = h->d_err;
+  F.dmax = h->d_dmax;
+  F.hdc = h->d_hdc;
+  return F;
+}
+
+int check_config(const siafd_b200_config &c, std::string &why) {
+  char b[256];
+  if (c.Mx < 2 || c.My < 2 || c.Mz < 2 || c.xm < 1 || c.ym < 1 || c.xs < 0 || c.ys < 0 || c.xs + c.xm > c.Mx ||
+      c.ys + c.ym > c.My || c.z == nullptr || !(c.dx > 0) || !(c.dy > 0)) {
+    why = "invalid grid description";
+    return SIAFD_B200_ERR_BAD_CONFIG;
+  }
+  if (c.w_geom < 2 || c.w_3d_in < 2 || c.w_stag < 1 || c.w_uv < 1 || c.w_sliding < 0) {
+    // sia/SIAFD.cc:587-602 asserts
+    why = "stencil widths too small (need geometry>=2, enthalpy>=2, staggered>=1, u/v>=1)";
+    return SIAFD_B200_ERR_BAD_CONFIG;
+  }
+  if (c.gradient_method < 0 || c.gradient_method > 2) {
+    // sia/SIAFD.cc:216-219
+    snprintf(b, sizeof(b), "value of sia.surface_gradient_method (%d) is not valid", c.gradient_method);
+    why = b;
+    return SIAFD_B200_ERR_BAD_CONFIG;
+  }
+  if (c.flow_law < 0 || c.flow_law > 6) {
+    // rheology/FlowLawFactory.cc:96-103
+    snprintf(b, sizeof(b), "Selected ice flow law (%d) is not available", c.flow_law);
+    why = b;
+    return SIAFD_B200_ERR_BAD_CONFIG;
+  }
+  if (c.grain_size_age_coupling && c.flow_law != SIAFD_B200_FLOW_GK) {
+    // sia/SIAFD.cc:69-76
+    why = "flow law does not use grain size but sia.grain_size_age_coupling was set";
+    return SIAFD_B200_ERR_BAD_CONFIG;
+  }
+  for (int k = 1; k < c.Mz; ++k) {
+    if (!(c.z[k] > c.z[k - 1])) {
+      why = "vertical levels must be strictly increasing";
+      return SIAFD_B200_ERR_BAD_CONFIG;
+    }
+  }
+  return SIAFD_B200_OK;
+}
+
+void fill_dp(siafd_b200_handle *h) {
+  const siafd_b200_config &c = h->cfg;
+  DP &P = h->P;
+  std::memset(&P, 0, sizeof(P));
+  P.Mx = c.Mx, P.My = c.My, P.Mz = c.Mz;
+  P.xs = c.xs, P.xm = c.xm, P.ys = c.ys, P.ym = c.ym;
+  P.wg = c.w_geom, P.we = c.w_3d_in, P.wst = c.w_stag, P.wuv = c.w_uv, P.wsl = c.w_sliding;
+  P.dx = c.dx, P.dy = c.dy;
+  P.p_air = c.ec_p_air;
+  P.rg = c.ec_rho_i * c.ec_g; // first product of "m_rho_i * m_g * depth", EnthalpyConverter.cc:150
+  P.ec_beta = c.ec_beta, P.c_i = c.ec_c_i, P.inv_c_i = 1.0 / c.ec_c_i, P.c_w = c.ec_c_w, P.L0 = c.ec_L;
+  P.T_melting = c.ec_T_melting, P.T_0 = c.ec_T_0;
+  P.law = c.flow_law;
+  P.n = c.fl_n, P.nm1 = c.fl_n - 1, P.n_is_3 = (c.fl_n == 3.0);
+  P.e = c.fl_e, P.e_inter = c.fl_e_interglacial;
+  P.A_cold = c.fl_A_cold, P.A_warm = c.fl_A_warm, P.Q_cold = c.fl_Q_cold, P.Q_warm = c.fl_Q_warm;
+  P.T_crit = c.fl_T_crit, P.R = c.fl_R;
+  {
+    // rheology/FlowLaw.cc:45 and PatersonBudd.cc:57, evaluated like the reference does
+    const double beta_CC_grad = c.fl_beta * c.fl_rho * c.fl_g;
+    P.beta_ratio = beta_CC_grad / (c.fl_rho * c.fl_g);
+  }
+  P.gp_T0 = c.gpbld_T_0, P.gp_coeff = c.gpbld_water_frac_coeff, P.gp_limit = c.gpbld_water_frac_limit;
+  {
+    // softness_paterson_budd(T_0), rheology/FlowLaw.cc:89-94: a constant, evaluated once on the host
+    const double T = c.gpbld_T_0;
+    const double A = T < c.fl_T_crit ? c.fl_A_cold : c.fl_A_warm, Q = T < c.fl_T_crit ? c.fl_Q_cold : c.fl_Q_warm;
+    P.gp_softness_T0 = A * exp(-Q / (c.fl_R * T));
+  }
+  P.iso_A = c.iso_softness_A;
+  P.hk_Q = c.hooke_Q, P.hk_A = c.hooke_A, P.hk_C = c.hooke_C, P.hk_K = c.hooke_K, P.hk_Tr = c.hooke_Tr;
+  P.grain_size = c.grain_size;
+  P.limit_diffusivity = c.limit_diffusivity;
+  P.gs_age = c.grain_size_age_coupling, P.e_age = c.e_age_coupling;
+  P.use_age = (c.grain_size_age_coupling || c.e_age_coupling) ? 1 : 0;
+  P.D_limit = c.D_limit;
+  P.eemian_start = c.eemian_start, P.eemian_end = c.eemian_end, P.holocene_start = c.holocene_start;
+  P.years_per_second = c.years_per_second;
+  P.smoother_active = 0;
+  P.grad = c.gradient_method;
+  P.theta_min = c.theta_min;
+  P.gc_alpha = 1 - c.ec_rho_i / c.sea_water_density; // util/Mask.hh:72
+  P.gc_icefree = c.ice_free_thickness;
+  P.gc_dry = c.dry_simulation;
+}
+
+// periodic self-wrap in one direction (0: x over owned rows, 1: y over all columns)
+int wrap_dir(siafd_b200_handle *h, int f, int dir) {
+  const FieldMeta m = meta(h->cfg, f);
+  const siafd_b200_config &c = h->cfg;
+  const int w = m.width;
+  if (w <= 0) {
+    return SIAFD_B200_OK;
+  }
+  double *a = (double *)h->buf[f];
+  const long rowc = c.xm + 2 * w;
+  if (dir == 0) {
+    if (c.xm != c.Mx) {
+      return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "x self-wrap needs a patch spanning the whole x range");
+    }
+    // west ghosts <- east owned columns; east ghosts <- west owned columns
+    h->launches += launch_copy_region(a, rowc, 0, w, a, rowc, c.xm, w, w, c.ym, m.dof, h->stream);
+    h->launches += launch_copy_region(a, rowc, c.xm + w, w, a, rowc, w, w, w, c.ym, m.dof, h->stream);
+  } else {
+    if (c.ym != c.My) {
+      return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "y self-wrap needs a patch spanning the whole y range");
+    }
+    h->launches += launch_copy_region(a, rowc, 0, 0, a, rowc, 0, c.ym, (int)rowc, w, m.dof, h->stream);
+    h->launches += launch_copy_region(a, rowc, 0, c.ym + w, a, rowc, 0, w, (int)rowc, w, m.dof, h->stream);
+  }
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int status_from_bits(unsigned bits) {
+  if (bits & EB_NEG_THK) return SIAFD_B200_ERR_NEGATIVE_THICKNESS;
+  if (bits & EB_OMEGA) return SIAFD_B200_ERR_OMEGA_NEGATIVE;
+  if (bits & EB_BELOW) return SIAFD_B200_ERR_HEIGHT_BELOW_BASE;
+  if (bits & EB_ABOVE) return SIAFD_B200_ERR_HEIGHT_ABOVE_TOP;
+  return SIAFD_B200_OK;
+}
+
+int fetch_result(siafd_b200_handle *h) {
+  if (h->result_pending) {
+    CU(h, cudaMemcpyAsync(&h->h_res->dmax, h->d_dmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(&h->h_res->err, h->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(&h->h_res->hdc, h->d_hdc, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    h->result_pending = false;
+  }
+  CU(h, cudaStreamSynchronize(h->stream));
+  return SIAFD_B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int siafd_b200_abi_version(void) { return SIAFD_B200_ABI_VERSION; }
+
+// defaults: src/pism_config.cdl (line numbers in SURVEY.md section 5.6)
+void siafd_b200_default_config(siafd_b200_config *c) {
+  std::memset(c, 0, sizeof(*c));
+  c->w_geom = 2, c->w_3d_in = 2, c->w_stag = 1, c->w_uv = 1, c->w_sliding = 1;
+  c->ec_p_air = 0.0, c->ec_g = 9.81, c->ec_beta = 7.9e-8, c->ec_rho_i = 910.0, c->ec_c_i = 2009.0;
+  c->ec_c_w = 4170.0, c->ec_L = 3.34e5, c->ec_T_melting = 273.15, c->ec_T_0 = 223.15;
+  c->flow_law = SIAFD_B200_FLOW_GPBLD;
+  c->fl_n = 3.0, c->fl_e = 1.0, c->fl_e_interglacial = 1.0;
+  c->fl_A_cold = 3.61e-13, c->fl_A_warm = 1.73e3, c->fl_Q_cold = 6.0e4, c->fl_Q_warm = 13.9e4, c->fl_T_crit = 263.15;
+  c->fl_R = 8.31441, c->fl_rho = 910.0, c->fl_g = 9.81, c->fl_beta = 7.9e-8, c->fl_T_melting = 273.15;
+  c->gpbld_T_0 = 273.15, c->gpbld_water_frac_coeff = 181.25, c->gpbld_water_frac_limit = 0.01;
+  c->iso_softness_A = 3.1689e-24;
+  c->hooke_Q = 7.88e4, c->hooke_A = 4.42165e-9, c->hooke_C = 0.16612, c->hooke_K = 1.17, c->hooke_Tr = 273.39;
+  c->grain_size = 1.0e-3;
+  c->gradient_method = SIAFD_B200_GRAD_HASELOFF;
+  c->limit_diffusivity = 0, c->grain_size_age_coupling = 0, c->e_age_coupling = 0;
+  c->D_limit = 100.0;
+  const double secpera = 365.242198781 * 86400.0; // UDUNITS-2 year
+  c->eemian_start = -132000.0 * secpera, c->eemian_end = -114500.0 * secpera, c->holocene_start = -11000.0 * secpera;
+  c->years_per_second = 1.0 / secpera;
+  c->smoother_range = 5.0e3, c->theta_min = 0.0;
+  c->sea_water_density = 1028.0, c->ice_free_thickness = 0.01, c->dry_simulation = 0;
+}
+
+const char *siafd_b200_status_string(int s) {
+  switch (s) {
+  case SIAFD_B200_OK:
+    return "ok";
+  case SIAFD_B200_ERR_NEGATIVE_THICKNESS:
+    return "BedSmoother detects negative original thickness";
+  case SIAFD_B200_ERR_OMEGA_NEGATIVE:
+    return "omega is negative in BedSmoother.theta()";
+  case SIAFD_B200_ERR_HEIGHT_BELOW_BASE:
+    return "height is below base of ice (height must be non-negative)";
+  case SIAFD_B200_ERR_HEIGHT_ABOVE_TOP:
+    return "height is above top of computational grid Lz";
+  case SIAFD_B200_ERR_DIFFUSIVITY:
+    return "Maximum diffusivity of SIA flow is too high";
+  case SIAFD_B200_ERR_BAD_CONFIG:
+    return "invalid configuration";
+  case SIAFD_B200_ERR_CUDA:
+    return "CUDA failure";
+  case SIAFD_B200_ERR_BAD_ARGUMENT:
+    return "bad argument";
+  default:
+    return "unknown status";
+  }
+}
+
+int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handle **out) {
+  if (!cfg || !out) {
+    return fail(nullptr, SIAFD_B200_ERR_BAD_ARGUMENT, "null argument");
+  }
+  *out = nullptr;
+  std::string why;
+  int st = check_config(*cfg, why);
+  if (st != SIAFD_B200_OK) {
+    return fail(nullptr, st, "%s", why.c_str());
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    return fail(nullptr, SIAFD_B200_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) {
+      return fail(nullptr, SIAFD_B200_ERR_CUDA, "cudaGetDevice failed");
+    }
+  }
+  if (device >= ndev || cudaSetDevice(device) != cudaSuccess) {
+    return fail(nullptr, SIAFD_B200_ERR_CUDA, "cannot select CUDA device %d", device);
+  }
+  siafd_b200_handle *h = new siafd_b200_handle();
+  h->cfg = *cfg;
+  h->z.assign(cfg->z, cfg->z + cfg->Mz);
+  h->cfg.z = h->z.data();
+  h->device = device;
+  for (int f = 0; f < SIAFD_B200_F_COUNT; ++f) {
+    h->buf[f] = nullptr;
+    h->owned[f] = false;
+  }
+  fill_dp(h);
+  h->tuning.rows_per_cta = 64;
+  h->tuning.use_bulk_copy = 0;
+  h->tuning.skip_ice_free = 0;
+  h->tuning.tile_x = pick_tile_x(h->P, true);
+  if (h->tuning.tile_x == 0) {
+    delete h;
+    return fail(nullptr, SIAFD_B200_ERR_BAD_CONFIG, "Mz = %d is too large for the shared-memory column pipeline",
+                cfg->Mz);
+  }
+#define CUC(call)                                                                                                      \
+  do {                                                                                                                 \
+    cudaError_t e_ = (call);                                                                                           \
+    if (e_ != cudaSuccess) {                                                                                           \
+      int code_ = fail(nullptr, SIAFD_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                  \
+      siafd_b200_destroy(h);                                                                                           \
+      return code_;                                                                                                    \
+    }                                                                                                                  \
+  } while (0)
+  CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CUC(cudaMalloc(&h->d_z, sizeof(double) * cfg->Mz));
+  CUC(cudaMemcpy(h->d_z, h->z.data(), sizeof(double) * cfg->Mz, cudaMemcpyHostToDevice));
+  CUC(cudaMalloc(&h->d_err, sizeof(unsigned)));
+  CUC(cudaMalloc(&h->d_dmax, sizeof(unsigned long long)));
+  CUC(cudaMalloc(&h->d_hdc, sizeof(int)));
+  CUC(cudaMemset(h->d_err, 0, sizeof(unsigned)));
+  CUC(cudaMemset(h->d_dmax, 0, sizeof(unsigned long long)));
+  CUC(cudaMemset(h->d_hdc, 0, sizeof(int)));
+  CUC(cudaMallocHost(&h->h_res, sizeof(*h->h_res)));
+  std::memset(h->h_res, 0, sizeof(*h->h_res));
+#undef CUC
+  *out = h;
+  return SIAFD_B200_OK;
+}
+
+void siafd_b200_destroy(siafd_b200_handle *h) {
+  if (!h) {
+    return;
+  }
+  cudaSetDevice(h->device);
+  if (h->own_stream) {
+    cudaStreamSynchronize(h->own_stream);
+  }
+  for (int f = 0; f < SIAFD_B200_F_COUNT; ++f) {
+    if (h->buf[f] && h->owned[f]) {
+      cudaFree(h->buf[f]);
+    }
+  }
+  cudaFree(h->d_z);
+  cudaFree(h->d_err);
+  cudaFree(h->d_dmax);
+  cudaFree(h->d_hdc);
+  cudaFree(h->d_global_bed);
+  if (h->h_res) {
+    cudaFreeHost(h->h_res);
+  }
+  if (h->own_stream) {
+    cudaStreamDestroy(h->own_stream);
+  }
+  delete h;
+}
+
+const char *siafd_b200_last_error(const siafd_b200_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t siafd_b200_field_size(const siafd_b200_handle *h, int f) {
+  const FieldMeta m = meta(h->cfg, f);
+  return m.width < 0 ? -1 : field_cells(h->cfg, m.width) * m.dof;
+}
+int siafd_b200_field_width(const siafd_b200_handle *h, int f) { return meta(h->cfg, f).width; }
+int siafd_b200_field_dof(const siafd_b200_handle *h, int f) { return meta(h->cfg, f).dof; }
+
+int siafd_b200_bind(siafd_b200_handle *h, int f, void *device_ptr) {
+  if (f < 0 || f >= SIAFD_B200_F_COUNT) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad field id %d", f);
+  }
+  if (device_ptr && ((uintptr_t)device_ptr & 15u)) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "device pointer of field %d must be 16-byte aligned", f);
+  }
+  if (h->buf[f] == device_ptr) {
+    return SIAFD_B200_OK;
+  }
+  if (h->buf[f] && h->owned[f]) {
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaFree(h->buf[f]));
+  }
+  h->buf[f] = device_ptr;
+  h->owned[f] = false;
+  return SIAFD_B200_OK;
+}
+
+void *siafd_b200_device_ptr(siafd_b200_handle *h, int f) {
+  if (cudaSetDevice(h->device) != cudaSuccess || ensure(h, f) != SIAFD_B200_OK) {
+    return nullptr;
+  }
+  return h->buf[f];
+}
+
+int siafd_b200_set_stream(siafd_b200_handle *h, void *cuda_stream) {
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_upload(siafd_b200_handle *h, int f, const double *host) {
+  CU(h, cudaSetDevice(h->device));
+  int st = ensure(h, f);
+  if (st) return st;
+  const size_t bytes = (size_t)siafd_b200_field_size(h, f) * sizeof(double);
+  CU(h, cudaMemcpyAsync(h->buf[f], host, bytes, cudaMemcpyHostToDevice, h->stream));
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_download(siafd_b200_handle *h, int f, double *host) {
+  CU(h, cudaSetDevice(h->device));
+  int st = ensure(h, f);
+  if (st) return st;
+  const size_t bytes = (size_t)siafd_b200_field_size(h, f) * sizeof(double);
+  CU(h, cudaMemcpyAsync(host, h->buf[f], bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_wrap_ghosts(siafd_b200_handle *h, int f) {
+  CU(h, cudaSetDevice(h->device));
+  int st = ensure(h, f);
+  if (st) return st;
+  st = wrap_dir(h, f, 0);
+  if (st) return st;
+  return wrap_dir(h, f, 1);
+}
+
+// Strip geometry of the two-stage exchange.  Stage x (dir_x != 0): w columns, owned rows.
+// Stage y (dir_y != 0): w rows, all columns of the local array (x ghosts included).
+static bool halo_rect(const siafd_b200_handle *h, int f, int dir_x, int dir_y, int width, bool ghost_side, int *i0,
+                      int *j0, int *wc, int *hc) {
+  const FieldMeta m = meta(h->cfg, f);
+  if (m.width < 0 || width < 1 || width > m.width || ((dir_x != 0) == (dir_y != 0))) {
+    return false;
+  }
+  const int W = m.width, xm = h->cfg.xm, ym = h->cfg.ym;
+  if (dir_x != 0) {
+    *wc = width, *hc = ym, *j0 = W;
+    if (ghost_side) {
+      *i0 = dir_x < 0 ? W - width : W + xm;
+    } else {
+      *i0 = dir_x < 0 ? W : W + xm - width;
+    }
+  } else {
+    *wc = xm + 2 * W, *hc = width, *i0 = 0;
+    if (ghost_side) {
+      *j0 = dir_y < 0 ? W - width : W + ym;
+    } else {
+      *j0 = dir_y < 0 ? W : W + ym - width;
+    }
+  }
+  return true;
+}
+
+int64_t siafd_b200_halo_count(const siafd_b200_handle *h, int f, int dir_x, int dir_y, int width) {
+  int i0, j0, wc, hc;
+  if (!halo_rect(h, f, dir_x, dir_y, width, false, &i0, &j0, &wc, &hc)) {
+    return -1;
+  }
+  return (int64_t)wc * hc * meta(h->cfg, f).dof;
+}
+
+int siafd_b200_halo_pack(siafd_b200_handle *h, int f, int dir_x, int dir_y, int width, double *device_buf) {
+  CU(h, cudaSetDevice(h->device));
+  int st = ensure(h, f);
+  if (st) return st;
+  int i0, j0, wc, hc;
+  if (!halo_rect(h, f, dir_x, dir_y, width, false, &i0, &j0, &wc, &hc)) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad halo description");
+  }
+  const FieldMeta m = meta(h->cfg, f);
+  h->launches += launch_copy_region(device_buf, wc, 0, 0, (const double *)h->buf[f], h->cfg.xm + 2 * m.width, i0, j0, wc,
+                                    hc, m.dof, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_halo_unpack(siafd_b200_handle *h, int f, int dir_x, int dir_y, int width, const double *device_buf) {
+  CU(h, cudaSetDevice(h->device));
+  int st = ensure(h, f);
+  if (st) return st;
+  int i0, j0, wc, hc;
+  if (!halo_rect(h, f, dir_x, dir_y, width, true, &i0, &j0, &wc, &hc)) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad halo description");
+  }
+  const FieldMeta m = meta(h->cfg, f);
+  h->launches += launch_copy_region((double *)h->buf[f], h->cfg.xm + 2 * m.width, i0, j0, device_buf, wc, 0, 0, wc, hc,
+                                    m.dof, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_preprocess_bed(siafd_b200_handle *h, const double *global_bed_host) {
+  CU(h, cudaSetDevice(h->device));
+  const siafd_b200_config &c = h->cfg;
+  const int five[5] = {SIAFD_B200_F_TOPGSMOOTH, SIAFD_B200_F_MAXTL, SIAFD_B200_F_C2, SIAFD_B200_F_C3, SIAFD_B200_F_C4};
+  for (int q = 0; q < 5; ++q) {
+    int st = ensure(h, five[q]);
+    if (st) return st;
+  }
+  if (c.smoother_range <= 0.0) {
+    // sia/BedSmoother.cc:101-109: topgsmooth is a ghosted copy of topg (done per update from the
+    // uploaded bed), theta() returns 1
+    h->bedNx = h->bedNy = -1;
+    h->P.smoother_active = 0;
+    h->smoother_set = false;
+    return SIAFD_B200_OK;
+  }
+  // sia/BedSmoother.cc:111-137
+  int Nx = (int)ceil(c.smoother_range / c.dx), Ny = (int)ceil(c.smoother_range / c.dy);
+  if (Nx < 1) Nx = 1;
+  if (Ny < 1) Ny = 1;
+  if (Nx >= c.Mx || Ny >= c.My) {
+    return fail(h, SIAFD_B200_ERR_BAD_CONFIG,
+                "input Nx, Ny in bed smoother is too large because domain of smoothing exceeds IceGrid domain");
+  }
+  const size_t bytes = (size_t)c.Mx * c.My * sizeof(double);
+  if (!h->d_global_bed) {
+    CU(h, cudaMalloc(&h->d_global_bed, bytes));
+  }
+  CU(h, cudaMemcpyAsync(h->d_global_bed, global_bed_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->launches += launch_preprocess_bed(h->P, h->d_global_bed, Nx, Ny, (double *)h->buf[SIAFD_B200_F_TOPGSMOOTH],
+                                       (double *)h->buf[SIAFD_B200_F_MAXTL], (double *)h->buf[SIAFD_B200_F_C2],
+                                       (double *)h->buf[SIAFD_B200_F_C3], (double *)h->buf[SIAFD_B200_F_C4], h->stream);
+  CU(h, cudaGetLastError());
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->bedNx = Nx, h->bedNy = Ny;
+  h->P.smoother_active = 1;
+  h->smoother_set = true;
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_set_smoothed_bed(siafd_b200_handle *h, const double *topgsmooth, const double *maxtl, const double *C2,
+                                const double *C3, const double *C4, int smoother_active) {
+  int st;
+  if ((st = siafd_b200_upload(h, SIAFD_B200_F_TOPGSMOOTH, topgsmooth))) return st;
+  if ((st = siafd_b200_upload(h, SIAFD_B200_F_MAXTL, maxtl))) return st;
+  if ((st = siafd_b200_upload(h, SIAFD_B200_F_C2, C2))) return st;
+  if ((st = siafd_b200_upload(h, SIAFD_B200_F_C3, C3))) return st;
+  if ((st = siafd_b200_upload(h, SIAFD_B200_F_C4, C4))) return st;
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->P.smoother_active = smoother_active ? 1 : 0;
+  h->smoother_set = true;
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_compute_gradient(siafd_b200_handle *h) {
+  CU(h, cudaSetDevice(h->device));
+  const int need[] = {SIAFD_B200_F_SURFACE, SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK, SIAFD_B200_F_BED,
+                      SIAFD_B200_F_H_X,     SIAFD_B200_F_H_Y,       SIAFD_B200_F_W_I,  SIAFD_B200_F_W_J};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  const Fields F = fields_of(h);
+  h->launches += launch_gradient(h->P, F, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, double current_time) {
+  CU(h, cudaSetDevice(h->device));
+  const siafd_b200_config &c = h->cfg;
+  const int need[] = {SIAFD_B200_F_SURFACE,    SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK,  SIAFD_B200_F_BED,
+                      SIAFD_B200_F_ENTHALPY,   SIAFD_B200_F_TOPGSMOOTH, SIAFD_B200_F_MAXTL, SIAFD_B200_F_C2,
+                      SIAFD_B200_F_C3,         SIAFD_B200_F_C4,        SIAFD_B200_F_H_X,   SIAFD_B200_F_H_Y,
+                      SIAFD_B200_F_THK_SMOOTH, SIAFD_B200_F_THETA,     SIAFD_B200_F_D,     SIAFD_B200_F_FLUX};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  if (full_update) {
+    int st;
+    if ((st = ensure(h, SIAFD_B200_F_U))) return st;
+    if ((st = ensure(h, SIAFD_B200_F_V))) return st;
+    if ((st = ensure(h, SIAFD_B200_F_SLIDING))) return st; // zero-filled = ZeroSliding
+  }
+  if (h->P.use_age && !h->buf[SIAFD_B200_F_AGE]) {
+    // sia/SIAFD.cc:78-86
+    return fail(h, SIAFD_B200_ERR_BAD_CONFIG, "SIAFD: age is needed (age coupling is on) but no age field was provided");
+  }
+  if (c.smoother_range > 0.0 && !h->smoother_set) {
+    return fail(h, SIAFD_B200_ERR_BAD_CONFIG,
+                "bed smoother is on (range %.1f m): call siafd_b200_preprocess_bed or _set_smoothed_bed first",
+                c.smoother_range);
+  }
+  if (!(c.smoother_range > 0.0) && !h->smoother_set) {
+    // sia/BedSmoother.cc:101-109: topgsmooth = ghosted copy of the bed; maxtl, C2..C4 stay zero
+    const size_t bytes = (size_t)siafd_b200_field_size(h, SIAFD_B200_F_BED) * sizeof(double);
+    CU(h, cudaMemcpyAsync(h->buf[SIAFD_B200_F_TOPGSMOOTH], h->buf[SIAFD_B200_F_BED], bytes, cudaMemcpyDeviceToDevice,
+                          h->stream));
+  }
+  h->P.current_time = current_time;
+  const Fields F = fields_of(h);
+  CU(h, cudaMemsetAsync(h->d_err, 0, sizeof(unsigned), h->stream));
+  CU(h, cudaMemsetAsync(h->d_dmax, 0, sizeof(unsigned long long), h->stream));
+  CU(h, cudaMemsetAsync(h->d_hdc, 0, sizeof(int), h->stream));
+  h->launches += launch_prep2d(h->P, F, h->stream); // sia/SIAFD.cc:580-582
+  Tuning T = h->tuning;
+  T.tile_x = pick_tile_x(h->P, full_update != 0);
+  if (h->tuning.tile_x > 0 && h->tuning.tile_x < T.tile_x) {
+    T.tile_x = h->tuning.tile_x;
+  }
+  const int n = launch_fused(h->P, F, full_update != 0, T, h->stream);
+  if (n < 0) {
+    return fail(h, SIAFD_B200_ERR_CUDA, "could not configure the fused kernel (shared memory %zu bytes)",
+                fused_smem_bytes(h->P, full_update != 0, T.tile_x));
+  }
+  h->launches += n;
+  CU(h, cudaGetLastError());
+  h->result_pending = true;
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_finish(siafd_b200_handle *h) {
+  CU(h, cudaSetDevice(h->device));
+  int st = fetch_result(h);
+  if (st) return st;
+  st = status_from_bits(h->h_res->err);
+  if (st) {
+    return fail(h, st, "%s", siafd_b200_status_string(st));
+  }
+  double dmax;
+  std::memcpy(&dmax, &h->h_res->dmax, sizeof(double));
+  if (dmax > h->cfg.D_limit) {
+    // sia/SIAFD.cc:752-760
+    return fail(h, SIAFD_B200_ERR_DIFFUSIVITY,
+                "Maximum diffusivity of SIA flow (%f m2/s) is too high.\n"
+                "This probably means that the bed elevation or the ice thickness is too rough.\n"
+                "Increase stress_balance.sia.max_diffusivity to suppress this message.",
+                dmax);
+  }
+  return SIAFD_B200_OK;
+}
+
+double siafd_b200_max_diffusivity(siafd_b200_handle *h) {
+  if (cudaSetDevice(h->device) != cudaSuccess || fetch_result(h) != SIAFD_B200_OK) {
+    return NAN;
+  }
+  double dmax;
+  std::memcpy(&dmax, &h->h_res->dmax, sizeof(double));
+  return dmax;
+}
+
+int siafd_b200_high_diffusivity_count(siafd_b200_handle *h) {
+  if (cudaSetDevice(h->device) != cudaSuccess || fetch_result(h) != SIAFD_B200_OK) {
+    return -1;
+  }
+  return h->h_res->hdc;
+}
+
+int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out, int full_update) {
+  if (!h || !in || !out) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "null argument");
+  }
+  CU(h, cudaSetDevice(h->device));
+  const siafd_b200_config &c = h->cfg;
+  const bool whole = (c.xm == c.Mx && c.ym == c.My);
+  if (!whole) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT,
+                "siafd_b200_update is the single-rank form; a decomposed patch must use the split calls with ghost "
+                "exchanges at SIAFD.cc:498-499 and :946-947");
+  }
+  struct {
+    int f;
+    const double *p;
+  } ins[] = {{SIAFD_B200_F_SURFACE, in->surface},   {SIAFD_B200_F_THICKNESS, in->thickness},
+             {SIAFD_B200_F_MASK, in->mask},         {SIAFD_B200_F_BED, in->bed},
+             {SIAFD_B200_F_ENTHALPY, in->enthalpy}, {SIAFD_B200_F_AGE, in->age},
+             {SIAFD_B200_F_SLIDING, in->sliding}};
+  int st;
+  for (auto &q : ins) {
+    if (!q.p) {
+      continue;
+    }
+    if (in->memory_space == 0) {
+      if ((st = siafd_b200_upload(h, q.f, q.p))) return st;
+    } else {
+      if ((st = siafd_b200_bind(h, q.f, (void *)q.p))) return st;
+    }
+    if (!in->ghosts_valid) {
+      if ((st = siafd_b200_wrap_ghosts(h, q.f))) return st;
+    }
+  }
+  if (!in->surface || !in->thickness || !in->mask || !in->enthalpy) {
+    if (!h->buf[SIAFD_B200_F_SURFACE] || !h->buf[SIAFD_B200_F_THICKNESS] || !h->buf[SIAFD_B200_F_MASK] ||
+        !h->buf[SIAFD_B200_F_ENTHALPY]) {
+      return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "surface, thickness, mask and enthalpy are required");
+    }
+  }
+  struct {
+    int f;
+    double *p;
+  } outs[] = {{SIAFD_B200_F_H_X, out->h_x}, {SIAFD_B200_F_H_Y, out->h_y}, {SIAFD_B200_F_D, out->D},
+              {SIAFD_B200_F_FLUX, out->flux}, {SIAFD_B200_F_U, out->u},   {SIAFD_B200_F_V, out->v}};
+  if (out->memory_space != 0) {
+    for (auto &q : outs) {
+      if (q.p && (st = siafd_b200_bind(h, q.f, q.p))) return st;
+    }
+  }
+  if ((st = siafd_b200_compute_gradient(h))) return st;
+  if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
+    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_X))) return st;
+    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_Y))) return st;
+  }
+  if ((st = siafd_b200_compute_flux_velocity(h, full_update, in->current_time))) return st;
+  if (full_update) { // sia/SIAFD.cc:946-947
+    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_U))) return st;
+    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_V))) return st;
+  }
+  if (out->memory_space == 0) {
+    for (auto &q : outs) {
+      if (!q.p) continue;
+      if (!full_update && (q.f == SIAFD_B200_F_U || q.f == SIAFD_B200_F_V)) continue; // G10: untouched
+      const size_t bytes = (size_t)siafd_b200_field_size(h, q.f) * sizeof(double);
+      CU(h, cudaMemcpyAsync(q.p, h->buf[q.f], bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  return siafd_b200_finish(h);
+}
+
+int siafd_b200_geometry_compute(siafd_b200_handle *h, int64_t n, const double *sea_level_dev, const double *bed_dev,
+                                const double *thickness_dev, double *mask_out_dev, double *surface_out_dev) {
+  CU(h, cudaSetDevice(h->device));
+  h->launches += launch_geometry(h->P, n, sea_level_dev, bed_dev, thickness_dev, mask_out_dev, surface_out_dev, h->stream);
+  CU(h, cudaGetLastError());
+  CU(h, cudaStreamSynchronize(h->stream));
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev, const double *enthalpy_dev,
+                      const double *pressure_dev, const double *grainsize_dev, double *result_dev) {
+  CU(h, cudaSetDevice(h->device));
+  const int k = launch_flow_n(h->P, n, stress_dev, enthalpy_dev, pressure_dev, grainsize_dev, result_dev, h->stream);
+  if (k < 0) {
+    return fail(h, SIAFD_B200_ERR_BAD_CONFIG, "unknown flow law");
+  }
+  h->launches += k;
+  CU(h, cudaGetLastError());
+  CU(h, cudaStreamSynchronize(h->stream));
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_copy, int skip_ice_free_rows) {
+  if (rows_per_cta > 0) h->tuning.rows_per_cta = rows_per_cta;
+  if (use_bulk_copy >= 0) h->tuning.use_bulk_copy = use_bulk_copy ? 1 : 0;
+  if (skip_ice_free_rows >= 0) h->tuning.skip_ice_free = skip_ice_free_rows ? 1 : 0;
+  return SIAFD_B200_OK;
+}
+
+int64_t siafd_b200_launch_count(const siafd_b200_handle *h) { return h->launches; }
+
+} // extern "C"

@@ -1,0 +1,45 @@
+// siafd_kernels.cuh -- launch interface between the C ABI (siafd_capi.cu) and the kernels.
+#pragma once
+#include "siafd_device.cuh"
+
+namespace siafd {
+
+// Device pointers of one handle (PISM local ghosted layout, see include/siafd_b200.h).
+struct Fields {
+  const double *h, *H, *mask, *bed, *E, *age, *sliding;
+  const double *topgsmooth, *maxtl, *C2, *C3, *C4;
+  double *thk_smooth, *theta, *w_i, *w_j;
+  double *h_x, *h_y, *D, *Q, *u, *v;
+  const double *z;           // Mz levels
+  unsigned *err;             // error bits (EB_*)
+  unsigned long long *dmax;  // bit pattern of max D (D >= 0, so unsigned order == double order)
+  int *hdc;                  // high_diffusivity_counter
+};
+
+struct Tuning {
+  int rows_per_cta;  // rows of the extended patch one CTA marches over
+  int tile_x;        // extended columns per CTA strip (16, 8 or 4 by shared-memory fit)
+  int use_bulk_copy; // 1: cp.async.bulk + mbarrier row loads; 0: 8-byte cp.async
+  int skip_ice_free; // 1: do not load enthalpy rows no staggered point needs
+};
+
+// number of kernel launches each call makes is returned (for gpu_launches accounting)
+int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
+int launch_gradient(const DP &P, const Fields &F, cudaStream_t s);
+int launch_fused(const DP &P, const Fields &F, bool full, const Tuning &T, cudaStream_t s);
+size_t fused_smem_bytes(const DP &P, bool full, int tile_x);
+int pick_tile_x(const DP &P, bool full);
+
+// copy a rectangle of cells between two [rows][cells][dof] arrays (ghost wrap, halo pack/unpack)
+int launch_copy_region(double *dst, long dst_row_cells, int dst_i0, int dst_j0, const double *src, long src_row_cells,
+                       int src_i0, int src_j0, int width_cells, int height_cells, int dof, cudaStream_t s);
+
+int launch_geometry(const DP &P, long n, const double *sea_level, const double *bed, const double *thk, double *mask_out,
+                    double *surf_out, cudaStream_t s);
+int launch_flow_n(const DP &P, long n, const double *stress, const double *E, const double *p, const double *gs,
+                  double *out, cudaStream_t s);
+// BedSmoother::preprocess_bed for this patch (+wg ghosts) from the global bed on device
+int launch_preprocess_bed(const DP &P, const double *global_bed, int Nx, int Ny, double *topgsmooth, double *maxtl,
+                          double *C2, double *C3, double *C4, cudaStream_t s);
+
+} // namespace siafd

@@ -1,0 +1,238 @@
+"""Host-side mirror of the reference's SSB_Modifier / SIAFD interface over the C ABI.
+
+Same method names, argument meaning and error behaviour as
+  * stressbalance::SSB_Modifier   src/stressbalance/SSB_Modifier.hh:39-72
+  * stressbalance::SIAFD          src/stressbalance/sia/SIAFD.hh:50-131, SIAFD.cc:42-155
+  * stressbalance::Inputs         src/stressbalance/StressBalance.hh:41-65
+  * Geometry                      src/geometry/Geometry.cc:30-42, :121-187
+so that tests read like the reference's own (test/miscellaneous.py:321-363, siafd_test.cc).
+Fields are numpy arrays (host path: every update copies in and out, like a drop-in under
+PISM would) or torch CUDA tensors (device-resident path), always in PISM's local ghosted
+layout.  All arithmetic happens in libsiafd_b200.so; nothing here computes physics.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import F, lib
+
+
+class PISMRuntimeError(RuntimeError):
+    """pism::RuntimeError (src/util/error_handling.hh:47-68); .status is the C ABI code."""
+
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    """Raw address of a numpy array or torch tensor (must be float64, C-contiguous)."""
+    if a is None:
+        return None
+    if _is_torch(a):
+        import torch
+        assert a.dtype == torch.float64 and a.is_contiguous()
+        return a.data_ptr()
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def _as_pd(a):
+    p = _ptr(a)
+    return C.cast(C.c_void_p(p), C.POINTER(C.c_double)) if p else None
+
+
+class Geometry:
+    """The four 2D fields SIAFD reads from pism::Geometry, ghost width 2 (Geometry.cc:36-42)."""
+
+    def __init__(self, bed_elevation, ice_thickness, ice_surface_elevation=None, cell_type=None,
+                 sea_level_elevation=None):
+        self.bed_elevation = bed_elevation
+        self.ice_thickness = ice_thickness
+        self.ice_surface_elevation = ice_surface_elevation
+        self.cell_type = cell_type
+        self.sea_level_elevation = sea_level_elevation
+
+
+class Inputs:
+    """stressbalance::Inputs (StressBalance.hh:41-65): only the members SIAFD reads."""
+
+    def __init__(self, geometry=None, enthalpy=None, age=None, new_bed_elevation=True):
+        self.geometry = geometry
+        self.new_bed_elevation = new_bed_elevation  # default true, StressBalance.cc:40
+        self.enthalpy = enthalpy
+        self.age = age
+
+
+class SSB_Modifier:
+    """Owned outputs and getters of SSB_Modifier (SSB_Modifier.cc:30-91)."""
+
+    def __init__(self, grid, patch):
+        self.grid, self.patch = grid, patch
+        self.m_D_max = 0.0
+        self.m_diffusive_flux = None
+        self.m_u = None
+        self.m_v = None
+
+    def init(self):
+        pass
+
+    def diffusive_flux(self):
+        return self.m_diffusive_flux
+
+    def max_diffusivity(self):
+        return self.m_D_max
+
+    def velocity_u(self):
+        return self.m_u
+
+    def velocity_v(self):
+        return self.m_v
+
+
+class SIAFD(SSB_Modifier):
+    """stressbalance::SIAFD on a B200 (SIAFD.cc:42-155)."""
+
+    def __init__(self, grid, config=None, patch=None, device=-1, current_time=0.0, global_bed=None, **overrides):
+        patch = patch or grid.whole()
+        super().__init__(grid, patch)
+        cfg = config if config is not None else capi.default_config()
+        for k, v in overrides.items():
+            if k == "flow_law" and isinstance(v, str):
+                v = capi.FLOW_LAWS[v]
+            if k == "gradient_method" and isinstance(v, str):
+                v = capi.GRADIENTS[v]
+            if not hasattr(cfg, k):
+                raise AttributeError("unknown configuration parameter %s" % k)
+            setattr(cfg, k, v)
+        cfg.Mx, cfg.My, cfg.Mz = grid.Mx, grid.My, grid.Mz
+        cfg.xs, cfg.xm, cfg.ys, cfg.ym = patch.xs, patch.xm, patch.ys, patch.ym
+        cfg.dx, cfg.dy = grid.dx, grid.dy
+        self._z = np.ascontiguousarray(grid.z, dtype=np.float64)
+        cfg.z = self._z.ctypes.data_as(C.POINTER(C.c_double))
+        self.config = cfg
+        self.current_time = current_time
+        self._global_bed = global_bed
+        self._h = C.c_void_p()
+        status = lib.siafd_b200_create(C.byref(cfg), device, C.byref(self._h))
+        if status != capi.OK:
+            raise PISMRuntimeError(status, lib.siafd_b200_last_error(None).decode())
+        self._host_out = {}
+        self._bed_smoother_ready = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib.siafd_b200_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _check(self, status):
+        if status != capi.OK:
+            raise PISMRuntimeError(status, lib.siafd_b200_last_error(self._h).decode())
+
+    def field_shape(self, name):
+        w = lib.siafd_b200_field_width(self._h, F[name])
+        dof = lib.siafd_b200_field_dof(self._h, F[name])
+        s = (self.patch.ym + 2 * w, self.patch.xm + 2 * w)
+        return s if dof == 1 else s + (dof,)
+
+    def _host_array(self, name):
+        a = self._host_out.get(name)
+        if a is None:
+            a = np.zeros(self.field_shape(name), dtype=np.float64)
+            self._host_out[name] = a
+        return a
+
+    def download(self, name):
+        """Copy any device field (incl. scratch such as thk_smooth, theta) to a fresh numpy array."""
+        a = np.empty(self.field_shape(name), dtype=np.float64)
+        self._check(lib.siafd_b200_download(self._h, F[name], a.ctypes.data))
+        return a
+
+    def upload(self, name, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == self.field_shape(name), (name, a.shape, self.field_shape(name))
+        self._check(lib.siafd_b200_upload(self._h, F[name], a.ctypes.data))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self):
+        return lib.siafd_b200_launch_count(self._h)
+
+    def set_tuning(self, rows_per_cta=0, use_bulk_copy=-1, skip_ice_free_rows=-1):
+        self._check(lib.siafd_b200_set_tuning(self._h, rows_per_cta, use_bulk_copy, skip_ice_free_rows))
+
+    # -- the SSB_Modifier interface ------------------------------------------------------------
+    def init(self):
+        """SIAFD::init (SIAFD.cc:98-118): nothing to allocate lazily here; kept for interface parity."""
+        super().init()
+
+    def preprocess_bed(self, global_bed):
+        """BedSmoother::preprocess_bed (BedSmoother.cc:99-153) from the global [My, Mx] bed."""
+        g = np.ascontiguousarray(global_bed, dtype=np.float64)
+        assert g.shape == (self.grid.My, self.grid.Mx)
+        self._check(lib.siafd_b200_preprocess_bed(self._h, g.ctypes.data))
+        self._bed_smoother_ready = True
+
+    def update(self, sliding_velocity, inputs, full_update):
+        """SIAFD::update(sliding_velocity, inputs, full_update), SIAFD.cc:122-155."""
+        geo = inputs.geometry
+        if inputs.new_bed_elevation and self.config.smoother_range > 0.0:  # SIAFD.cc:130-134
+            if self._global_bed is None:
+                raise PISMRuntimeError(capi.ERR_BAD_CONFIG,
+                                       "bed smoother is on: pass global_bed= to SIAFD() or call preprocess_bed()")
+            self.preprocess_bed(self._global_bed)
+        device = _is_torch(inputs.enthalpy) and inputs.enthalpy.is_cuda
+        cin = capi.Inputs()
+        cin.surface, cin.thickness = _as_pd(geo.ice_surface_elevation), _as_pd(geo.ice_thickness)
+        cin.mask, cin.bed = _as_pd(geo.cell_type), _as_pd(geo.bed_elevation)
+        cin.enthalpy, cin.age = _as_pd(inputs.enthalpy), _as_pd(inputs.age)
+        cin.sliding = _as_pd(sliding_velocity)
+        cin.current_time = self.current_time
+        cin.memory_space = 1 if device else 0
+        cin.ghosts_valid = 1
+        self._keep = (geo, inputs, sliding_velocity)  # keep arrays alive across the call
+        cout = capi.Outputs()
+        names = ["h_x", "h_y", "D", "flux"] + (["u", "v"] if full_update else [])
+        if device:
+            import torch
+            for n in names + ["u", "v"]:
+                if n not in self._host_out:
+                    self._host_out[n] = torch.zeros(self.field_shape(n), dtype=torch.float64,
+                                                    device=inputs.enthalpy.device)
+            arrs = {n: self._host_out[n] for n in names}
+        else:
+            arrs = {n: self._host_array(n) for n in names}
+        for n in names:
+            setattr(cout, n, _as_pd(arrs[n]))
+        cout.memory_space = 1 if device else 0
+        status = lib.siafd_b200_update(self._h, C.byref(cin), C.byref(cout), 1 if full_update else 0)
+        self.m_D_max = lib.siafd_b200_max_diffusivity(self._h)
+        self.m_h_x, self.m_h_y, self.m_D = arrs["h_x"], arrs["h_y"], arrs["D"]
+        self.m_diffusive_flux = arrs["flux"]
+        if full_update:
+            self.m_u, self.m_v = arrs["u"], arrs["v"]
+        self._check(status)
+
+    # SIAFD.cc:963-977
+    def surface_gradient_x(self):
+        return self.m_h_x
+
+    def surface_gradient_y(self):
+        return self.m_h_y
+
+    def diffusivity(self):
+        return self.m_D
+
+    def high_diffusivity_count(self):
+        return lib.siafd_b200_high_diffusivity_count(self._h)

@@ -1,0 +1,89 @@
+"""Exact solutions used by pismv tests C and F/G, restated in numpy.
+
+Reference sources (compiled unmodified into oracle/_ref/libpism_exact.so where the reference
+tree is mounted; tests/test_exact_solutions.py checks these restatements against that build):
+  * exactC:  src/verification/tests/exactTestsABCD.c:94-121
+  * exactFG: src/verification/tests/exactTestsFG.cc:41-205
+plus the set-ups that turn them into SIAFD inputs:
+  * Test C:  src/verification/iceCompModel.cc:301-356, src/pismv.cc:96-102
+  * Test F/G: src/verification/iCMthermo.cc:101-136, src/stressbalance/sia/siafd_test.cc:154-224
+"""
+import numpy as np
+
+SperA = 31556926.0  # exactTestsABCD.c:26, exactTestsFG.cc:43
+
+
+def exactC(t, r):
+    """H(t, r), M(t, r) of Test C (exactTestsABCD.c:94-121). t in seconds, r array in metres."""
+    r = np.asarray(r, dtype=np.float64)
+    n, H0, R0 = 3.0, 3600.0, 750000.0
+    lam, alpha, beta = 5.0, -1.0, 2.0
+    t0 = 15208.0 * SperA
+    Rmargin = R0 * (t / t0) ** beta
+    with np.errstate(invalid="ignore"):
+        inner = 1.0 - ((t / t0) ** (-beta) * (r / R0)) ** ((n + 1) / n)
+        H = np.where(r < Rmargin, H0 * (t / t0) ** (-alpha) * np.where(inner > 0, inner, 0.0) ** (n / (2 * n + 1)), 0.0)
+    if t > 0.1 * SperA:
+        M = (lam / t) * H
+    else:
+        Rm = R0 * (0.1 * SperA / t0) ** beta
+        M = np.where(r < Rm, 5 * H0 / t0, 0.0)
+    return H, M
+
+
+def _p3(x):
+    # exactTestsFG.cc:30-33
+    return -6.0 + x * (6.0 + x * (-3.0 + x))
+
+
+def exactFG(t, r, z, Cp):
+    """Test F (Cp = 0) / G exact solution at one radius r (0 < r < L) on levels z.
+
+    Returns dict(H, T[Mz], U[Mz]) -- the quantities SIAFD inputs and checks need
+    (exactTestsFG.cc:41-130); w, Sig, Sigc are not restated (out of this path's scope).
+    """
+    z = np.asarray(z, dtype=np.float64)
+    H0, L = 3000.0, 750000.0
+    Tp = 2000.0 * SperA
+    g, Rgas = 9.81, 8.314
+    rho, k, n = 910.0, 2.1, 3.0
+    A, Q = 3.615e-13, 6.0e4
+    Ggeo, ST, Tmin = 0.042, 1.67e-5, 223.15
+    if r <= 0 or r >= L:
+        raise ValueError("exactFG(): code and derivation assume 0 < r < L  !")
+    power = n / (2 * n + 2)
+    Hconst = H0 / (1 - 1 / n) ** power
+    s = r / L
+    lamhat = (1 + 1 / n) * s - (1 / n) + (1 - s) ** (1 + 1 / n) - s ** (1 + 1 / n)
+    if 0.3 * L < r < 0.9 * L:
+        f = np.cos(np.pi * (r - 0.6 * L) / (0.6 * L)) ** 2.0
+    else:
+        f = 0.0
+    goft = Cp * np.sin(2.0 * np.pi * t / Tp)
+    H = Hconst * lamhat ** power + goft * f
+    Ts = Tmin + ST * r
+    nusqrt = np.sqrt(1 + (4.0 * H * Ggeo) / (k * Ts))
+    nu = (k * Ts / (2.0 * Ggeo)) * (1 + nusqrt)
+    T = np.where(z < H, Ts * (nu + H) / (nu + z), Ts)
+    lamhatr = ((1 + 1 / n) / L) * (1 - (1 - s) ** (1 / n) - s ** (1 / n))
+    if 0.3 * L < r < 0.9 * L:
+        fr = -(np.pi / (0.6 * L)) * np.sin(2.0 * np.pi * (r - 0.6 * L) / (0.6 * L))
+    else:
+        fr = 0.0
+    Hr = Hconst * power * lamhat ** (power - 1) * lamhatr + goft * fr
+    if Hr > 0:
+        raise ValueError("exactFG(): assumes H_r negative for all 0 < r < L !")
+    mu = Q / (Rgas * Ts * (nu + H))
+    surfArr = np.exp(-Q / (Rgas * Ts))
+    Uconst = 2.0 * (rho * g) ** n * A
+    omega = Uconst * (-Hr) ** n * surfArr * mu ** (-n - 1)
+    I3 = np.where(z < H, _p3(mu * H) * np.exp(mu * H) - _p3(mu * (H - z)) * np.exp(mu * (H - z)),
+                  _p3(mu * H) * np.exp(mu * H) - _p3(0.0))
+    U = omega * I3
+    return {"H": float(H), "T": T, "U": U}
+
+
+def radius(grid):
+    """radius(grid, i, j) = sqrt(x^2 + y^2) (src/util/IceGrid.cc `radius`), as a [My, Mx] array."""
+    X, Y = np.meshgrid(grid.x, grid.y)
+    return np.sqrt(X * X + Y * Y)
