@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- SIAFD column-updates/s on B200s, with roofline, end-to-end and CPU-baseline figures.
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Workload (BASELINE.json configs[4]): synthetic dome 4096 x 4096 x 101, gpbld flow law, haseloff
+gradient, bed smoother off, full_update = true; strong scaling: the same grid split over N GPUs with
+PISM's DMDA decomposition (IceGrid.cc:443-499), ghost exchange over NCCL.
+One "step" = one SIAFD::update() of every column of the grid.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SIAFD column-updates/sec"
+UNIT = "column-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=4096, help="Mx = My of the dome")
+    ap.add_argument("--mz", type=int, default=101)
+    ap.add_argument("--flux-only", action="store_true", help="time full_update = false instead")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-domain", type=int, default=256, help="edge of each CPU-baseline sample domain")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--rows-per-cta", type=int, default=0)
+    ap.add_argument("--bulk", type=int, default=-1)
+    ap.add_argument("--no-input-exchange", action="store_true",
+                    help="skip the per-step width-2 exchange of the inputs' ghosts (N > 1)")
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_column(Mz, full):
+    """read E, write u and v (3D) + 48 B of 2D reads + 64 B of 2D writes."""
+    return (24 * Mz + 112) if full else (8 * Mz + 112)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (rank 0)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference; PETSc/MPI are not installable here)
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(domain, Mz, nthreads, min_seconds, steps=None, warmup=1, full=True):
+    """Time the CPU restatement on `nthreads` independent domain x domain x Mz dome domains, one per
+    host thread (OpenMP), same flow law / gradient / smoother settings as the GPU workload.
+    Returns (column-updates/s, seconds per step, steps, sample description)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import cases
+    import oracle_lib as O
+    grid, cfg, inputs, _ = cases.case("dome_%d_%d" % (domain, Mz))
+    runs = []
+    for _ in range(nthreads):
+        inp = {k: np.array(v, copy=True) for k, v in inputs.items()}
+        runs.append(O.Run(cfg.oracle_params(grid), inp))
+    P = (O.Params * nthreads)(*[r.p for r in runs])
+    Fa = (O.Fields * nthreads)(*[r.f for r in runs])
+    L = O.lib()
+    cols = grid.Mx * grid.My * nthreads
+
+    def one():
+        st = L.orc_siafd_update_many(nthreads, P, Fa, 1 if full else 0, nthreads)
+        assert st == 0, st
+
+    for _ in range(warmup):
+        one()
+    times = []
+    t_begin = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.perf_counter() - t_begin >= min_seconds and len(times) >= 2:
+            break
+    total = sum(times)
+    sample = ("%d independent dome domains %dx%dx%d (one per host thread, OpenMP), %d updates each; "
+              "restated reference (oracle port), PETSc/MPI unavailable" % (nthreads, domain, domain, Mz, len(times)))
+    return cols * len(times) / total, total / len(times), len(times), sample
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nthreads = os.cpu_count() or 1
+    full = not args.flux_only
+    value, sec, steps, sample = cpu_arm(args.cpu_domain, args.mz, nthreads, 0.0, steps=args.steps,
+                                        warmup=max(args.warmup, 1), full=full)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, "host cores only"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, decomposition):
+    return {
+        "workload": "synthetic dome %dx%dx%d SIAFD::update full_update=%s (BASELINE configs[4])" %
+                    (args.size, args.size, args.mz, "false" if args.flux_only else "true"),
+        "flow_law": "gpbld", "gradient": "haseloff", "bed_smoother": "off", "dx_m": 5000.0,
+        "decomposition": decomposition,
+        "l2": "inputs exceed L2 (%.1f GB enthalpy read + %.1f GB u,v written per step vs 126 MB L2)" %
+              (args.size ** 2 * args.mz * 8 / 1e9, 2 * args.size ** 2 * args.mz * 8 / 1e9),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_main(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pism_b200 import capi, grid as G, synthetic as S
+    from pism_b200.capi import F, lib
+    from pism_b200.halo import HaloExchanger, global_max
+    from pism_b200.sia import SIAFD, PISMRuntimeError
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N = world
+    full = not args.flux_only
+
+    M, Mz = args.size, args.mz
+    L = (M - 1) / 2.0 * 5000.0
+    grid = G.Grid(M, M, Mz, L, L, 4000.0)
+    patches = G.decompose(M, M, N)
+    patch = patches[rank]
+    cfg = capi.default_config()
+    cfg.smoother_range = 0.0
+    sia = SIAFD(grid, config=cfg, patch=patch, device=local_rank)
+    if args.rows_per_cta or args.bulk >= 0:
+        sia.set_tuning(args.rows_per_cta, args.bulk, -1)
+    stream = torch.cuda.current_stream()
+    assert lib.siafd_b200_set_stream(sia.handle, stream.cuda_stream) == 0
+
+    # ---- inputs resident in HBM, outputs too; bound as the handle's field storage ----
+    t_gen = time.perf_counter()
+    inp = S.dome(grid, patch, sia.config, device=dev)
+    fields = {"surface": inp["surface"], "thickness": inp["thickness"], "mask": inp["mask"], "bed": inp["bed"],
+              "enthalpy": inp["enthalpy"], "sliding": inp["sliding"]}
+    for name in ("h_x", "h_y", "D", "flux", "u", "v"):
+        fields[name] = torch.zeros(sia.field_shape(name), dtype=torch.float64, device=dev)
+    for name, t in fields.items():
+        assert t.is_contiguous()
+        st = lib.siafd_b200_bind(sia.handle, F[name], t.data_ptr())
+        assert st == 0, (name, lib.siafd_b200_last_error(sia.handle))
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+
+    halo = HaloExchanger(patch, sia)
+    wg, we, ws = sia.config.w_geom, sia.config.w_3d_in, sia.config.w_sliding
+    multi = N > 1
+
+    def check(st):
+        if st != 0:
+            raise PISMRuntimeError(st, lib.siafd_b200_last_error(sia.handle).decode())
+
+    def step_device():
+        """SIAFD::update on device-resident fields, ghost exchanges where the reference has them."""
+        if multi and not args.no_input_exchange:
+            for name, w in (("surface", wg), ("thickness", wg), ("mask", wg), ("bed", wg), ("enthalpy", we)):
+                halo.exchange(name, fields[name], w)
+        check(lib.siafd_b200_compute_gradient(sia.handle))
+        for name in ("h_x", "h_y"):          # SIAFD.cc:498-499
+            if multi:
+                halo.exchange(name, fields[name], 1)
+            else:
+                check(lib.siafd_b200_wrap_ghosts(sia.handle, F[name]))
+        check(lib.siafd_b200_compute_flux_velocity(sia.handle, 1 if full else 0, 0.0))
+        if full:
+            for name in ("u", "v"):          # SIAFD.cc:946-947
+                if multi:
+                    halo.exchange(name, fields[name], 1)
+                else:
+                    check(lib.siafd_b200_wrap_ghosts(sia.handle, F[name]))
+        check(lib.siafd_b200_finish(sia.handle))              # error flags + D_max (host sync, as in PISM)
+        return global_max(lib.siafd_b200_max_diffusivity(sia.handle), dev)   # SIAFD.cc:748
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if multi:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    # ---- timed region: K steps, device-resident ----
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    check(lib.siafd_b200_kernel_timing(sia.handle, 1))
+    launches0 = sia.launch_count()
+    if sampler:
+        sampler.start()
+    ms, dmax = timed(step_device, args.steps, 0)
+    clocks = sampler.stop() if sampler else None
+    launches = sia.launch_count() - launches0
+    nk = C.c_int(0)
+    kernel_ms = lib.siafd_b200_kernel_time_ms(sia.handle, C.byref(nk))
+    check(lib.siafd_b200_kernel_timing(sia.handle, 0))
+    cols_total = M * M
+    value = cols_total * args.steps / (ms / 1e3)
+
+    # roofline of the dominant (fused) kernel on this rank; report the slowest rank's
+    B = algorithmic_bytes_per_column(Mz, full)
+    k_avg_ms = kernel_ms / max(nk.value, 1)
+    if multi:
+        t = torch.tensor([k_avg_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        k_avg_ms = float(t.item())
+    peak, peak_src = measured_peak()
+    achieved = B * patch.xm * patch.ym / (k_avg_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_sia_fused", "kernel_ms": k_avg_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_column": B, "columns_per_launch": patch.xm * patch.ym,
+                "whole_step_frac": B * cols_total / N / (ms / args.steps / 1e3) / 1e9 / peak}
+    tr = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("bytes_per_launch_%d" % M)
+        except Exception:
+            pass
+
+    # ---- end to end through the reference-facing call with HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        h2d = d2h = 0
+        for name in ("surface", "thickness", "mask", "bed", "enthalpy", "sliding"):
+            host[name] = torch.empty(fields[name].shape, dtype=torch.float64, pin_memory=True)
+            host[name].copy_(fields[name])
+            h2d += host[name].numel() * 8
+        outs = ["h_x", "h_y", "D", "flux"] + (["u", "v"] if full else [])
+        for name in outs:
+            host[name] = torch.empty(fields[name].shape, dtype=torch.float64, pin_memory=True)
+            d2h += host[name].numel() * 8
+        torch.cuda.synchronize()
+
+        def pd(t):
+            return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_double))
+
+        cin, cout = capi.Inputs(), capi.Outputs()
+        cin.surface, cin.thickness, cin.mask, cin.bed = pd(host["surface"]), pd(host["thickness"]), pd(host["mask"]), pd(host["bed"])
+        cin.enthalpy, cin.sliding = pd(host["enthalpy"]), pd(host["sliding"])
+        cin.current_time, cin.memory_space, cin.ghosts_valid = 0.0, 0, 1
+        cout.h_x, cout.h_y, cout.D, cout.flux = pd(host["h_x"]), pd(host["h_y"]), pd(host["D"]), pd(host["flux"])
+        if full:
+            cout.u, cout.v = pd(host["u"]), pd(host["v"])
+        cout.memory_space = 0
+
+        def step_e2e():
+            if not multi:
+                check(lib.siafd_b200_update(sia.handle, C.byref(cin), C.byref(cout), 1 if full else 0))
+                return lib.siafd_b200_max_diffusivity(sia.handle)
+            for name in ("surface", "thickness", "mask", "bed", "enthalpy", "sliding"):
+                check(lib.siafd_b200_upload(sia.handle, F[name], host[name].data_ptr()))
+            d = step_device()
+            for name in outs:
+                check(lib.siafd_b200_download(sia.handle, F[name], host[name].data_ptr()))
+            return d
+
+        ms_e, dmax_e = timed(step_e2e, args.e2e_steps, 1)
+        e2e = {"value": cols_total * args.e2e_steps / (ms_e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d * N if not multi else int(h2d * N), "d2h_bytes_per_step": int(d2h * N),
+               "ms_per_step": ms_e / args.e2e_steps, "steps": args.e2e_steps,
+               "api": "siafd_b200_update(host pointers)" if not multi else "upload + split update + download",
+               "host_memory": "pinned"}
+        assert dmax_e == dmax
+        del host
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu_baseline:
+        nthreads = os.cpu_count() or 1
+        v, sec, steps_c, sample = cpu_arm(args.cpu_domain, Mz, nthreads, args.cpu_seconds, full=full)
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, "%dx%d (PISM DMDA rule)" % (patch.Nx, patch.Ny)),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "D_max": dmax, "halo_bytes_per_step_per_rank": halo.bytes_sent // max(args.steps + W, 1),
+            "input_generation_s": t_gen,
+        }
+        print(json.dumps(line))
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -192,6 +192,9 @@ int siafd_b200_download(siafd_b200_handle *h, int field, double *host);
 /* Periodic self-wrap of a field's ghosts on device (single rank owning the whole domain in
  * the wrapped direction; util/IceGrid.cc:870-872: the DMDA is always periodic). */
 int siafd_b200_wrap_ghosts(siafd_b200_handle *h, int field);
+/* One direction only: dir 0 = x over the owned rows, dir 1 = y over all columns (x ghosts included).
+ * A rank whose periodic neighbour in that direction is itself uses this in place of an exchange. */
+int siafd_b200_wrap_ghosts_dir(siafd_b200_handle *h, int field, int dir);
 /* Multi-rank halo exchange support: pack the owned strip that a neighbour needs into a
  * contiguous device buffer / unpack a received strip into the ghost region.
  * dir_x, dir_y in {-1,0,1} name the neighbour; width = ghost width to exchange (<= field
@@ -236,10 +239,15 @@ int siafd_b200_geometry_compute(siafd_b200_handle *h, int64_t n, const double *s
 int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev, const double *enthalpy_dev,
                       const double *pressure_dev, const double *grainsize_dev, double *result_dev);
 
-/* Kernel tuning knobs (tile rows per CTA etc.); 0 keeps the default.  For benchmarking. */
+/* Kernel tuning knobs, for benchmarking: rows_per_cta > 0 sets the row-segment length one CTA
+ * marches over (0 keeps it); use_bulk_copy / skip_ice_free_rows: 0 or 1 sets, -1 keeps. */
 int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_copy, int skip_ice_free_rows);
 /* Number of kernel launches issued by this handle since create (bench.py's gpu_launches). */
 int64_t siafd_b200_launch_count(const siafd_b200_handle *h);
+/* CUDA-event timing of the fused kernel alone, on the handle's stream (bench.py's roofline):
+ * enable, run updates (<= 256), then read the accumulated milliseconds and launch count. */
+int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable);
+double siafd_b200_kernel_time_ms(siafd_b200_handle *h, int *launches_out);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,7 @@ def _load():
         "siafd_b200_upload": (C.c_int, [vp, C.c_int, vp]),
         "siafd_b200_download": (C.c_int, [vp, C.c_int, vp]),
         "siafd_b200_wrap_ghosts": (C.c_int, [vp, C.c_int]),
+        "siafd_b200_wrap_ghosts_dir": (C.c_int, [vp, C.c_int, C.c_int]),
         "siafd_b200_halo_count": (i64, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
         "siafd_b200_halo_pack": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "siafd_b200_halo_unpack": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
@@ -94,6 +95,8 @@ def _load():
         "siafd_b200_flow_n": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
         "siafd_b200_set_tuning": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "siafd_b200_launch_count": (i64, [vp]),
+        "siafd_b200_kernel_timing": (C.c_int, [vp, C.c_int]),
+        "siafd_b200_kernel_time_ms": (C.c_double, [vp, C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not export a declared symbol

@@ -40,6 +40,10 @@ struct siafd_b200_handle {
   double *d_global_bed = nullptr;
   Tuning tuning;
   int64_t launches = 0;
+  // CUDA-event pairs around the fused kernel (bench.py's roofline timing), a ring of 256
+  std::vector<cudaEvent_t> ev_start, ev_stop;
+  int ev_count = 0;
+  bool timing = false;
   std::string err;
 };
 
@@ -437,6 +441,10 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   if (h->h_res) {
     cudaFreeHost(h->h_res);
   }
+  for (size_t q = 0; q < h->ev_start.size(); ++q) {
+    cudaEventDestroy(h->ev_start[q]);
+    cudaEventDestroy(h->ev_stop[q]);
+  }
   if (h->own_stream) {
     cudaStreamDestroy(h->own_stream);
   }
@@ -510,6 +518,16 @@ int siafd_b200_wrap_ghosts(siafd_b200_handle *h, int f) {
   st = wrap_dir(h, f, 0);
   if (st) return st;
   return wrap_dir(h, f, 1);
+}
+
+int siafd_b200_wrap_ghosts_dir(siafd_b200_handle *h, int f, int dir) {
+  CU(h, cudaSetDevice(h->device));
+  int st = ensure(h, f);
+  if (st) return st;
+  if (dir != 0 && dir != 1) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "dir must be 0 (x) or 1 (y)");
+  }
+  return wrap_dir(h, f, dir);
 }
 
 // Strip geometry of the two-stage exchange.  Stage x (dir_x != 0): w columns, owned rows.
@@ -688,7 +706,15 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, doub
   if (h->tuning.tile_x > 0 && h->tuning.tile_x < T.tile_x) {
     T.tile_x = h->tuning.tile_x;
   }
+  const bool timed = h->timing && h->ev_count < (int)h->ev_start.size();
+  if (timed) {
+    CU(h, cudaEventRecord(h->ev_start[h->ev_count], h->stream));
+  }
   const int n = launch_fused(h->P, F, full_update != 0, T, h->stream);
+  if (timed) {
+    CU(h, cudaEventRecord(h->ev_stop[h->ev_count], h->stream));
+    h->ev_count += 1;
+  }
   if (n < 0) {
     return fail(h, SIAFD_B200_ERR_CUDA, "could not configure the fused kernel (shared memory %zu bytes)",
                 fused_smem_bytes(h->P, full_update != 0, T.tile_x));
@@ -836,5 +862,39 @@ int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_c
 }
 
 int64_t siafd_b200_launch_count(const siafd_b200_handle *h) { return h->launches; }
+
+int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable) {
+  CU(h, cudaSetDevice(h->device));
+  if (enable && h->ev_start.empty()) {
+    h->ev_start.resize(256);
+    h->ev_stop.resize(256);
+    for (size_t q = 0; q < h->ev_start.size(); ++q) {
+      CU(h, cudaEventCreate(&h->ev_start[q]));
+      CU(h, cudaEventCreate(&h->ev_stop[q]));
+    }
+  }
+  h->timing = enable != 0;
+  h->ev_count = 0;
+  return SIAFD_B200_OK;
+}
+
+double siafd_b200_kernel_time_ms(siafd_b200_handle *h, int *launches_out) {
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) {
+    return -1.0;
+  }
+  double total = 0.0;
+  for (int q = 0; q < h->ev_count; ++q) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_start[q], h->ev_stop[q]) != cudaSuccess) {
+      return -1.0;
+    }
+    total += ms;
+  }
+  if (launches_out) {
+    *launches_out = h->ev_count;
+  }
+  h->ev_count = 0;
+  return total;
+}
 
 } // extern "C"

@@ -1,0 +1,180 @@
+"""Oracle-only checks (CPU): exact solutions, decomposition independence, semantics gotchas."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as O
+from pism_b200 import grid as G
+from pism_b200 import verification as V
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_EXACT), reason="oracle/_ref not built (needs /root/reference)")
+def test_numpy_exact_solutions_match_reference_build():
+    """pism_b200.verification restates exactC / exactFG; check against the reference's own sources
+    compiled unmodified (oracle/Makefile target `ref`)."""
+    ref = C.CDLL(O.REF_EXACT)
+    pd = C.POINTER(C.c_double)
+    ref.ref_exactC.argtypes = [C.c_double, C.c_double, pd, pd]
+    ref.ref_exactFG.argtypes = [C.c_double, C.c_double, C.c_int, pd, C.c_double] + [pd] * 7
+    H, M = C.c_double(), C.c_double()
+    for t in (15208.0 * V.SperA, 20000.0 * V.SperA, 0.05 * V.SperA):
+        for r in np.linspace(0.0, 900e3, 61):
+            ref.ref_exactC(t, r, C.byref(H), C.byref(M))
+            h, m = V.exactC(t, np.array([r]))
+            assert abs(h[0] - H.value) <= 1e-12 * max(1.0, H.value)
+            assert abs(m[0] - M.value) <= 1e-12 * max(1e-12, abs(M.value))
+    z = np.linspace(0.0, 4000.0, 31)
+    for t, Cp in ((0.0, 0.0), (500 * V.SperA, 200.0)):
+        for r in np.linspace(1.0, 749.9e3, 41):
+            out = [np.zeros(31) for _ in range(5)]
+            assert ref.ref_exactFG(t, r, 31, z.ctypes.data_as(pd), Cp, C.byref(H), C.byref(M),
+                                   *[a.ctypes.data_as(pd) for a in out]) == 0
+            e = V.exactFG(t, r, z, Cp)
+            assert abs(e["H"] - H.value) <= 1e-13 * H.value
+            assert np.max(np.abs(e["T"] - out[0])) <= 1e-12
+            assert np.max(np.abs(e["U"] - out[1])) <= 1e-13 * np.max(np.abs(out[1])) + 1e-30
+    # spot values recorded in SURVEY.md section 8(c)
+    assert abs(V.exactC(15208.0 * V.SperA, np.array([300e3]))[0][0] - 3099.659127) < 1e-6
+    assert abs(V.exactFG(0.0, 300e3, z, 0.0)["H"] - 2503.108496) < 1e-6
+
+
+def test_test_C_diffusivity_against_exact_solution():
+    """Isothermal SIA: D = Gamma H^(n+2) |grad h|^(n-1), Gamma = 2 A (rho g)^n / (n+2)
+    (Bueler et al. 2005; exactTestsABCD.c constants).  On Test C's exact thickness the computed
+    staggered D must converge to it away from the margin (second order in dx and dz)."""
+    errs = []
+    for size, Mz in ((31, 31), (61, 61)):
+        grid = G.Grid(size, size, Mz, 1000e3, 1000e3, 4000.0)
+        cfg = cases.Cfg(flow_law="isothermal_glen", iso_softness_A=1.0e-16 / cases.SECPERA_UDUNITS,
+                        smoother_range=0.0, dry_simulation=1, gradient_method="mahaffy", **cases.cold_converter())
+        from pism_b200 import synthetic as S
+        inputs = cases.to_numpy(S.test_C_state(grid, grid.whole(), cfg))
+        run = cases.oracle_run(grid, cfg, inputs, full=False)
+        assert run.status == 0
+        D = cases.interior(run.a["D"], 1)[:, :, 0]  # i-offset points
+        t0 = 15208.0 * V.SperA
+        xs = grid.x + 0.5 * grid.dx
+        X, Y = np.meshgrid(xs, grid.y)
+        r = np.sqrt(X * X + Y * Y)
+        H, _ = V.exactC(t0, r)
+        eps = 1.0
+        Hp, _ = V.exactC(t0, r + eps)
+        Hm, _ = V.exactC(t0, np.maximum(r - eps, 0.0))
+        slope = np.abs(Hp - Hm) / (2 * eps)
+        Gamma = 2.0 * cfg.iso_softness_A * (910.0 * 9.81) ** 3 / 5.0
+        Dex = Gamma * H ** 5 * slope ** 2
+        sel = (r > 100e3) & (r < 550e3) & (np.arange(size)[None, :] < size - 1)
+        errs.append(np.max(np.abs(D[sel] - Dex[sel]) / Dex[sel]))
+    assert errs[0] < 0.08 and errs[1] < 0.04 and errs[1] < 0.6 * errs[0], errs
+
+
+def test_test_F_surface_velocity_against_exact_solution():
+    """Shape of siafd_test.cc:105-151: one full update on the Test F state, surface speed vs exactFG."""
+    grid, cfg, inputs, _ = cases.case("Fs")
+    run = cases.oracle_run(grid, cfg, inputs, full=True)
+    assert run.status == 0
+    u, v = cases.interior(run.a["u"], 1), cases.interior(run.a["v"], 1)
+    w = cfg.w_geom
+    H = cases.interior(inputs["thickness"], w)
+    Uex = cases.interior(inputs["exact_surface_speed"], w)
+    r = cases.interior(inputs["radius"], w)
+    maxerr, n = 0.0, 0
+    for j in range(grid.My):
+        for i in range(grid.Mx):
+            if 1.0 <= r[j, i] <= 750000.0 - 1.0 and H[j, i] > 0:
+                # IceModelVec3::getValZ: linear interpolation in z (util/iceModelVec3.cc)
+                k = grid.k_below_height(H[j, i])
+                lam = (H[j, i] - grid.z[k]) / (grid.z[k + 1] - grid.z[k])
+                us = u[j, i, k] + lam * (u[j, i, k + 1] - u[j, i, k])
+                vs = v[j, i, k] + lam * (v[j, i, k + 1] - v[j, i, k])
+                uex, vex = grid.x[i] / r[j, i] * Uex[j, i], grid.y[j] / r[j, i] * Uex[j, i]
+                maxerr = max(maxerr, np.hypot(us - uex, vs - vex))
+                n += 1
+    secpera = V.SperA
+    # the 31^2 Test G golden row of test_17.sh has maxUvec 0.945 m/a after 1000 model years; a single
+    # update from the exact state must be in that range, and tiny next to the ~10 m/a speeds
+    print("Test F 31x31x31: max |U_surface error| = %.4f m/a, max exact speed = %.4f m/a" %
+          (maxerr * secpera, np.max(Uex) * secpera))
+    assert n > 300 and maxerr * secpera < 1.0, maxerr * secpera
+    assert np.max(Uex) * secpera > 2.0 and maxerr < 0.2 * np.max(Uex)
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4, 6])
+@pytest.mark.parametrize("name", ["C2t", "C4s"])
+def test_decomposition_independence(name, nranks):
+    """test/regression/test_02.sh: results must not depend on the number of ranks, bit for bit.
+    Patches get their ghosts by copying from neighbours exactly where the reference communicates
+    (SIAFD.cc:498-499 and :946-947)."""
+    grid, cfg, inputs, gb = cases.case(name)
+    whole = cases.oracle_run(grid, cfg, inputs, gb, full=True)
+    assert whole.status == 0
+    patches = G.decompose(grid.Mx, grid.My, nranks)
+    p0 = cfg.oracle_params(grid)
+    sm = O.preprocess_bed(p0, gb) if cfg.smoother_range > 0 else None
+    runs = []
+    for pt in patches:
+        loc = {k: G.global_to_local(cases.interior(inputs[k], w), pt, w)
+               for k, w in (("surface", cfg.w_geom), ("thickness", cfg.w_geom), ("mask", cfg.w_geom),
+                            ("bed", cfg.w_geom), ("enthalpy", cfg.w_3d_in), ("sliding", cfg.w_sliding))}
+        smoothed = None
+        if sm is not None:
+            smoothed = {k: G.global_to_local(sm[k], pt, cfg.w_geom) for k in ("topgsmooth", "maxtl", "C2", "C3", "C4")}
+            smoothed["active"] = sm["active"]
+        runs.append(O.Run(cfg.oracle_params(grid, pt), loc, smoothed))
+
+    def exchange(field, w):
+        """Ghost update: assemble the global owned values, then re-cut every patch with ghosts."""
+        shape = runs[0].a[field].shape[2:]
+        g = np.zeros((grid.My, grid.Mx) + shape)
+        for pt, r in zip(patches, runs):
+            g[pt.ys:pt.ys + pt.ym, pt.xs:pt.xs + pt.xm] = cases.interior(r.a[field], w)
+        for pt, r in zip(patches, runs):
+            r.a[field][...] = G.global_to_local(g, pt, w)
+        return g
+
+    for r in runs:
+        assert r.gradient() == 0
+    if cfg.gradient_method == O.GRADIENTS["haseloff"]:
+        exchange("h_x", 1)
+        exchange("h_y", 1)
+    for r in runs:
+        assert r.flux_velocity(True) == 0
+    for field, w in (("u", 1), ("v", 1), ("D", 1), ("Q", 1), ("h_x", 1), ("h_y", 1)):
+        g = np.zeros((grid.My, grid.Mx) + runs[0].a[field].shape[2:])
+        for pt, r in zip(patches, runs):
+            g[pt.ys:pt.ys + pt.ym, pt.xs:pt.xs + pt.xm] = cases.interior(r.a[field], w)
+        assert np.array_equal(g, cases.interior(whole.a[field], w)), field
+    assert max(r.D_max for r in runs) == whole.D_max
+
+
+def test_semantics_gotchas():
+    """SURVEY.md 8(a'): G2 edge override for both offsets, G3 delta unaffected, G9/G10."""
+    grid, cfg, inputs, _ = cases.case("dome_48_21")
+    # make ice reach the domain edge so the override matters
+    w = cfg.w_geom
+    tilt = 300.0 * (np.arange(grid.Mx)[None, :] / grid.Mx + np.arange(grid.My)[:, None] / grid.My)
+    for k in ("thickness", "surface"):
+        inputs[k][w:-w, w:-w] = np.maximum(inputs[k][w:-w, w:-w], 500.0) + tilt
+        G.wrap_ghosts(inputs[k], w)
+    inputs["mask"][...] = 2.0
+    cfg.D_limit = 1.0e9  # this small, steep dome is far above the default 100 m2/s
+    run = cases.oracle_run(grid, cfg, inputs, full=True)
+    assert run.status == 0
+    D = cases.interior(run.a["D"], 1)
+    assert np.all(D[:, grid.Mx - 1, :] == 0.0) and np.all(D[grid.My - 1, :, :] == 0.0)   # G2
+    assert np.any(cases.interior(run.a["delta_0"], 1)[:, grid.Mx - 1, :] != 0.0)         # G3
+    assert np.all(D[:-1, :-1, :] >= 0.0) and run.D_max == D.max()
+    # G10: full_update = false leaves u, v untouched
+    run2 = cases.oracle_run(grid, cfg, inputs, full=False)
+    assert np.all(run2.a["u"] == 0.0) and np.array_equal(run2.a["D"], run.a["D"])
+    # limit_diffusivity: D >= D_limit is capped and counted (G13)
+    cfg.limit_diffusivity, cfg.D_limit = 1, 0.5 * run.D_max
+    run3 = cases.oracle_run(grid, cfg, inputs, full=False)
+    assert run3.status == 0 and run3.D_max == cfg.D_limit and run3.f.high_diffusivity_counter > 0
+    # not limiting and D_max > D_limit -> the reference throws (SIAFD.cc:752-760)
+    cfg.limit_diffusivity = 0
+    run4 = cases.oracle_run(grid, cfg, inputs, full=False)
+    assert run4.status == 5
