@@ -220,6 +220,7 @@ void fill_dp(siafd_b200_handle *h) {
   P.e = c.fl_e, P.e_inter = c.fl_e_interglacial;
   P.A_cold = c.fl_A_cold, P.A_warm = c.fl_A_warm, P.Q_cold = c.fl_Q_cold, P.Q_warm = c.fl_Q_warm;
   P.T_crit = c.fl_T_crit, P.R = c.fl_R;
+  P.QoR_cold = c.fl_Q_cold / c.fl_R, P.QoR_warm = c.fl_Q_warm / c.fl_R;
   {
     // rheology/FlowLaw.cc:45 and PatersonBudd.cc:57, evaluated like the reference does
     const double beta_CC_grad = c.fl_beta * c.fl_rho * c.fl_g;
@@ -386,8 +387,8 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   }
   fill_dp(h);
   h->tuning.rows_per_cta = 64;
-  h->tuning.use_bulk_copy = 0;
-  h->tuning.skip_ice_free = 0;
+  h->tuning.use_bulk_copy = 1;
+  h->tuning.skip_ice_free = 1;
   h->tuning.tile_x = pick_tile_x(h->P, true);
   if (h->tuning.tile_x == 0) {
     delete h;

@@ -28,6 +28,7 @@ struct DP {
   int law, n_is_3;
   double n, nm1, e, e_inter;
   double A_cold, A_warm, Q_cold, Q_warm, T_crit, R;
+  double QoR_cold, QoR_warm; // Q / R, for the lean Arrhenius evaluation in siafd_fused.cu
   double beta_ratio; // m_beta_CC_grad / (m_rho * m_g), rheology/PatersonBudd.cc:57
   double gp_T0, gp_coeff, gp_limit, gp_softness_T0; // rheology/GPBLD.cc:49-61
   double iso_A;

@@ -6,8 +6,7 @@
 //   k_prep2d        BedSmoother::smoothed_thk + ::theta      sia/BedSmoother.cc:284-327, :351-404
 //   k_eta           eta = H^((2n+2)/n)                        sia/SIAFD.cc:241-245
 //   k_grad_*        surface_gradient_{mahaffy,eta,haseloff}   sia/SIAFD.cc:224-496
-//   k_sia_fused     compute_diffusivity + compute_diffusive_flux + compute_I +
-//                   compute_3d_horizontal_velocity, fused     sia/SIAFD.cc:543-948
+//   k_sia_fused     (siafd_fused.cu) diffusivity + flux + I + 3D velocity, fused   sia/SIAFD.cc:543-948
 //   k_copy_region   ghost wrap / halo pack (DMLocalToLocal)   util/iceModelVec.cc:630-643
 //   k_geometry      GeometryCalculator::compute               util/Mask.hh:96-133
 //   k_flow_n        FlowLaw::flow_n                           rheology/FlowLaw.cc:107-119
@@ -25,44 +24,6 @@
 namespace siafd {
 
 #define FULLMASK 0xffffffffu
-
-// ---------------------------------------------------------------------------------------------
-// small PTX helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-// mbarrier + 1-D bulk copy (TMA engine, no tensor map: rows are contiguous runs of doubles)
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile("{\n"
-               ".reg .pred p;\n"
-               "WAIT_LOOP:\n"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-               "@p bra.uni WAIT_DONE;\n"
-               "bra.uni WAIT_LOOP;\n"
-               "WAIT_DONE:\n"
-               "}\n" ::"r"(smem_u32(bar)),
-               "r"(parity)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // k_prep2d: thk_smooth and theta on owned + wg ghosts (no communication, like the reference)
@@ -283,438 +244,6 @@ __global__ void k_grad_haseloff_b(const __grid_constant__ DP P, const Fields F) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// The fused diffusivity / flux / I / velocity kernel
-// ---------------------------------------------------------------------------------------------
-//
-// CTA = strip of TX "extended" columns [ca, cb) x row segment [ra, rb) of the extended patch
-// (owned + 1 ghost ring = the reference's PointsWithGhosts(1) iteration space).
-// blockDim.x = 16 * (TX + 2): half-warp "groups" g = 0 .. TX+1; lane l = z level within a chunk
-// of 16 levels.  Per row r, group g integrates two staggered columns together:
-//   A: o = 0 (i-offset) at column c0 = ca - 1 + g   (g = 0 is the west halo column: its I feeds
-//                                                     the u,v of column ca, its D belongs to the
-//                                                     neighbouring strip)
-//   B: o = 1 (j-offset) at column c1 = ca + g
-// then (full update) group g writes u,v of the regular column c1 in row r from
-//   I_e = I0[g+1], I_w = I0[g], I_n = I1[cur][g], I_s = I1[prev][g].
-// Shared memory: z[Mz] | E rows: 3 slots x (TX+2) columns x Mz | [age rows likewise] |
-//                I0: (TX+1) x Mz | I1: 2 x TX x Mz.
-// Enthalpy row r+2 streams in (cp.async or one cp.async.bulk) while row r is integrated.
-
-// lane l of group g fetches one scalar of row r:
-//  0,1: thk_smooth at the two ends of A      2,3: theta at the two ends of A     4,5: h_x,h_y of A
-//  6,7: thk_smooth at the two ends of B      8,9: theta at the two ends of B   10,11: h_x,h_y of B
-// 12,13: sliding u,v at (c1, r)             14,15: h_x,h_y of the east staggered point (c1, r, 0)
-__device__ __forceinline__ double fetch_scalar(const DP &P, const Fields &F, int r, int g, int l, int ca, int ncol,
-                                               bool has_west, int ra, bool full) {
-  const int c0 = ca - 1 + g, c1 = ca + g;
-  const bool validA = (g <= ncol) && (g > 0 || has_west) && (r >= ra);
-  const bool validB = (g < ncol);
-  const double *ptr = nullptr;
-  switch (l) {
-  case 0:
-    if (validA) ptr = F.thk_smooth + idx2(P, c0, r, P.wg);
-    break;
-  case 1:
-    if (validA) ptr = F.thk_smooth + idx2(P, c0 + 1, r, P.wg);
-    break;
-  case 2:
-    if (validA) ptr = F.theta + idx2(P, c0, r, P.wg);
-    break;
-  case 3:
-    if (validA) ptr = F.theta + idx2(P, c0 + 1, r, P.wg);
-    break;
-  case 4:
-    if (validA) ptr = F.h_x + idx2(P, c0, r, P.wst) * 2;
-    break;
-  case 5:
-    if (validA) ptr = F.h_y + idx2(P, c0, r, P.wst) * 2;
-    break;
-  case 6:
-    if (validB) ptr = F.thk_smooth + idx2(P, c1, r, P.wg);
-    break;
-  case 7:
-    if (validB) ptr = F.thk_smooth + idx2(P, c1, r + 1, P.wg);
-    break;
-  case 8:
-    if (validB) ptr = F.theta + idx2(P, c1, r, P.wg);
-    break;
-  case 9:
-    if (validB) ptr = F.theta + idx2(P, c1, r + 1, P.wg);
-    break;
-  case 10:
-    if (validB) ptr = F.h_x + idx2(P, c1, r, P.wst) * 2 + 1;
-    break;
-  case 11:
-    if (validB) ptr = F.h_y + idx2(P, c1, r, P.wst) * 2 + 1;
-    break;
-  case 12:
-  case 13: {
-    const bool owned = validB && c1 >= P.xs && c1 < P.xs + P.xm && r >= P.ys && r < P.ys + P.ym;
-    if (full && owned && F.sliding != nullptr) ptr = F.sliding + idx2(P, c1, r, P.wsl) * 2 + (l - 12);
-    break;
-  }
-  case 14:
-    if (full && validB && r >= ra) ptr = F.h_x + idx2(P, c1, r, P.wst) * 2;
-    break;
-  default:
-    if (full && validB && r >= ra) ptr = F.h_y + idx2(P, c1, r, P.wst) * 2;
-    break;
-  }
-  return ptr ? __ldg(ptr) : 0.0;
-}
-
-// IceGrid::kBelowHeight (util/IceGrid.cc:427-440; GSL bsearch: largest k in [0, Mz-2] with z[k] <= height)
-__device__ __forceinline__ int k_below_height(const double *z_s, int Mz, double height, unsigned *err) {
-  if (height < 0.0 - 1.0e-6) {
-    atomicOr(err, EB_BELOW);
-    return 0;
-  }
-  if (height > z_s[Mz - 1] + 1.0e-6) {
-    atomicOr(err, EB_ABOVE);
-    return 0;
-  }
-  int ilo = 0, ihi = Mz - 1;
-  while (ihi > ilo + 1) {
-    const int m = (ihi + ilo) >> 1;
-    if (z_s[m] > height) {
-      ihi = m;
-    } else {
-      ilo = m;
-    }
-  }
-  return ilo;
-}
-
-__device__ __forceinline__ double scan16(double x, int l) {
-#pragma unroll
-  for (int d = 1; d < 16; d <<= 1) {
-    const double y = __shfl_up_sync(FULLMASK, x, d, 16);
-    if (l >= d) {
-      x += y;
-    }
-  }
-  return x;
-}
-
-__device__ __forceinline__ double sum16(double x) {
-#pragma unroll
-  for (int d = 8; d >= 1; d >>= 1) {
-    x += __shfl_xor_sync(FULLMASK, x, d, 16);
-  }
-  return x;
-}
-
-template <int LAW, bool FULL>
-__global__ void __launch_bounds__(288, 2)
-    k_sia_fused(const __grid_constant__ DP P, const Fields F, const int TX, const int RS, const int use_bulk) {
-  extern __shared__ __align__(16) double sm[];
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const int l = tid & 15, g = tid >> 4;
-  const int Mz = P.Mz;
-  const int NCE = TX + 2; // enthalpy columns per row slot
-
-  // ---- shared memory carve-up (all offsets in doubles; every region starts 16B-aligned) ----
-  const int Mz2 = (Mz + 1) & ~1;
-  const long slotE = ((long)NCE * Mz + 2 + 1) & ~1L; // +2: bulk copies may start one double early
-  double *z_s = sm;
-  double *E_s = z_s + Mz2;
-  double *A_s = E_s + 3 * slotE; // age rows (only when P.use_age)
-  double *I0_s = A_s + (P.use_age ? 3 * slotE : 0);
-  double *I1_s = I0_s + (FULL ? (((long)(TX + 1) * Mz + 1) & ~1L) : 0);
-  unsigned long long *bars = (unsigned long long *)(I1_s + (FULL ? (((long)2 * TX * Mz + 1) & ~1L) : 0));
-
-  const int ca = (P.xs - 1) + blockIdx.x * TX;
-  const int cb = min(ca + TX, P.xs + P.xm + 1);
-  const int ncol = cb - ca;
-  const int ra = (P.ys - 1) + blockIdx.y * RS;
-  const int rb = min(ra + RS, P.ys + P.ym + 1);
-  const bool has_west = blockIdx.x > 0;
-  const int r0 = (FULL && blockIdx.y > 0) ? ra - 1 : ra; // warm-up row: I1 of the row below the segment
-
-  for (int k = tid; k < Mz; k += NT) {
-    z_s[k] = F.z[k];
-  }
-  if (use_bulk && tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  // ---- enthalpy (and age) row loader: columns [ca-1, cb] of row r -> slot ----
-  const int rowcount = (ncol + 2) * Mz;
-  const long NXe = P.xm + 2 * P.we;
-  auto row_goff = [&](int r) -> long { return ((long)(r - (P.ys - P.we)) * NXe + (ca - 1 - (P.xs - P.we))) * Mz; };
-  // with bulk copies the row lands shifted by (goff & 1) doubles so that source and destination are 16B-aligned
-  auto issue_row = [&](int r, int slot) {
-    const long goff = row_goff(r);
-    if (use_bulk) {
-      if (tid == 0) {
-        const long a0 = goff & ~1L;
-        const long a1 = (goff + rowcount + 1) & ~1L;
-        unsigned bytes = (unsigned)((a1 - a0) * 8);
-        if (P.use_age) {
-          mbar_expect_tx(&bars[slot], 2 * bytes);
-          bulk_g2s(E_s + slot * slotE, F.E + a0, bytes, &bars[slot]);
-          bulk_g2s(A_s + slot * slotE, F.age + a0, bytes, &bars[slot]);
-        } else {
-          mbar_expect_tx(&bars[slot], bytes);
-          bulk_g2s(E_s + slot * slotE, F.E + a0, bytes, &bars[slot]);
-        }
-      }
-    } else {
-      double *dst = E_s + slot * slotE;
-      const double *src = F.E + goff;
-      for (int e = tid; e < rowcount; e += NT) {
-        cp_async8(dst + e, src + e);
-      }
-      if (P.use_age) {
-        double *dstA = A_s + slot * slotE;
-        const double *srcA = F.age + goff;
-        for (int e = tid; e < rowcount; e += NT) {
-          cp_async8(dstA + e, srcA + e);
-        }
-      }
-      cp_async_commit();
-    }
-  };
-
-  unsigned bar_phase = 0; // bit s = parity to wait for on bars[s]
-  auto wait_row = [&](int slot) {
-    if (use_bulk) {
-      mbar_wait(&bars[slot], (bar_phase >> slot) & 1u);
-      bar_phase ^= (1u << slot);
-    }
-  };
-
-  // prologue: rows r0 and r0 + 1 (r0 + 1 <= rb always exists in the ghosted array)
-  issue_row(r0, 0);
-  issue_row(r0 + 1, 1);
-  if (!use_bulk) {
-    cp_async_wait_all();
-  } else {
-    wait_row(0);
-    wait_row(1);
-  }
-  __syncthreads();
-
-  double sc_next = fetch_scalar(P, F, r0, g, l, ca, ncol, has_west, ra, FULL);
-  double prev_hxB = 0.0, prev_hyB = 0.0; // h_x, h_y of the j-offset point one row below (stage B "south")
-  double dmax_local = 0.0;
-  int hdc_local = 0;
-
-  for (int r = r0; r < rb; ++r) {
-    const int it = r - r0;
-    const int s_cur = it % 3, s_nxt = (it + 1) % 3, s_pre = (it + 2) % 3;
-    const bool prefetch = (r + 2 <= rb);
-    if (prefetch) {
-      issue_row(r + 2, s_pre);
-    }
-    const double sc = sc_next;
-    if (r + 1 < rb) {
-      sc_next = fetch_scalar(P, F, r + 1, g, l, ca, ncol, has_west, ra, FULL);
-    }
-
-    // ---------------- stage A: integrate the two staggered columns of this group ----------------
-    const bool validA = (g <= ncol) && (g > 0 || has_west) && (r >= ra);
-    const bool validB = (g < ncol);
-    const double tsA0 = __shfl_sync(FULLMASK, sc, 0, 16), tsA1 = __shfl_sync(FULLMASK, sc, 1, 16);
-    const double thA0 = __shfl_sync(FULLMASK, sc, 2, 16), thA1 = __shfl_sync(FULLMASK, sc, 3, 16);
-    const double hxA = __shfl_sync(FULLMASK, sc, 4, 16), hyA = __shfl_sync(FULLMASK, sc, 5, 16);
-    const double tsB0 = __shfl_sync(FULLMASK, sc, 6, 16), tsB1 = __shfl_sync(FULLMASK, sc, 7, 16);
-    const double thB0 = __shfl_sync(FULLMASK, sc, 8, 16), thB1 = __shfl_sync(FULLMASK, sc, 9, 16);
-    const double hxB = __shfl_sync(FULLMASK, sc, 10, 16), hyB = __shfl_sync(FULLMASK, sc, 11, 16);
-    const double ub = __shfl_sync(FULLMASK, sc, 12, 16), vb = __shfl_sync(FULLMASK, sc, 13, 16);
-    const double hxe = __shfl_sync(FULLMASK, sc, 14, 16), hye = __shfl_sync(FULLMASK, sc, 15, 16);
-
-    // sia/SIAFD.cc:627-639
-    const double thkA = 0.5 * (tsA0 + tsA1), thkB = 0.5 * (tsB0 + tsB1);
-    const bool actA = validA && (thkA != 0.0), actB = validB && (thkB != 0.0);
-    const int ksA = actA ? k_below_height(z_s, Mz, thkA, F.err) : -1;
-    const int ksB = actB ? k_below_height(z_s, Mz, thkB, F.err) : -1;
-    // sia/SIAFD.cc:686, :693-696
-    const double alphaA = sqrt(hxA * hxA + hyA * hyA), alphaB = sqrt(hxB * hxB + hyB * hyB);
-    const double thetaA = 0.5 * (thA0 + thA1), thetaB = 0.5 * (thB0 + thB1);
-    const double c2A = P.e * thetaA * 2.0, c2B = P.e * thetaB * 2.0; // e_factor * theta_local * 2.0 (no age coupling)
-
-    const double *Ecur = E_s + s_cur * slotE + (use_bulk ? (row_goff(r) & 1) : 0);
-    const double *Enxt = E_s + s_nxt * slotE + (use_bulk ? (row_goff(r + 1) & 1) : 0);
-    const double *EaA = Ecur + (long)g * Mz, *EbA = Ecur + (long)(g + 1) * Mz;
-    const double *EaB = Ecur + (long)(g + 1) * Mz, *EbB = Enxt + (long)(g + 1) * Mz;
-    const double *Acur = A_s + s_cur * slotE + (use_bulk ? (row_goff(r) & 1) : 0);
-    const double *Anxt = A_s + s_nxt * slotE + (use_bulk ? (row_goff(r + 1) & 1) : 0);
-
-    double *I0row = I0_s + (long)g * Mz;               // o = 0 point of this group (index g <-> column ca-1+g)
-    double *I1row = I1_s + ((long)(it & 1) * TX + g) * Mz; // o = 1 point, slot by row parity
-
-    int nch = max(actA ? (ksA >> 4) + 1 : 0, actB ? (ksB >> 4) + 1 : 0);
-    nch = max(nch, __shfl_xor_sync(FULLMASK, nch, 16));
-
-    double carryA = 0.0, carryB = 0.0, dpA = 0.0, dpB = 0.0, lastA = 0.0, lastB = 0.0;
-    for (int c = 0; c < nch; ++c) {
-      const int k = (c << 4) + l;
-      const int kk = min(k, Mz - 1);
-      const double zk = z_s[kk];
-      const double dz = zk - z_s[max(kk - 1, 0)];
-      const bool inA = (k <= ksA), inB = (k <= ksB);
-      double dA = 0.0, dB = 0.0, depA = 0.0, depB = 0.0;
-      if (inA) {
-        depA = thkA - zk;                              // :641-643
-        const double p = P.p_air + P.rg * depA;        // EnthalpyConverter.cc:146-152
-        const double Eavg = 0.5 * (EaA[k] + EbA[k]);   // :677-684
-        double c2 = c2A, gs = P.grain_size;
-        if (P.use_age) {                               // :649-675
-          const double age = 0.5 * (Acur[(long)g * Mz + k] + Acur[(long)(g + 1) * Mz + k]);
-          if (P.gs_age) gs = grain_size_vostok(age * P.years_per_second);
-          if (P.e_age) c2 = (interglacial(P, P.current_time - age) ? P.e_inter : P.e) * thetaA * 2.0;
-        }
-        const double fl = flow_eval<LAW>(P, alphaA * p, Eavg, p, gs); // :688-691
-        dA = c2 * p * fl;                              // :696
-      }
-      if (inB) {
-        depB = thkB - zk;
-        const double p = P.p_air + P.rg * depB;
-        const double Eavg = 0.5 * (EaB[k] + EbB[k]);
-        double c2 = c2B, gs = P.grain_size;
-        if (P.use_age) {
-          const double age = 0.5 * (Acur[(long)(g + 1) * Mz + k] + Anxt[(long)(g + 1) * Mz + k]);
-          if (P.gs_age) gs = grain_size_vostok(age * P.years_per_second);
-          if (P.e_age) c2 = (interglacial(P, P.current_time - age) ? P.e_inter : P.e) * thetaB * 2.0;
-        }
-        const double fl = flow_eval<LAW>(P, alphaB * p, Eavg, p, gs);
-        dB = c2 * p * fl;
-      }
-      // delta[k-1]: from the lane below, or the last lane of the previous chunk
-      double pA = __shfl_up_sync(FULLMASK, dA, 1, 16), pB = __shfl_up_sync(FULLMASK, dB, 1, 16);
-      if (l == 0) {
-        pA = lastA;
-        pB = lastB;
-      }
-      lastA = __shfl_sync(FULLMASK, dA, 15, 16);
-      lastB = __shfl_sync(FULLMASK, dB, 15, 16);
-      double tA = 0.0, tB = 0.0;
-      if (inA && k >= 1) {
-        tA = 0.5 * dz * (pA + dA);                                // compute_I, :855-858
-        dpA += 0.5 * dz * ((depA + dz) * pA + depA * dA);         // D trapezoid, :701-705
-      }
-      if (inB && k >= 1) {
-        tB = 0.5 * dz * (pB + dB);
-        dpB += 0.5 * dz * ((depB + dz) * pB + depB * dB);
-      }
-      if (k == ksA) dpA += 0.5 * depA * depA * dA;                // :707-708 (dz = thk - z[ks] = depth[ks])
-      if (k == ksB) dpB += 0.5 * depB * depB * dB;
-      if (FULL) {
-        const double IA = scan16(tA, l) + carryA, IB = scan16(tB, l) + carryB;
-        carryA = __shfl_sync(FULLMASK, IA, 15, 16);
-        carryB = __shfl_sync(FULLMASK, IB, 15, 16);
-        if (k < Mz) {
-          if (g <= ncol) I0row[k] = IA;
-          if (validB) I1row[k] = IB;
-        }
-      }
-    }
-    if (FULL) {
-      // above the ice (and ice-free / absent points): I stays at its last value (:861-863), 0 if no ice
-      for (int k = (nch << 4) + l; k < Mz; k += 16) {
-        if (g <= ncol) I0row[k] = carryA;
-        if (validB) I1row[k] = carryB;
-      }
-    }
-
-    // D, flux, D_max (lane 0 of the group), sia/SIAFD.cc:711-731, :772-793
-    dpA = sum16(dpA);
-    dpB = sum16(dpB);
-    if (l == 0 && r >= ra) {
-      const bool edge_r = (r < 0 || r >= P.My - 1);
-      if (validA && g >= 1) { // own cell (c0 >= ca)
-        const int c0 = ca - 1 + g;
-        double D = actA ? dpA : 0.0;
-        if (actA) {
-          if (c0 < 0 || c0 >= P.Mx - 1 || edge_r) D = 0.0;
-          if (P.limit_diffusivity && D >= P.D_limit) {
-            D = P.D_limit;
-            hdc_local += 1;
-          }
-          dmax_local = fmax(dmax_local, D);
-        }
-        const long s = idx2(P, c0, r, P.wst) * 2;
-        F.D[s] = D;
-        F.Q[s] = -D * hxA;
-      }
-      if (validB) {
-        const int c1 = ca + g;
-        double D = actB ? dpB : 0.0;
-        if (actB) {
-          if (c1 < 0 || c1 >= P.Mx - 1 || edge_r) D = 0.0;
-          if (P.limit_diffusivity && D >= P.D_limit) {
-            D = P.D_limit;
-            hdc_local += 1;
-          }
-          dmax_local = fmax(dmax_local, D);
-        }
-        const long s = idx2(P, c1, r, P.wst) * 2 + 1;
-        F.D[s] = D;
-        F.Q[s] = -D * hyB;
-      }
-    }
-
-    if (FULL) {
-      __syncthreads();
-      // ---------------- stage B: u, v of the regular column (c1, r), sia/SIAFD.cc:904-943 ----------------
-      const int c1 = ca + g;
-      if (validB && r >= ra && c1 >= P.xs && c1 < P.xs + P.xm && r >= P.ys && r < P.ys + P.ym) {
-        const double *Ie = I0_s + (long)(g + 1) * Mz, *Iw = I0_s + (long)g * Mz;
-        const double *In = I1_s + ((long)(it & 1) * TX + g) * Mz, *Is = I1_s + ((long)((it + 1) & 1) * TX + g) * Mz;
-        const long o = idx2(P, c1, r, P.wuv) * Mz;
-        for (int k = l; k < Mz; k += 16) {
-          const double ie = Ie[k], iw = Iw[k], in = In[k], is = Is[k];
-          F.u[o + k] = ub - 0.25 * (ie * hxe + iw * hxA + in * hxB + is * prev_hxB);
-          F.v[o + k] = vb - 0.25 * (ie * hye + iw * hyA + in * hyB + is * prev_hyB);
-        }
-      }
-      prev_hxB = hxB;
-      prev_hyB = hyB;
-    }
-
-    if (!use_bulk) {
-      cp_async_wait_all();
-    } else if (prefetch) {
-      wait_row(s_pre);
-    }
-    __syncthreads();
-  }
-
-  // ---- D_max / counter reduction: warp shuffle -> shared -> one atomic per CTA ----
-  {
-    unsigned long long m = (unsigned long long)__double_as_longlong(dmax_local);
-    int cnt = hdc_local;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(FULLMASK, m, d);
-      m = (o > m) ? o : m;
-      cnt += __shfl_xor_sync(FULLMASK, cnt, d);
-    }
-    __shared__ unsigned long long wm[32];
-    __shared__ int wc[32];
-    if ((tid & 31) == 0) {
-      wm[tid >> 5] = m;
-      wc[tid >> 5] = cnt;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const int nw = (NT + 31) >> 5;
-      for (int w = 1; w < nw; ++w) {
-        m = (wm[w] > m) ? wm[w] : m;
-        cnt += wc[w];
-      }
-      if (m != 0ull) atomicMax(F.dmax, m);
-      if (cnt != 0) atomicAdd(F.hdc, cnt);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // rectangle copy (ghost wrap, halo pack / unpack)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_copy_region(double *__restrict__ dst, long dst_row_cells, int dst_i0, int dst_j0,
@@ -840,71 +369,6 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s) {
     k_grad_haseloff_b<<<nblk((long)P.xm * P.ym, 256), 256, 0, s>>>(P, F);
     return 2;
   }
-}
-
-size_t fused_smem_bytes(const DP &P, bool full, int TX) {
-  const long Mz = P.Mz, Mz2 = (Mz + 1) & ~1L;
-  const long slotE = ((long)(TX + 2) * Mz + 2 + 1) & ~1L;
-  long d = Mz2 + 3 * slotE + (P.use_age ? 3 * slotE : 0);
-  if (full) {
-    d += (((long)(TX + 1) * Mz + 1) & ~1L) + (((long)2 * TX * Mz + 1) & ~1L);
-  }
-  return (size_t)d * 8 + 3 * 8 /* mbarriers */ + 16;
-}
-
-// largest strip width whose shared memory allows two CTAs per SM (else one), 227 KB usable per SM
-int pick_tile_x(const DP &P, bool full) {
-  const int cand[3] = {16, 8, 4};
-  for (int q = 0; q < 3; ++q) {
-    if (fused_smem_bytes(P, full, cand[q]) + 1024 <= (size_t)(227 * 1024) / 2) return cand[q];
-  }
-  for (int q = 0; q < 3; ++q) {
-    if (fused_smem_bytes(P, full, cand[q]) <= (size_t)227 * 1024) return cand[q];
-  }
-  return 0; // does not fit: Mz too large
-}
-
-template <int LAW, bool FULL>
-static int launch_fused_t(const DP &P, const Fields &F, const Tuning &T, cudaStream_t s) {
-  const int TX = T.tile_x;
-  const int RS = T.rows_per_cta;
-  const size_t smem = fused_smem_bytes(P, FULL, TX);
-  static size_t configured = 0; // per instantiation
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(k_sia_fused<LAW, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess) {
-      return -1;
-    }
-    configured = smem;
-  }
-  dim3 grid((unsigned)((P.xm + 2 + TX - 1) / TX), (unsigned)((P.ym + 2 + RS - 1) / RS));
-  k_sia_fused<LAW, FULL><<<grid, 16 * (TX + 2), smem, s>>>(P, F, TX, RS, T.use_bulk_copy);
-  return 1;
-}
-
-template <bool FULL> static int launch_fused_f(const DP &P, const Fields &F, const Tuning &T, cudaStream_t s) {
-  switch (P.law) {
-  case LAW_ISO:
-    return launch_fused_t<LAW_ISO, FULL>(P, F, T, s);
-  case LAW_PB:
-    return launch_fused_t<LAW_PB, FULL>(P, F, T, s);
-  case LAW_GPBLD:
-    return launch_fused_t<LAW_GPBLD, FULL>(P, F, T, s);
-  case LAW_HOOKE:
-    return launch_fused_t<LAW_HOOKE, FULL>(P, F, T, s);
-  case LAW_ARR:
-    return launch_fused_t<LAW_ARR, FULL>(P, F, T, s);
-  case LAW_ARRWARM:
-    return launch_fused_t<LAW_ARRWARM, FULL>(P, F, T, s);
-  case LAW_GK:
-    return launch_fused_t<LAW_GK, FULL>(P, F, T, s);
-  default:
-    return -1;
-  }
-}
-
-int launch_fused(const DP &P, const Fields &F, bool full, const Tuning &T, cudaStream_t s) {
-  return full ? launch_fused_f<true>(P, F, T, s) : launch_fused_f<false>(P, F, T, s);
 }
 
 int launch_copy_region(double *dst, long dst_row_cells, int dst_i0, int dst_j0, const double *src, long src_row_cells,
