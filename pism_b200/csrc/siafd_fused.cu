@@ -14,11 +14,11 @@
 //            owned + 1 ghost ring = the reference's PointsWithGhosts(1) iteration space.  The CTA marches
 //            over its rows; row r + 2 of the enthalpy streams into shared memory (one cp.async.bulk per row,
 //            mbarrier-tracked; 8-byte cp.async as an alternative) while row r is integrated.
-//   group  = half-warp (16 lanes) = 16 consecutive z levels of ONE staggered column per chunk; a group
-//            integrates two staggered columns of its regular column together (ILP 2):
+//   group  = half-warp (16 lanes) working on the two staggered columns of one regular column together (ILP 2):
 //              A: o = 0 (i-offset) at column c0 = ca - 1 + g     (g = 0: west halo, feeds u,v of column ca)
 //              B: o = 1 (j-offset) at column c1 = ca + g
-//            delta(z) per lane, trapezoid sums by half-warp prefix scans (I) and lane partials (D).
+//            Lane l integrates a run of Lc = ceil((ks+1)/16) consecutive z levels serially in registers
+//            (delta, the D and I trapezoids); one half-warp scan per column per row stitches the runs.
 //   stage B: group g writes u, v of regular column c1 from I_e = I0[g+1], I_w = I0[g], I_n = I1[cur][g],
 //            I_s = I1[prev][g] with 16 lanes across z: 128-byte coalesced stores.
 //   Ice-free staggered points (thk == 0, SIAFD.cc:631-637) are flagged, never integrated and never stored;
@@ -85,27 +85,46 @@ __device__ __forceinline__ double rcp_fast(double a) {
   return r;
 }
 
+// Constants of exp_fast live in constant memory so that DFMA takes them as c[bank][offset] operands
+// (literal doubles cost two UMOVs each inside the level loop, measured in profiles/).
+__constant__ double EXPC[16] = {
+    1.4426950408889634e+0,   // [0]  log2(e)
+    -6.9314718055994529e-1,  // [1]  -ln2 (high part)
+    -2.3190468138462996e-17, // [2]  -ln2 (low part)
+    1.6059043836821613e-10,  // [3]  1/13!
+    2.0876756987868100e-09,  // [4]  1/12!
+    2.5052108385441720e-08,  // [5]  1/11!
+    2.7557319223985888e-07,  // [6]  1/10!
+    2.7557319223985893e-06,  // [7]  1/9!
+    2.4801587301587302e-05,  // [8]  1/8!
+    1.9841269841269841e-04,  // [9]  1/7!
+    1.3888888888888889e-03,  // [10] 1/6!
+    8.3333333333333332e-03,  // [11] 1/5!
+    4.1666666666666664e-02,  // [12] 1/4!
+    1.6666666666666666e-01,  // [13] 1/3!
+    6755399441055744.0,      // [14] 1.5 * 2^52
+    0.0};
+
 // exp(x) for |x| < 700 (no overflow / underflow / NaN handling): Cody-Waite reduction by ln 2, degree-13
 // Taylor polynomial on [-ln2/2, ln2/2] (truncation 4e-18), exponent patched in.  Error <= ~1 ulp.
 __device__ __forceinline__ double exp_fast(double x) {
-  const double SHIFT = 6755399441055744.0; // 1.5 * 2^52
-  double t = fma(x, 1.4426950408889634e+0, SHIFT);
+  double t = fma(x, EXPC[0], EXPC[14]);
   const int n = __double2loint(t);
-  t -= SHIFT;
-  double r = fma(t, -6.9314718055994529e-1, x);
-  r = fma(t, -2.3190468138462996e-17, r);
-  double p = 1.6059043836821613e-10;     // 1/13!
-  p = fma(p, r, 2.0876756987868100e-09); // 1/12!
-  p = fma(p, r, 2.5052108385441720e-08); // 1/11!
-  p = fma(p, r, 2.7557319223985888e-07); // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06); // 1/9!
-  p = fma(p, r, 2.4801587301587302e-05); // 1/8!
-  p = fma(p, r, 1.9841269841269841e-04); // 1/7!
-  p = fma(p, r, 1.3888888888888889e-03); // 1/6!
-  p = fma(p, r, 8.3333333333333332e-03); // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02); // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01); // 1/3!
-  p = fma(p, r, 5.0000000000000000e-01);
+  t -= EXPC[14];
+  double r = fma(t, EXPC[1], x);
+  r = fma(t, EXPC[2], r);
+  double p = EXPC[3];
+  p = fma(p, r, EXPC[4]);
+  p = fma(p, r, EXPC[5]);
+  p = fma(p, r, EXPC[6]);
+  p = fma(p, r, EXPC[7]);
+  p = fma(p, r, EXPC[8]);
+  p = fma(p, r, EXPC[9]);
+  p = fma(p, r, EXPC[10]);
+  p = fma(p, r, EXPC[11]);
+  p = fma(p, r, EXPC[12]);
+  p = fma(p, r, EXPC[13]);
+  p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
@@ -117,41 +136,71 @@ __device__ __forceinline__ double arrhenius(double A, double Q_over_R, double T)
   return A * exp_fast(-Q_over_R * rcp_fast(T));
 }
 
-// Lean restatement of flow_eval<LAW> (siafd_device.cuh) for the laws on the measured path.  `s2` is
-// pow(stress, n - 1) (stress * stress for n = 3), computed by the caller.
-template <int LAW>
-__device__ __forceinline__ double flow_lean(const DP &P, double stress, double s2, double E, double p, double gs) {
+// Lean restatement of flow_eval<LAW> (siafd_device.cuh) for NV independent (stress, E, p) triples at once.
+// Straight-line code (no branch on the common path), so that the compiler interleaves the NV dependent
+// FP64 chains: the kernel is bound by the latency of those chains, not by FP64 throughput (profiles/).
+// Returns flow = softness(E, p) * stress^(n-1); inputs may be garbage for masked-out lanes (finite in,
+// result discarded by the caller).
+template <int LAW, int NV>
+__device__ __forceinline__ void flow_lean_v(const DP &P, const double (&stress)[NV], const double (&E)[NV],
+                                            const double (&p)[NV], const double (&gs)[NV], double (&out)[NV]) {
+  double s2[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    s2[j] = P.n_is_3 ? stress[j] * stress[j] : pow(stress[j], P.nm1); // pow(stress, n-1), FlowLaw.cc:104
+  }
   if (LAW == LAW_ISO) {
-    return P.iso_A * s2;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) out[j] = P.iso_A * s2[j];
   } else if (LAW == LAW_ARR || LAW == LAW_ARRWARM || LAW == LAW_PB) {
-    const double T_m = fma(-P.ec_beta, p, P.T_melting);
-    const double E_cts = P.c_i * (T_m - P.T_0);
-    double T = (E < E_cts) ? fma(E, P.inv_c_i, P.T_0) : T_m; // EnthalpyConverter::temperature, :180-188
-    if (LAW == LAW_ARR) {
-      return arrhenius(P.A_cold, P.QoR_cold, T) * s2;
-    } else if (LAW == LAW_ARRWARM) {
-      return arrhenius(P.A_warm, P.QoR_warm, T) * s2;
+    double T[NV], A[NV], QoR[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const double T_m = fma(-P.ec_beta, p[j], P.T_melting);
+      const double E_cts = P.c_i * (T_m - P.T_0);
+      T[j] = (E[j] < E_cts) ? fma(E[j], P.inv_c_i, P.T_0) : T_m; // EnthalpyConverter::temperature, :180-188
+      if (LAW == LAW_ARR) {
+        A[j] = P.A_cold, QoR[j] = P.QoR_cold;
+      } else if (LAW == LAW_ARRWARM) {
+        A[j] = P.A_warm, QoR[j] = P.QoR_warm;
+      } else {
+        T[j] = fma(P.beta_ratio, p[j], T[j]); // rheology/PatersonBudd.cc:57
+        const bool cold = T[j] < P.T_crit;
+        A[j] = cold ? P.A_cold : P.A_warm, QoR[j] = cold ? P.QoR_cold : P.QoR_warm;
+      }
     }
-    T = fma(P.beta_ratio, p, T); // rheology/PatersonBudd.cc:57
-    const bool cold = T < P.T_crit;
-    return arrhenius(cold ? P.A_cold : P.A_warm, cold ? P.QoR_cold : P.QoR_warm, T) * s2;
+    double x[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[j] = -QoR[j] * rcp_fast(T[j]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) out[j] = A[j] * exp_fast(x[j]) * s2[j];
   } else if (LAW == LAW_GPBLD) {
-    // rheology/GPBLD.cc:49-61
-    const double T_m = fma(-P.ec_beta, p, P.T_melting);
-    const double E_s = P.c_i * (T_m - P.T_0);
-    double softness;
-    if (E < E_s) {
-      const double T_pa = fma(E, P.inv_c_i, P.T_0) - T_m + P.T_melting; // EnthalpyConverter.cc:196-198
-      const bool cold = T_pa < P.T_crit;
-      softness = arrhenius(cold ? P.A_cold : P.A_warm, cold ? P.QoR_cold : P.QoR_warm, T_pa);
-    } else {
-      const double Lm = fma(P.c_w - P.c_i, T_m - 273.15, P.L0); // EnthalpyConverter::L, :365-367
-      const double omega = fmin((E - E_s) * rcp_fast(Lm), P.gp_limit);
-      softness = P.gp_softness_T0 * fma(P.gp_coeff, omega, 1.0);
+    // rheology/GPBLD.cc:49-61.  Cold branch evaluated for every lane; the (rare) temperate lanes are patched.
+    double T_m[NV], E_s[NV], T_pa[NV], A[NV], QoR[NV], x[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      T_m[j] = fma(-P.ec_beta, p[j], P.T_melting);
+      E_s[j] = P.c_i * (T_m[j] - P.T_0);
+      T_pa[j] = fma(E[j], P.inv_c_i, P.T_0) - T_m[j] + P.T_melting; // EnthalpyConverter.cc:196-198
+      const bool cold = T_pa[j] < P.T_crit;
+      A[j] = cold ? P.A_cold : P.A_warm, QoR[j] = cold ? P.QoR_cold : P.QoR_warm;
     }
-    return softness * s2;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[j] = -QoR[j] * rcp_fast(T_pa[j]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) out[j] = A[j] * exp_fast(x[j]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (!(E[j] < E_s[j])) { // temperate ice
+        const double Lm = fma(P.c_w - P.c_i, T_m[j] - 273.15, P.L0); // EnthalpyConverter::L, :365-367
+        const double omega = fmin((E[j] - E_s[j]) * rcp_fast(Lm), P.gp_limit);
+        out[j] = P.gp_softness_T0 * fma(P.gp_coeff, omega, 1.0);
+      }
+      out[j] *= s2[j];
+    }
   } else {
-    return flow_eval<LAW>(P, stress, E, p, gs); // hooke, gk: generic libdevice path
+#pragma unroll
+    for (int j = 0; j < NV; ++j) out[j] = flow_eval<LAW>(P, stress[j], E[j], p[j], gs[j]); // hooke, gk
   }
 }
 
@@ -370,6 +419,7 @@ __global__ void __launch_bounds__(256, 2)
     const int s_cur = it % 3, s_nxt = (it + 1) % 3, s_pre = (it + 2) % 3;
     // prefetch row r + 2 if any staggered point will need it: rowflag(r+1) | (r+2) | (r+3) = bits 2,3,4
     const bool prefetch = (r + 2 <= rb) && ((rf & 28u) != 0);
+    const bool row_active = (rf & 6u) != 0; // rowflag(r) | rowflag(r + 1): can any staggered point of row r have ice?
     if (prefetch) {
       issue_row(it + 2, s_pre);
       slot_loaded |= (1u << s_pre);
@@ -388,115 +438,162 @@ __global__ void __launch_bounds__(256, 2)
     // ---------------- stage A: integrate the two staggered columns of this group ----------------
     const bool validA = (g <= ncol) && (g > 0 || has_west) && (r >= ra);
     const bool validB = (g < ncol);
-    const double tsA0 = __shfl_sync(FULLMASK, sc, 0, 16), tsA1 = __shfl_sync(FULLMASK, sc, 1, 16);
-    const double tsB0 = __shfl_sync(FULLMASK, sc, 6, 16), tsB1 = __shfl_sync(FULLMASK, sc, 7, 16);
     const double hxA = __shfl_sync(FULLMASK, sc, 4, 16), hyA = __shfl_sync(FULLMASK, sc, 5, 16);
     const double hxB = __shfl_sync(FULLMASK, sc, 10, 16), hyB = __shfl_sync(FULLMASK, sc, 11, 16);
 
-    // sia/SIAFD.cc:627-639
-    const double thkA = 0.5 * (tsA0 + tsA1), thkB = 0.5 * (tsB0 + tsB1);
-    const bool actA = validA && (thkA != 0.0), actB = validB && (thkB != 0.0);
-    const bool any_act = __any_sync(FULLMASK, actA || actB);
+    bool actA = false, actB = false;
+    double thkA = 0.0, thkB = 0.0;
+    if (row_active) { // CTA-uniform: some thk_smooth > 0 in rows r, r + 1 of this strip
+      const double tsA0 = __shfl_sync(FULLMASK, sc, 0, 16), tsA1 = __shfl_sync(FULLMASK, sc, 1, 16);
+      const double tsB0 = __shfl_sync(FULLMASK, sc, 6, 16), tsB1 = __shfl_sync(FULLMASK, sc, 7, 16);
+      thkA = 0.5 * (tsA0 + tsA1), thkB = 0.5 * (tsB0 + tsB1); // sia/SIAFD.cc:627-628
+      actA = validA && (thkA != 0.0), actB = validB && (thkB != 0.0); // :631-637
+    }
+    const bool any_act = row_active && __any_sync(FULLMASK, actA || actB);
 
     double DA = 0.0, DB = 0.0;
-    double *I0row = I0_s + oA;                              // o = 0 point of this group (index g)
-    double *I1row = I1_s + ((it & 1) * TX + g) * Mz;        // o = 1 point, slot by row parity
+    double *I0row = I0_s + oA;                       // o = 0 point of this group (index g)
+    double *I1row = I1_s + ((it & 1) * TX + g) * Mz; // o = 1 point, slot by row parity
 
     if (any_act) { // warp-uniform
       const double thA0 = __shfl_sync(FULLMASK, sc, 2, 16), thA1 = __shfl_sync(FULLMASK, sc, 3, 16);
       const double thB0 = __shfl_sync(FULLMASK, sc, 8, 16), thB1 = __shfl_sync(FULLMASK, sc, 9, 16);
-      const int ksA = actA ? k_below_height(z_s, Mz, thkA, F.err) : -1;
+      const int ksA = actA ? k_below_height(z_s, Mz, thkA, F.err) : -1; // :639
       const int ksB = actB ? k_below_height(z_s, Mz, thkB, F.err) : -1;
       // sia/SIAFD.cc:686, :693-696
       const double alphaA = sqrt(hxA * hxA + hyA * hyA), alphaB = sqrt(hxB * hxB + hyB * hyB);
       const double thetaA = 0.5 * (thA0 + thA1), thetaB = 0.5 * (thB0 + thB1);
       const double c2A = P.e * thetaA * 2.0, c2B = P.e * thetaB * 2.0; // e_factor * theta_local * 2.0
 
+      // Each lane integrates a RUN of Lc consecutive levels [l Lc, (l+1) Lc) of both columns, serially and
+      // in registers; 16 Lc >= ks + 1.  The trapezoid that straddles two runs and the offsets of the runs
+      // are added afterwards (one half-warp scan per column per row).
+      int Lc = max(ksA, ksB);
+      Lc = max(Lc, __shfl_xor_sync(FULLMASK, Lc, 16));
+      Lc = (Lc >> 4) + 1;
+      const int k0 = l * Lc;
+
       const int shc = use_bulk ? (int)((goff0 + (long)it * gstride) & 1) : 0;
       const int shn = use_bulk ? (int)((goff0 + (long)(it + 1) * gstride) & 1) : 0;
       const double *Ecur = E_s + s_cur * slotE + shc;
       const double *Enxt = E_s + s_nxt * slotE + shn;
-      const double *EaA = Ecur + oA + l, *EbA = Ecur + oE + l; // columns c0, c0 + 1 of row r
-      const double *EbB = Enxt + oE + l;                       // column c1 of row r + 1 (EaB == EbA)
-      const double *zl = z_s + l, *hzl = hz_s + l;
+      // (groups past the strip's last column read a clamped column: loads are unconditional, results masked)
+      const int eA = min(g, ncol + 1) * Mz + k0, eE = min(g + 1, ncol + 1) * Mz + k0;
+      const double *EaA = Ecur + eA, *Emd = Ecur + eE; // columns c0 and c0 + 1 (= c1) of row r
+      const double *EbB = Enxt + eE;                   // column c1 of row r + 1
+      const double *zl = z_s + k0, *hzl = hz_s + k0;
+      double *I0p = I0row + k0, *I1p = I1row + k0;
 
-      int nch = max(ksA, ksB);
-      nch = max(nch, __shfl_xor_sync(FULLMASK, nch, 16));
-      nch = (nch >> 4) + 1; // chunks of 16 levels to visit (nch >= 1 here)
-
-      double carryA = 0.0, carryB = 0.0, dpA = 0.0, dpB = 0.0, lastA = 0.0, lastB = 0.0;
-      for (int c = 0, k = l; c < nch; ++c, k += 16) {
-        const int q = c << 4;
-        const bool inA = (k <= ksA), inB = (k <= ksB);
-        double dA = 0.0, dB = 0.0, depA = 0.0, depB = 0.0, hz = 0.0;
-        if (inA || inB) {
-          const double zk = zl[q];
-          hz = hzl[q];
-          const double Emid = EbA[q]; // shared by A (its far end) and B (its near end)
-          if (inA) {
-            depA = thkA - zk;                                   // :641-643
-            const double p = fma(P.rg, depA, P.p_air);          // EnthalpyConverter.cc:146-152
-            const double Eavg = 0.5 * (EaA[q] + Emid);          // :677-684
-            const double stress = alphaA * p;                   // :688
-            double c2 = c2A, gs = P.grain_size;
-            if (P.use_age) {                                    // :649-675
-              const double *Ac = A_s + s_cur * slotE + shc;
-              const double age = 0.5 * (Ac[oA + k] + Ac[oE + k]);
-              if (P.gs_age) gs = grain_size_vostok(age * P.years_per_second);
-              if (P.e_age) c2 = (interglacial(P, P.current_time - age) ? P.e_inter : P.e) * thetaA * 2.0;
+      double prevA = 0.0, prevB = 0.0, firstA = 0.0, firstB = 0.0, depFA = 0.0, depFB = 0.0;
+      double runA = 0.0, runB = 0.0, dpA = 0.0, dpB = 0.0;
+      const double *Ac = A_s + s_cur * slotE + shc, *An = A_s + s_nxt * slotE + shn;
+      // Two levels (k, k + 1) of both columns per trip: four independent flow-law chains in flight.
+      // j = 0: A at k, 1: B at k, 2: A at k + 1, 3: B at k + 1.  Masked-out slots compute on clamped loads.
+      for (int m = 0; m < Lc; m += 2) {
+        const int k = k0 + m;
+        const bool two = (m + 1 < Lc);
+        const bool in0A = (k <= ksA), in0B = (k <= ksB), in1A = two && (k + 1 <= ksA), in1B = two && (k + 1 <= ksB);
+        const int q0 = min(k, Mz - 1) - k0, q1 = min(k + 1, Mz - 1) - k0; // in-bounds offsets from the run start
+        const double z0 = zl[q0], z1 = zl[q1], hz0 = hzl[q0], hz1 = hzl[q1];
+        const double Em0 = Emd[q0], Em1 = Emd[q1]; // far end of A, near end of B
+        double dep[4], pr[4], Ea[4], st[4], gsz[4], fl[4], c2[4];
+        dep[0] = thkA - z0, dep[1] = thkB - z0, dep[2] = thkA - z1, dep[3] = thkB - z1;      // :641-643
+        Ea[0] = 0.5 * (EaA[q0] + Em0), Ea[1] = 0.5 * (Em0 + EbB[q0]);                        // :677-684
+        Ea[2] = 0.5 * (EaA[q1] + Em1), Ea[3] = 0.5 * (Em1 + EbB[q1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pr[j] = fma(P.rg, dep[j], P.p_air);              // EnthalpyConverter.cc:146-152
+          st[j] = ((j & 1) ? alphaB : alphaA) * pr[j];     // :688
+          gsz[j] = P.grain_size;
+          c2[j] = (j & 1) ? c2B : c2A;
+        }
+        if (P.use_age) { // :649-675 (uniform branch; off by default)
+          double age[4];
+          age[0] = 0.5 * (Ac[eA + q0] + Ac[eE + q0]), age[1] = 0.5 * (Ac[eE + q0] + An[eE + q0]);
+          age[2] = 0.5 * (Ac[eA + q1] + Ac[eE + q1]), age[3] = 0.5 * (Ac[eE + q1] + An[eE + q1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (P.gs_age) gsz[j] = grain_size_vostok(age[j] * P.years_per_second);
+            if (P.e_age) {
+              c2[j] = (interglacial(P, P.current_time - age[j]) ? P.e_inter : P.e) * ((j & 1) ? thetaB : thetaA) * 2.0;
             }
-            const double s2 = P.n_is_3 ? stress * stress : pow(stress, P.nm1);
-            dA = c2 * p * flow_lean<LAW>(P, stress, s2, Eavg, p, gs); // :691-696
-          }
-          if (inB) {
-            depB = thkB - zk;
-            const double p = fma(P.rg, depB, P.p_air);
-            const double Eavg = 0.5 * (Emid + EbB[q]);
-            const double stress = alphaB * p;
-            double c2 = c2B, gs = P.grain_size;
-            if (P.use_age) {
-              const double *Ac = A_s + s_cur * slotE + shc, *An = A_s + s_nxt * slotE + shn;
-              const double age = 0.5 * (Ac[oE + k] + An[oE + k]);
-              if (P.gs_age) gs = grain_size_vostok(age * P.years_per_second);
-              if (P.e_age) c2 = (interglacial(P, P.current_time - age) ? P.e_inter : P.e) * thetaB * 2.0;
-            }
-            const double s2 = P.n_is_3 ? stress * stress : pow(stress, P.nm1);
-            dB = c2 * p * flow_lean<LAW>(P, stress, s2, Eavg, p, gs);
           }
         }
-        // delta[k-1]: from the lane below, or the last lane of the previous chunk
-        double pA = __shfl_up_sync(FULLMASK, dA, 1, 16), pB = __shfl_up_sync(FULLMASK, dB, 1, 16);
-        if (l == 0) {
-          pA = lastA;
-          pB = lastB;
-        }
-        lastA = __shfl_sync(FULLMASK, dA, 15, 16);
-        lastB = __shfl_sync(FULLMASK, dB, 15, 16);
-        const double dz = hz + hz;
-        // trapezoids (hz = 0 at k = 0, and dA = pA-term masked for k > ks):
-        //   I:  0.5 dz (delta[k-1] + delta[k])                                  compute_I, :855-858
-        //   D:  0.5 dz ((depth[k] + dz) delta[k-1] + depth[k] delta[k])         :701-705
-        const double tA = inA ? hz * (pA + dA) : 0.0;
-        const double tB = inB ? hz * (pB + dB) : 0.0;
-        if (inA) dpA = fma(hz, fma(depA + dz, pA, depA * dA), dpA);
-        if (inB) dpB = fma(hz, fma(depB + dz, pB, depB * dB), dpB);
-        if (k == ksA) dpA = fma(0.5 * depA * depA, dA, dpA);     // :707-708 (dz = thk - z[ks] = depth[ks])
-        if (k == ksB) dpB = fma(0.5 * depB * depB, dB, dpB);
-        if (FULL) {
-          const double IA = scan16(tA, l) + carryA, IB = scan16(tB, l) + carryB;
-          carryA = __shfl_sync(FULLMASK, IA, 15, 16);
-          carryB = __shfl_sync(FULLMASK, IB, 15, 16);
-          if (k < Mz) {
-            if (actA) I0row[k] = IA;
-            if (actB) I1row[k] = IB;
+        flow_lean_v<LAW, 4>(P, st, Ea, pr, gsz, fl); // :691
+        const double d0A = in0A ? c2[0] * pr[0] * fl[0] : 0.0, d0B = in0B ? c2[1] * pr[1] * fl[1] : 0.0; // :696
+        const double d1A = in1A ? c2[2] * pr[2] * fl[2] : 0.0, d1B = in1B ? c2[3] * pr[3] * fl[3] : 0.0;
+        // trapezoids   I: 0.5 dz (delta[k-1] + delta[k])                          compute_I, :855-858
+        //              D: 0.5 dz ((depth[k] + dz) delta[k-1] + depth[k] delta[k])  :701-705
+        if (m == 0) { // the trapezoid ending at the first level of the run needs the lane below: deferred
+          firstA = d0A, firstB = d0B, depFA = dep[0], depFB = dep[1];
+        } else {
+          const double dz = hz0 + hz0;
+          if (in0A) {
+            runA = fma(hz0, prevA + d0A, runA);
+            dpA = fma(hz0, fma(dep[0] + dz, prevA, dep[0] * d0A), dpA);
           }
+          if (in0B) {
+            runB = fma(hz0, prevB + d0B, runB);
+            dpB = fma(hz0, fma(dep[1] + dz, prevB, dep[1] * d0B), dpB);
+          }
+        }
+        if (k == ksA) dpA = fma(0.5 * dep[0] * dep[0], d0A, dpA); // :707-708 (dz = thk - z[ks] = depth[ks])
+        if (k == ksB) dpB = fma(0.5 * dep[1] * dep[1], d0B, dpB);
+        if (FULL && k < Mz) { // run-local prefix; offset added below
+          if (actA) I0p[m] = runA;
+          if (actB) I1p[m] = runB;
+        }
+        prevA = d0A, prevB = d0B;
+        if (two) {
+          const double dz = hz1 + hz1;
+          if (in1A) {
+            runA = fma(hz1, d0A + d1A, runA);
+            dpA = fma(hz1, fma(dep[2] + dz, d0A, dep[2] * d1A), dpA);
+          }
+          if (in1B) {
+            runB = fma(hz1, d0B + d1B, runB);
+            dpB = fma(hz1, fma(dep[3] + dz, d0B, dep[3] * d1B), dpB);
+          }
+          if (k + 1 == ksA) dpA = fma(0.5 * dep[2] * dep[2], d1A, dpA);
+          if (k + 1 == ksB) dpB = fma(0.5 * dep[3] * dep[3], d1B, dpB);
+          if (FULL && k + 1 < Mz) {
+            if (actA) I0p[m + 1] = runA;
+            if (actB) I1p[m + 1] = runB;
+          }
+          prevA = d1A, prevB = d1B;
+        }
+      }
+      // trapezoid across the run boundary: delta of the last level of the lane below (0 above the ice)
+      double leftA = __shfl_up_sync(FULLMASK, prevA, 1, 16), leftB = __shfl_up_sync(FULLMASK, prevB, 1, 16);
+      double tFA = 0.0, tFB = 0.0;
+      if (l > 0 && k0 < Mz) {
+        const double hz0 = hz_s[k0], dz0 = hz0 + hz0;
+        if (k0 <= ksA) {
+          tFA = hz0 * (leftA + firstA);
+          dpA = fma(hz0, fma(depFA + dz0, leftA, depFA * firstA), dpA);
+        }
+        if (k0 <= ksB) {
+          tFB = hz0 * (leftB + firstB);
+          dpB = fma(hz0, fma(depFB + dz0, leftB, depFB * firstB), dpB);
         }
       }
       if (FULL) {
+        const double inclA = scan16(runA + tFA, l), inclB = scan16(runB + tFB, l);
+        double offA = __shfl_up_sync(FULLMASK, inclA, 1, 16), offB = __shfl_up_sync(FULLMASK, inclB, 1, 16);
+        if (l == 0) offA = offB = 0.0;
+        const double addA = offA + tFA, addB = offB + tFB;
+        const double topA = __shfl_sync(FULLMASK, inclA, 15, 16), topB = __shfl_sync(FULLMASK, inclB, 15, 16);
+        const int mend = min(Lc, Mz - k0);
+        if (l > 0) {
+          for (int m = 0; m < mend; ++m) {
+            if (actA) I0p[m] += addA;
+            if (actB) I1p[m] += addB;
+          }
+        }
         // above the ice I keeps its last value (:861-863)
-        for (int k = (nch << 4) + l; k < Mz; k += 16) {
-          if (actA) I0row[k] = carryA;
-          if (actB) I1row[k] = carryB;
+        for (int k = (Lc << 4) + l; k < Mz; k += 16) {
+          if (actA) I0row[k] = topA;
+          if (actB) I1row[k] = topB;
         }
       }
       DA = sum16(dpA);
