@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,6 +40,7 @@ struct siafd_b200_handle {
   int bedNx = -1, bedNy = -1;
   double *d_global_bed = nullptr;
   Tuning tuning;
+  double inv_dz = 0.0; // (Mz - 1) / Lz when the levels are equally spaced, else 0
   int64_t launches = 0;
   // CUDA-event pairs around the fused kernel (bench.py's roofline timing), a ring of 256
   std::vector<cudaEvent_t> ev_start, ev_stop;
@@ -389,6 +391,19 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.rows_per_cta = 64;
   h->tuning.use_bulk_copy = 1;
   h->tuning.skip_ice_free = 1;
+  h->tuning.variant = 1;
+  h->tuning.wz = 8;
+  if (const char *e = getenv("SIAFD_B200_VARIANT")) h->tuning.variant = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_WZ")) h->tuning.wz = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_ROWS")) h->tuning.rows_per_cta = atoi(e) > 0 ? atoi(e) : 64;
+  {
+    const double Lz = cfg->z[cfg->Mz - 1] - cfg->z[0], dz = Lz / (cfg->Mz - 1);
+    bool uniform = cfg->z[0] == 0.0;
+    for (int k = 0; k < cfg->Mz && uniform; ++k) {
+      uniform = std::fabs(cfg->z[k] - k * dz) <= 1e-9 * Lz;
+    }
+    h->inv_dz = uniform ? 1.0 / dz : 0.0;
+  }
   h->tuning.tile_x = pick_tile_x(h->P, true);
   if (h->tuning.tile_x == 0) {
     delete h;
@@ -711,7 +726,10 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, doub
   if (timed) {
     CU(h, cudaEventRecord(h->ev_start[h->ev_count], h->stream));
   }
-  const int n = launch_fused(h->P, F, full_update != 0, T, h->stream);
+  const int n = (T.variant == 1)
+                    ? launch_slab(h->P, F, full_update != 0, T, (long)siafd_b200_field_size(h, SIAFD_B200_F_ENTHALPY),
+                                  h->inv_dz, h->stream)
+                    : launch_fused(h->P, F, full_update != 0, T, h->stream);
   if (timed) {
     CU(h, cudaEventRecord(h->ev_stop[h->ev_count], h->stream));
     h->ev_count += 1;

@@ -21,12 +21,15 @@ struct Tuning {
   int tile_x;        // extended columns per CTA strip (16, 8 or 4 by shared-memory fit)
   int use_bulk_copy; // 1: cp.async.bulk + mbarrier row loads; 0: 8-byte cp.async
   int skip_ice_free; // 1: do not load enthalpy rows no staggered point needs
+  int variant;       // 0: half-warp-per-column kernel (siafd_fused.cu); 1: row-slab kernel (siafd_slab.cu)
+  int wz;            // slab kernel: z ranges per column (8 or 16)
 };
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
 int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
 int launch_gradient(const DP &P, const Fields &F, cudaStream_t s);
 int launch_fused(const DP &P, const Fields &F, bool full, const Tuning &T, cudaStream_t s);
+int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, double inv_dz, cudaStream_t s);
 size_t fused_smem_bytes(const DP &P, bool full, int tile_x);
 int pick_tile_x(const DP &P, bool full);
 
