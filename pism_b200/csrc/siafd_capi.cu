@@ -728,7 +728,7 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, doub
   }
   const int n = (T.variant == 1)
                     ? launch_slab(h->P, F, full_update != 0, T, (long)siafd_b200_field_size(h, SIAFD_B200_F_ENTHALPY),
-                                  h->inv_dz, h->stream)
+                                  (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, h->stream)
                     : launch_fused(h->P, F, full_update != 0, T, h->stream);
   if (timed) {
     CU(h, cudaEventRecord(h->ev_stop[h->ev_count], h->stream));

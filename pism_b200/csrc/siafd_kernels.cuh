@@ -29,7 +29,8 @@ struct Tuning {
 int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
 int launch_gradient(const DP &P, const Fields &F, cudaStream_t s);
 int launch_fused(const DP &P, const Fields &F, bool full, const Tuning &T, cudaStream_t s);
-int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, double inv_dz, cudaStream_t s);
+int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz,
+                cudaStream_t s);
 size_t fused_smem_bytes(const DP &P, bool full, int tile_x);
 int pick_tile_x(const DP &P, bool full);
 

@@ -13,18 +13,19 @@
 //             reference's PointsWithGhosts(1)) x a segment of RS extended rows, marched row by row.
 //             Strips overlap by one column: lane column 0 of every strip but the first only provides the
 //             west face (I_w) of lane column 1, so a strip owns NC - 1 columns.
-//   stage A : thread (c, w), c = lane column, w = z range.  A warp holds NC = 16 adjacent columns in each
-//             half: shared-memory columns are Mz (odd) doubles apart, so the column-strided reads of the
-//             enthalpy and writes of I are bank-conflict free, and every per-column scalar (thickness, k_s,
-//             slope, theta) is per lane -- no shuffles, no scans.  The thread integrates levels
-//             [w Lc, (w+1) Lc) of BOTH staggered points of its column (i-offset "A", j-offset "B"; two
-//             independent flow-law chains) serially in registers; Lc = ceil((ks + 1) / WZ) per column.
-//             The WZ partial sums of a column are stitched through shared memory (two barriers).
-//   stage B : thread (q, li): column q, lanes li = 0..WZ-1 across z: u, v of the regular column from
+//   stage A : thread (c, pt, w): lane column c, staggered point pt (0: i-offset, 1: j-offset), z range w.
+//             A warp is one z range of both points of NC = 16 adjacent columns.  Shared-memory columns are Mz
+//             (odd) doubles apart, so the column-strided reads of the enthalpy and writes of I are bank-
+//             conflict free, and every per-column scalar (thickness, k_s, slope, theta) is per lane -- no
+//             scans.  The thread integrates levels [w Lc, (w+1) Lc) of its point serially in registers;
+//             Lc = ceil((ks + 1) / WZ) per column.  The WZ partial sums of a column are stitched through
+//             shared memory (two barriers).
+//   stage B : thread (q, li): column q, 2 WZ lanes li across z: u, v of the regular column from
 //             I_e, I_w (I0 of lane columns q, q - 1), I_n, I_s (I1 of this and the previous row).
-//   Rows of the enthalpy arrive by one cp.async.bulk per row (mbarrier-tracked, issued one row ahead of
-//   use into the slot the previous row just vacated); rows no staggered point needs are never loaded,
-//   and rows of a strip without ice skip stage A altogether (u, v = sliding velocity, SIAFD.cc:631-637).
+//   One mbarrier-tracked group of cp.async.bulk copies per row brings the enthalpy row AND the row's 2D
+//   scalars (thk_smooth, theta, h_x, h_y) into shared memory, issued one row ahead of use into the slot
+//   the previous row just vacated; rows no staggered point needs are never loaded, and rows of a strip
+//   without ice skip stage A altogether (u, v = sliding velocity, SIAFD.cc:631-637).
 //
 // Arithmetic deviations from the reference's glibc build, all far inside the 1e-10 bar:
 // FMA contraction; exp() and the division inside the Arrhenius factor use an inlined 1-ulp exp and a
@@ -68,17 +69,23 @@ struct SlabArgs {
   int use_bulk;  // 1: cp.async.bulk rows (column stride Mz); 0: 8-byte cp.async (column stride Mz | 1)
   int skip_rows; // 1: do not load enthalpy rows no staggered point needs
   long nE;       // doubles in the enthalpy array (bulk copies are clamped to it)
+  long n2;       // doubles in a geometry-width 2D array
   double inv_dz; // (Mz - 1) / Lz if the levels are equally spaced, else 0
 };
 
+// per-slot staging area of a row's 2D scalars (offsets in doubles)
+enum : int { AUX_TS = 0, AUX_TH = 18, AUX_HX = 36, AUX_HY = 68, AUX_N = 100 };
+
 template <int LAW, bool FULL, int NC, int WZ>
-__global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
+__global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     k_sia_slab(const __grid_constant__ DP P, const Fields F, const SlabArgs A) {
+  static_assert(NC <= 16, "AUX_* offsets and the partner shuffle assume at most 16 lane columns");
   extern __shared__ __align__(16) double sm[];
-  constexpr int NT = NC * WZ;
+  constexpr int NT = 2 * NC * WZ;
   constexpr int OWN = NC - 1;
+  constexpr int LB = NT / NC; // stage B lanes per column
   const int tid = threadIdx.x;
-  const int c = tid % NC, w = tid / NC; // stage A role
+  const int c = tid % NC, pt = (tid / NC) & 1, w = tid / (2 * NC); // stage A role
   const int lane = tid & 31;
   const int Mz = P.Mz;
   const int S = A.use_bulk ? Mz : (Mz | 1); // shared-memory column stride
@@ -89,12 +96,12 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
   double2 *zz = (double2 *)sm;
   double *E_s = sm + 2 * Mz;
   double *A_s = E_s + 2 * slotE; // age rows (only with age coupling)
-  double *I0_s = A_s + (P.use_age ? 2 * slotE : 0);
+  double *aux = A_s + (P.use_age ? 2 * slotE : 0);
+  double *I0_s = aux + 2 * AUX_N;
   double *I1_s = I0_s + (FULL ? colI : 0);
-  double *sL = I1_s + (FULL ? 2 * colI : 0); // [2][WZ][NC] delta at the last level of a range
+  double *sL = I1_s + (FULL ? 2 * colI : 0); // [2][WZ][NC] delta at the last level of a range; then D of a range
   double *sT = sL + 2 * WZ * NC;             // [2][WZ][NC] I increment over a range
-  double *sD = sT + 2 * WZ * NC;             // [2][WZ][NC] D contribution of a range
-  double *cf = sD + 2 * WZ * NC;             // [2][NC][4]  h_x, h_y of the o = 0 and o = 1 points, by row parity
+  double *cf = sT + 2 * WZ * NC;             // [2][NC][4]  h_x, h_y of the o = 0 and o = 1 points, by row parity
   unsigned long long *bars = (unsigned long long *)(cf + 2 * NC * 4);
 
   const int ca = (P.xs - 1) + blockIdx.x * OWN;
@@ -103,7 +110,8 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
   const bool col_ok = i_c <= ilast;
   const int iv = min(i_c, ilast);
   const bool own_c = col_ok && (c >= 1 || blockIdx.x == 0); // this strip writes D, Q of the column
-  const int ncolE = min(NC + 1, ilast + 2 - ca);            // enthalpy columns ca .. ca + ncolE - 1
+  const int ncolE = min(NC + 1, ilast + 2 - ca);            // enthalpy / thk_smooth columns ca .. ca + ncolE - 1
+  const int ncolS = ncolE - 1;                              // valid lane columns
   const int ra = (P.ys - 1) + blockIdx.y * A.RS;
   const int rb = min(ra + A.RS, P.ys + P.ym + 1);
   const int r0 = (FULL && blockIdx.y > 0) ? ra - 1 : ra; // warm-up row: I1 of the row below the segment
@@ -118,13 +126,14 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
     fence_mbar_init();
   }
 
-  // ---- which enthalpy rows are needed at all: rowts(rho) = any thk_smooth > 0 in columns [ca, ca + NC] ----
+  // ---- which rows are needed at all: rowts(rho) = any thk_smooth > 0 in columns [ca, ca + NC] ----
   // need(rho) = rowts(rho-1) | rowts(rho) | rowts(rho+1).  Every warp evaluates the flags itself (lanes =
   // columns, one ballot), so no broadcast is needed.  Bit q of `rf` = rowts(r + q - 1).
   const int wgx = P.xm + 2 * P.wg;
   const bool flag_lane = lane < ncolE;
-  const double *ts_col = F.thk_smooth + (ca - (P.xs - P.wg)) + lane; // column of this lane, local row 0
-  const int row_lo = P.ys - P.wg, row_hi = P.ys + P.ym + P.wg;       // valid rows [row_lo, row_hi)
+  const long cb2 = ca - (P.xs - P.wg);                         // local column of lane column 0 in a geometry array
+  const double *ts_col = F.thk_smooth + cb2 + lane;            // column of this lane, local row 0
+  const int row_lo = P.ys - P.wg, row_hi = P.ys + P.ym + P.wg; // valid rows [row_lo, row_hi)
   auto rowts_load = [&](int rho) -> double {
     return (flag_lane && rho >= row_lo && rho < row_hi) ? __ldg(ts_col + (long)(rho - row_lo) * wgx) : 0.0;
   };
@@ -140,13 +149,20 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
   }
   double ts_pref = A.skip_rows ? rowts_load(r0 + 4) : 0.0; // rowts(r + 4), consumed next iteration
 
-  // ---- enthalpy (and age) row loader: columns [ca, ca + ncolE) of row r -> slot ----
+  // ---- row loader: enthalpy (and age) columns [ca, ca + ncolE) and the 2D scalars of row r -> slot ----
   const int rowcount = ncolE * Mz;
   const long NXe = P.xm + 2 * P.we;
   const long goff0 = ((long)(r0 - (P.ys - P.we)) * NXe + (ca - (P.xs - P.we))) * Mz; // row r0
   const long gstride = NXe * Mz;
-  auto issue_row = [&](int it_row, int slot) { // it_row = r - r0
+  const long g2off0 = (long)(r0 - row_lo) * wgx + cb2; // thk_smooth / theta, row r0
+  const long sst = 2L * (P.xm + 2 * P.wst);
+  const long gsoff0 = idx2(P, ca, r0, P.wst) * 2; // h_x / h_y, row r0 (even: always 16-byte aligned)
+  auto issue_row = [&](int it_row, int slot) {    // it_row = r - r0
     const long goff = goff0 + (long)it_row * gstride;
+    const long g2 = g2off0 + (long)it_row * wgx;
+    const long gs = gsoff0 + (long)it_row * sst;
+    const bool stag_row = (r0 + it_row) <= P.ys + P.ym; // row rb is only ever a "north" row
+    double *ax = aux + slot * AUX_N;
     if (A.use_bulk) {
       if (tid == 0) {
         const long a0 = goff & ~1L;
@@ -156,10 +172,24 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
           E_s[slot * slotE + (goff - a0) + rowcount - 1] = F.E[goff + rowcount - 1];
           if (P.use_age) A_s[slot * slotE + (goff - a0) + rowcount - 1] = F.age[goff + rowcount - 1];
         }
-        const unsigned bytes = (unsigned)((a1 - a0) * 8);
-        mbar_expect_tx(&bars[slot], P.use_age ? 2 * bytes : bytes);
-        bulk_g2s(E_s + slot * slotE, F.E + a0, bytes, &bars[slot]);
-        if (P.use_age) bulk_g2s(A_s + slot * slotE, F.age + a0, bytes, &bars[slot]);
+        const long b0 = g2 & ~1L;
+        long b1 = (g2 + ncolE + 1) & ~1L;
+        if (b1 > A.n2) {
+          b1 -= 2;
+          ax[AUX_TS + (g2 - b0) + ncolE - 1] = F.thk_smooth[g2 + ncolE - 1];
+          ax[AUX_TH + (g2 - b0) + ncolE - 1] = F.theta[g2 + ncolE - 1];
+        }
+        const unsigned bytesE = (unsigned)((a1 - a0) * 8), bytes2 = (unsigned)((b1 - b0) * 8);
+        const unsigned bytesS = stag_row ? (unsigned)(ncolS * 16) : 0u;
+        mbar_expect_tx(&bars[slot], (P.use_age ? 2 * bytesE : bytesE) + 2 * bytes2 + 2 * bytesS);
+        bulk_g2s(E_s + slot * slotE, F.E + a0, bytesE, &bars[slot]);
+        if (P.use_age) bulk_g2s(A_s + slot * slotE, F.age + a0, bytesE, &bars[slot]);
+        bulk_g2s(ax + AUX_TS, F.thk_smooth + b0, bytes2, &bars[slot]);
+        bulk_g2s(ax + AUX_TH, F.theta + b0, bytes2, &bars[slot]);
+        if (stag_row) {
+          bulk_g2s(ax + AUX_HX, F.h_x + gs, bytesS, &bars[slot]);
+          bulk_g2s(ax + AUX_HY, F.h_y + gs, bytesS, &bars[slot]);
+        }
       }
     } else {
       const unsigned dst = smem_u32(E_s + slot * slotE);
@@ -173,6 +203,15 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
         for (int e = tid; e < rowcount; e += NT) {
           cp_async8(dstA + 8u * ((e / Mz) * S + e % Mz), srcA + e);
         }
+      }
+      const unsigned dx = smem_u32(ax);
+      if (tid < ncolE) {
+        cp_async8(dx + 8u * (AUX_TS + tid), F.thk_smooth + g2 + tid);
+        cp_async8(dx + 8u * (AUX_TH + tid), F.theta + g2 + tid);
+      }
+      if (stag_row && tid < 2 * ncolS) {
+        cp_async8(dx + 8u * (AUX_HX + tid), F.h_x + gs + tid);
+        cp_async8(dx + 8u * (AUX_HY + tid), F.h_y + gs + tid);
       }
       cp_async_commit();
     }
@@ -190,17 +229,12 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
     pending |= 2u;
   }
 
-  // ---- addresses of the per-row 2D scalars of this thread's column (row r0) ----
-  const long sg = P.xm + 2 * P.wg, sst = 2L * (P.xm + 2 * P.wst);
-  const double *ts_p = F.thk_smooth + idx2(P, iv, r0, P.wg); // (i, r); +1: east; +sg: north
-  const double *th_p = F.theta + idx2(P, iv, r0, P.wg);
-  const double *hx_p = F.h_x + idx2(P, iv, r0, P.wst) * 2; // [0]: o = 0, [1]: o = 1
-  const double *hy_p = F.h_y + idx2(P, iv, r0, P.wst) * 2;
-  double *D_p = F.D + idx2(P, iv, r0, P.wst) * 2;
-  double *Q_p = F.Q + idx2(P, iv, r0, P.wst) * 2;
+  double *DQ_D = F.D + idx2(P, iv, r0, P.wst) * 2 + pt;
+  double *DQ_Q = F.Q + idx2(P, iv, r0, P.wst) * 2 + pt;
+  const double *hq_p = (pt ? F.h_y : F.h_x) + idx2(P, iv, r0, P.wst) * 2 + pt; // slope the flux of this point uses
 
   // stage B role: column q (lane column index), li across z
-  const int q = tid / WZ, li = tid % WZ;
+  const int q = tid / LB, li = tid % LB;
   const int i_q = ca + q;
   const bool uv_col = FULL && q >= 1 && i_q >= P.xs && i_q < P.xs + P.xm;
   const long uv_row = (long)(P.xm + 2 * P.wuv) * Mz;
@@ -211,9 +245,9 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
 
   double dmax_local = 0.0;
   int hdc_local = 0;
-  // logical state of the I arrays (CTA-uniform): valid = materialised in shared memory; otherwise "all zero"
-  bool I1_valid[2] = {false, false};
-  bool I0_valid = false;
+  // logical state of the I arrays (CTA-uniform): bit set = materialised in shared memory, else "all zero".
+  // bit 0, 1: I1 slots; bit 2: I0
+  unsigned ivalid = 0;
 
   for (int r = r0; r < rb; ++r) {
     const int it = r - r0;
@@ -226,37 +260,11 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
       ts_pref = rowts_load(r + 5);
     }
     const long ro = (long)it; // row offset from r0
-    double hx0 = 0.0, hy0 = 0.0, hx1 = 0.0, hy1 = 0.0;
-    if (w == 0 || row_active) {
-      hx0 = __ldg(hx_p + ro * sst), hx1 = __ldg(hx_p + ro * sst + 1);
-      hy0 = __ldg(hy_p + ro * sst), hy1 = __ldg(hy_p + ro * sst + 1);
-    }
 
-    double DA = 0.0, DB = 0.0;
-    bool actA = false, actB = false;
+    double Dsum = 0.0, hx = 0.0, hy = 0.0;
+    bool act = false;
     if (row_active) {
-      // ---------------- stage A: integrate z range w of the two staggered columns of lane column c ------------
-      const double tsC = __ldg(ts_p + ro * sg), tsE = __ldg(ts_p + ro * sg + 1), tsN = __ldg(ts_p + (ro + 1) * sg);
-      const double thC = __ldg(th_p + ro * sg), thE = __ldg(th_p + ro * sg + 1), thN = __ldg(th_p + (ro + 1) * sg);
-      const double thkA = 0.5 * (tsC + tsE), thkB = 0.5 * (tsC + tsN); // sia/SIAFD.cc:627-628
-      const bool iceA = col_ok && (thkA != 0.0);                       // :631-637
-      actA = iceA && (r >= ra); // (the warm-up row only needs the j-offset point)
-      actB = col_ok && (thkB != 0.0);
-      const int ksA0 = iceA ? k_below_height2(zz, Mz, thkA, A.inv_dz, F.err) : -1; // :639
-      const int ksB = actB ? k_below_height2(zz, Mz, thkB, A.inv_dz, F.err) : -1;
-      const int ksA = actA ? ksA0 : -1;
-      // sia/SIAFD.cc:686, :693-696
-      const double alphaA = sqrt(hx0 * hx0 + hy0 * hy0), alphaB = sqrt(hx1 * hx1 + hy1 * hy1);
-      const double thetaA = 0.5 * (thC + thE), thetaB = 0.5 * (thC + thN);
-      const double c2A = P.e * thetaA * 2.0, c2B = P.e * thetaB * 2.0; // e_factor * theta_local * 2.0
-
-      // levels per z range of this column: a function of the column alone, never of the CTA tiling, so that
-      // the order of every sum -- and with it every bit of the result -- is independent of the decomposition
-      const int Lc = (max(ksA0, ksB) + WZ) / WZ;
-      const int k0 = w * Lc;
-      const int keA = min(k0 + Lc - 1, ksA), keB = min(k0 + Lc - 1, ksB); // last level of this thread (empty: < k0)
-      const int ke = max(keA, keB);
-
+      // ---------------- stage A: integrate z range w of staggered point pt of lane column c ------------
       if (pending) { // CTA-uniform
         if (A.use_bulk) {
           if (pending & 1u) { mbar_wait(&bars[0], bar_phase & 1u); bar_phase ^= 1u; }
@@ -267,174 +275,147 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
         }
         pending = 0;
       }
+      const int cc = min(c, ncolS - 1); // (lanes past the patch read a clamped column; results masked)
+      const double *axc = aux + s_cur * AUX_N, *axn = aux + s_nxt * AUX_N;
+      const int sh2c = A.use_bulk ? (int)((g2off0 + ro * wgx) & 1) : 0;
+      const int sh2n = A.use_bulk ? (int)((g2off0 + (ro + 1) * wgx) & 1) : 0;
+      const double tsC = axc[AUX_TS + sh2c + cc], thC = axc[AUX_TH + sh2c + cc];
+      const double ts2 = pt ? axn[AUX_TS + sh2n + cc] : axc[AUX_TS + sh2c + cc + 1];
+      const double th2 = pt ? axn[AUX_TH + sh2n + cc] : axc[AUX_TH + sh2c + cc + 1];
+      hx = axc[AUX_HX + 2 * cc + pt], hy = axc[AUX_HY + 2 * cc + pt];
+      const double thk = 0.5 * (tsC + ts2); // sia/SIAFD.cc:627-628
+      const bool ice = col_ok && (thk != 0.0); // :631-637
+      act = ice && (pt == 1 || r >= ra);       // (the warm-up row only needs the j-offset point)
+      const int ks0 = ice ? k_below_height2(zz, Mz, thk, A.inv_dz, F.err) : -1; // :639
+      const int ks = act ? ks0 : -1;
+      // levels per z range of this column: a function of the column alone, never of the CTA tiling, so that
+      // the order of every sum -- and with it every bit of the result -- is independent of the decomposition
+      const int Lc = (max(ks0, __shfl_xor_sync(FULLMASK, ks0, NC)) + WZ) / WZ;
+      const int k0 = w * Lc;
+      const int ke = min(k0 + Lc - 1, ks); // last level of this thread (empty range: ke < k0)
+      // sia/SIAFD.cc:686, :693-696
+      const double alpha = sqrt(hx * hx + hy * hy);
+      const double theta = 0.5 * (thC + th2);
+      const double c2c = P.e * theta * 2.0; // e_factor * theta_local * 2.0
+
       const int shc = A.use_bulk ? (int)((goff0 + ro * gstride) & 1) : 0;
       const int shn = A.use_bulk ? (int)((goff0 + (ro + 1) * gstride) & 1) : 0;
-      const int cE = min(c, ncolE - 2); // (lanes past the patch read a clamped column; results masked)
-      const double *Ec = E_s + s_cur * slotE + shc + cE * S;         // column (i, r)
-      const double *Ee = Ec + S;                                     // (i + 1, r)
-      const double *En = E_s + s_nxt * slotE + shn + cE * S;         // (i, r + 1)
-      const double *Ac = A_s + s_cur * slotE + shc + cE * S, *An = A_s + s_nxt * slotE + shn + cE * S;
-      double *I0c = I0_s + c * S, *I1c = I1_s + (s_cur * NC + c) * S;
+      const int o1 = s_cur * slotE + shc + cc * S;                                        // column (i, r)
+      const int o2 = pt ? (s_nxt * slotE + shn + cc * S) : (s_cur * slotE + shc + (cc + 1) * S); // (i, r+1) or (i+1, r)
+      const double *E1 = E_s + o1, *E2 = E_s + o2;
+      double *Ic = pt ? (I1_s + (s_cur * NC + c) * S) : (I0_s + c * S);
 
-      double prevA = 0.0, prevB = 0.0, firstA = 0.0, firstB = 0.0;
-      double runA = 0.0, runB = 0.0, dpA = 0.0, dpB = 0.0;
+      double prev = 0.0, first = 0.0, run = 0.0, dp = 0.0;
       for (int k = k0; k <= ke; ++k) {
-        const bool pA = (k <= keA), pB = (k <= keB);
         const double2 zh = zz[k];
-        const double e0 = Ec[k], e1 = Ee[k], e2 = En[k];
-        double dep[2], pr[2], Ea[2], st[2], gsz[2], fl[2], c2[2];
-        dep[0] = thkA - zh.x, dep[1] = thkB - zh.x;              // :641-643
-        Ea[0] = 0.5 * (e0 + e1), Ea[1] = 0.5 * (e0 + e2);         // :677-684
-        pr[0] = fma(P.rg, dep[0], P.p_air), pr[1] = fma(P.rg, dep[1], P.p_air); // EnthalpyConverter.cc:146-152
-        st[0] = alphaA * pr[0], st[1] = alphaB * pr[1];           // :688
-        gsz[0] = gsz[1] = P.grain_size;
-        c2[0] = c2A, c2[1] = c2B;
+        const double dep = thk - zh.x;                 // :641-643
+        double Ea[1], pr[1], st[1], gsz[1], fl[1];
+        Ea[0] = 0.5 * (E1[k] + E2[k]);                 // :677-684
+        pr[0] = fma(P.rg, dep, P.p_air);               // EnthalpyConverter.cc:146-152
+        st[0] = alpha * pr[0];                         // :688
+        gsz[0] = P.grain_size;
+        double c2 = c2c;
         if (P.use_age) { // :649-675 (uniform branch; off by default)
-          const double ag[2] = {0.5 * (Ac[k] + Ac[S + k]), 0.5 * (Ac[k] + An[k])};
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (P.gs_age) gsz[j] = grain_size_vostok(ag[j] * P.years_per_second);
-            if (P.e_age) {
-              c2[j] = (interglacial(P, P.current_time - ag[j]) ? P.e_inter : P.e) * (j ? thetaB : thetaA) * 2.0;
-            }
-          }
+          const double ag = 0.5 * (A_s[o1 + k] + A_s[o2 + k]);
+          if (P.gs_age) gsz[0] = grain_size_vostok(ag * P.years_per_second);
+          if (P.e_age) c2 = (interglacial(P, P.current_time - ag) ? P.e_inter : P.e) * theta * 2.0;
         }
-        flow_lean_v<LAW, 2>(P, st, Ea, pr, gsz, fl); // :691
-        const double dA = pA ? c2[0] * pr[0] * fl[0] : 0.0, dB = pB ? c2[1] * pr[1] * fl[1] : 0.0; // :696
+        flow_lean_v<LAW, 1>(P, st, Ea, pr, gsz, fl); // :691
+        const double d = c2 * pr[0] * fl[0];         // :696
         // trapezoids   I: 0.5 dz (delta[k-1] + delta[k])                          compute_I, :855-858
         //              D: 0.5 dz ((depth[k] + dz) delta[k-1] + depth[k] delta[k])  :701-705
-        if (k == k0) { // the trapezoid ending at the first level of the range needs the range below: deferred
-          firstA = dA, firstB = dB;
-        } else {
-          const double dz = zh.y + zh.y;
-          if (pA) {
-            runA = fma(zh.y, prevA + dA, runA);
-            dpA = fma(zh.y, fma(dep[0] + dz, prevA, dep[0] * dA), dpA);
-          }
-          if (pB) {
-            runB = fma(zh.y, prevB + dB, runB);
-            dpB = fma(zh.y, fma(dep[1] + dz, prevB, dep[1] * dB), dpB);
-          }
-        }
-        if (k == ksA) dpA = fma(0.5 * dep[0] * dep[0], dA, dpA); // :707-708 (dz = thk - z[ks] = depth[ks])
-        if (k == ksB) dpB = fma(0.5 * dep[1] * dep[1], dB, dpB);
-        if (FULL) { // range-local prefix; the offset of the range is added below
-          if (pA) I0c[k] = runA;
-          if (pB) I1c[k] = runB;
-        }
-        if (pA) prevA = dA;
-        if (pB) prevB = dB;
+        // (the trapezoid ending at the first level of the range needs the range below: added after the loop)
+        const bool is_first = (k == k0);
+        const double hz = is_first ? 0.0 : zh.y;
+        run = fma(hz, prev + d, run);
+        dp = fma(hz, fma(dep + (zh.y + zh.y), prev, dep * d), dp);
+        if (FULL) Ic[k] = run; // range-local prefix; the offset of the range is added below
+        first = is_first ? d : first;
+        prev = d;
       }
-      sL[(0 * WZ + w) * NC + c] = prevA;
-      sL[(1 * WZ + w) * NC + c] = prevB;
-      __syncthreads(); // #1: last deltas visible; every read of enthalpy row r is done
+      if (ke >= k0 && ke == ks) { // :707-708 (dz = thk - z[ks] = depth[ks])
+        const double depk = thk - zz[ks].x;
+        dp = fma(0.5 * depk * depk, prev, dp);
+      }
+      sL[(pt * WZ + w) * NC + c] = prev;
+      __syncthreads(); // #1: last deltas visible; every read of row r's slot is done
       if (prefetch) {
         issue_row(it + 2, s_cur);
         pending |= (1u << s_cur);
       }
       // trapezoid across the lower boundary of this range (the range below ends at k0 - 1)
-      double bIA = 0.0, bIB = 0.0, bDA = 0.0, bDB = 0.0;
-      if (w > 0) {
-        const double2 zh = zz[min(k0, Mz - 1)];
-        const double dz = zh.y + zh.y;
-        if (keA >= k0) {
-          const double dl = sL[(0 * WZ + w - 1) * NC + c], depF = thkA - zh.x;
-          bIA = zh.y * (dl + firstA);
-          bDA = zh.y * fma(depF + dz, dl, depF * firstA);
-        }
-        if (keB >= k0) {
-          const double dl = sL[(1 * WZ + w - 1) * NC + c], depF = thkB - zh.x;
-          bIB = zh.y * (dl + firstB);
-          bDB = zh.y * fma(depF + dz, dl, depF * firstB);
-        }
+      double bI = 0.0, bD = 0.0;
+      if (w > 0 && ke >= k0) {
+        const double2 zh = zz[k0];
+        const double dl = sL[(pt * WZ + w - 1) * NC + c], depF = thk - zh.x;
+        bI = zh.y * (dl + first);
+        bD = zh.y * fma(depF + (zh.y + zh.y), dl, depF * first);
       }
-      sT[(0 * WZ + w) * NC + c] = runA + bIA; // empty range: 0
-      sT[(1 * WZ + w) * NC + c] = runB + bIB;
-      sD[(0 * WZ + w) * NC + c] = dpA + bDA;
-      sD[(1 * WZ + w) * NC + c] = dpB + bDB;
+      sT[(pt * WZ + w) * NC + c] = run + bI; // empty range: 0
+      // D of this range goes where the last delta of the range below was: only this thread reads that entry
+      sL[(pt * WZ + ((w + WZ - 1) % WZ)) * NC + c] = dp + bD;
       __syncthreads(); // #2
       if (FULL) {
-        double offA = 0.0, offB = 0.0, totA = 0.0, totB = 0.0;
+        double off = 0.0, tot = 0.0;
 #pragma unroll
         for (int ww = 0; ww < WZ; ++ww) {
-          const double tA = sT[(0 * WZ + ww) * NC + c], tB = sT[(1 * WZ + ww) * NC + c];
-          if (ww < w) offA += tA, offB += tB;
-          totA += tA, totB += tB;
+          const double t = sT[(pt * WZ + ww) * NC + c];
+          off += (ww < w) ? t : 0.0;
+          tot += t;
         }
         if (w > 0) {
-          const double addA = offA + bIA, addB = offB + bIB;
-          for (int k = k0; k <= ke; ++k) {
-            if (k <= keA) I0c[k] += addA;
-            if (k <= keB) I1c[k] += addB;
-          }
+          const double add = off + bI;
+          for (int k = k0; k <= ke; ++k) Ic[k] += add;
         }
         // above the ice I keeps its last value (:861-863); ice-free points (ks = -1): I = 0 everywhere
-        for (int k = ksA + 1 + w; k < Mz; k += WZ) I0c[k] = totA;
-        for (int k = ksB + 1 + w; k < Mz; k += WZ) I1c[k] = totB;
+        for (int k = ks + 1 + w; k < Mz; k += WZ) Ic[k] = tot;
       }
       if (w == 0) {
 #pragma unroll
-        for (int ww = 0; ww < WZ; ++ww) {
-          DA += sD[(0 * WZ + ww) * NC + c];
-          DB += sD[(1 * WZ + ww) * NC + c];
-        }
+        for (int ww = 0; ww < WZ; ++ww) Dsum += sL[(pt * WZ + ww) * NC + c];
       }
-      if (FULL) {
-        I0_valid = true;
-        I1_valid[s_cur] = true;
-      }
+      if (FULL) ivalid |= 4u | (1u << s_cur);
     } else {
       if (prefetch) { // nothing reads the slot of row r: it can be refilled at once
         issue_row(it + 2, s_cur);
         pending |= (1u << s_cur);
       }
-      if (FULL) {
-        I0_valid = false;
-        I1_valid[s_cur] = false;
-      }
+      if (FULL) ivalid &= ~(4u | (1u << s_cur));
     }
 
-    // D, flux, D_max (thread w = 0 of the column), sia/SIAFD.cc:711-731, :772-793
+    // D, flux, D_max (thread w = 0 of the point), sia/SIAFD.cc:711-731, :772-793
     if (w == 0) {
       if (FULL) {
-        double *cfr = cf + (s_cur * NC + c) * 4;
-        cfr[0] = hx0, cfr[1] = hy0, cfr[2] = hx1, cfr[3] = hy1;
+        double *cfr = cf + (s_cur * NC + c) * 4 + 2 * pt;
+        cfr[0] = hx, cfr[1] = hy; // (rows without ice: 0, multiplied by I = 0 in stage B)
       }
       if (own_c && r >= ra) {
-        const bool edge_r = (r < 0 || r >= P.My - 1);
-        const bool edge = (i_c < 0 || i_c >= P.Mx - 1 || edge_r);
-        double D0 = 0.0, D1 = 0.0;
-        if (actA) {
-          D0 = edge ? 0.0 : DA;
-          if (P.limit_diffusivity && D0 >= P.D_limit) {
-            D0 = P.D_limit;
+        const bool edge = (i_c < 0 || i_c >= P.Mx - 1 || r < 0 || r >= P.My - 1);
+        const double hq = row_active ? (pt ? hy : hx) : __ldg(hq_p + ro * sst);
+        double D = 0.0;
+        if (act) {
+          D = edge ? 0.0 : Dsum;
+          if (P.limit_diffusivity && D >= P.D_limit) {
+            D = P.D_limit;
             hdc_local += 1;
           }
-          dmax_local = fmax(dmax_local, D0);
+          dmax_local = fmax(dmax_local, D);
         }
-        if (actB) {
-          D1 = edge ? 0.0 : DB;
-          if (P.limit_diffusivity && D1 >= P.D_limit) {
-            D1 = P.D_limit;
-            hdc_local += 1;
-          }
-          dmax_local = fmax(dmax_local, D1);
-        }
-        *reinterpret_cast<double2 *>(D_p + ro * sst) = make_double2(D0, D1);
-        *reinterpret_cast<double2 *>(Q_p + ro * sst) = make_double2(-D0 * hx0, -D1 * hy1);
+        DQ_D[ro * sst] = D;
+        DQ_Q[ro * sst] = -D * hq;
       }
     }
 
     if (FULL) {
-      const bool any_valid = I0_valid || I1_valid[0] || I1_valid[1];
+      const bool any_valid = ivalid != 0;
       if (any_valid) {
         // materialise logically-zero arrays (only at the edge of the ice)
-        if (!I0_valid) {
+        if (!(ivalid & 4u)) {
           for (int e = tid; e < NC * S; e += NT) I0_s[e] = 0.0;
         }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          if (!I1_valid[s]) {
+          if (!(ivalid & (1u << s))) {
             for (int e = tid; e < NC * S; e += NT) I1_s[s * NC * S + e] = 0.0;
           }
         }
@@ -451,18 +432,20 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
         double *vp = F.v + uv0 + (long)(r - (P.ys - P.wuv)) * uv_row + li;
         if (!any_valid) {
           // no ice at any staggered point of this and the previous row: I == 0, u = sliding velocity (G9)
-          for (int k = li; k < Mz; k += WZ, up += WZ, vp += WZ) {
+          for (int k = li; k < Mz; k += LB, up += LB, vp += LB) {
             *up = ub;
             *vp = vb;
           }
         } else {
           const double *cE = cf + (s_cur * NC + q) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + q) * 4;
+          const bool south = (ivalid & (1u << s_nxt)) != 0;
           const double hxe = cE[0], hye = cE[1], hxn = cE[2], hyn = cE[3];
           const double hxw = cW[0], hyw = cW[1];
-          const double hxs = I1_valid[s_nxt] ? cS[2] : 0.0, hys = I1_valid[s_nxt] ? cS[3] : 0.0;
+          const double hxs = south ? cS[2] : 0.0, hys = south ? cS[3] : 0.0;
           const double *Ie = I0_s + q * S + li, *Iw = Ie - S;
           const double *In = I1_s + (s_cur * NC + q) * S + li, *Is = I1_s + (s_nxt * NC + q) * S + li;
-          for (int k = li; k < Mz; k += WZ, up += WZ, vp += WZ, Ie += WZ, Iw += WZ, In += WZ, Is += WZ) {
+#pragma unroll 2
+          for (int k = li; k < Mz; k += LB, up += LB, vp += LB, Ie += LB, Iw += LB, In += LB, Is += LB) {
             const double ie = *Ie, iw = *Iw, in = *In, is = *Is;
             *up = ub - 0.25 * (ie * hxe + iw * hxw + in * hxn + is * hxs);
             *vp = vb - 0.25 * (ie * hye + iw * hyw + in * hyn + is * hys);
@@ -471,7 +454,7 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
       }
       if (any_valid) {
         // the zero-filled arrays now ARE valid zeros for the next row's "previous row" role
-        I1_valid[s_cur] = true;
+        ivalid |= (1u << s_cur);
         __syncthreads(); // #4: stage B reads done before the next row's stage A overwrites I0 / I1[s_nxt]
       }
     }
@@ -487,8 +470,9 @@ __global__ void __launch_bounds__(NC *WZ, (NC * WZ <= 128) ? 3 : 2)
       m = (o > m) ? o : m;
       cnt += __shfl_xor_sync(FULLMASK, cnt, d);
     }
-    __shared__ unsigned long long wm[32];
-    __shared__ int wc[32];
+    __syncthreads(); // sT is free
+    unsigned long long *wm = (unsigned long long *)sT;
+    int *wc = (int *)(sT + 32);
     if ((tid & 31) == 0) {
       wm[tid >> 5] = m;
       wc[tid >> 5] = cnt;
@@ -513,12 +497,13 @@ static size_t slab_smem_bytes(const DP &P, bool full, int NC, int WZ, bool bulk)
   const long Mz = P.Mz, S = bulk ? Mz : (Mz | 1);
   const long slotE = ((NC + 1) * S + 2 + 1) & ~1L;
   const long colI = (NC * S + 1) & ~1L;
-  long d = 2 * Mz + 2 * slotE + (P.use_age ? 2 * slotE : 0) + (full ? 3 * colI : 0) + 3 * 2 * WZ * NC + 2 * NC * 4;
+  long d = 2 * Mz + 2 * slotE + (P.use_age ? 2 * slotE : 0) + 2 * AUX_N + (full ? 3 * colI : 0) + 2 * 2 * WZ * NC +
+           2 * NC * 4;
   return (size_t)d * 8 + 2 * 8 /* mbarriers */ + 16;
 }
 
 template <int LAW, bool FULL, int NC, int WZ>
-static int launch_slab_t(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A, cudaStream_t s) {
+static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaStream_t s) {
   const size_t smem = slab_smem_bytes(P, FULL, NC, WZ, A.use_bulk != 0);
   if (smem > (size_t)227 * 1024) return -1;
   static size_t configured = 0; // per instantiation
@@ -529,21 +514,19 @@ static int launch_slab_t(const DP &P, const Fields &F, const Tuning &T, const Sl
     }
     configured = smem;
   }
-  (void)T;
   dim3 grid((unsigned)((P.xm + 1 + (NC - 2)) / (NC - 1)), (unsigned)((P.ym + 2 + A.RS - 1) / A.RS));
-  k_sia_slab<LAW, FULL, NC, WZ><<<grid, NC * WZ, smem, s>>>(P, F, A);
+  k_sia_slab<LAW, FULL, NC, WZ><<<grid, 2 * NC * WZ, smem, s>>>(P, F, A);
   return 1;
 }
 
-template <int LAW, bool FULL> static int launch_slab_l(const DP &P, const Fields &F, const Tuning &T, SlabArgs A,
+template <int LAW, bool FULL> static int launch_slab_l(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
                                                        cudaStream_t s) {
   // 16 lane columns unless shared memory cannot hold them (very tall grids): then 8
-  const bool fits16 = slab_smem_bytes(P, FULL, 16, 8, A.use_bulk != 0) <= (size_t)227 * 1024;
-  if (fits16) {
-    if (T.wz == 16) return launch_slab_t<LAW, FULL, 16, 16>(P, F, T, A, s);
-    return launch_slab_t<LAW, FULL, 16, 8>(P, F, T, A, s);
+  (void)T;
+  if (slab_smem_bytes(P, FULL, 16, 8, A.use_bulk != 0) <= (size_t)227 * 1024) {
+    return launch_slab_t<LAW, FULL, 16, 8>(P, F, A, s);
   }
-  return launch_slab_t<LAW, FULL, 8, 16>(P, F, T, A, s);
+  return launch_slab_t<LAW, FULL, 8, 16>(P, F, A, s);
 }
 
 template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
@@ -568,12 +551,14 @@ template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, cons
   }
 }
 
-int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, double inv_dz, cudaStream_t s) {
+int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz,
+                cudaStream_t s) {
   SlabArgs A;
   A.RS = T.rows_per_cta;
   A.use_bulk = (T.use_bulk_copy && (P.Mz & 1)) ? 1 : 0; // even Mz: padded columns, 8-byte cp.async
   A.skip_rows = T.skip_ice_free;
   A.nE = nE;
+  A.n2 = n2;
   A.inv_dz = inv_dz;
   return full ? launch_slab_f<true>(P, F, T, A, s) : launch_slab_f<false>(P, F, T, A, s);
 }
