@@ -223,6 +223,9 @@ void fill_dp(siafd_b200_handle *h) {
   P.A_cold = c.fl_A_cold, P.A_warm = c.fl_A_warm, P.Q_cold = c.fl_Q_cold, P.Q_warm = c.fl_Q_warm;
   P.T_crit = c.fl_T_crit, P.R = c.fl_R;
   P.QoR_cold = c.fl_Q_cold / c.fl_R, P.QoR_warm = c.fl_Q_warm / c.fl_R;
+  P.lnA_cold = log(c.fl_A_cold), P.lnA_warm = log(c.fl_A_warm);
+  P.hic = 0.5 / c.ec_c_i;
+  P.cts2_a = 2.0 * c.ec_c_i * (c.ec_T_melting - c.ec_T_0), P.cts2_b = 2.0 * c.ec_c_i * c.ec_beta;
   {
     // rheology/FlowLaw.cc:45 and PatersonBudd.cc:57, evaluated like the reference does
     const double beta_CC_grad = c.fl_beta * c.fl_rho * c.fl_g;
@@ -392,7 +395,7 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.use_bulk_copy = 1;
   h->tuning.skip_ice_free = 1;
   h->tuning.variant = 1;
-  h->tuning.wz = 8;
+  h->tuning.wz = 4;
   if (const char *e = getenv("SIAFD_B200_VARIANT")) h->tuning.variant = atoi(e);
   if (const char *e = getenv("SIAFD_B200_WZ")) h->tuning.wz = atoi(e);
   if (const char *e = getenv("SIAFD_B200_ROWS")) h->tuning.rows_per_cta = atoi(e) > 0 ? atoi(e) : 64;

@@ -29,6 +29,9 @@ struct DP {
   double n, nm1, e, e_inter;
   double A_cold, A_warm, Q_cold, Q_warm, T_crit, R;
   double QoR_cold, QoR_warm; // Q / R, for the lean Arrhenius evaluation in siafd_fused.cu
+  // the same factor in the form exp(lnA - (Q/R) / T) (siafd_slab.cu): ln A; 0.5 / c_i; and the cold-ice test
+  // E < E_cts(p) as (E_ij + E_offset) < cts2_a - cts2_b p, cts2_a = 2 c_i (T_melting - T_0), cts2_b = 2 c_i beta
+  double lnA_cold, lnA_warm, hic, cts2_a, cts2_b;
   double beta_ratio; // m_beta_CC_grad / (m_rho * m_g), rheology/PatersonBudd.cc:57
   double gp_T0, gp_coeff, gp_limit, gp_softness_T0; // rheology/GPBLD.cc:49-61
   double iso_A;

@@ -44,6 +44,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
@@ -103,6 +104,40 @@ __device__ __forceinline__ double exp_fast(double x) {
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// exp(x) for |x| < 700 with a 16-entry table: x = (16 m + j) ln2 / 16 + r, |r| <= ln2 / 32, so that a degree-6
+// polynomial suffices (truncation 4.4e-16 relative): exp(x) = 2^m * 2^(j/16) * p(r).  11 FP64 operations against
+// 17 of exp_fast.  `tab` is EXPT staged in shared memory (lanes index it independently).  Error <= ~2 ulp.
+static __constant__ double EXPT[16] = {
+    1.0,                1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,  1.241857812073484,
+    1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407, 1.6104903319492543,
+    1.681792830507429,  1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+static __constant__ double EXPD[10] = {
+    23.083120654223414,     // [0] 16 / ln2
+    -0.043321698784993146,  // [1] -ln2 / 16 (high part, 42 bits)
+    -3.436201886692732e-15, // [2] -ln2 / 16 (low part)
+    0.001388888888888889,   // [3] 1/6!
+    0.008333333333333333,   // [4] 1/5!
+    0.041666666666666664,   // [5] 1/4!
+    0.16666666666666666,    // [6] 1/3!
+    6755399441055744.0,     // [7] 1.5 * 2^52
+    0.0, 0.0};
+__device__ __forceinline__ double exp_tab(double x, const double *tab) {
+  double t = fma(x, EXPD[0], EXPD[7]);
+  const int n = __double2loint(t);
+  t -= EXPD[7];
+  double r = fma(t, EXPD[1], x);
+  r = fma(t, EXPD[2], r);
+  double p = EXPD[3];
+  p = fma(p, r, EXPD[4]);
+  p = fma(p, r, EXPD[5]);
+  p = fma(p, r, EXPD[6]);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= tab[n & 15];
+  return __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
 }
 
 // A * exp(-Q / (R * T)) of FlowLaw::softness_paterson_budd (rheology/FlowLaw.cc:89-94) and the arr / arrwarm

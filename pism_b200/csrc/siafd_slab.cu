@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   double *sL = I1_s + (FULL ? 2 * colI : 0); // [2][WZ][NC] delta at the last level of a range; then D of a range
   double *sT = sL + 2 * WZ * NC;             // [2][WZ][NC] I increment over a range
   double *cf = sT + 2 * WZ * NC;             // [2][NC][4]  h_x, h_y of the o = 0 and o = 1 points, by row parity
-  unsigned long long *bars = (unsigned long long *)(cf + 2 * NC * 4);
+  double *tab16 = cf + 2 * NC * 4;           // 2^(j/16), for exp_tab
+  unsigned long long *bars = (unsigned long long *)(tab16 + 16);
 
   const int ca = (P.xs - 1) + blockIdx.x * OWN;
   const int ilast = P.xs + P.xm; // last extended column
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     const double zk = F.z[k];
     zz[k] = make_double2(zk, (k > 0) ? 0.5 * (zk - F.z[k - 1]) : 0.0);
   }
+  if (tid < 16) tab16[tid] = EXPT[tid];
   if (A.use_bulk && tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -127,27 +129,33 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   }
 
   // ---- which rows are needed at all: rowts(rho) = any thk_smooth > 0 in columns [ca, ca + NC] ----
-  // need(rho) = rowts(rho-1) | rowts(rho) | rowts(rho+1).  Every warp evaluates the flags itself (lanes =
-  // columns, one ballot), so no broadcast is needed.  Bit q of `rf` = rowts(r + q - 1).
+  // need(rho) = rowts(rho-1) | rowts(rho) | rowts(rho+1).  All flags of the CTA's rows are computed up front, by
+  // every warp for itself (lane = row, one ballot per 32 rows), so that the march over rows without ice never
+  // waits on a load: bit j of the 96-bit word fw2:fw1:fw0 = rowts(r0 - 1 + j).
   const int wgx = P.xm + 2 * P.wg;
-  const bool flag_lane = lane < ncolE;
   const long cb2 = ca - (P.xs - P.wg);                         // local column of lane column 0 in a geometry array
-  const double *ts_col = F.thk_smooth + cb2 + lane;            // column of this lane, local row 0
   const int row_lo = P.ys - P.wg, row_hi = P.ys + P.ym + P.wg; // valid rows [row_lo, row_hi)
-  auto rowts_load = [&](int rho) -> double {
-    return (flag_lane && rho >= row_lo && rho < row_hi) ? __ldg(ts_col + (long)(rho - row_lo) * wgx) : 0.0;
-  };
-  unsigned rf = 0;
+  unsigned fw0 = 0xffffffffu, fw1 = 0xffffffffu, fw2 = 0xffffffffu;
   if (A.skip_rows) {
+    unsigned fw[3];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      const double v = rowts_load(r0 + q - 1);
-      if (__ballot_sync(FULLMASK, v > 0.0)) rf |= (1u << q);
+    for (int b = 0; b < 3; ++b) {
+      const int rho = r0 - 1 + 32 * b + lane;
+      double m = 0.0;
+      if (rho >= row_lo && rho < row_hi && rho <= rb + 3) {
+        const double *tsr = F.thk_smooth + (long)(rho - row_lo) * wgx + cb2;
+        for (int e = 0; e < ncolE; ++e) m = fmax(m, __ldg(tsr + e));
+      }
+      fw[b] = __ballot_sync(FULLMASK, m > 0.0);
     }
-  } else {
-    rf = 0xffffffffu;
+    fw0 = fw[0], fw1 = fw[1], fw2 = fw[2];
   }
-  double ts_pref = A.skip_rows ? rowts_load(r0 + 4) : 0.0; // rowts(r + 4), consumed next iteration
+  // bits 0..4 of the result = rowts(r - 1 .. r + 3) for row r = r0 + it
+  auto row_flags = [&](int it) -> unsigned {
+    const unsigned lo = it < 32 ? fw0 : (it < 64 ? fw1 : fw2), hi = it < 32 ? fw1 : (it < 64 ? fw2 : 0u);
+    return __funnelshift_r(lo, hi, it & 31) & 31u;
+  };
+  unsigned rf = row_flags(0);
 
   // ---- row loader: enthalpy (and age) columns [ca, ca + ncolE) and the 2D scalars of row r -> slot ----
   const int rowcount = ncolE * Mz;
@@ -231,7 +239,6 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
 
   double *DQ_D = F.D + idx2(P, iv, r0, P.wst) * 2 + pt;
   double *DQ_Q = F.Q + idx2(P, iv, r0, P.wst) * 2 + pt;
-  const double *hq_p = (pt ? F.h_y : F.h_x) + idx2(P, iv, r0, P.wst) * 2 + pt; // slope the flux of this point uses
 
   // stage B role: column q (lane column index), li across z
   const int q = tid / LB, li = tid % LB;
@@ -242,6 +249,17 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   const double *sl_p =
       (FULL && uv_col && F.sliding != nullptr) ? F.sliding + idx2(P, i_q, P.ys - P.wsl, P.wsl) * 2 : nullptr;
   const long ssl = 2L * (P.xm + 2 * P.wsl);
+
+  // Sliding velocity of stage B's column: the LB lanes that share a column hold the values of LB consecutive
+  // rows (lane li: row rbase + block * LB + li) and hand them out by shuffle; the next block is loaded a whole
+  // block ahead, so that rows without ice (~100 cycles each) never wait on a load.
+  const int rbase = max(ra, P.ys), rend = min(rb, P.ys + P.ym); // stage B rows [rbase, rend)
+  auto sliding_load = [&](int rho) -> double2 {
+    return (sl_p != nullptr && rho < rend) ? __ldg(reinterpret_cast<const double2 *>(sl_p + (long)(rho - (P.ys - P.wsl)) * ssl))
+                                           : make_double2(0.0, 0.0);
+  };
+  double2 sv_cur = make_double2(0.0, 0.0), sv_nxt = make_double2(0.0, 0.0);
+  if (FULL) sv_cur = sliding_load(rbase + li), sv_nxt = sliding_load(rbase + LB + li);
 
   double dmax_local = 0.0;
   int hdc_local = 0;
@@ -254,12 +272,19 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     const int s_cur = it & 1, s_nxt = s_cur ^ 1;
     const bool row_active = (rf & 6u) != 0;                    // rowts(r) | rowts(r + 1)
     const bool prefetch = (r + 2 <= rb) && ((rf & 28u) != 0); // rowts(r+1) | (r+2) | (r+3)
-    if (A.skip_rows) { // shift the row-flag window by one row; rowts(r + 4) arrives, rowts(r + 5) is requested
-      const unsigned newbit = __ballot_sync(FULLMASK, ts_pref > 0.0) ? 1u : 0u;
-      rf = (rf >> 1) | (newbit << 4);
-      ts_pref = rowts_load(r + 5);
-    }
+    rf = row_flags(it + 1);
     const long ro = (long)it; // row offset from r0
+    double2 sv = make_double2(0.0, 0.0);
+    if (FULL && r >= rbase && r < rend) { // CTA-uniform
+      const int j = (r - rbase) % LB;
+      if (j == 0 && r > rbase) {
+        sv_cur = sv_nxt;
+        sv_nxt = sliding_load(r + LB + li);
+      }
+      const int src = (lane & ~(LB - 1)) | j;
+      sv.x = __shfl_sync(FULLMASK, sv_cur.x, src);
+      sv.y = __shfl_sync(FULLMASK, sv_cur.y, src);
+    }
 
     double Dsum = 0.0, hx = 0.0, hy = 0.0;
     bool act = false;
@@ -306,6 +331,58 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       double *Ic = pt ? (I1_s + (s_cur * NC + c) * S) : (I0_s + c * S);
 
       double prev = 0.0, first = 0.0, run = 0.0, dp = 0.0;
+      constexpr bool ARRH = (LAW == LAW_ARR || LAW == LAW_ARRWARM || LAW == LAW_PB || LAW == LAW_GPBLD);
+      if (ARRH && P.n_is_3 && !P.use_age) {
+        // Arrhenius-type laws with Glen exponent 3 (the default path).  Same quantities as the generic loop
+        // below, regrouped (every regrouping is exact in real arithmetic and moves results by a few ulp):
+        //   E = (E1 + E2) / 2 is kept as the sum s; T = s (0.5 / c_i) + T_0; the cold-ice test E < E_cts(p) is
+        //   s < cts2_a - cts2_b p; T_pa = T - T_m + T_melting = T + beta p; A exp(-Q / (R T)) = exp(ln A - (Q/R) / T);
+        //   delta = (e theta 2 alpha^2) p^3 softness;  (depth[k] + dz) delta[k-1] = depth[k-1] delta[k-1].
+        const double K = c2c * (hx * hx + hy * hy);
+        double gprev = 0.0; // depth[k-1] * delta[k-1]
+        for (int k = k0; k <= ke; ++k) {
+          const double2 zh = zz[k];
+          const double s = E1[k] + E2[k];
+          const double dep = thk - zh.x;
+          const double pr = fma(P.rg, dep, P.p_air);
+          const double Tc = fma(s, P.hic, P.T_0); // E / c_i + T_0
+          double T, lnA, QoR;
+          if (LAW == LAW_GPBLD) {
+            T = fma(P.ec_beta, pr, Tc); // EnthalpyConverter.cc:196-198
+          } else {
+            const double T_m = fma(-P.ec_beta, pr, P.T_melting);
+            T = fmin(Tc, T_m); // EnthalpyConverter::temperature, :180-188
+            if (LAW == LAW_PB) T = fma(P.beta_ratio, pr, T); // rheology/PatersonBudd.cc:57
+          }
+          if (LAW == LAW_ARR) {
+            lnA = P.lnA_cold, QoR = P.QoR_cold;
+          } else if (LAW == LAW_ARRWARM) {
+            lnA = P.lnA_warm, QoR = P.QoR_warm;
+          } else {
+            const bool cold = T < P.T_crit; // rheology/FlowLaw.cc:89-94
+            lnA = cold ? P.lnA_cold : P.lnA_warm, QoR = cold ? P.QoR_cold : P.QoR_warm;
+          }
+          double soft = exp_tab(fma(-QoR, rcp_fast(T), lnA), tab16);
+          if (LAW == LAW_GPBLD) {
+            const double cts2 = fma(-P.cts2_b, pr, P.cts2_a);
+            if (!(s < cts2)) { // temperate ice, rheology/GPBLD.cc:55-60
+              const double T_m = fma(-P.ec_beta, pr, P.T_melting);
+              const double Lm = fma(P.c_w - P.c_i, T_m - 273.15, P.L0); // EnthalpyConverter::L, :365-367
+              const double omega = fmin(0.5 * (s - cts2) * rcp_fast(Lm), P.gp_limit);
+              soft = P.gp_softness_T0 * fma(P.gp_coeff, omega, 1.0);
+            }
+          }
+          const double d = (K * (pr * pr * pr)) * soft;
+          const double g = dep * d;
+          const bool is_first = (k == k0);
+          const double hz = is_first ? 0.0 : zh.y;
+          run = fma(hz, prev + d, run);
+          dp = fma(hz, gprev + g, dp);
+          if (FULL) Ic[k] = run;
+          first = is_first ? d : first;
+          prev = d, gprev = g;
+        }
+      } else
       for (int k = k0; k <= ke; ++k) {
         const double2 zh = zz[k];
         const double dep = thk - zh.x;                 // :641-643
@@ -391,7 +468,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       }
       if (own_c && r >= ra) {
         const bool edge = (i_c < 0 || i_c >= P.Mx - 1 || r < 0 || r >= P.My - 1);
-        const double hq = row_active ? (pt ? hy : hx) : __ldg(hq_p + ro * sst);
+        const double hq = pt ? hy : hx; // (rows without ice: D = 0 and the flux is written as -0 * 0)
         double D = 0.0;
         if (act) {
           D = edge ? 0.0 : Dsum;
@@ -423,11 +500,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       }
       // ---------------- stage B: u, v of the regular column (i_q, r), sia/SIAFD.cc:904-943 ----------------
       if (uv_col && r >= ra && r >= P.ys && r < P.ys + P.ym) {
-        double ub = 0.0, vb = 0.0;
-        if (sl_p != nullptr) {
-          const double2 sv = __ldg(reinterpret_cast<const double2 *>(sl_p + (long)(r - (P.ys - P.wsl)) * ssl));
-          ub = sv.x, vb = sv.y;
-        }
+        const double ub = sv.x, vb = sv.y;
         double *up = F.u + uv0 + (long)(r - (P.ys - P.wuv)) * uv_row + li;
         double *vp = F.v + uv0 + (long)(r - (P.ys - P.wuv)) * uv_row + li;
         if (!any_valid) {
@@ -442,10 +515,21 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
           const double hxe = cE[0], hye = cE[1], hxn = cE[2], hyn = cE[3];
           const double hxw = cW[0], hyw = cW[1];
           const double hxs = south ? cS[2] : 0.0, hys = south ? cS[3] : 0.0;
-          const double *Ie = I0_s + q * S + li, *Iw = Ie - S;
+          const double *Ie = I0_s + q * S + li, *Iw;
           const double *In = I1_s + (s_cur * NC + q) * S + li, *Is = I1_s + (s_nxt * NC + q) * S + li;
-#pragma unroll 2
-          for (int k = li; k < Mz; k += LB, up += LB, vp += LB, Ie += LB, Iw += LB, In += LB, Is += LB) {
+          int k = li;
+          for (; k + 3 * LB < Mz; k += 4 * LB, up += 4 * LB, vp += 4 * LB, Ie += 4 * LB, In += 4 * LB, Is += 4 * LB) {
+            double ie[4], iw[4], in[4], is[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LB], iw[j] = (Ie - S)[j * LB], in[j] = In[j * LB], is[j] = Is[j * LB];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              up[j * LB] = ub - 0.25 * (ie[j] * hxe + iw[j] * hxw + in[j] * hxn + is[j] * hxs);
+              vp[j * LB] = vb - 0.25 * (ie[j] * hye + iw[j] * hyw + in[j] * hyn + is[j] * hys);
+            }
+          }
+          Iw = Ie - S;
+          for (; k < Mz; k += LB, up += LB, vp += LB, Ie += LB, Iw += LB, In += LB, Is += LB) {
             const double ie = *Ie, iw = *Iw, in = *In, is = *Is;
             *up = ub - 0.25 * (ie * hxe + iw * hxw + in * hxn + is * hxs);
             *vp = vb - 0.25 * (ie * hye + iw * hyw + in * hyn + is * hys);
@@ -498,7 +582,7 @@ static size_t slab_smem_bytes(const DP &P, bool full, int NC, int WZ, bool bulk)
   const long slotE = ((NC + 1) * S + 2 + 1) & ~1L;
   const long colI = (NC * S + 1) & ~1L;
   long d = 2 * Mz + 2 * slotE + (P.use_age ? 2 * slotE : 0) + 2 * AUX_N + (full ? 3 * colI : 0) + 2 * 2 * WZ * NC +
-           2 * NC * 4;
+           2 * NC * 4 + 16;
   return (size_t)d * 8 + 2 * 8 /* mbarriers */ + 16;
 }
 
@@ -522,8 +606,9 @@ static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaSt
 template <int LAW, bool FULL> static int launch_slab_l(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
                                                        cudaStream_t s) {
   // 16 lane columns unless shared memory cannot hold them (very tall grids): then 8
-  (void)T;
   if (slab_smem_bytes(P, FULL, 16, 8, A.use_bulk != 0) <= (size_t)227 * 1024) {
+    if (T.wz == 4) return launch_slab_t<LAW, FULL, 16, 4>(P, F, A, s);
+    if (T.wz == 2) return launch_slab_t<LAW, FULL, 16, 2>(P, F, A, s);
     return launch_slab_t<LAW, FULL, 16, 8>(P, F, A, s);
   }
   return launch_slab_t<LAW, FULL, 8, 16>(P, F, A, s);
@@ -554,7 +639,7 @@ template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, cons
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz,
                 cudaStream_t s) {
   SlabArgs A;
-  A.RS = T.rows_per_cta;
+  A.RS = T.rows_per_cta < 88 ? T.rows_per_cta : 88; // the row flags of a CTA live in a 96-bit word
   A.use_bulk = (T.use_bulk_copy && (P.Mz & 1)) ? 1 : 0; // even Mz: padded columns, 8-byte cp.async
   A.skip_rows = T.skip_ice_free;
   A.nE = nE;
