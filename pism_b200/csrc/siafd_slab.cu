@@ -340,47 +340,65 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
         //   delta = (e theta 2 alpha^2) p^3 softness;  (depth[k] + dz) delta[k-1] = depth[k-1] delta[k-1].
         const double K = c2c * (hx * hx + hy * hy);
         double gprev = 0.0; // depth[k-1] * delta[k-1]
-        for (int k = k0; k <= ke; ++k) {
-          const double2 zh = zz[k];
-          const double s = E1[k] + E2[k];
-          const double dep = thk - zh.x;
-          const double pr = fma(P.rg, dep, P.p_air);
-          const double Tc = fma(s, P.hic, P.T_0); // E / c_i + T_0
-          double T, lnA, QoR;
-          if (LAW == LAW_GPBLD) {
-            T = fma(P.ec_beta, pr, Tc); // EnthalpyConverter.cc:196-198
-          } else {
-            const double T_m = fma(-P.ec_beta, pr, P.T_melting);
-            T = fmin(Tc, T_m); // EnthalpyConverter::temperature, :180-188
-            if (LAW == LAW_PB) T = fma(P.beta_ratio, pr, T); // rheology/PatersonBudd.cc:57
-          }
-          if (LAW == LAW_ARR) {
-            lnA = P.lnA_cold, QoR = P.QoR_cold;
-          } else if (LAW == LAW_ARRWARM) {
-            lnA = P.lnA_warm, QoR = P.QoR_warm;
-          } else {
-            const bool cold = T < P.T_crit; // rheology/FlowLaw.cc:89-94
-            lnA = cold ? P.lnA_cold : P.lnA_warm, QoR = cold ? P.QoR_cold : P.QoR_warm;
-          }
-          double soft = exp_tab(fma(-QoR, rcp_fast(T), lnA), tab16);
-          if (LAW == LAW_GPBLD) {
-            const double cts2 = fma(-P.cts2_b, pr, P.cts2_a);
-            if (!(s < cts2)) { // temperate ice, rheology/GPBLD.cc:55-60
-              const double T_m = fma(-P.ec_beta, pr, P.T_melting);
-              const double Lm = fma(P.c_w - P.c_i, T_m - 273.15, P.L0); // EnthalpyConverter::L, :365-367
-              const double omega = fmin(0.5 * (s - cts2) * rcp_fast(Lm), P.gp_limit);
-              soft = P.gp_softness_T0 * fma(P.gp_coeff, omega, 1.0);
+        // two levels (k, k + 1) per trip: two independent Arrhenius chains in flight per thread
+        for (int k = k0; k <= ke; k += 2) {
+          const bool two = (k + 1 <= ke);
+          const int kb = two ? k + 1 : k; // (an odd last trip evaluates level k twice; the second copy is dropped)
+          double2 zh[2];
+          double s[2], dep[2], pr[2], T[2], lnA[2], QoR[2], soft[2], cts2[2];
+          zh[0] = zz[k], zh[1] = zz[kb];
+          s[0] = E1[k] + E2[k], s[1] = E1[kb] + E2[kb];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            dep[j] = thk - zh[j].x;
+            pr[j] = fma(P.rg, dep[j], P.p_air);
+            const double Tc = fma(s[j], P.hic, P.T_0); // E / c_i + T_0
+            if (LAW == LAW_GPBLD) {
+              T[j] = fma(P.ec_beta, pr[j], Tc); // EnthalpyConverter.cc:196-198
+            } else {
+              const double T_m = fma(-P.ec_beta, pr[j], P.T_melting);
+              T[j] = fmin(Tc, T_m); // EnthalpyConverter::temperature, :180-188
+              if (LAW == LAW_PB) T[j] = fma(P.beta_ratio, pr[j], T[j]); // rheology/PatersonBudd.cc:57
+            }
+            if (LAW == LAW_ARR) {
+              lnA[j] = P.lnA_cold, QoR[j] = P.QoR_cold;
+            } else if (LAW == LAW_ARRWARM) {
+              lnA[j] = P.lnA_warm, QoR[j] = P.QoR_warm;
+            } else {
+              const bool cold = T[j] < P.T_crit; // rheology/FlowLaw.cc:89-94
+              lnA[j] = cold ? P.lnA_cold : P.lnA_warm, QoR[j] = cold ? P.QoR_cold : P.QoR_warm;
             }
           }
-          const double d = (K * (pr * pr * pr)) * soft;
-          const double g = dep * d;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) soft[j] = exp_tab(fma(-QoR[j], rcp_fast(T[j]), lnA[j]), tab16);
+          if (LAW == LAW_GPBLD) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) cts2[j] = fma(-P.cts2_b, pr[j], P.cts2_a);
+            if (!(s[0] < cts2[0]) || !(s[1] < cts2[1])) { // temperate ice, rheology/GPBLD.cc:55-60
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                if (!(s[j] < cts2[j])) {
+                  const double T_m = fma(-P.ec_beta, pr[j], P.T_melting);
+                  const double Lm = fma(P.c_w - P.c_i, T_m - 273.15, P.L0); // EnthalpyConverter::L, :365-367
+                  const double omega = fmin(0.5 * (s[j] - cts2[j]) * rcp_fast(Lm), P.gp_limit);
+                  soft[j] = P.gp_softness_T0 * fma(P.gp_coeff, omega, 1.0);
+                }
+              }
+            }
+          }
+          const double d0 = (K * (pr[0] * pr[0] * pr[0])) * soft[0], d1 = (K * (pr[1] * pr[1] * pr[1])) * soft[1];
+          const double g0 = dep[0] * d0, g1 = dep[1] * d1;
           const bool is_first = (k == k0);
-          const double hz = is_first ? 0.0 : zh.y;
-          run = fma(hz, prev + d, run);
-          dp = fma(hz, gprev + g, dp);
+          const double hz0 = is_first ? 0.0 : zh[0].y;
+          run = fma(hz0, prev + d0, run);
+          dp = fma(hz0, gprev + g0, dp);
           if (FULL) Ic[k] = run;
-          first = is_first ? d : first;
-          prev = d, gprev = g;
+          first = is_first ? d0 : first;
+          const double hz1 = two ? zh[1].y : 0.0;
+          run = fma(hz1, d0 + d1, run);
+          dp = fma(hz1, g0 + g1, dp);
+          if (FULL && two) Ic[kb] = run;
+          prev = two ? d1 : d0, gprev = two ? g1 : g0;
         }
       } else
       for (int k = k0; k <= ke; ++k) {
