@@ -323,7 +323,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = B * patch.xm * patch.ym / (k_avg_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_sia_fused", "kernel_ms": k_avg_ms, "peak_source": peak_src,
+                "traffic": None, "kernel": "k_sia_slab", "kernel_ms": k_avg_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_column": B, "columns_per_launch": patch.xm * patch.ym,
                 "whole_step_frac": B * cols_total / N / (ms / args.steps / 1e3) / 1e9 / peak}
     tr = os.path.join(ROOT, "profiles", "dram_traffic.json")

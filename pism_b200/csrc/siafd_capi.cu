@@ -394,9 +394,7 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.rows_per_cta = 64;
   h->tuning.use_bulk_copy = 1;
   h->tuning.skip_ice_free = 1;
-  h->tuning.variant = 1;
   h->tuning.wz = 4;
-  if (const char *e = getenv("SIAFD_B200_VARIANT")) h->tuning.variant = atoi(e);
   if (const char *e = getenv("SIAFD_B200_WZ")) h->tuning.wz = atoi(e);
   if (const char *e = getenv("SIAFD_B200_ROWS")) h->tuning.rows_per_cta = atoi(e) > 0 ? atoi(e) : 64;
   {
@@ -407,8 +405,7 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
     }
     h->inv_dz = uniform ? 1.0 / dz : 0.0;
   }
-  h->tuning.tile_x = pick_tile_x(h->P, true);
-  if (h->tuning.tile_x == 0) {
+  if (slab_smem_need(h->P, true, (cfg->Mz & 1) != 0) > (size_t)227 * 1024) {
     delete h;
     return fail(nullptr, SIAFD_B200_ERR_BAD_CONFIG, "Mz = %d is too large for the shared-memory column pipeline",
                 cfg->Mz);
@@ -720,26 +717,20 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, doub
   CU(h, cudaMemsetAsync(h->d_dmax, 0, sizeof(unsigned long long), h->stream));
   CU(h, cudaMemsetAsync(h->d_hdc, 0, sizeof(int), h->stream));
   h->launches += launch_prep2d(h->P, F, h->stream); // sia/SIAFD.cc:580-582
-  Tuning T = h->tuning;
-  T.tile_x = pick_tile_x(h->P, full_update != 0);
-  if (h->tuning.tile_x > 0 && h->tuning.tile_x < T.tile_x) {
-    T.tile_x = h->tuning.tile_x;
-  }
+  const Tuning T = h->tuning;
   const bool timed = h->timing && h->ev_count < (int)h->ev_start.size();
   if (timed) {
     CU(h, cudaEventRecord(h->ev_start[h->ev_count], h->stream));
   }
-  const int n = (T.variant == 1)
-                    ? launch_slab(h->P, F, full_update != 0, T, (long)siafd_b200_field_size(h, SIAFD_B200_F_ENTHALPY),
-                                  (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, h->stream)
-                    : launch_fused(h->P, F, full_update != 0, T, h->stream);
+  const int n = launch_slab(h->P, F, full_update != 0, T, (long)siafd_b200_field_size(h, SIAFD_B200_F_ENTHALPY),
+                            (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, h->stream);
   if (timed) {
     CU(h, cudaEventRecord(h->ev_stop[h->ev_count], h->stream));
     h->ev_count += 1;
   }
   if (n < 0) {
     return fail(h, SIAFD_B200_ERR_CUDA, "could not configure the fused kernel (shared memory %zu bytes)",
-                fused_smem_bytes(h->P, full_update != 0, T.tile_x));
+                slab_smem_need(h->P, full_update != 0, (h->P.Mz & 1) != 0));
   }
   h->launches += n;
   CU(h, cudaGetLastError());

@@ -28,7 +28,7 @@ struct DP {
   int law, n_is_3;
   double n, nm1, e, e_inter;
   double A_cold, A_warm, Q_cold, Q_warm, T_crit, R;
-  double QoR_cold, QoR_warm; // Q / R, for the lean Arrhenius evaluation in siafd_fused.cu
+  double QoR_cold, QoR_warm; // Q / R, for the lean Arrhenius evaluation (siafd_math.cuh)
   // the same factor in the form exp(lnA - (Q/R) / T) (siafd_slab.cu): ln A; 0.5 / c_i; and the cold-ice test
   // E < E_cts(p) as (E_ij + E_offset) < cts2_a - cts2_b p, cts2_a = 2 c_i (T_melting - T_0), cts2_b = 2 c_i beta
   double lnA_cold, lnA_warm, hic, cts2_a, cts2_b;

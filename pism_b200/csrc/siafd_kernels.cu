@@ -6,17 +6,14 @@
 //   k_prep2d        BedSmoother::smoothed_thk + ::theta      sia/BedSmoother.cc:284-327, :351-404
 //   k_eta           eta = H^((2n+2)/n)                        sia/SIAFD.cc:241-245
 //   k_grad_*        surface_gradient_{mahaffy,eta,haseloff}   sia/SIAFD.cc:224-496
-//   k_sia_fused     (siafd_fused.cu) diffusivity + flux + I + 3D velocity, fused   sia/SIAFD.cc:543-948
+//   k_sia_slab      (siafd_slab.cu) diffusivity + flux + I + 3D velocity, fused    sia/SIAFD.cc:543-948
 //   k_copy_region   ghost wrap / halo pack (DMLocalToLocal)   util/iceModelVec.cc:630-643
 //   k_geometry      GeometryCalculator::compute               util/Mask.hh:96-133
 //   k_flow_n        FlowLaw::flow_n                           rheology/FlowLaw.cc:107-119
 //   k_bed_*         BedSmoother::preprocess_bed               sia/BedSmoother.cc:157-267
 //
 // The fused kernel never writes delta or I to HBM (the reference round-trips four 3D scratch
-// fields): a CTA marches over rows of a 16-column strip, keeps the enthalpy rows it needs in
-// shared memory (async copies two rows ahead), integrates every staggered column with 16
-// lanes across z (half-warp prefix sums) and hands I(z) to the velocity stage through shared
-// memory.  See DESIGN.md.
+// fields); see siafd_slab.cu and DESIGN.md.
 #include "siafd_kernels.cuh"
 
 #include <cstdio>

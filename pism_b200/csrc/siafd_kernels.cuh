@@ -18,21 +18,17 @@ struct Fields {
 
 struct Tuning {
   int rows_per_cta;  // rows of the extended patch one CTA marches over
-  int tile_x;        // extended columns per CTA strip (16, 8 or 4 by shared-memory fit)
   int use_bulk_copy; // 1: cp.async.bulk + mbarrier row loads; 0: 8-byte cp.async
   int skip_ice_free; // 1: do not load enthalpy rows no staggered point needs
-  int variant;       // 0: half-warp-per-column kernel (siafd_fused.cu); 1: row-slab kernel (siafd_slab.cu)
-  int wz;            // slab kernel: z ranges per column (8 or 16)
+  int wz;            // z ranges per column (2, 4 or 8)
 };
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
 int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
 int launch_gradient(const DP &P, const Fields &F, cudaStream_t s);
-int launch_fused(const DP &P, const Fields &F, bool full, const Tuning &T, cudaStream_t s);
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz,
                 cudaStream_t s);
-size_t fused_smem_bytes(const DP &P, bool full, int tile_x);
-int pick_tile_x(const DP &P, bool full);
+size_t slab_smem_need(const DP &P, bool full, bool bulk); // shared memory of the smallest configuration
 
 // copy a rectangle of cells between two [rows][cells][dof] arrays (ghost wrap, halo pack/unpack)
 int launch_copy_region(double *dst, long dst_row_cells, int dst_i0, int dst_j0, const double *src, long src_row_cells,

@@ -32,6 +32,10 @@
 // Newton reciprocal; sums over z are taken per z range and then added.
 #include "siafd_math.cuh"
 
+#ifndef SLAB_NL
+#define SLAB_NL 3 // levels per trip of the Arrhenius loop
+#endif
+
 namespace siafd {
 
 // IceGrid::kBelowHeight (util/IceGrid.cc:427-440; GSL bsearch: largest k in [0, Mz-2] with z[k] <= height).
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       const int ks = act ? ks0 : -1;
       // levels per z range of this column: a function of the column alone, never of the CTA tiling, so that
       // the order of every sum -- and with it every bit of the result -- is independent of the decomposition
-      const int Lc = (max(ks0, __shfl_xor_sync(FULLMASK, ks0, NC)) + WZ) / WZ;
+      const int Lc = (ks0 + WZ) / WZ;
       const int k0 = w * Lc;
       const int ke = min(k0 + Lc - 1, ks); // last level of this thread (empty range: ke < k0)
       // sia/SIAFD.cc:686, :693-696
@@ -340,16 +344,22 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
         //   delta = (e theta 2 alpha^2) p^3 softness;  (depth[k] + dz) delta[k-1] = depth[k-1] delta[k-1].
         const double K = c2c * (hx * hx + hy * hy);
         double gprev = 0.0; // depth[k-1] * delta[k-1]
-        // two levels (k, k + 1) per trip: two independent Arrhenius chains in flight per thread
-        for (int k = k0; k <= ke; k += 2) {
-          const bool two = (k + 1 <= ke);
-          const int kb = two ? k + 1 : k; // (an odd last trip evaluates level k twice; the second copy is dropped)
-          double2 zh[2];
-          double s[2], dep[2], pr[2], T[2], lnA[2], QoR[2], soft[2], cts2[2];
-          zh[0] = zz[k], zh[1] = zz[kb];
-          s[0] = E1[k] + E2[k], s[1] = E1[kb] + E2[kb];
+        // NL levels (k .. k + NL - 1) per trip: NL independent Arrhenius chains in flight per thread
+        constexpr int NL = SLAB_NL;
+        for (int k = k0; k <= ke; k += NL) {
+          // (a short last trip evaluates the last level again in the unused slots; those copies are dropped)
+          double2 zh[NL];
+          double s[NL], dep[NL], pr[NL], T[NL], lnA[NL], QoR[NL], soft[NL], cts2[NL], d[NL], g[NL];
+          bool in[NL];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < NL; ++j) {
+            in[j] = (k + j <= ke);
+            const int kj = min(k + j, ke);
+            zh[j] = zz[kj];
+            s[j] = E1[kj] + E2[kj];
+          }
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
             dep[j] = thk - zh[j].x;
             pr[j] = fma(P.rg, dep[j], P.p_air);
             const double Tc = fma(s[j], P.hic, P.T_0); // E / c_i + T_0
@@ -370,13 +380,17 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
             }
           }
 #pragma unroll
-          for (int j = 0; j < 2; ++j) soft[j] = exp_tab(fma(-QoR[j], rcp_fast(T[j]), lnA[j]), tab16);
+          for (int j = 0; j < NL; ++j) soft[j] = exp_tab(fma(-QoR[j], rcp_fast(T[j]), lnA[j]), tab16);
           if (LAW == LAW_GPBLD) {
+            bool any_temperate = false;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) cts2[j] = fma(-P.cts2_b, pr[j], P.cts2_a);
-            if (!(s[0] < cts2[0]) || !(s[1] < cts2[1])) { // temperate ice, rheology/GPBLD.cc:55-60
+            for (int j = 0; j < NL; ++j) {
+              cts2[j] = fma(-P.cts2_b, pr[j], P.cts2_a);
+              any_temperate |= !(s[j] < cts2[j]);
+            }
+            if (any_temperate) { // temperate ice, rheology/GPBLD.cc:55-60
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
+              for (int j = 0; j < NL; ++j) {
                 if (!(s[j] < cts2[j])) {
                   const double T_m = fma(-P.ec_beta, pr[j], P.T_melting);
                   const double Lm = fma(P.c_w - P.c_i, T_m - 273.15, P.L0); // EnthalpyConverter::L, :365-367
@@ -386,19 +400,21 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
               }
             }
           }
-          const double d0 = (K * (pr[0] * pr[0] * pr[0])) * soft[0], d1 = (K * (pr[1] * pr[1] * pr[1])) * soft[1];
-          const double g0 = dep[0] * d0, g1 = dep[1] * d1;
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
+            d[j] = (K * (pr[j] * pr[j] * pr[j])) * soft[j];
+            g[j] = dep[j] * d[j];
+          }
           const bool is_first = (k == k0);
-          const double hz0 = is_first ? 0.0 : zh[0].y;
-          run = fma(hz0, prev + d0, run);
-          dp = fma(hz0, gprev + g0, dp);
-          if (FULL) Ic[k] = run;
-          first = is_first ? d0 : first;
-          const double hz1 = two ? zh[1].y : 0.0;
-          run = fma(hz1, d0 + d1, run);
-          dp = fma(hz1, g0 + g1, dp);
-          if (FULL && two) Ic[kb] = run;
-          prev = two ? d1 : d0, gprev = two ? g1 : g0;
+          first = is_first ? d[0] : first;
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
+            const double hz = (in[j] && !(j == 0 && is_first)) ? zh[j].y : 0.0;
+            run = fma(hz, prev + d[j], run);
+            dp = fma(hz, gprev + g[j], dp);
+            if (FULL && in[j]) Ic[k + j] = run;
+            prev = in[j] ? d[j] : prev, gprev = in[j] ? g[j] : gprev;
+          }
         }
       } else
       for (int k = k0; k <= ke; ++k) {
@@ -528,12 +544,13 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
             *vp = vb;
           }
         } else {
+          // u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s): the factor -0.25 goes into the slopes
           const double *cE = cf + (s_cur * NC + q) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + q) * 4;
           const bool south = (ivalid & (1u << s_nxt)) != 0;
-          const double hxe = cE[0], hye = cE[1], hxn = cE[2], hyn = cE[3];
-          const double hxw = cW[0], hyw = cW[1];
-          const double hxs = south ? cS[2] : 0.0, hys = south ? cS[3] : 0.0;
-          const double *Ie = I0_s + q * S + li, *Iw;
+          const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
+          const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
+          const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
+          const double *Ie = I0_s + q * S + li;
           const double *In = I1_s + (s_cur * NC + q) * S + li, *Is = I1_s + (s_nxt * NC + q) * S + li;
           int k = li;
           for (; k + 3 * LB < Mz; k += 4 * LB, up += 4 * LB, vp += 4 * LB, Ie += 4 * LB, In += 4 * LB, Is += 4 * LB) {
@@ -542,15 +559,14 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
             for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LB], iw[j] = (Ie - S)[j * LB], in[j] = In[j * LB], is[j] = Is[j * LB];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              up[j * LB] = ub - 0.25 * (ie[j] * hxe + iw[j] * hxw + in[j] * hxn + is[j] * hxs);
-              vp[j * LB] = vb - 0.25 * (ie[j] * hye + iw[j] * hyw + in[j] * hyn + is[j] * hys);
+              up[j * LB] = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
+              vp[j * LB] = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
             }
           }
-          Iw = Ie - S;
-          for (; k < Mz; k += LB, up += LB, vp += LB, Ie += LB, Iw += LB, In += LB, Is += LB) {
-            const double ie = *Ie, iw = *Iw, in = *In, is = *Is;
-            *up = ub - 0.25 * (ie * hxe + iw * hxw + in * hxn + is * hxs);
-            *vp = vb - 0.25 * (ie * hye + iw * hyw + in * hyn + is * hys);
+          for (; k < Mz; k += LB, up += LB, vp += LB, Ie += LB, In += LB, Is += LB) {
+            const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
+            *up = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
+            *vp = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
           }
         }
       }
@@ -629,7 +645,7 @@ template <int LAW, bool FULL> static int launch_slab_l(const DP &P, const Fields
     if (T.wz == 2) return launch_slab_t<LAW, FULL, 16, 2>(P, F, A, s);
     return launch_slab_t<LAW, FULL, 16, 8>(P, F, A, s);
   }
-  return launch_slab_t<LAW, FULL, 8, 16>(P, F, A, s);
+  return launch_slab_t<LAW, FULL, 8, 4>(P, F, A, s);
 }
 
 template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
@@ -653,6 +669,8 @@ template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, cons
     return -1;
   }
 }
+
+size_t slab_smem_need(const DP &P, bool full, bool bulk) { return slab_smem_bytes(P, full, 8, 4, bulk); }
 
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz,
                 cudaStream_t s) {
