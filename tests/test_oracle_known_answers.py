@@ -13,38 +13,12 @@ import pytest
 
 import oracle_lib as O
 
-# test/miscellaneous.py:634-671
-FLOW_TABLE = {
-    "arr": [3.91729503e-18, 6.42803396e-17, 1.05746828e-16, 1.05746828e-16,
-            9.79323757e-17, 1.60700849e-15, 2.64367070e-15, 2.64367070e-15,
-            3.91729503e-16, 6.42803396e-15, 1.05746828e-14, 1.05746828e-14,
-            8.81391381e-16, 1.44630764e-14, 2.37930363e-14, 2.37930363e-14],
-    "arrwarm": [1.59798478e-19, 1.04360343e-16, 3.30653997e-16, 3.30653997e-16,
-                3.99496194e-18, 2.60900856e-15, 8.26634991e-15, 8.26634991e-15,
-                1.59798478e-17, 1.04360343e-14, 3.30653997e-14, 3.30653997e-14,
-                3.59546574e-17, 2.34810771e-14, 7.43971492e-14, 7.43971492e-14],
-    "gk": [1.1636334595808724e-16, 6.217445758362754e-15, 2.5309103327753672e-14,
-           2.5309103327753672e-14, 2.5947947614616463e-16, 2.0065832524499375e-14,
-           9.158056141786197e-14, 9.158056141786197e-14, 4.493111202368685e-16,
-           3.469816186746473e-14, 1.6171243121742907e-13, 1.6171243121742907e-13,
-           7.12096200221403e-16, 4.879162291119208e-14, 2.2895389865988545e-13, 2.2895389865988545e-13],
-    "gpbld": [4.65791754e-18, 1.45114704e-16, 4.54299921e-16, 8.66009225e-16,
-              1.16447938e-16, 3.62786761e-15, 1.13574980e-14, 2.16502306e-14,
-              4.65791754e-16, 1.45114704e-14, 4.54299921e-14, 8.66009225e-14,
-              1.04803145e-15, 3.26508084e-14, 1.02217482e-13, 1.94852076e-13],
-    "hooke": [5.26775897e-18, 2.12325906e-16, 5.32397091e-15, 5.32397091e-15,
-              1.31693974e-16, 5.30814764e-15, 1.33099273e-13, 1.33099273e-13,
-              5.26775897e-16, 2.12325906e-14, 5.32397091e-13, 5.32397091e-13,
-              1.18524577e-15, 4.77733287e-14, 1.19789346e-12, 1.19789346e-12],
-    "isothermal_glen": [3.16890000e-16, 3.16890000e-16, 3.16890000e-16, 3.16890000e-16,
-                        7.92225000e-15, 7.92225000e-15, 7.92225000e-15, 7.92225000e-15,
-                        3.16890000e-14, 3.16890000e-14, 3.16890000e-14, 3.16890000e-14,
-                        7.13002500e-14, 7.13002500e-14, 7.13002500e-14, 7.13002500e-14],
-    "pb": [4.65791754e-18, 1.45114704e-16, 4.54299921e-16, 4.54299921e-16,
-           1.16447938e-16, 3.62786761e-15, 1.13574980e-14, 1.13574980e-14,
-           4.65791754e-16, 1.45114704e-14, 4.54299921e-14, 4.54299921e-14,
-           1.04803145e-15, 3.26508084e-14, 1.02217482e-13, 1.02217482e-13],
-}
+# The golden numbers live in tests/golden/reference_kats.json (copied verbatim from the reference's tests).
+import json
+import os
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kats.json")))
+FLOW_TABLE = GOLDEN["flow_table"]["values"]  # test/miscellaneous.py:634-671
 
 
 def flow_table_inputs(p):
@@ -123,8 +97,8 @@ def test_bed_smoother_ranges():
     theta = np.zeros((p.My + 2 * w, p.Mx + 2 * w))
     assert L.orc_theta(C.byref(p), C.byref(run.f), O.dptr(theta)) == 0
     stored = {"topg": [-500.0, 500.0],
-              "topg_smoothed": [-372.9924735817933, 372.9924735817933],
-              "theta": [0.7147300652935706, 0.9884843647808601]}
+              "topg_smoothed": GOLDEN["bed_smoother"]["topg_smoothed_range"],
+              "theta": GOLDEN["bed_smoother"]["theta_range"]}
     inner = theta[w:-w, w:-w]
     computed = {"topg": [topg.min(), topg.max()],
                 "topg_smoothed": [sm["topgsmooth"].min(), sm["topgsmooth"].max()],
