@@ -1,0 +1,174 @@
+// SIAFD_B200.hh -- C++ host side of the B200 SIAFD: the reference's SSB_Modifier / SIAFD interface
+// (src/stressbalance/SSB_Modifier.hh:39-72, src/stressbalance/sia/SIAFD.hh:50-131) over the C ABI of
+// include/siafd_b200.h.  Same method names, argument meaning and error behaviour (pism::RuntimeError) as the
+// reference, so that it drops in under StressBalance (StressBalance.cc:169-211) and GeometryEvolution.
+// Nothing here computes physics: update() marshals raw pointers of the (PISM-owned, host) ghosted arrays to
+// siafd_b200_update and converts the status code back into an exception.
+//
+// This header is written against pism_mirror.hh so that it compiles and is tested without PETSc/MPI; over
+// PISM's own headers the class body is the same ("The shim a PISM maintainer adds").
+#pragma once
+#include "pism_mirror.hh"
+
+#include "../../include/siafd_b200.h"
+
+namespace pism {
+namespace stressbalance {
+
+// SSB_Modifier.hh:39-72: owned outputs and getters
+class SSB_Modifier {
+public:
+  explicit SSB_Modifier(IceGrid::ConstPtr g)
+      : m_grid(g), m_config(g->config()), m_D_max(0.0), m_diffusive_flux(g, "diffusive_flux", WITH_GHOSTS, 1),
+        m_u(g, "uvel", WITH_GHOSTS, 1), m_v(g, "vvel", WITH_GHOSTS, 1) {} // SSB_Modifier.cc:30-58
+  virtual ~SSB_Modifier() {}
+  virtual void init() {}
+  virtual void update(const IceModelVec2V &sliding_velocity, const Inputs &inputs, bool full_update) = 0;
+  virtual const IceModelVec2Stag &diffusive_flux() { return m_diffusive_flux; }
+  virtual double max_diffusivity() const { return m_D_max; }
+  const IceModelVec3 &velocity_u() const { return m_u; }
+  const IceModelVec3 &velocity_v() const { return m_v; }
+
+protected:
+  IceGrid::ConstPtr m_grid;
+  Config::Ptr m_config;
+  double m_D_max;
+  IceModelVec2Stag m_diffusive_flux;
+  IceModelVec3 m_u, m_v;
+};
+
+class SIAFD_B200 : public SSB_Modifier {
+public:
+  // SIAFD::SIAFD, SIAFD.cc:42-91: everything the reference's constructor, FlowLaw (rheology/FlowLaw.cc:33-58) and
+  // EnthalpyConverter (util/EnthalpyConverter.cc:55-69) read from Config goes into siafd_b200_config
+  explicit SIAFD_B200(IceGrid::ConstPtr g, int device = -1)
+      : SSB_Modifier(g), m_handle(NULL), m_stencil_width((int)m_config->get_number("grid.max_stencil_width")),
+        m_h_x(g, "h_x", WITH_GHOSTS, 1), m_h_y(g, "h_y", WITH_GHOSTS, 1), m_D(g, "diffusivity", WITH_GHOSTS, 1) {
+    siafd_b200_config c;
+    siafd_b200_default_config(&c);
+    c.Mx = (int)g->Mx(), c.My = (int)g->My(), c.Mz = (int)g->Mz();
+    c.xs = g->xs(), c.xm = g->xm(), c.ys = g->ys(), c.ym = g->ym();
+    c.dx = g->dx(), c.dy = g->dy();
+    c.z = g->z().data();
+    c.w_geom = m_stencil_width, c.w_3d_in = m_stencil_width, c.w_stag = 1, c.w_uv = 1, c.w_sliding = 1;
+    const Config &cf = *m_config;
+    c.ec_p_air = cf.get_number("surface.pressure");
+    c.ec_g = cf.get_number("constants.standard_gravity");
+    c.ec_beta = cf.get_number("constants.ice.beta_Clausius_Clapeyron");
+    c.ec_rho_i = cf.get_number("constants.ice.density");
+    c.ec_c_i = cf.get_number("constants.ice.specific_heat_capacity");
+    c.ec_c_w = cf.get_number("constants.fresh_water.specific_heat_capacity");
+    c.ec_L = cf.get_number("constants.fresh_water.latent_heat_of_fusion");
+    c.ec_T_melting = cf.get_number("constants.fresh_water.melting_point_temperature");
+    c.ec_T_0 = cf.get_number("enthalpy_converter.T_reference");
+    if (cf.get_flag("enthalpy_converter.cold_mode")) { // ColdEnthalpyConverter, EnthalpyConverter.cc:287-296
+      c.ec_T_melting = 1e6;
+      c.ec_beta = 0.0;
+    }
+    c.flow_law = flow_law_id(cf.get_string("stress_balance.sia.flow_law"));
+    c.fl_n = cf.get_number("stress_balance.sia.Glen_exponent");
+    c.fl_e = cf.get_number("stress_balance.sia.enhancement_factor");
+    c.fl_e_interglacial = cf.get_number("stress_balance.sia.enhancement_factor_interglacial");
+    c.fl_A_cold = cf.get_number("flow_law.Paterson_Budd.A_cold");
+    c.fl_A_warm = cf.get_number("flow_law.Paterson_Budd.A_warm");
+    c.fl_Q_cold = cf.get_number("flow_law.Paterson_Budd.Q_cold");
+    c.fl_Q_warm = cf.get_number("flow_law.Paterson_Budd.Q_warm");
+    c.fl_T_crit = cf.get_number("flow_law.Paterson_Budd.T_critical");
+    c.fl_R = cf.get_number("constants.ideal_gas_constant");
+    c.fl_rho = cf.get_number("constants.ice.density");
+    c.fl_g = cf.get_number("constants.standard_gravity");
+    c.fl_beta = cf.get_number("constants.ice.beta_Clausius_Clapeyron");
+    c.fl_T_melting = cf.get_number("constants.fresh_water.melting_point_temperature");
+    c.gpbld_T_0 = cf.get_number("constants.fresh_water.melting_point_temperature");
+    c.gpbld_water_frac_coeff = cf.get_number("flow_law.gpbld.water_frac_coeff");
+    c.gpbld_water_frac_limit = cf.get_number("flow_law.gpbld.water_frac_observed_limit");
+    c.iso_softness_A = cf.get_number("flow_law.isothermal_Glen.ice_softness");
+    c.hooke_Q = cf.get_number("flow_law.Hooke.Q"), c.hooke_A = cf.get_number("flow_law.Hooke.A");
+    c.hooke_C = cf.get_number("flow_law.Hooke.C"), c.hooke_K = cf.get_number("flow_law.Hooke.k");
+    c.hooke_Tr = cf.get_number("flow_law.Hooke.Tr");
+    c.grain_size = cf.get_number("constants.ice.grain_size");
+    c.gradient_method = gradient_id(cf.get_string("stress_balance.sia.surface_gradient_method"));
+    c.limit_diffusivity = cf.get_flag("stress_balance.sia.limit_diffusivity") ? 1 : 0;
+    c.grain_size_age_coupling = cf.get_flag("stress_balance.sia.grain_size_age_coupling") ? 1 : 0;
+    c.e_age_coupling = cf.get_flag("stress_balance.sia.e_age_coupling") ? 1 : 0;
+    c.D_limit = cf.get_number("stress_balance.sia.max_diffusivity");
+    c.eemian_start = cf.get_number("time.eemian_start");
+    c.eemian_end = cf.get_number("time.eemian_end");
+    c.holocene_start = cf.get_number("time.holocene_start");
+    c.smoother_range = cf.get_number("stress_balance.sia.bed_smoother.range");
+    c.theta_min = cf.get_number("stress_balance.sia.bed_smoother.theta_min");
+    c.sea_water_density = cf.get_number("constants.sea_water.density");
+    c.ice_free_thickness = cf.get_number("geometry.ice_free_thickness_standard");
+    c.dry_simulation = cf.get_flag("ocean.always_grounded") ? 1 : 0;
+    const int status = siafd_b200_create(&c, device, &m_handle);
+    if (status != SIAFD_B200_OK) {
+      throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(NULL));
+    }
+  }
+  virtual ~SIAFD_B200() { siafd_b200_destroy(m_handle); }
+
+  virtual void init() { SSB_Modifier::init(); } // SIAFD.cc:98-118 (log messages only)
+
+  // SIAFD::update, SIAFD.cc:122-155.  `full_update == false` leaves m_u, m_v untouched (:149-154).
+  virtual void update(const IceModelVec2V &sliding_velocity, const Inputs &inputs, bool full_update) {
+    const Geometry &geometry = *inputs.geometry;
+    if (inputs.new_bed_elevation) { // :130-134 (BedSmoother::preprocess_bed on the owned part of the bed)
+      std::vector<double> bed((size_t)m_grid->Mx() * m_grid->My());
+      for (int j = 0; j < m_grid->ym(); ++j)
+        for (int i = 0; i < m_grid->xm(); ++i) bed[(size_t)j * m_grid->Mx() + i] = geometry.bed_elevation(i, j);
+      check(siafd_b200_preprocess_bed(m_handle, bed.data()));
+    }
+    siafd_b200_inputs in;
+    in.surface = geometry.ice_surface_elevation.get_array();
+    in.thickness = geometry.ice_thickness.get_array();
+    in.mask = geometry.cell_type.get_array();
+    in.bed = geometry.bed_elevation.get_array();
+    in.enthalpy = inputs.enthalpy->get_array();
+    in.age = inputs.age ? inputs.age->get_array() : NULL;
+    in.sliding = sliding_velocity.get_array();
+    in.current_time = m_grid->current_time(); // :564
+    in.memory_space = 0;
+    in.ghosts_valid = 1; // PISM's Vecs always carry valid ghosts at this point
+    siafd_b200_outputs out;
+    out.h_x = m_h_x.get_array(), out.h_y = m_h_y.get_array(), out.D = m_D.get_array();
+    out.flux = m_diffusive_flux.get_array();
+    out.u = m_u.get_array(), out.v = m_v.get_array();
+    out.memory_space = 0, out.pad = 0;
+    check(siafd_b200_update(m_handle, &in, &out, full_update ? 1 : 0));
+    m_D_max = siafd_b200_max_diffusivity(m_handle); // :748 (one rank: the local max is the global max)
+  }
+
+  const IceModelVec2Stag &surface_gradient_x() const { return m_h_x; } // SIAFD.cc:963-973
+  const IceModelVec2Stag &surface_gradient_y() const { return m_h_y; }
+  const IceModelVec2Stag &diffusivity() const { return m_D; }
+  siafd_b200_handle *handle() { return m_handle; }
+
+private:
+  // status code -> RuntimeError, with the message the reference would have thrown
+  void check(int status) {
+    if (status != SIAFD_B200_OK) {
+      throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(m_handle));
+    }
+  }
+  // rheology/FlowLawFactory.cc:71-87
+  static int flow_law_id(const std::string &name) {
+    const char *names[] = {"isothermal_glen", "pb", "gpbld", "hooke", "arr", "arrwarm", "gk"};
+    for (int k = 0; k < 7; ++k)
+      if (name == names[k]) return k;
+    throw RuntimeError::formatted(SIAFD_B200_ERR_BAD_CONFIG, "Selected ice flow law \"%s\" is not available", name.c_str());
+  }
+  // SIAFD.cc:197-220
+  static int gradient_id(const std::string &name) {
+    if (name == "haseloff") return SIAFD_B200_GRAD_HASELOFF;
+    if (name == "mahaffy") return SIAFD_B200_GRAD_MAHAFFY;
+    if (name == "eta") return SIAFD_B200_GRAD_ETA;
+    throw RuntimeError::formatted(SIAFD_B200_ERR_BAD_CONFIG, "value of sia.surface_gradient_method, option '-gradient %s', is not valid",
+                                  name.c_str());
+  }
+  siafd_b200_handle *m_handle;
+  const int m_stencil_width;
+  IceModelVec2Stag m_h_x, m_h_y, m_D;
+};
+
+} // namespace stressbalance
+} // namespace pism

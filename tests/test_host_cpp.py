@@ -1,0 +1,57 @@
+"""The C++ host class (pism_b200/host/SIAFD_B200.hh: the reference's SSB_Modifier / SIAFD interface over the C ABI,
+on PETSc-free mirrors of PISM's containers) driven by tests/host_cpp/siafd_test.cc, which has the shape of the
+reference's src/stressbalance/sia/siafd_test.cc (verification test F through the class)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DIR = os.path.join(HERE, "host_cpp")
+EXE = os.path.join(DIR, "siafd_test")
+
+
+def build():
+    if not os.path.exists(os.path.join(HERE, "..", "oracle", "_ref", "libpism_exact.so")):
+        pytest.skip("oracle/_ref/libpism_exact.so (the reference's exact solutions) has not been built")
+    subprocess.run(["make", "-C", DIR], check=True, stdout=subprocess.DEVNULL)
+
+
+def test_host_class_compiles_and_fails_loudly_without_a_gpu():
+    build()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; covered by the gpu test")
+    r = subprocess.run([EXE, "-Mx", "21", "-My", "21", "-Mz", "11"], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "PISM ERROR" in r.stderr and "no CUDA device" in r.stderr and "no CPU path" in r.stderr
+
+
+@pytest.mark.gpu
+def test_siafd_test_F_through_the_cpp_class():
+    build()
+    r = subprocess.run([EXE, "-Mx", "61", "-My", "61", "-Mz", "61"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    m = re.search(r"surf vels :\s+maxUvec\s+avUvec\s+([-\d.eE+]+)\s+([-\d.eE+]+)", out)
+    maxU, avU = float(m.group(1)), float(m.group(2))
+    # Test F surface speeds are O(1-5 m/a); one update on a 61^3 grid must be within a few cm/a of exact
+    # (the reference's own golden error after 1000 a at 31^2 is 0.95 m/a, test/regression/test_17.sh)
+    assert 0.0 < maxU < 0.1 and avU < 0.02, out
+    vals = {k: float(v) for k, v in re.findall(r"^(D_max|sum_D|sum_absQ|sum_absU_mid) (\S+)$", out, re.M)}
+    assert "flux_only_ok 1" in out
+    assert re.search(r"error_path status 4: .*above top of computational grid", out), out
+    # the same state through the Python mirror (tests/cases.py "F") must give the same numbers
+    import gpu_util as U
+    grid, cfg, inputs, gb = cases.case("F")
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, True)
+    assert abs(sia.max_diffusivity() - vals["D_max"]) <= 1e-12 * vals["D_max"]
+    D = cases.interior(sia.diffusivity(), cfg.w_stag)
+    assert abs(D.sum() - vals["sum_D"]) <= 1e-11 * vals["sum_D"]
+    u = cases.interior(sia.velocity_u(), cfg.w_uv)
+    assert abs(np.abs(u[:, :, grid.Mz // 2]).sum() - vals["sum_absU_mid"]) <= 1e-11 * vals["sum_absU_mid"]
