@@ -227,7 +227,12 @@ def main():
     sia = SIAFD(grid, config=cfg, patch=patch, device=local_rank)
     if args.rows_per_cta or args.bulk >= 0:
         sia.set_tuning(args.rows_per_cta, args.bulk, -1)
-    stream = torch.cuda.current_stream()
+    # One explicit stream carries everything: the library's kernels, torch's tensor ops and the NCCL transfers
+    # (torch.distributed orders its communication stream against the CURRENT stream).  The legacy default
+    # stream (handle 0) cannot be handed to the library: 0 means "use the handle's own stream" there.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     assert lib.siafd_b200_set_stream(sia.handle, stream.cuda_stream) == 0
 
     # ---- inputs resident in HBM, outputs too; bound as the handle's field storage ----
