@@ -200,7 +200,7 @@ def main():
     import torch.distributed as dist
     from pism_b200 import capi, grid as G, synthetic as S
     from pism_b200.capi import F, lib
-    from pism_b200.halo import HaloExchanger, global_max
+    from pism_b200.halo import PeerHalo, device_view, global_max
     from pism_b200.sia import SIAFD, PISMRuntimeError
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,6 +212,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL announces its version on stdout at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     N = world
@@ -237,21 +240,22 @@ def main():
 
     # ---- inputs resident in HBM, outputs too; bound as the handle's field storage ----
     t_gen = time.perf_counter()
+    # the fields live in the handle's own device storage (exportable to the neighbours over CUDA IPC); torch
+    # sees them as views
     inp = S.dome(grid, patch, sia.config, device=dev)
-    fields = {"surface": inp["surface"], "thickness": inp["thickness"], "mask": inp["mask"], "bed": inp["bed"],
-              "enthalpy": inp["enthalpy"], "sliding": inp["sliding"]}
-    for name in ("h_x", "h_y", "D", "flux", "u", "v"):
-        fields[name] = torch.zeros(sia.field_shape(name), dtype=torch.float64, device=dev)
-    for name, t in fields.items():
-        assert t.is_contiguous()
-        st = lib.siafd_b200_bind(sia.handle, F[name], t.data_ptr())
-        assert st == 0, (name, lib.siafd_b200_last_error(sia.handle))
+    fields = {}
+    for name in ("surface", "thickness", "mask", "bed", "enthalpy", "sliding", "h_x", "h_y", "D", "flux", "u", "v"):
+        fields[name] = device_view(sia, name, sia.field_shape(name), dev)
+        if name in inp:
+            fields[name].copy_(inp[name])
+    del inp
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
 
-    halo = HaloExchanger(patch, sia)
     wg, we, ws = sia.config.w_geom, sia.config.w_3d_in, sia.config.w_sliding
     multi = N > 1
+    halo = PeerHalo(patch, patches, sia, ["surface", "thickness", "mask", "bed", "enthalpy", "h_x", "h_y", "u", "v"]) \
+        if multi else None
 
     def check(st):
         if st != 0:
@@ -260,20 +264,19 @@ def main():
     def step_device():
         """SIAFD::update on device-resident fields, ghost exchanges where the reference has them."""
         if multi and not args.no_input_exchange:
-            for name, w in (("surface", wg), ("thickness", wg), ("mask", wg), ("bed", wg), ("enthalpy", we)):
-                halo.exchange(name, fields[name], w)
+            halo.exchange([("surface", wg), ("thickness", wg), ("mask", wg), ("bed", wg), ("enthalpy", we)], 0)
         check(lib.siafd_b200_compute_gradient(sia.handle))
-        for name in ("h_x", "h_y"):          # SIAFD.cc:498-499
-            if multi:
-                halo.exchange(name, fields[name], 1)
-            else:
+        if multi:                            # SIAFD.cc:498-499
+            halo.exchange([("h_x", 1), ("h_y", 1)], 1)
+        else:
+            for name in ("h_x", "h_y"):
                 check(lib.siafd_b200_wrap_ghosts(sia.handle, F[name]))
         check(lib.siafd_b200_compute_flux_velocity(sia.handle, 1 if full else 0, 0.0))
-        if full:
-            for name in ("u", "v"):          # SIAFD.cc:946-947
-                if multi:
-                    halo.exchange(name, fields[name], 1)
-                else:
+        if full:                             # SIAFD.cc:946-947
+            if multi:
+                halo.exchange([("u", 1), ("v", 1)], 2)
+            else:
+                for name in ("u", "v"):
                     check(lib.siafd_b200_wrap_ghosts(sia.handle, F[name]))
         check(lib.siafd_b200_finish(sia.handle))              # error flags + D_max (host sync, as in PISM)
         return global_max(lib.siafd_b200_max_diffusivity(sia.handle), dev)   # SIAFD.cc:748
@@ -399,7 +402,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, "%dx%d (PISM DMDA rule)" % (patch.Nx, patch.Ny)),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "D_max": dmax, "halo_bytes_per_step_per_rank": halo.bytes_sent // max(args.steps + W, 1),
+            "clocks": clocks, "D_max": dmax, "halo_bytes_per_step_per_rank": (halo.bytes_sent // max(args.steps + W + 1, 1)) if halo else 0,
+            "halo_transport": "direct stores into CUDA-IPC-mapped neighbour arrays (NVLink), 3 phases/step" if halo else None,
             "input_generation_s": t_gen,
         }
         print(json.dumps(line))

@@ -204,6 +204,20 @@ int64_t siafd_b200_halo_count(const siafd_b200_handle *h, int field, int dir_x, 
 int siafd_b200_halo_pack(siafd_b200_handle *h, int field, int dir_x, int dir_y, int width, double *device_buf);
 int siafd_b200_halo_unpack(siafd_b200_handle *h, int field, int dir_x, int dir_y, int width, const double *device_buf);
 
+/* Multi-rank halo exchange over peer memory (one process per GPU of one NVLink node): the neighbours' local
+ * arrays are mapped with CUDA IPC, and a phase's strips (BOX stencil: 4 edges + 4 corners per field) are stored
+ * straight into their ghost cells by ONE kernel; arrival counters in a small pad order the phases.
+ *   dir = 0..7 numbers the neighbours (dx,dy) = (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1).
+ * Setup: every rank exports the fields it exchanges (handle-owned storage only) and its pad (field = -1),
+ * the 64-byte handles travel by any host channel, ipc_open maps a peer's handle once, halo_attach records the
+ * mapped base (NULL = the neighbour is this rank itself) and the neighbour's patch size for a direction.
+ * Per phase: halo_push(fields, widths, phase) then halo_wait(phase); both are stream-ordered, no host sync. */
+int siafd_b200_ipc_export(siafd_b200_handle *h, int field, void *handle64);
+int siafd_b200_ipc_open(siafd_b200_handle *h, const void *handle64, void **peer_ptr);
+int siafd_b200_halo_attach(siafd_b200_handle *h, int field, int dir, void *peer_base, int peer_xm, int peer_ym);
+int siafd_b200_halo_push(siafd_b200_handle *h, int n, const int *fields, const int *widths, int phase);
+int siafd_b200_halo_wait(siafd_b200_handle *h, int phase);
+
 /* BedSmoother::preprocess_bed on the GLOBAL bed (Mx*My doubles, [j][i], no ghosts; host
  * pointer).  Every rank passes the same array and gets its own patch (+ghosts) of
  * topgsmooth, maxtl, C2, C3, C4 on device.  Call when Inputs::new_bed_elevation. */

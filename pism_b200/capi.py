@@ -83,6 +83,11 @@ def _load():
         "siafd_b200_halo_count": (i64, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
         "siafd_b200_halo_pack": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "siafd_b200_halo_unpack": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        "siafd_b200_ipc_export": (C.c_int, [vp, C.c_int, vp]),
+        "siafd_b200_ipc_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "siafd_b200_halo_attach": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]),
+        "siafd_b200_halo_push": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+        "siafd_b200_halo_wait": (C.c_int, [vp, C.c_int]),
         "siafd_b200_preprocess_bed": (C.c_int, [vp, vp]),
         "siafd_b200_set_smoothed_bed": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
         "siafd_b200_compute_gradient": (C.c_int, [vp]),

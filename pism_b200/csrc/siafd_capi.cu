@@ -39,6 +39,17 @@ struct siafd_b200_handle {
   bool smoother_set = false;
   int bedNx = -1, bedNy = -1;
   double *d_global_bed = nullptr;
+  // peer halo exchange: per field and neighbour direction the mapped base of the neighbour's array (nullptr =
+  // this rank) and its patch size; the arrival-counter pad [4 phases][8 dirs] and the neighbours' pads
+  struct Peer {
+    double *base = nullptr;
+    int xm = 0, ym = 0;
+    bool attached = false;
+  } peers[SIAFD_B200_F_COUNT][8];
+  unsigned long long *d_pad = nullptr, *peer_pad[8] = {};
+  bool pad_attached[8] = {};
+  unsigned long long halo_step[4] = {0, 0, 0, 0};
+  std::vector<void *> ipc_mapped;
   Tuning tuning;
   double inv_dz = 0.0; // (Mz - 1) / Lz when the levels are equally spaced, else 0
   int64_t launches = 0;
@@ -454,6 +465,8 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   cudaFree(h->d_dmax);
   cudaFree(h->d_hdc);
   cudaFree(h->d_global_bed);
+  for (void *p : h->ipc_mapped) cudaIpcCloseMemHandle(p);
+  cudaFree(h->d_pad);
   if (h->h_res) {
     cudaFreeHost(h->h_res);
   }
@@ -607,6 +620,117 @@ int siafd_b200_halo_unpack(siafd_b200_handle *h, int f, int dir_x, int dir_y, in
   const FieldMeta m = meta(h->cfg, f);
   h->launches += launch_copy_region((double *)h->buf[f], h->cfg.xm + 2 * m.width, i0, j0, device_buf, wc, 0, 0, wc, hc,
                                     m.dof, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+// ---- peer halo exchange -------------------------------------------------------------------------------
+static const int HALO_DX[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, HALO_DY[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+
+static int ensure_pad(siafd_b200_handle *h) {
+  if (!h->d_pad) {
+    CU(h, cudaMalloc(&h->d_pad, 32 * sizeof(unsigned long long)));
+    CU(h, cudaMemset(h->d_pad, 0, 32 * sizeof(unsigned long long)));
+  }
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_ipc_export(siafd_b200_handle *h, int field, void *handle64) {
+  CU(h, cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  void *p = nullptr;
+  if (field < 0) {
+    int st = ensure_pad(h);
+    if (st) return st;
+    p = h->d_pad;
+  } else {
+    int st = ensure(h, field);
+    if (st) return st;
+    if (!h->owned[field]) {
+      return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "field %d is bound to caller memory: only handle-owned storage can be exported",
+                  field);
+    }
+    p = h->buf[field];
+  }
+  CU(h, cudaStreamSynchronize(h->stream)); // the zero-fill of a fresh buffer
+  CU(h, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), p));
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_ipc_open(siafd_b200_handle *h, const void *handle64, void **peer_ptr) {
+  CU(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  std::memcpy(&mh, handle64, sizeof(mh));
+  CU(h, cudaIpcOpenMemHandle(peer_ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->ipc_mapped.push_back(*peer_ptr);
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_halo_attach(siafd_b200_handle *h, int field, int dir, void *peer_base, int peer_xm, int peer_ym) {
+  if (dir < 0 || dir > 7 || field >= SIAFD_B200_F_COUNT) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad halo attachment (field %d, dir %d)", field, dir);
+  }
+  if (field < 0) {
+    int st = ensure_pad(h);
+    if (st) return st;
+    h->peer_pad[dir] = peer_base ? (unsigned long long *)peer_base : h->d_pad;
+    h->pad_attached[dir] = true;
+    return SIAFD_B200_OK;
+  }
+  h->peers[field][dir].base = (double *)peer_base;
+  h->peers[field][dir].xm = peer_xm, h->peers[field][dir].ym = peer_ym;
+  h->peers[field][dir].attached = true;
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_halo_push(siafd_b200_handle *h, int n, const int *fields, const int *widths, int phase) {
+  CU(h, cudaSetDevice(h->device));
+  if (phase < 0 || phase > 3 || n < 1 || n > 6) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: phase in 0..3 and 1..6 fields");
+  }
+  const siafd_b200_config &c = h->cfg;
+  HaloBatch B;
+  B.n = 0;
+  for (int q = 0; q < n; ++q) {
+    const int f = fields[q], w = widths[q];
+    int st = ensure(h, f);
+    if (st) return st;
+    const FieldMeta m = meta(c, f);
+    if (w < 1 || w > m.width) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: bad width %d for field %d", w, f);
+    const int W = m.width;
+    for (int d = 0; d < 8; ++d) {
+      const siafd_b200_handle::Peer &P = h->peers[f][d];
+      if (!P.attached || !h->pad_attached[d]) {
+        return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: field %d / direction %d not attached", f, d);
+      }
+      const int dx = HALO_DX[d], dy = HALO_DY[d];
+      HaloDesc &D = B.d[B.n++];
+      D.src = (const double *)h->buf[f];
+      D.dst = P.base ? P.base : (double *)h->buf[f];
+      const int pxm = P.base ? P.xm : c.xm, pym = P.base ? P.ym : c.ym;
+      D.src_row_cells = c.xm + 2 * W, D.dst_row_cells = pxm + 2 * W;
+      D.dof = m.dof, D.pad = 0;
+      // my owned strip facing the neighbour -> the neighbour's ghost cells facing me (local array indices)
+      D.wc = dx == 0 ? c.xm : w, D.hc = dy == 0 ? c.ym : w;
+      D.src_i0 = W + (dx > 0 ? c.xm - w : 0), D.src_j0 = W + (dy > 0 ? c.ym - w : 0);
+      D.dst_i0 = dx > 0 ? W - w : (dx < 0 ? W + pxm : W);
+      D.dst_j0 = dy > 0 ? W - w : (dy < 0 ? W + pym : W);
+    }
+  }
+  h->launches += launch_halo_push(B, h->stream);
+  HaloSignal S;
+  h->halo_step[phase] += 1;
+  S.value = h->halo_step[phase];
+  for (int d = 0; d < 8; ++d) S.slot[d] = h->peer_pad[d] + phase * 8 + (7 - d); // the neighbour sees me in direction 7 - d
+  h->launches += launch_halo_signal(S, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_halo_wait(siafd_b200_handle *h, int phase) {
+  CU(h, cudaSetDevice(h->device));
+  if (phase < 0 || phase > 3 || !h->d_pad) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_wait: nothing was pushed");
+  h->launches += launch_halo_wait(h->d_pad + phase * 8, h->halo_step[phase], h->stream);
   CU(h, cudaGetLastError());
   return SIAFD_B200_OK;
 }

@@ -16,6 +16,7 @@
 // fields); see siafd_slab.cu and DESIGN.md.
 #include "siafd_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 namespace siafd {
@@ -255,6 +256,40 @@ __global__ void k_copy_region(double *__restrict__ dst, long dst_row_cells, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// peer halo exchange: the ghost update of util/iceModelVec.cc:630-643 as direct stores into the neighbours'
+// arrays (peer memory over NVLink).  blockIdx.y = strip, blockIdx.x strides over its elements.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_halo_push(const __grid_constant__ HaloBatch B) {
+  const HaloDesc &D = B.d[blockIdx.y];
+  const long rowlen = (long)D.wc * D.dof;
+  const long n = rowlen * D.hc;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    const long jj = q / rowlen, e = q - jj * rowlen;
+    D.dst[((D.dst_j0 + jj) * D.dst_row_cells + D.dst_i0) * D.dof + e] =
+        D.src[((D.src_j0 + jj) * D.src_row_cells + D.src_i0) * D.dof + e];
+  }
+}
+// runs after k_halo_push in stream order: every strip has landed when the counters move
+__global__ void k_halo_signal(const __grid_constant__ HaloSignal S) {
+  __threadfence_system();
+  if (threadIdx.x < 8 && S.slot[threadIdx.x] != nullptr) {
+    *reinterpret_cast<volatile unsigned long long *>(S.slot[threadIdx.x]) = S.value;
+  }
+  __threadfence_system();
+}
+// spins until all eight neighbours have delivered the strips of this phase (they never wait for this rank
+// before signalling, so the wait cannot deadlock)
+__global__ void k_halo_wait(const unsigned long long *slots, unsigned long long value) {
+  if (threadIdx.x < 8) {
+    const volatile unsigned long long *p = slots + threadIdx.x;
+    while (*p < value) {
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------
 // GeometryCalculator::compute, util/Mask.hh:96-133
 // ---------------------------------------------------------------------------------------------
 __global__ void k_geometry(const __grid_constant__ DP P, long n, const double *sea_level, const double *bed,
@@ -376,6 +411,23 @@ int launch_copy_region(double *dst, long dst_row_cells, int dst_i0, int dst_j0, 
   if (blocks > 148u * 32u) blocks = 148u * 32u; // grid-stride beyond that
   k_copy_region<<<blocks, 256, 0, s>>>(dst, dst_row_cells, dst_i0, dst_j0, src, src_row_cells, src_i0, src_j0, wc, hc,
                                        dof);
+  return 1;
+}
+
+int launch_halo_push(const HaloBatch &B, cudaStream_t s) {
+  if (B.n <= 0) return 0;
+  long nmax = 1;
+  for (int q = 0; q < B.n; ++q) nmax = std::max(nmax, (long)B.d[q].wc * B.d[q].dof * B.d[q].hc);
+  const unsigned bx = (unsigned)std::min<long>((nmax + 255) / 256, 64);
+  k_halo_push<<<dim3(bx, (unsigned)B.n), 256, 0, s>>>(B);
+  return 1;
+}
+int launch_halo_signal(const HaloSignal &S, cudaStream_t s) {
+  k_halo_signal<<<1, 32, 0, s>>>(S);
+  return 1;
+}
+int launch_halo_wait(const unsigned long long *slots8, unsigned long long value, cudaStream_t s) {
+  k_halo_wait<<<1, 32, 0, s>>>(slots8, value);
   return 1;
 }
 

@@ -34,6 +34,27 @@ size_t slab_smem_need(const DP &P, bool full, bool bulk); // shared memory of th
 int launch_copy_region(double *dst, long dst_row_cells, int dst_i0, int dst_j0, const double *src, long src_row_cells,
                        int src_i0, int src_j0, int width_cells, int height_cells, int dof, cudaStream_t s);
 
+// Peer halo exchange (CUDA IPC mapped neighbour arrays): one kernel copies every strip of a phase straight into
+// the neighbours' ghost cells over NVLink, a second one raises the neighbours' arrival counters, a third waits
+// for this rank's own counters.
+struct HaloDesc {
+  const double *src;
+  double *dst;
+  long src_row_cells, dst_row_cells;
+  int src_i0, src_j0, dst_i0, dst_j0, wc, hc, dof, pad;
+};
+struct HaloBatch {
+  HaloDesc d[48];
+  int n;
+};
+struct HaloSignal {
+  unsigned long long *slot[8]; // where to write, one per neighbour direction
+  unsigned long long value;
+};
+int launch_halo_push(const HaloBatch &B, cudaStream_t s);
+int launch_halo_signal(const HaloSignal &S, cudaStream_t s);
+int launch_halo_wait(const unsigned long long *slots8, unsigned long long value, cudaStream_t s);
+
 int launch_geometry(const DP &P, long n, const double *sea_level, const double *bed, const double *thk, double *mask_out,
                     double *surf_out, cudaStream_t s);
 int launch_flow_n(const DP &P, long n, const double *stress, const double *E, const double *p, const double *gs,

@@ -9,6 +9,8 @@ own periodic neighbour in a direction wraps locally instead.  Strips are packed 
 library's copy kernel on CUDA tensors (siafd_b200_halo_pack / _unpack) and by slicing on CPU tensors
 (host-logic tests).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -104,3 +106,75 @@ def global_max(value, device, group=None):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+DIRS = [(-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]  # siafd_b200.h: dir = 0..7
+
+
+class PeerHalo:
+    """Ghost exchange by direct stores into the neighbours' arrays (CUDA IPC peer memory over NVLink), the GPU
+    path of IceModelVec::update_ghosts for one process per GPU on one node.  Setup maps every neighbour's
+    arrays once (handles travel through torch.distributed); afterwards a phase is two stream-ordered calls,
+    `siafd_b200_halo_push` + `siafd_b200_halo_wait`: three small launches, no host synchronisation, BOX
+    corners included.  Fields must live in the handle's own storage (not bound tensors)."""
+
+    def __init__(self, patch, patches, sia, names, group=None):
+        self.patch, self.sia = patch, sia
+        h = sia.handle
+        mine = {}
+        for name in list(names) + [None]:
+            buf = (C.c_ubyte * 64)()
+            st = lib.siafd_b200_ipc_export(h, -1 if name is None else F[name], buf)
+            assert st == 0, lib.siafd_b200_last_error(h)
+            mine[name] = bytes(buf)
+        world = dist.get_world_size(group)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        mapped = {}  # (rank, name) -> peer pointer: a handle is opened once per process
+        self.bytes_per_push = {}
+        for name in list(names) + [None]:
+            f = -1 if name is None else F[name]
+            for d, (dx, dy) in enumerate(DIRS):
+                nb = patch.neighbor(dx, dy)
+                if nb == patch.rank:
+                    ptr = None
+                else:
+                    if (nb, name) not in mapped:
+                        out = C.c_void_p()
+                        st = lib.siafd_b200_ipc_open(h, everyone[nb][name], C.byref(out))
+                        assert st == 0, lib.siafd_b200_last_error(h)
+                        mapped[(nb, name)] = out.value
+                    ptr = mapped[(nb, name)]
+                st = lib.siafd_b200_halo_attach(h, f, d, ptr, patches[nb].xm, patches[nb].ym)
+                assert st == 0, lib.siafd_b200_last_error(h)
+        dist.barrier(group=group)  # nobody pushes before everybody has mapped
+        self.bytes_sent = 0
+
+    def exchange(self, names_widths, phase):
+        """update_ghosts() of several fields at once: [(name, width), ...]."""
+        n = len(names_widths)
+        fa = (C.c_int * n)(*[F[nm] for nm, _ in names_widths])
+        wa = (C.c_int * n)(*[w for _, w in names_widths])
+        h = self.sia.handle
+        st = lib.siafd_b200_halo_push(h, n, fa, wa, phase)
+        assert st == 0, lib.siafd_b200_last_error(h)
+        st = lib.siafd_b200_halo_wait(h, phase)
+        assert st == 0, lib.siafd_b200_last_error(h)
+        p = self.patch
+        for nm, w in names_widths:
+            dof = lib.siafd_b200_field_dof(h, F[nm])
+            self.bytes_sent += 8 * dof * (2 * w * p.ym + 2 * w * (p.xm + 2 * w))
+
+
+def device_view(sia, name, shape, device):
+    """torch view of the handle-owned device storage of a field (no copy)."""
+
+    class _Buf:
+        pass
+
+    b = _Buf()
+    ptr = lib.siafd_b200_device_ptr(sia.handle, F[name])
+    assert ptr, lib.siafd_b200_last_error(sia.handle)
+    b.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2,
+                                  "strides": None}
+    return torch.as_tensor(b, device=device)
