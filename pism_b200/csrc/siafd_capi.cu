@@ -7,6 +7,7 @@
 #include "../../include/siafd_b200.h"
 #include "siafd_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -39,6 +40,8 @@ struct siafd_b200_handle {
   bool smoother_set = false;
   int bedNx = -1, bedNy = -1;
   double *d_global_bed = nullptr;
+  cudaStream_t s_up = nullptr, s_dn = nullptr; // upload / download legs of the pipelined host update
+  std::vector<cudaEvent_t> ev_pipe;
   // peer halo exchange: per field and neighbour direction the mapped base of the neighbour's array (nullptr =
   // this rank) and its patch size; the arrival-counter pad [4 phases][8 dirs] and the neighbours' pads
   struct Peer {
@@ -406,6 +409,10 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.use_bulk_copy = 1;
   h->tuning.skip_ice_free = 1;
   h->tuning.wz = 4;
+  h->tuning.pipeline_host = 1;
+  h->tuning.pipeline_band = 4;
+  if (const char *e = getenv("SIAFD_B200_PIPELINE")) h->tuning.pipeline_host = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_BAND")) h->tuning.pipeline_band = atoi(e);
   if (const char *e = getenv("SIAFD_B200_WZ")) h->tuning.wz = atoi(e);
   if (const char *e = getenv("SIAFD_B200_ROWS")) h->tuning.rows_per_cta = atoi(e) > 0 ? atoi(e) : 64;
   {
@@ -470,6 +477,9 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   if (h->h_res) {
     cudaFreeHost(h->h_res);
   }
+  for (cudaEvent_t e : h->ev_pipe) cudaEventDestroy(e);
+  if (h->s_up) cudaStreamDestroy(h->s_up);
+  if (h->s_dn) cudaStreamDestroy(h->s_dn);
   for (size_t q = 0; q < h->ev_start.size(); ++q) {
     cudaEventDestroy(h->ev_start[q]);
     cudaEventDestroy(h->ev_stop[q]);
@@ -803,7 +813,8 @@ int siafd_b200_compute_gradient(siafd_b200_handle *h) {
   return SIAFD_B200_OK;
 }
 
-int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, double current_time) {
+// checks, scratch fields and the 2D preparation of SIAFD::compute_diffusivity (SIAFD.cc:555-582)
+static int flux_velocity_prepare(siafd_b200_handle *h, int full_update, double current_time) {
   CU(h, cudaSetDevice(h->device));
   const siafd_b200_config &c = h->cfg;
   const int need[] = {SIAFD_B200_F_SURFACE,    SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK,  SIAFD_B200_F_BED,
@@ -841,13 +852,20 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, doub
   CU(h, cudaMemsetAsync(h->d_dmax, 0, sizeof(unsigned long long), h->stream));
   CU(h, cudaMemsetAsync(h->d_hdc, 0, sizeof(int), h->stream));
   h->launches += launch_prep2d(h->P, F, h->stream); // sia/SIAFD.cc:580-582
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+// the fused kernel on the row segments [seg0, seg0 + nseg) (nseg < 0: all)
+static int flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0, int nseg) {
+  const Fields F = fields_of(h);
   const Tuning T = h->tuning;
   const bool timed = h->timing && h->ev_count < (int)h->ev_start.size();
   if (timed) {
     CU(h, cudaEventRecord(h->ev_start[h->ev_count], h->stream));
   }
   const int n = launch_slab(h->P, F, full_update != 0, T, (long)siafd_b200_field_size(h, SIAFD_B200_F_ENTHALPY),
-                            (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, h->stream);
+                            (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, seg0, nseg, h->stream);
   if (timed) {
     CU(h, cudaEventRecord(h->ev_stop[h->ev_count], h->stream));
     h->ev_count += 1;
@@ -860,6 +878,12 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, doub
   CU(h, cudaGetLastError());
   h->result_pending = true;
   return SIAFD_B200_OK;
+}
+
+int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, double current_time) {
+  int st = flux_velocity_prepare(h, full_update, current_time);
+  if (st) return st;
+  return flux_velocity_launch(h, full_update, 0, -1);
 }
 
 int siafd_b200_finish(siafd_b200_handle *h) {
@@ -899,6 +923,117 @@ int siafd_b200_high_diffusivity_count(siafd_b200_handle *h) {
   return h->h_res->hdc;
 }
 
+// siafd_b200_update with host arrays, full update: the three legs of the drop-in call -- host->device copy of the
+// enthalpy, the fused kernel, device->host copy of u and v -- run as a pipeline over bands of rows on three streams
+// (PCIe is full duplex), instead of one after the other.  The bands are whole row segments of the fused kernel, and
+// every array is contiguous in rows, so each leg of a band is one cudaMemcpyAsync / one launch.
+static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out) {
+  const siafd_b200_config &c = h->cfg;
+  int st;
+  if (!h->s_up) {
+    CU(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    CU(h, cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking));
+  }
+  const int RS = slab_rows_per_segment(h->tuning), nseg = slab_segments(h->P, h->tuning);
+  const int band = std::max(1, h->tuning.pipeline_band);
+  const int NB = (nseg + band - 1) / band;
+  while ((int)h->ev_pipe.size() < 2 * NB + 4) {
+    cudaEvent_t e;
+    CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev_pipe.push_back(e);
+  }
+  const int outs_f[] = {SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y, SIAFD_B200_F_D, SIAFD_B200_F_FLUX, SIAFD_B200_F_U, SIAFD_B200_F_V,
+                        SIAFD_B200_F_ENTHALPY};
+  for (int f : outs_f) {
+    if ((st = ensure(h, f))) return st;
+  }
+  cudaEvent_t ev_start = h->ev_pipe[2 * NB];
+  CU(h, cudaEventRecord(ev_start, h->stream)); // earlier work on the handle's stream (fresh buffers' zero-fill)
+  CU(h, cudaStreamWaitEvent(h->s_up, ev_start, 0));
+  CU(h, cudaStreamWaitEvent(h->s_dn, ev_start, 0));
+  // 2D inputs on the main stream (the gradient needs them first)
+  struct {
+    int f;
+    const double *p;
+  } small[] = {{SIAFD_B200_F_SURFACE, in->surface}, {SIAFD_B200_F_THICKNESS, in->thickness}, {SIAFD_B200_F_MASK, in->mask},
+               {SIAFD_B200_F_BED, in->bed}, {SIAFD_B200_F_SLIDING, in->sliding}};
+  for (auto &q : small) {
+    if (q.p && (st = siafd_b200_upload(h, q.f, q.p))) return st;
+  }
+  // enthalpy bands on the upload stream: band b reads local rows below (b + 1) band RS + w_3d_in (+1 of slack)
+  const int we = c.w_3d_in, wuv = c.w_uv;
+  const long rowsE = c.ym + 2 * we, rowE = (long)(c.xm + 2 * we) * c.Mz;
+  long up0 = 0;
+  for (int b = 0; b < NB; ++b) {
+    const long up1 = std::min<long>(rowsE, (long)std::min(nseg, (b + 1) * band) * RS + we + 1);
+    if (up1 > up0) {
+      CU(h, cudaMemcpyAsync((double *)h->buf[SIAFD_B200_F_ENTHALPY] + up0 * rowE, in->enthalpy + up0 * rowE,
+                            (size_t)(up1 - up0) * rowE * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
+      up0 = up1;
+    }
+    if (b == NB - 1 && up0 < rowsE) {
+      CU(h, cudaMemcpyAsync((double *)h->buf[SIAFD_B200_F_ENTHALPY] + up0 * rowE, in->enthalpy + up0 * rowE,
+                            (size_t)(rowsE - up0) * rowE * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
+      up0 = rowsE;
+    }
+    CU(h, cudaEventRecord(h->ev_pipe[b], h->s_up));
+  }
+  // gradient and 2D preparation while the first band is in flight
+  if ((st = siafd_b200_compute_gradient(h))) return st;
+  if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
+    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_X))) return st;
+    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_Y))) return st;
+  }
+  if ((st = flux_velocity_prepare(h, 1, in->current_time))) return st;
+  const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
+  const int uvf[2] = {SIAFD_B200_F_U, SIAFD_B200_F_V};
+  double *uvh[2] = {out->u, out->v};
+  for (int b = 0; b < NB; ++b) {
+    const int s0 = b * band, s1 = std::min(nseg, (b + 1) * band);
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_pipe[b], 0));
+    if ((st = flux_velocity_launch(h, 1, s0, s1 - s0))) return st;
+    // owned rows of this band (extended row e = ys - 1 + s RS ... ; owned rows are ys .. ys + ym - 1)
+    const int o0 = std::max(0, s0 * RS - 1), o1 = std::min(c.ym, s1 * RS - 1);
+    if (o1 > o0) {
+      for (int q = 0; q < 2; ++q) { // periodic wrap in x of the band's rows (SIAFD.cc:946-947), then download
+        double *a = (double *)h->buf[uvf[q]];
+        h->launches += launch_copy_region(a, c.xm + 2 * wuv, 0, wuv + o0, a, c.xm + 2 * wuv, c.xm, wuv + o0, wuv, o1 - o0, c.Mz,
+                                          h->stream);
+        h->launches += launch_copy_region(a, c.xm + 2 * wuv, c.xm + wuv, wuv + o0, a, c.xm + 2 * wuv, wuv, wuv + o0, wuv, o1 - o0,
+                                          c.Mz, h->stream);
+      }
+      CU(h, cudaEventRecord(h->ev_pipe[NB + b], h->stream));
+      CU(h, cudaStreamWaitEvent(h->s_dn, h->ev_pipe[NB + b], 0));
+      for (int q = 0; q < 2; ++q) {
+        const long off = (long)(wuv + o0) * rowUV;
+        CU(h, cudaMemcpyAsync(uvh[q] + off, (double *)h->buf[uvf[q]] + off, (size_t)(o1 - o0) * rowUV * sizeof(double),
+                              cudaMemcpyDeviceToHost, h->s_dn));
+      }
+    }
+  }
+  // ghost rows of u, v (periodic wrap in y), the 2D outputs, D_max and the error flags
+  for (int q = 0; q < 2; ++q) {
+    if ((st = wrap_dir(h, uvf[q], 1))) return st;
+    double *a = (double *)h->buf[uvf[q]];
+    CU(h, cudaMemcpyAsync(uvh[q], a, (size_t)wuv * rowUV * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const long off = (long)(wuv + c.ym) * rowUV;
+    CU(h, cudaMemcpyAsync(uvh[q] + off, a + off, (size_t)wuv * rowUV * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  struct {
+    int f;
+    double *p;
+  } outs2[] = {{SIAFD_B200_F_H_X, out->h_x}, {SIAFD_B200_F_H_Y, out->h_y}, {SIAFD_B200_F_D, out->D}, {SIAFD_B200_F_FLUX, out->flux}};
+  for (auto &q : outs2) {
+    if (!q.p) continue;
+    CU(h, cudaMemcpyAsync(q.p, h->buf[q.f], (size_t)siafd_b200_field_size(h, q.f) * sizeof(double), cudaMemcpyDeviceToHost,
+                          h->stream));
+  }
+  st = siafd_b200_finish(h);
+  CU(h, cudaStreamSynchronize(h->s_dn));
+  CU(h, cudaStreamSynchronize(h->s_up));
+  return st;
+}
+
 int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out, int full_update) {
   if (!h || !in || !out) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "null argument");
@@ -910,6 +1045,10 @@ int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT,
                 "siafd_b200_update is the single-rank form; a decomposed patch must use the split calls with ghost "
                 "exchanges at SIAFD.cc:498-499 and :946-947");
+  }
+  if (in->memory_space == 0 && out->memory_space == 0 && full_update && in->ghosts_valid && in->enthalpy && !in->age &&
+      out->u && out->v && in->surface && in->thickness && in->mask && h->tuning.pipeline_host) {
+    return update_host_pipelined(h, in, out);
   }
   struct {
     int f;

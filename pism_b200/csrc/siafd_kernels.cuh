@@ -21,13 +21,18 @@ struct Tuning {
   int use_bulk_copy; // 1: cp.async.bulk + mbarrier row loads; 0: 8-byte cp.async
   int skip_ice_free; // 1: do not load enthalpy rows no staggered point needs
   int wz;            // z ranges per column (2, 4 or 8)
+  int pipeline_host; // 1: siafd_b200_update with host arrays overlaps upload, kernel and download over row bands
+  int pipeline_band; // row segments per band of that pipeline
 };
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
 int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
 int launch_gradient(const DP &P, const Fields &F, cudaStream_t s);
-int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz,
-                cudaStream_t s);
+// one launch covers the row segments [seg0, seg0 + nseg) of the extended patch (nseg < 0: all from seg0)
+int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz, int seg0,
+                int nseg, cudaStream_t s);
+int slab_rows_per_segment(const Tuning &T);
+int slab_segments(const DP &P, const Tuning &T);
 size_t slab_smem_need(const DP &P, bool full, bool bulk); // shared memory of the smallest configuration
 
 // copy a rectangle of cells between two [rows][cells][dof] arrays (ghost wrap, halo pack/unpack)

@@ -75,6 +75,8 @@ struct SlabArgs {
   long nE;       // doubles in the enthalpy array (bulk copies are clamped to it)
   long n2;       // doubles in a geometry-width 2D array
   double inv_dz; // (Mz - 1) / Lz if the levels are equally spaced, else 0
+  int seg0;      // first row segment of this launch (a launch may cover a band of segments)
+  int nseg;      // segments in this launch
 };
 
 // per-slot staging area of a row's 2D scalars (offsets in doubles)
@@ -117,9 +119,10 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   const bool own_c = col_ok && (c >= 1 || blockIdx.x == 0); // this strip writes D, Q of the column
   const int ncolE = min(NC + 1, ilast + 2 - ca);            // enthalpy / thk_smooth columns ca .. ca + ncolE - 1
   const int ncolS = ncolE - 1;                              // valid lane columns
-  const int ra = (P.ys - 1) + blockIdx.y * A.RS;
+  const int seg = (int)blockIdx.y + A.seg0;
+  const int ra = (P.ys - 1) + seg * A.RS;
   const int rb = min(ra + A.RS, P.ys + P.ym + 1);
-  const int r0 = (FULL && blockIdx.y > 0) ? ra - 1 : ra; // warm-up row: I1 of the row below the segment
+  const int r0 = (FULL && seg > 0) ? ra - 1 : ra; // warm-up row: I1 of the row below the segment
 
   for (int k = tid; k < Mz; k += NT) {
     const double zk = F.z[k];
@@ -632,7 +635,7 @@ static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaSt
     }
     configured = smem;
   }
-  dim3 grid((unsigned)((P.xm + 1 + (NC - 2)) / (NC - 1)), (unsigned)((P.ym + 2 + A.RS - 1) / A.RS));
+  dim3 grid((unsigned)((P.xm + 1 + (NC - 2)) / (NC - 1)), (unsigned)A.nseg);
   k_sia_slab<LAW, FULL, NC, WZ><<<grid, 2 * NC * WZ, smem, s>>>(P, F, A);
   return 1;
 }
@@ -672,10 +675,18 @@ template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, cons
 
 size_t slab_smem_need(const DP &P, bool full, bool bulk) { return slab_smem_bytes(P, full, 8, 4, bulk); }
 
-int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz,
-                cudaStream_t s) {
+int slab_rows_per_segment(const Tuning &T) { return T.rows_per_cta < 88 ? T.rows_per_cta : 88; }
+int slab_segments(const DP &P, const Tuning &T) {
+  const int RS = slab_rows_per_segment(T);
+  return (P.ym + 2 + RS - 1) / RS;
+}
+
+int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz, int seg0,
+                int nseg, cudaStream_t s) {
   SlabArgs A;
-  A.RS = T.rows_per_cta < 88 ? T.rows_per_cta : 88; // the row flags of a CTA live in a 96-bit word
+  A.RS = slab_rows_per_segment(T); // the row flags of a CTA live in a 96-bit word
+  A.seg0 = seg0;
+  A.nseg = nseg < 0 ? slab_segments(P, T) - seg0 : nseg;
   A.use_bulk = (T.use_bulk_copy && (P.Mz & 1)) ? 1 : 0; // even Mz: padded columns, 8-byte cp.async
   A.skip_rows = T.skip_ice_free;
   A.nE = nE;
