@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   const int i_q = ca + q;
   const bool uv_col = FULL && q >= 1 && i_q >= P.xs && i_q < P.xs + P.xm;
   const long uv_row = (long)(P.xm + 2 * P.wuv) * Mz;
-  const long uv0 = FULL ? idx2(P, min(max(i_q, P.xs - P.wuv), P.xs + P.xm + P.wuv - 1), P.ys - P.wuv, P.wuv) * Mz : 0;
+  // Stage B stores run 16 lanes across z (128-byte pieces of a column): a 16-lane group takes NPASS = 16 / LB
+  // adjacent columns one after the other (LB >= 16: one column per LB lanes)
+  constexpr int LZ = (LB >= 16) ? LB : 16, NPASS = (LB >= 16) ? 1 : 16 / LB;
+  const int qg = (tid / LZ) * NPASS, lz = tid % LZ;
   const double *sl_p =
       (FULL && uv_col && F.sliding != nullptr) ? F.sliding + idx2(P, i_q, P.ys - P.wsl, P.wsl) * 2 : nullptr;
   const long ssl = 2L * (P.xm + 2 * P.wsl);
@@ -535,41 +538,48 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
         }
         __syncthreads(); // #3: I0, I1, cf final
       }
-      // ---------------- stage B: u, v of the regular column (i_q, r), sia/SIAFD.cc:904-943 ----------------
-      if (uv_col && r >= ra && r >= P.ys && r < P.ys + P.ym) {
-        const double ub = sv.x, vb = sv.y;
-        double *up = F.u + uv0 + (long)(r - (P.ys - P.wuv)) * uv_row + li;
-        double *vp = F.v + uv0 + (long)(r - (P.ys - P.wuv)) * uv_row + li;
-        if (!any_valid) {
-          // no ice at any staggered point of this and the previous row: I == 0, u = sliding velocity (G9)
-          for (int k = li; k < Mz; k += LB, up += LB, vp += LB) {
-            *up = ub;
-            *vp = vb;
-          }
-        } else {
-          // u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s): the factor -0.25 goes into the slopes
-          const double *cE = cf + (s_cur * NC + q) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + q) * 4;
-          const bool south = (ivalid & (1u << s_nxt)) != 0;
-          const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
-          const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
-          const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
-          const double *Ie = I0_s + q * S + li;
-          const double *In = I1_s + (s_cur * NC + q) * S + li, *Is = I1_s + (s_nxt * NC + q) * S + li;
-          int k = li;
-          for (; k + 3 * LB < Mz; k += 4 * LB, up += 4 * LB, vp += 4 * LB, Ie += 4 * LB, In += 4 * LB, Is += 4 * LB) {
-            double ie[4], iw[4], in[4], is[4];
+      // ---------------- stage B: u, v of the regular columns, sia/SIAFD.cc:904-943 ----------------
+      if (r >= rbase && r < rend) { // CTA-uniform
+        const bool south = (ivalid & (1u << s_nxt)) != 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LB], iw[j] = (Ie - S)[j * LB], in[j] = In[j * LB], is[j] = Is[j * LB];
+        for (int p = 0; p < NPASS; ++p) {
+          const int qp = qg + p, i_p = ca + qp;
+          const int srcl = (lane & ~(LZ - 1)) + p * LB; // a lane whose own column (tid / LB) is qp
+          const double ub = __shfl_sync(FULLMASK, sv.x, srcl), vb = __shfl_sync(FULLMASK, sv.y, srcl);
+          if (qp >= 1 && i_p >= P.xs && i_p < P.xs + P.xm) {
+            const long uvo = ((long)(r - (P.ys - P.wuv)) * (P.xm + 2 * P.wuv) + (i_p - P.xs + P.wuv)) * Mz + lz;
+            double *up = F.u + uvo, *vp = F.v + uvo;
+            if (!any_valid) {
+              // no ice at any staggered point of this and the previous row: I == 0, u = sliding velocity (G9)
+              for (int k = lz; k < Mz; k += LZ, up += LZ, vp += LZ) {
+                *up = ub;
+                *vp = vb;
+              }
+            } else {
+              // u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s): the factor -0.25 goes into the slopes
+              const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
+              const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
+              const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
+              const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
+              const double *Ie = I0_s + qp * S + lz;
+              const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
+              int k = lz;
+              for (; k + 3 * LZ < Mz; k += 4 * LZ, up += 4 * LZ, vp += 4 * LZ, Ie += 4 * LZ, In += 4 * LZ, Is += 4 * LZ) {
+                double ie[4], iw[4], in[4], is[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              up[j * LB] = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
-              vp[j * LB] = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
+                for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LZ], iw[j] = (Ie - S)[j * LZ], in[j] = In[j * LZ], is[j] = Is[j * LZ];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  up[j * LZ] = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
+                  vp[j * LZ] = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
+                }
+              }
+              for (; k < Mz; k += LZ, up += LZ, vp += LZ, Ie += LZ, In += LZ, Is += LZ) {
+                const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
+                *up = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
+                *vp = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
+              }
             }
-          }
-          for (; k < Mz; k += LB, up += LB, vp += LB, Ie += LB, In += LB, Is += LB) {
-            const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
-            *up = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
-            *vp = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
           }
         }
       }
