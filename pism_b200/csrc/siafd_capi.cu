@@ -227,6 +227,7 @@ void fill_dp(siafd_b200_handle *h) {
   P.xs = c.xs, P.xm = c.xm, P.ys = c.ys, P.ym = c.ym;
   P.wg = c.w_geom, P.we = c.w_3d_in, P.wst = c.w_stag, P.wuv = c.w_uv, P.wsl = c.w_sliding;
   P.dx = c.dx, P.dy = c.dy;
+  P.inv_dx = 1.0 / c.dx, P.inv_dy = 1.0 / c.dy;
   P.p_air = c.ec_p_air;
   P.rg = c.ec_rho_i * c.ec_g; // first product of "m_rho_i * m_g * depth", EnthalpyConverter.cc:150
   P.ec_beta = c.ec_beta, P.c_i = c.ec_c_i, P.inv_c_i = 1.0 / c.ec_c_i, P.c_w = c.ec_c_w, P.L0 = c.ec_L;

@@ -5,7 +5,7 @@
 //
 //   k_prep2d        BedSmoother::smoothed_thk + ::theta      sia/BedSmoother.cc:284-327, :351-404
 //   k_eta           eta = H^((2n+2)/n)                        sia/SIAFD.cc:241-245
-//   k_grad_*        surface_gradient_{mahaffy,eta,haseloff}   sia/SIAFD.cc:224-496
+//   k_grad_*        surface_gradient_{mahaffy,eta,haseloff}   sia/SIAFD.cc:224-496 (haseloff: both loops in one pass)
 //   k_sia_slab      (siafd_slab.cu) diffusivity + flux + I + 3D velocity, fused    sia/SIAFD.cc:543-948
 //   k_copy_region   ghost wrap / halo pack (DMLocalToLocal)   util/iceModelVec.cc:630-643
 //   k_geometry      GeometryCalculator::compute               util/Mask.hh:96-133
@@ -161,84 +161,95 @@ __global__ void k_grad_eta(const __grid_constant__ DP P, const Fields F) {
   }
 }
 
-// SIAFD::surface_gradient_haseloff, first loop (sia/SIAFD.cc:396-436), on owned + 1
-__global__ void k_grad_haseloff_a(const __grid_constant__ DP P, const Fields F) {
+// SIAFD::surface_gradient_haseloff in ONE pass.  The reference runs two loops (sia/SIAFD.cc:396-436 on owned + 1:
+// the direct components h_x(.,0), h_y(.,1) and the weights w_i, w_j; :438-496 on owned: the cross components
+// as weighted means of up to four direct neighbours).  A direct component and its weight are a function of two
+// adjacent cells only (surface + mask), so the second loop's neighbours are re-evaluated here from the cells
+// around (i, j) -- the same expressions, hence the same bits -- instead of being round-tripped through w_i,
+// w_j and the half-written staggered arrays.
+struct HasDirect {
+  double g; // the direct gradient component
+  double w; // its weight (0 or 1)
+};
+// i-offset point between (i, j) and (i + 1, j): sia/SIAFD.cc:399-416
+__device__ __forceinline__ HasDirect haseloff_direct(double h0, double h1, int M0, int M1, double d, double inv_d) {
+  HasDirect r;
+  if ((m_floating_ice(M0) && m_ice_free_ocean(M1)) || (m_ice_free_ocean(M0) && m_floating_ice(M1))) {
+    r.g = 0.0, r.w = 0.0;
+  } else if ((m_icy(M0) && m_ice_free(M1) && h1 > h0) || (m_ice_free(M0) && m_icy(M1) && h0 > h1)) {
+    r.g = 0.0, r.w = 0.0;
+  } else {
+    r.g = div_rn_by(h1 - h0, d, inv_d), r.w = 1.0;
+  }
+  return r;
+}
+// 1.0 / W for a sum W of up to four 0/1 weights (W in {1, 2, 3, 4}): the correctly rounded quotients
+__device__ __forceinline__ double inv_count(double W) {
+  return W == 1.0 ? 1.0 : (W == 2.0 ? 0.5 : (W == 3.0 ? (1.0 / 3.0) : 0.25));
+}
+__global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F) {
   const int nx = P.xm + 2;
   const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (long)nx * (P.ym + 2)) {
     return;
   }
   const int i = P.xs - 1 + (int)(q % nx), j = P.ys - 1 + (int)(q / nx);
-  const long g0 = idx2(P, i, j, P.wg), ge = idx2(P, i + 1, j, P.wg), gn = idx2(P, i, j + 1, P.wg);
-  const double h0 = F.h[g0], he = F.h[ge], hn = F.h[gn];
-  const int M0 = mask_int(F.mask[g0]), Me = mask_int(F.mask[ge]), Mn = mask_int(F.mask[gn]);
+  // the 3 x 3 cells around (i, j): c[b][a] = cell (i - 1 + a, j - 1 + b)
+  double h[3][3];
+  int M[3][3];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const long g = idx2(P, i - 1 + a, j - 1 + b, P.wg);
+      h[b][a] = F.h[g];
+      M[b][a] = mask_int(F.mask[g]);
+    }
+  }
   const long s = idx2(P, i, j, P.wst) * 2;
-  // x-derivative, i-offset
-  if ((m_floating_ice(M0) && m_ice_free_ocean(Me)) || (m_ice_free_ocean(M0) && m_floating_ice(Me))) {
-    F.h_x[s + 0] = 0.0;
-    F.w_i[g0] = 0.0;
-  } else if ((m_icy(M0) && m_ice_free(Me) && he > h0) || (m_ice_free(M0) && m_icy(Me) && h0 > he)) {
-    F.h_x[s + 0] = 0.0;
-    F.w_i[g0] = 0.0;
-  } else {
-    F.h_x[s + 0] = (he - h0) / P.dx;
-    F.w_i[g0] = 1.0;
+  // direct components of this point (first loop)
+  const HasDirect x00 = haseloff_direct(h[1][1], h[1][2], M[1][1], M[1][2], P.dx, P.inv_dx); // h_x(i, j, 0), w_i(i, j)
+  const HasDirect y00 = haseloff_direct(h[1][1], h[2][1], M[1][1], M[2][1], P.dy, P.inv_dy); // h_y(i, j, 1), w_j(i, j)
+  F.h_x[s + 0] = x00.g;
+  F.h_y[s + 1] = y00.g;
+  F.w_i[idx2(P, i, j, P.wg)] = x00.w; // (kept: the reference leaves them in its work vectors)
+  F.w_j[idx2(P, i, j, P.wg)] = y00.w;
+  if (i < P.xs || i >= P.xs + P.xm || j < P.ys || j >= P.ys + P.ym) {
+    return; // the second loop runs over owned points only; its ghosts come from the exchange (:498-499)
   }
-  // y-derivative, j-offset
-  if ((m_floating_ice(M0) && m_ice_free_ocean(Mn)) || (m_ice_free_ocean(M0) && m_floating_ice(Mn))) {
-    F.h_y[s + 1] = 0.0;
-    F.w_j[g0] = 0.0;
-  } else if ((m_icy(M0) && m_ice_free(Mn) && hn > h0) || (m_ice_free(M0) && m_icy(Mn) && h0 > hn)) {
-    F.h_y[s + 1] = 0.0;
-    F.w_j[g0] = 0.0;
-  } else {
-    F.h_y[s + 1] = (hn - h0) / P.dy;
-    F.w_j[g0] = 1.0;
-  }
-}
-
-// second loop (sia/SIAFD.cc:438-496), on owned points only
-__global__ void k_grad_haseloff_b(const __grid_constant__ DP P, const Fields F) {
-  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= (long)P.xm * P.ym) {
-    return;
-  }
-  const int i = P.xs + (int)(q % P.xm), j = P.ys + (int)(q / P.xm);
-#define WI(a, b) F.w_i[idx2(P, (a), (b), P.wg)]
-#define WJ(a, b) F.w_j[idx2(P, (a), (b), P.wg)]
-#define HX0(a, b) F.h_x[idx2(P, (a), (b), P.wst) * 2 + 0]
-#define HY1(a, b) F.h_y[idx2(P, (a), (b), P.wst) * 2 + 1]
-  const bool icy = m_icy(mask_int(F.mask[idx2(P, i, j, P.wg)]));
-  const long s = idx2(P, i, j, P.wst) * 2;
+  const bool icy = m_icy(M[1][1]);
+  // neighbours of the second loop, each evaluated as the first loop evaluates it at its own point
+  const HasDirect xm0 = haseloff_direct(h[1][0], h[1][1], M[1][0], M[1][1], P.dx, P.inv_dx); // (i-1, j)
+  const HasDirect xm1 = haseloff_direct(h[2][0], h[2][1], M[2][0], M[2][1], P.dx, P.inv_dx); // (i-1, j+1)
+  const HasDirect x01 = haseloff_direct(h[2][1], h[2][2], M[2][1], M[2][2], P.dx, P.inv_dx); // (i, j+1)
+  const HasDirect y0m = haseloff_direct(h[0][1], h[1][1], M[0][1], M[1][1], P.dy, P.inv_dy); // (i, j-1)
+  const HasDirect y1m = haseloff_direct(h[0][2], h[1][2], M[0][2], M[1][2], P.dy, P.inv_dy); // (i+1, j-1)
+  const HasDirect y10 = haseloff_direct(h[1][2], h[2][2], M[1][2], M[2][2], P.dy, P.inv_dy); // (i+1, j)
   double r;
-  // x-derivative, j-offset
-  if (WJ(i, j) > 0) {
-    const double W = WI(i, j) + WI(i - 1, j) + WI(i - 1, j + 1) + WI(i, j + 1);
-    r = (W > 0) ? __dmul_rn(1.0 / W, (HX0(i, j) + HX0(i - 1, j) + HX0(i - 1, j + 1) + HX0(i, j + 1))) : 0.0;
+  // x-derivative, j-offset (:441-467)
+  if (y00.w > 0) {
+    const double W = x00.w + xm0.w + xm1.w + x01.w;
+    r = (W > 0) ? __dmul_rn(inv_count(W), (x00.g + xm0.g + xm1.g + x01.g)) : 0.0;
   } else if (icy) {
-    const double W = WI(i, j) + WI(i - 1, j);
-    r = (W > 0) ? __dmul_rn(1.0 / W, (HX0(i, j) + HX0(i - 1, j))) : 0.0;
+    const double W = x00.w + xm0.w;
+    r = (W > 0) ? __dmul_rn(inv_count(W), (x00.g + xm0.g)) : 0.0;
   } else {
-    const double W = WI(i, j + 1) + WI(i - 1, j + 1);
-    r = (W > 0) ? __dmul_rn(1.0 / W, (HX0(i - 1, j + 1) + HX0(i, j + 1))) : 0.0;
+    const double W = x01.w + xm1.w;
+    r = (W > 0) ? __dmul_rn(inv_count(W), (xm1.g + x01.g)) : 0.0;
   }
   F.h_x[s + 1] = r;
-  // y-derivative, i-offset
-  if (WI(i, j) > 0) {
-    const double W = WJ(i, j) + WJ(i, j - 1) + WJ(i + 1, j - 1) + WJ(i + 1, j);
-    r = (W > 0) ? __dmul_rn(1.0 / W, (HY1(i, j) + HY1(i, j - 1) + HY1(i + 1, j - 1) + HY1(i + 1, j))) : 0.0;
+  // y-derivative, i-offset (:469-495)
+  if (x00.w > 0) {
+    const double W = y00.w + y0m.w + y1m.w + y10.w;
+    r = (W > 0) ? __dmul_rn(inv_count(W), (y00.g + y0m.g + y1m.g + y10.g)) : 0.0;
   } else if (icy) {
-    const double W = WJ(i, j) + WJ(i, j - 1);
-    r = (W > 0) ? __dmul_rn(1.0 / W, (HY1(i, j) + HY1(i, j - 1))) : 0.0;
+    const double W = y00.w + y0m.w;
+    r = (W > 0) ? __dmul_rn(inv_count(W), (y00.g + y0m.g)) : 0.0;
   } else {
-    const double W = WJ(i + 1, j - 1) + WJ(i + 1, j);
-    r = (W > 0) ? __dmul_rn(1.0 / W, (HY1(i + 1, j - 1) + HY1(i + 1, j))) : 0.0;
+    const double W = y1m.w + y10.w;
+    r = (W > 0) ? __dmul_rn(inv_count(W), (y1m.g + y10.g)) : 0.0;
   }
   F.h_y[s + 0] = r;
-#undef WI
-#undef WJ
-#undef HX0
-#undef HY1
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -397,9 +408,8 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s) {
     k_grad_eta<<<nblk(n1, 256), 256, 0, s>>>(P, F);
     return 2;
   default:
-    k_grad_haseloff_a<<<nblk(n1, 256), 256, 0, s>>>(P, F);
-    k_grad_haseloff_b<<<nblk((long)P.xm * P.ym, 256), 256, 0, s>>>(P, F);
-    return 2;
+    k_grad_haseloff<<<nblk(n1, 256), 256, 0, s>>>(P, F);
+    return 1;
   }
 }
 

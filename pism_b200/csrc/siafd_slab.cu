@@ -32,6 +32,9 @@
 // Newton reciprocal; sums over z are taken per z range and then added.
 #include "siafd_math.cuh"
 
+#ifndef SLAB_LZ
+#define SLAB_LZ 16 // lanes across z in stage B
+#endif
 #ifndef SLAB_NL
 #define SLAB_NL 3 // levels per trip of the Arrhenius loop
 #endif
@@ -254,22 +257,22 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   const long uv_row = (long)(P.xm + 2 * P.wuv) * Mz;
   // Stage B stores run 16 lanes across z (128-byte pieces of a column): a 16-lane group takes NPASS = 16 / LB
   // adjacent columns one after the other (LB >= 16: one column per LB lanes)
-  constexpr int LZ = (LB >= 16) ? LB : 16, NPASS = (LB >= 16) ? 1 : 16 / LB;
+  constexpr int LZW = SLAB_LZ, LZ = (LB >= LZW) ? LB : LZW, NPASS = (LB >= LZW) ? 1 : LZW / LB;
   const int qg = (tid / LZ) * NPASS, lz = tid % LZ;
   const double *sl_p =
       (FULL && uv_col && F.sliding != nullptr) ? F.sliding + idx2(P, i_q, P.ys - P.wsl, P.wsl) * 2 : nullptr;
   const long ssl = 2L * (P.xm + 2 * P.wsl);
 
   // Sliding velocity of stage B's column: the LB lanes that share a column hold the values of LB consecutive
-  // rows (lane li: row rbase + block * LB + li) and hand them out by shuffle; the next block is loaded a whole
-  // block ahead, so that rows without ice (~100 cycles each) never wait on a load.
+  // rows (lane li: row rbase + block * LB + li) and hand them out by shuffle; blocks are loaded two blocks
+  // ahead, so that rows without ice never wait on a load.
   const int rbase = max(ra, P.ys), rend = min(rb, P.ys + P.ym); // stage B rows [rbase, rend)
   auto sliding_load = [&](int rho) -> double2 {
     return (sl_p != nullptr && rho < rend) ? __ldg(reinterpret_cast<const double2 *>(sl_p + (long)(rho - (P.ys - P.wsl)) * ssl))
                                            : make_double2(0.0, 0.0);
   };
-  double2 sv_cur = make_double2(0.0, 0.0), sv_nxt = make_double2(0.0, 0.0);
-  if (FULL) sv_cur = sliding_load(rbase + li), sv_nxt = sliding_load(rbase + LB + li);
+  double2 sv_cur = make_double2(0.0, 0.0), sv_nxt = make_double2(0.0, 0.0), sv_nx2 = make_double2(0.0, 0.0);
+  if (FULL) sv_cur = sliding_load(rbase + li), sv_nxt = sliding_load(rbase + LB + li), sv_nx2 = sliding_load(rbase + 2 * LB + li);
 
   double dmax_local = 0.0;
   int hdc_local = 0;
@@ -288,8 +291,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     if (FULL && r >= rbase && r < rend) { // CTA-uniform
       const int j = (r - rbase) % LB;
       if (j == 0 && r > rbase) {
-        sv_cur = sv_nxt;
-        sv_nxt = sliding_load(r + LB + li);
+        sv_cur = sv_nxt, sv_nxt = sv_nx2;
+        sv_nx2 = sliding_load(r + 2 * LB + li); // two blocks ahead: rows without ice pass in well under 100 cycles
       }
       const int src = (lane & ~(LB - 1)) | j;
       sv.x = __shfl_sync(FULLMASK, sv_cur.x, src);
