@@ -269,15 +269,13 @@ def main():
         if multi:                            # SIAFD.cc:498-499
             halo.exchange([("h_x", 1), ("h_y", 1)], 1)
         else:
-            for name in ("h_x", "h_y"):
-                check(lib.siafd_b200_wrap_ghosts(sia.handle, F[name]))
+            check(lib.siafd_b200_wrap_ghosts_many(sia.handle, 2, (C.c_int * 2)(F["h_x"], F["h_y"])))
         check(lib.siafd_b200_compute_flux_velocity(sia.handle, 1 if full else 0, 0.0))
         if full:                             # SIAFD.cc:946-947
             if multi:
                 halo.exchange([("u", 1), ("v", 1)], 2)
             else:
-                for name in ("u", "v"):
-                    check(lib.siafd_b200_wrap_ghosts(sia.handle, F[name]))
+                check(lib.siafd_b200_wrap_ghosts_many(sia.handle, 2, (C.c_int * 2)(F["u"], F["v"])))
         check(lib.siafd_b200_finish(sia.handle))              # error flags + D_max (host sync, as in PISM)
         return global_max(lib.siafd_b200_max_diffusivity(sia.handle), dev)   # SIAFD.cc:748
 

@@ -192,6 +192,8 @@ int siafd_b200_download(siafd_b200_handle *h, int field, double *host);
 /* Periodic self-wrap of a field's ghosts on device (single rank owning the whole domain in
  * the wrapped direction; util/IceGrid.cc:870-872: the DMDA is always periodic). */
 int siafd_b200_wrap_ghosts(siafd_b200_handle *h, int field);
+/* Several fields (1..6) in ONE launch: all four edge and four corner strips of each. */
+int siafd_b200_wrap_ghosts_many(siafd_b200_handle *h, int n, const int *fields);
 /* One direction only: dir 0 = x over the owned rows, dir 1 = y over all columns (x ghosts included).
  * A rank whose periodic neighbour in that direction is itself uses this in place of an exchange. */
 int siafd_b200_wrap_ghosts_dir(siafd_b200_handle *h, int field, int dir);

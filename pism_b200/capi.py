@@ -80,6 +80,7 @@ def _load():
         "siafd_b200_download": (C.c_int, [vp, C.c_int, vp]),
         "siafd_b200_wrap_ghosts": (C.c_int, [vp, C.c_int]),
         "siafd_b200_wrap_ghosts_dir": (C.c_int, [vp, C.c_int, C.c_int]),
+        "siafd_b200_wrap_ghosts_many": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int)]),
         "siafd_b200_halo_count": (i64, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
         "siafd_b200_halo_pack": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "siafd_b200_halo_unpack": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

@@ -694,39 +694,64 @@ int siafd_b200_halo_attach(siafd_b200_handle *h, int field, int dir, void *peer_
   return SIAFD_B200_OK;
 }
 
+// descriptors of the eight strips (4 edges, 4 corners) of field f going to the neighbours (self if !to_peers)
+static int halo_descriptors(siafd_b200_handle *h, int f, int w, bool to_peers, HaloBatch &B) {
+  const siafd_b200_config &c = h->cfg;
+  const FieldMeta m = meta(c, f);
+  if (w < 1 || w > m.width) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "ghost update: bad width %d for field %d", w, f);
+  const int W = m.width;
+  for (int d = 0; d < 8; ++d) {
+    const siafd_b200_handle::Peer &P = h->peers[f][d];
+    if (to_peers && (!P.attached || !h->pad_attached[d])) {
+      return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: field %d / direction %d not attached", f, d);
+    }
+    const bool remote = to_peers && P.base != nullptr;
+    const int dx = HALO_DX[d], dy = HALO_DY[d];
+    HaloDesc &D = B.d[B.n++];
+    D.src = (const double *)h->buf[f];
+    D.dst = remote ? P.base : (double *)h->buf[f];
+    const int pxm = remote ? P.xm : c.xm, pym = remote ? P.ym : c.ym;
+    D.src_row_cells = c.xm + 2 * W, D.dst_row_cells = pxm + 2 * W;
+    D.dof = m.dof, D.pad = 0;
+    // my owned strip facing the neighbour -> the neighbour's ghost cells facing me (local array indices)
+    D.wc = dx == 0 ? c.xm : w, D.hc = dy == 0 ? c.ym : w;
+    D.src_i0 = W + (dx > 0 ? c.xm - w : 0), D.src_j0 = W + (dy > 0 ? c.ym - w : 0);
+    D.dst_i0 = dx > 0 ? W - w : (dx < 0 ? W + pxm : W);
+    D.dst_j0 = dy > 0 ? W - w : (dy < 0 ? W + pym : W);
+  }
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_wrap_ghosts_many(siafd_b200_handle *h, int n, const int *fields) {
+  CU(h, cudaSetDevice(h->device));
+  const siafd_b200_config &c = h->cfg;
+  if (c.xm != c.Mx || c.ym != c.My) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "periodic self-wrap needs a patch spanning the whole domain");
+  }
+  if (n < 1 || n > 6) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "wrap_ghosts_many: 1..6 fields");
+  HaloBatch B;
+  B.n = 0;
+  for (int q = 0; q < n; ++q) {
+    int st = ensure(h, fields[q]);
+    if (st) return st;
+    if ((st = halo_descriptors(h, fields[q], meta(c, fields[q]).width, false, B))) return st;
+  }
+  h->launches += launch_halo_push(B, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
 int siafd_b200_halo_push(siafd_b200_handle *h, int n, const int *fields, const int *widths, int phase) {
   CU(h, cudaSetDevice(h->device));
   if (phase < 0 || phase > 3 || n < 1 || n > 6) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: phase in 0..3 and 1..6 fields");
   }
-  const siafd_b200_config &c = h->cfg;
   HaloBatch B;
   B.n = 0;
   for (int q = 0; q < n; ++q) {
-    const int f = fields[q], w = widths[q];
-    int st = ensure(h, f);
+    int st = ensure(h, fields[q]);
     if (st) return st;
-    const FieldMeta m = meta(c, f);
-    if (w < 1 || w > m.width) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: bad width %d for field %d", w, f);
-    const int W = m.width;
-    for (int d = 0; d < 8; ++d) {
-      const siafd_b200_handle::Peer &P = h->peers[f][d];
-      if (!P.attached || !h->pad_attached[d]) {
-        return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: field %d / direction %d not attached", f, d);
-      }
-      const int dx = HALO_DX[d], dy = HALO_DY[d];
-      HaloDesc &D = B.d[B.n++];
-      D.src = (const double *)h->buf[f];
-      D.dst = P.base ? P.base : (double *)h->buf[f];
-      const int pxm = P.base ? P.xm : c.xm, pym = P.base ? P.ym : c.ym;
-      D.src_row_cells = c.xm + 2 * W, D.dst_row_cells = pxm + 2 * W;
-      D.dof = m.dof, D.pad = 0;
-      // my owned strip facing the neighbour -> the neighbour's ghost cells facing me (local array indices)
-      D.wc = dx == 0 ? c.xm : w, D.hc = dy == 0 ? c.ym : w;
-      D.src_i0 = W + (dx > 0 ? c.xm - w : 0), D.src_j0 = W + (dy > 0 ? c.ym - w : 0);
-      D.dst_i0 = dx > 0 ? W - w : (dx < 0 ? W + pxm : W);
-      D.dst_j0 = dy > 0 ? W - w : (dy < 0 ? W + pym : W);
-    }
+    if ((st = halo_descriptors(h, fields[q], widths[q], true, B))) return st;
   }
   h->launches += launch_halo_push(B, h->stream);
   HaloSignal S;
@@ -982,8 +1007,8 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   // gradient and 2D preparation while the first band is in flight
   if ((st = siafd_b200_compute_gradient(h))) return st;
   if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
-    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_X))) return st;
-    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_Y))) return st;
+    const int hxy[2] = {SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
+    if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
   }
   if ((st = flux_velocity_prepare(h, 1, in->current_time))) return st;
   const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
@@ -1090,13 +1115,13 @@ int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b
   }
   if ((st = siafd_b200_compute_gradient(h))) return st;
   if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
-    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_X))) return st;
-    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_H_Y))) return st;
+    const int hxy[2] = {SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
+    if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
   }
   if ((st = siafd_b200_compute_flux_velocity(h, full_update, in->current_time))) return st;
   if (full_update) { // sia/SIAFD.cc:946-947
-    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_U))) return st;
-    if ((st = siafd_b200_wrap_ghosts(h, SIAFD_B200_F_V))) return st;
+    const int uv[2] = {SIAFD_B200_F_U, SIAFD_B200_F_V};
+    if ((st = siafd_b200_wrap_ghosts_many(h, 2, uv))) return st;
   }
   if (out->memory_space == 0) {
     for (auto &q : outs) {
