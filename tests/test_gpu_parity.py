@@ -38,6 +38,9 @@ CASES = [
     ("dome_64_31_rough_eta", True, False),  # eta gradient over a rough bed
     ("dome_33_13", True, True),             # ragged: strip/segment remainders, Mz < 16
     ("dome_50_17_mahaffy", True, True),
+    ("dome_48_20", True, True),             # even Mz: padded shared-memory columns, 8-byte cp.async row loader
+    ("dome_48_20", False, True),
+    ("dome_24_401", True, True),            # tall grid: the 8-lane-column configuration of the fused kernel
 ]
 
 
@@ -60,6 +63,32 @@ def test_update_matches_oracle(name, full, exact_grad, record_property):
         assert sia.high_diffusivity_count() == run.f.high_diffusivity_counter > 0
     if not full:
         assert sia.velocity_u() is None   # G10: u, v untouched
+
+
+@pytest.mark.parametrize("name,w_sliding", [("dome_96_31", 1), ("C4s", 1), ("C4s_nosmooth", 0), ("dome_33_13", 2)])
+def test_nonzero_sliding_velocity(name, w_sliding):
+    """u = u_b - ... with a sliding velocity that differs at every point (the reference adds it for all Mz levels,
+    SIAFD.cc:935-942), including the columns and rows without ice, where u, v are the sliding velocity alone."""
+    grid, cfg, inputs, gb = cases.case(name)
+    cfg.w_sliding = w_sliding
+    My, Mx = grid.My, grid.Mx
+    jj, ii = np.meshgrid(np.arange(-w_sliding, My + w_sliding), np.arange(-w_sliding, Mx + w_sliding), indexing="ij")
+    sl = np.zeros((My + 2 * w_sliding, Mx + 2 * w_sliding, 2))
+    sl[..., 0] = 1e-6 * (1.0 + np.sin(0.37 * ii) * np.cos(0.11 * jj)) + 1e-9 * (ii + 1000 * jj)
+    sl[..., 1] = -2e-6 * np.cos(0.23 * ii + 0.05 * jj) + 1e-9 * (7 * ii - jj)
+    inputs["sliding"] = np.ascontiguousarray(sl)
+    run = cases.oracle_run(grid, cfg, inputs, gb, full=True)
+    assert run.status == 0
+    for rows in (64, 5):   # long and short row segments: the lane-distributed sliding FIFO wraps several times
+        sia = U.make_sia(grid, cfg, gb)
+        sia.set_tuning(rows_per_cta=rows)
+        U.gpu_update(sia, inputs, True)
+        U.compare_with_oracle(sia, run, cfg, True)
+        # columns without any ice around them carry exactly the sliding velocity
+        u, ub = cases.interior(sia.velocity_u(), cfg.w_uv), cases.interior(sl[..., 0], w_sliding)
+        free = cases.interior(sia.download("thk_smooth"), cfg.w_geom) == 0
+        free &= np.roll(free, 1, 0) & np.roll(free, -1, 0) & np.roll(free, 1, 1) & np.roll(free, -1, 1)
+        assert free.any() and np.array_equal(u[free], np.repeat(ub[free][:, None], grid.Mz, axis=1))
 
 
 def test_age_coupling_matches_oracle():
