@@ -333,7 +333,7 @@ def main():
                 "algorithmic_bytes_per_column": B, "columns_per_launch": patch.xm * patch.ym,
                 "whole_step_frac": B * cols_total / N / (ms / args.steps / 1e3) / 1e9 / peak}
     tr = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and N == 1 and full:
         try:
             roofline["traffic"] = json.load(open(tr)).get("bytes_per_launch_%d" % M)
         except Exception:
