@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--rows-per-cta", type=int, default=0)
     ap.add_argument("--bulk", type=int, default=-1)
+    ap.add_argument("--with-w", action="store_true",
+                    help="also time StressBalance::compute_vertical_velocity (SURVEY 8f N2) after the update; "
+                         "reported under 'vertical_velocity', not part of the metric")
     ap.add_argument("--no-input-exchange", action="store_true",
                     help="skip the per-step width-2 exchange of the inputs' ghosts (N > 1)")
     return ap.parse_args()
@@ -339,6 +342,16 @@ def main():
         except Exception:
             pass
 
+    vertical = None
+    if args.with_w and full and not multi:
+        def w_step():
+            check(lib.siafd_b200_compute_vertical_velocity(sia.handle, 0, 0))
+        ms_w, _ = timed(w_step, args.steps, 3)
+        bw = 24 * Mz  # read u, v once, write w
+        vertical = {"kernel": "k_vertical_velocity", "ms": ms_w / args.steps, "algorithmic_bytes_per_column": bw,
+                    "achieved_GBps": bw * cols_total / (ms_w / args.steps / 1e3) / 1e9,
+                    "frac": bw * cols_total / (ms_w / args.steps / 1e3) / 1e9 / peak}
+
     # ---- end to end through the reference-facing call with HOST buffers ----
     e2e = None
     if not args.no_e2e:
@@ -400,7 +413,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, "%dx%d (PISM DMDA rule)" % (patch.Nx, patch.Ny)),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "D_max": dmax, "halo_bytes_per_step_per_rank": (halo.bytes_sent // max(args.steps + W + 1, 1)) if halo else 0,
+            "clocks": clocks, "D_max": dmax, "vertical_velocity": vertical, "halo_bytes_per_step_per_rank": (halo.bytes_sent // max(args.steps + W + 1, 1)) if halo else 0,
             "halo_transport": "direct stores into CUDA-IPC-mapped neighbour arrays (NVLink), 3 phases/step" if halo else None,
             "input_generation_s": t_gen,
         }

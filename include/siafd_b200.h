@@ -93,7 +93,9 @@ enum {
   SIAFD_B200_F_THETA = 19,      /* scratch 2D, w_geom (m_work_2d_1) */
   SIAFD_B200_F_W_I = 20,
   SIAFD_B200_F_W_J = 21, /* scratch 2D, w_geom: haseloff weights / eta */
-  SIAFD_B200_F_COUNT = 22
+  SIAFD_B200_F_W = 22,          /* vertical velocity, 3D, no ghosts (StressBalance.cc:142) */
+  SIAFD_B200_F_BASAL_MELT = 23, /* basal melt rate (Inputs::basal_melt_rate), 2D, no ghosts */
+  SIAFD_B200_F_COUNT = 24
 };
 
 /* Everything SIAFD's constructor and update() read from Config/IceGrid
@@ -234,6 +236,13 @@ int siafd_b200_set_smoothed_bed(siafd_b200_handle *h, const double *topgsmooth, 
 int siafd_b200_compute_gradient(siafd_b200_handle *h);                 /* SIAFD.cc:137 */
 int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update,
                                      double current_time);             /* SIAFD.cc:141-153 */
+/* SURVEY.md 8(f) N2 -- StressBalance::compute_vertical_velocity (stressbalance/StressBalance.cc:283-424), the next
+ * consumer of u, v: w from incompressibility, w(0) = -basal_melt_rate (0 without one), centered differences with
+ * one-sided ones at ice margins, or first-order "upstream" ones (stress_balance.vertical_velocity_approximation).
+ * Reads the handle's mask, u, v (ghosts valid, i.e. after the wrap / exchange of SIAFD.cc:946-947) and, if
+ * use_basal_melt, SIAFD_B200_F_BASAL_MELT; writes SIAFD_B200_F_W.  Asynchronous on the handle's stream. */
+int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int use_basal_melt);
+
 /* Waits for the stream, then evaluates the reference's error conditions; returns the status
  * (collective callers reduce it over ranks before acting on it, cf. ParallelSection). */
 int siafd_b200_finish(siafd_b200_handle *h);

@@ -1246,4 +1246,100 @@ int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, i
   return worst;
 }
 
+// ---------------------------------------------------------------------------------------
+// StressBalance::compute_vertical_velocity  (src/stressbalance/StressBalance.cc:283-424)
+// the next consumer of u, v.  mask: 2D, ghost width w_geom; u, v: 3D, ghost
+// width w_uv with valid ghosts; basal_melt_rate: owned points only ([ym][xm]) or NULL; w: 3D,
+// owned points only (WITHOUT_GHOSTS, StressBalance.cc:142).
+// ---------------------------------------------------------------------------------------
+int orc_vertical_velocity(const orc_params *p, const double *mask, const double *u, const double *v,
+                          const double *basal_melt_rate, int use_upstream_fd, double *w) {
+  const int Mz = p->Mz, wg = p->w_geom, wuv = p->w_uv;
+  const long nxg = p->xm + 2 * wg, nxu = p->xm + 2 * wuv;
+  const double dx = p->dx, dy = p->dy;
+  std::vector<double> u_x_plus_v_y(Mz);
+  auto M = [&](int i, int j) { return (int)floor(mask[(long)(j - (p->ys - wg)) * nxg + (i - (p->xs - wg))] + 0.5); };
+  auto icy = [&](int i, int j) { const int m = M(i, j); return m == 2 || m == 3; };
+  auto ice_free = [&](int i, int j) { return !icy(i, j); };
+  auto col = [&](const double *a, int i, int j) {
+    return a + ((long)(j - (p->ys - wuv)) * nxu + (i - (p->xs - wuv))) * Mz;
+  };
+  for (int j = p->ys; j < p->ys + p->ym; ++j) {
+    for (int i = p->xs; i < p->xs + p->xm; ++i) {
+      double *w_ij = w + ((long)(j - p->ys) * p->xm + (i - p->xs)) * Mz;
+      const double *u_w = col(u, i - 1, j), *u_ij = col(u, i, j), *u_e = col(u, i + 1, j);
+      const double *v_s = col(v, i, j - 1), *v_ij = col(v, i, j), *v_n = col(v, i, j + 1);
+      double west = 1.0, east = 1.0, south = 1.0, north = 1.0;
+      double D_x = 0, D_y = 0;
+      {
+        if (use_upstream_fd) {
+          const double uw = 0.5 * (u_w[0] + u_ij[0]), ue = 0.5 * (u_ij[0] + u_e[0]);
+          if (uw > 0.0 and ue >= 0.0) {
+            west = 1.0;
+            east = 0.0;
+          } else if (uw <= 0.0 and ue < 0.0) {
+            west = 0.0;
+            east = 1.0;
+          } else {
+            west = 1.0;
+            east = 1.0;
+          }
+        }
+        if ((icy(i, j) and ice_free(i + 1, j)) or (ice_free(i, j) and icy(i + 1, j))) {
+          east = 0;
+        }
+        if ((icy(i, j) and ice_free(i - 1, j)) or (ice_free(i, j) and icy(i - 1, j))) {
+          west = 0;
+        }
+        if (east + west > 0) {
+          D_x = 1.0 / (dx * (east + west));
+        } else {
+          D_x = 0.0;
+        }
+      }
+      {
+        if (use_upstream_fd) {
+          const double vs = 0.5 * (v_s[0] + v_ij[0]), vn = 0.5 * (v_ij[0] + v_n[0]);
+          if (vs > 0.0 and vn >= 0.0) {
+            south = 1.0;
+            north = 0.0;
+          } else if (vs <= 0.0 and vn < 0.0) {
+            south = 0.0;
+            north = 1.0;
+          } else {
+            south = 1.0;
+            north = 1.0;
+          }
+        }
+        if ((icy(i, j) and ice_free(i, j + 1)) or (ice_free(i, j) and icy(i, j + 1))) {
+          north = 0;
+        }
+        if ((icy(i, j) and ice_free(i, j - 1)) or (ice_free(i, j) and icy(i, j - 1))) {
+          south = 0;
+        }
+        if (north + south > 0) {
+          D_y = 1.0 / (dy * (north + south));
+        } else {
+          D_y = 0.0;
+        }
+      }
+      for (int k = 0; k < Mz; ++k) {
+        double u_x = D_x * (west * (u_ij[k] - u_w[k]) + east * (u_e[k] - u_ij[k])),
+               v_y = D_y * (south * (v_ij[k] - v_s[k]) + north * (v_n[k] - v_ij[k]));
+        u_x_plus_v_y[k] = u_x + v_y;
+      }
+      if (basal_melt_rate != NULL) {
+        w_ij[0] = -basal_melt_rate[(long)(j - p->ys) * p->xm + (i - p->xs)];
+      } else {
+        w_ij[0] = 0.0;
+      }
+      for (int k = 1; k < Mz; ++k) {
+        const double dz = p->z[k] - p->z[k - 1];
+        w_ij[k] = w_ij[k - 1] - (0.5 * dz) * (u_x_plus_v_y[k] + u_x_plus_v_y[k - 1]);
+      }
+    }
+  }
+  return ORC_OK;
+}
+
 } // extern "C"

@@ -169,6 +169,10 @@ int orc_siafd_flux_velocity(const orc_params *p, orc_fields *f, int full); /* SI
 /* Convenience for a single whole-domain patch: gradient, wrap, flux+velocity, wrap. */
 int orc_siafd_update_single(const orc_params *p, orc_fields *f, int full);
 /* Many independent patches at once, OpenMP over patches (CPU baseline). */
+/* StressBalance::compute_vertical_velocity (StressBalance.cc:283-424): mask w_geom, u / v w_uv (ghosts valid),
+ * basal_melt_rate owned-only or NULL, w owned-only. */
+int orc_vertical_velocity(const orc_params *p, const double *mask, const double *u, const double *v,
+                          const double *basal_melt_rate, int use_upstream_fd, double *w);
 int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, int nthreads);
 
 #ifdef __cplusplus

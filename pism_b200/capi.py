@@ -12,7 +12,7 @@ OK, ERR_NEGATIVE_THICKNESS, ERR_OMEGA_NEGATIVE, ERR_HEIGHT_BELOW_BASE, ERR_HEIGH
 ERR_DIFFUSIVITY, ERR_BAD_CONFIG, ERR_CUDA, ERR_BAD_ARGUMENT = 5, 6, 7, 8
 
 FIELDS = ["surface", "thickness", "mask", "bed", "enthalpy", "age", "sliding", "topgsmooth", "maxtl", "C2", "C3",
-          "C4", "h_x", "h_y", "D", "flux", "u", "v", "thk_smooth", "theta", "w_i", "w_j"]
+          "C4", "h_x", "h_y", "D", "flux", "u", "v", "thk_smooth", "theta", "w_i", "w_j", "w", "basal_melt"]
 F = {name: i for i, name in enumerate(FIELDS)}
 
 _i32, _f64, _pd = C.c_int32, C.c_double, C.POINTER(C.c_double)
@@ -93,6 +93,7 @@ def _load():
         "siafd_b200_set_smoothed_bed": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
         "siafd_b200_compute_gradient": (C.c_int, [vp]),
         "siafd_b200_compute_flux_velocity": (C.c_int, [vp, C.c_int, C.c_double]),
+        "siafd_b200_compute_vertical_velocity": (C.c_int, [vp, C.c_int, C.c_int]),
         "siafd_b200_finish": (C.c_int, [vp]),
         "siafd_b200_max_diffusivity": (C.c_double, [vp]),
         "siafd_b200_high_diffusivity_count": (C.c_int, [vp]),

@@ -124,6 +124,10 @@ FieldMeta meta(const siafd_b200_config &c, int f) {
   case SIAFD_B200_F_U:
   case SIAFD_B200_F_V:
     return {c.w_uv, c.Mz};
+  case SIAFD_B200_F_W:
+    return {0, c.Mz};
+  case SIAFD_B200_F_BASAL_MELT:
+    return {0, 1};
   default:
     return {-1, 0};
   }
@@ -910,6 +914,25 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, doub
   int st = flux_velocity_prepare(h, full_update, current_time);
   if (st) return st;
   return flux_velocity_launch(h, full_update, 0, -1);
+}
+
+int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int use_basal_melt) {
+  CU(h, cudaSetDevice(h->device));
+  const int need[] = {SIAFD_B200_F_MASK, SIAFD_B200_F_U, SIAFD_B200_F_V, SIAFD_B200_F_W};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  if (use_basal_melt) {
+    int st = ensure(h, SIAFD_B200_F_BASAL_MELT);
+    if (st) return st;
+  }
+  h->launches += launch_vertical_velocity(h->P, (const double *)h->buf[SIAFD_B200_F_MASK], (const double *)h->buf[SIAFD_B200_F_U],
+                                          (const double *)h->buf[SIAFD_B200_F_V],
+                                          use_basal_melt ? (const double *)h->buf[SIAFD_B200_F_BASAL_MELT] : nullptr,
+                                          upstream, h->d_z, (double *)h->buf[SIAFD_B200_F_W], h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
 }
 
 int siafd_b200_finish(siafd_b200_handle *h) {

@@ -301,6 +301,81 @@ __global__ void k_halo_wait(const unsigned long long *slots, unsigned long long 
 }
 
 // ---------------------------------------------------------------------------------------------
+// StressBalance::compute_vertical_velocity, stressbalance/StressBalance.cc:283-424.
+// One warp per column, lanes across z: the six columns it reads (u west / centre / east, v south / centre /
+// north) and the one it writes are contiguous in z, so every access is coalesced; the running integral
+// w[k] = w[k-1] - dz/2 (s[k] + s[k-1]), s = u_x + v_y, is a warp scan with a carry between 32-level chunks.
+// HBM-bound: 24 Mz bytes per column (u, v read once -- the neighbours come from L2 -- and w written).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_vertical_velocity(const __grid_constant__ DP P, const double *__restrict__ mask,
+                                    const double *__restrict__ u, const double *__restrict__ v,
+                                    const double *__restrict__ bmr, int upstream, const double *__restrict__ z,
+                                    double *__restrict__ w) {
+  const long col = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (col >= (long)P.xm * P.ym) {
+    return; // whole warps leave together
+  }
+  const int i = P.xs + (int)(col % P.xm), j = P.ys + (int)(col / P.xm);
+  const int Mz = P.Mz;
+  const int M0 = mask_int(mask[idx2(P, i, j, P.wg)]), Me = mask_int(mask[idx2(P, i + 1, j, P.wg)]),
+            Mw = mask_int(mask[idx2(P, i - 1, j, P.wg)]), Mn = mask_int(mask[idx2(P, i, j + 1, P.wg)]),
+            Ms = mask_int(mask[idx2(P, i, j - 1, P.wg)]);
+  const double *u_ij = u + idx2(P, i, j, P.wuv) * Mz, *u_w = u_ij - Mz, *u_e = u_ij + Mz;
+  const double *v_ij = v + idx2(P, i, j, P.wuv) * Mz;
+  const long rowuv = (long)(P.xm + 2 * P.wuv) * Mz;
+  const double *v_s = v_ij - rowuv, *v_n = v_ij + rowuv;
+  double west = 1.0, east = 1.0, south = 1.0, north = 1.0;
+  if (upstream) { // :336-350, :372-386 (basal velocities decide the direction)
+    const double uw = 0.5 * (u_w[0] + u_ij[0]), ue = 0.5 * (u_ij[0] + u_e[0]);
+    if (uw > 0.0 && ue >= 0.0) {
+      west = 1.0, east = 0.0;
+    } else if (uw <= 0.0 && ue < 0.0) {
+      west = 0.0, east = 1.0;
+    }
+    const double vs = 0.5 * (v_s[0] + v_ij[0]), vn = 0.5 * (v_ij[0] + v_n[0]);
+    if (vs > 0.0 && vn >= 0.0) {
+      south = 1.0, north = 0.0;
+    } else if (vs <= 0.0 && vn < 0.0) {
+      south = 0.0, north = 1.0;
+    }
+  }
+  // one-sided differences at ice margins (:352-357, :388-393)
+  if ((m_icy(M0) && m_ice_free(Me)) || (m_ice_free(M0) && m_icy(Me))) east = 0;
+  if ((m_icy(M0) && m_ice_free(Mw)) || (m_ice_free(M0) && m_icy(Mw))) west = 0;
+  if ((m_icy(M0) && m_ice_free(Mn)) || (m_ice_free(M0) && m_icy(Mn))) north = 0;
+  if ((m_icy(M0) && m_ice_free(Ms)) || (m_ice_free(M0) && m_icy(Ms))) south = 0;
+  const double D_x = (east + west > 0) ? 1.0 / (P.dx * (east + west)) : 0.0;
+  const double D_y = (north + south > 0) ? 1.0 / (P.dy * (north + south)) : 0.0;
+  double *w_ij = w + col * Mz;
+  double wacc = (bmr != nullptr) ? -bmr[col] : 0.0; // w at the base (:409-413)
+  double carry = 0.0;                              // s at the last level of the previous chunk
+  for (int k0 = 0; k0 < Mz; k0 += 32) {
+    const int k = k0 + lane;
+    const bool valid = k < Mz;
+    double sk = 0.0, hdz = 0.0;
+    if (valid) {
+      const double u_x = D_x * (west * (u_ij[k] - u_w[k]) + east * (u_e[k] - u_ij[k]));
+      const double v_y = D_y * (south * (v_ij[k] - v_s[k]) + north * (v_n[k] - v_ij[k]));
+      sk = u_x + v_y;
+      hdz = (k > 0) ? 0.5 * (z[k] - z[k - 1]) : 0.0;
+    }
+    double sprev = __shfl_up_sync(FULLMASK, sk, 1);
+    if (lane == 0) sprev = carry;
+    double t = -hdz * (sk + sprev); // w[k] - w[k-1] (:418-422); 0 at k = 0 and past the top
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double y = __shfl_up_sync(FULLMASK, t, d);
+      t += (lane >= d) ? y : 0.0;
+    }
+    const double wk = wacc + t;
+    if (valid) w_ij[k] = wk;
+    wacc = __shfl_sync(FULLMASK, wk, 31);
+    carry = __shfl_sync(FULLMASK, sk, 31);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // GeometryCalculator::compute, util/Mask.hh:96-133
 // ---------------------------------------------------------------------------------------------
 __global__ void k_geometry(const __grid_constant__ DP P, long n, const double *sea_level, const double *bed,
@@ -438,6 +513,14 @@ int launch_halo_signal(const HaloSignal &S, cudaStream_t s) {
 }
 int launch_halo_wait(const unsigned long long *slots8, unsigned long long value, cudaStream_t s) {
   k_halo_wait<<<1, 32, 0, s>>>(slots8, value);
+  return 1;
+}
+
+int launch_vertical_velocity(const DP &P, const double *mask, const double *u, const double *v, const double *bmr,
+                             int upstream, const double *z, double *w, cudaStream_t s) {
+  const long threads = (long)P.xm * P.ym * 32;
+  if (threads <= 0) return 0;
+  k_vertical_velocity<<<nblk(threads, 256), 256, 0, s>>>(P, mask, u, v, bmr, upstream, z, w);
   return 1;
 }
 

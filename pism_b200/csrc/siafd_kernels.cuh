@@ -60,6 +60,9 @@ int launch_halo_push(const HaloBatch &B, cudaStream_t s);
 int launch_halo_signal(const HaloSignal &S, cudaStream_t s);
 int launch_halo_wait(const unsigned long long *slots8, unsigned long long value, cudaStream_t s);
 
+// StressBalance::compute_vertical_velocity (stressbalance/StressBalance.cc:283-424)
+int launch_vertical_velocity(const DP &P, const double *mask, const double *u, const double *v, const double *bmr,
+                             int upstream, const double *z, double *w, cudaStream_t s);
 int launch_geometry(const DP &P, long n, const double *sea_level, const double *bed, const double *thk, double *mask_out,
                     double *surf_out, cudaStream_t s);
 int launch_flow_n(const DP &P, long n, const double *stress, const double *E, const double *p, const double *gs,

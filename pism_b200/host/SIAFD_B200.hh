@@ -170,5 +170,51 @@ private:
   IceModelVec2Stag m_h_x, m_h_y, m_D;
 };
 
+// The SIA-only StressBalance container (stressbalance/StressBalance.cc:140-212 with ZeroSliding as the shallow
+// stress balance, factory.cc:59-64): update() runs the modifier and, on a full update, the vertical velocity
+// from incompressibility (StressBalance.cc:283-424) on the device fields the modifier left
+// there.  Strain heating and the CFL reductions (8(f) N3) are not part of it yet.
+class StressBalance_B200 {
+public:
+  StressBalance_B200(IceGrid::ConstPtr g, SIAFD_B200 *modifier)
+      : m_grid(g), m_modifier(modifier), m_zero_sliding(g, "velbar", WITH_GHOSTS, 1), m_w(g, "wvel_rel", WITHOUT_GHOSTS) {
+    m_zero_sliding.set(0.0); // ZeroSliding
+  }
+  ~StressBalance_B200() { delete m_modifier; } // StressBalance.cc:157-160
+  void init() { m_modifier->init(); }
+  void update(const Inputs &inputs, bool full_update) {
+    m_modifier->update(m_zero_sliding, inputs, full_update);
+    if (full_update) {
+      siafd_b200_handle *h = m_modifier->handle();
+      int status = SIAFD_B200_OK;
+      if (inputs.basal_melt_rate) {
+        status = siafd_b200_upload(h, SIAFD_B200_F_BASAL_MELT, inputs.basal_melt_rate->get_array());
+      }
+      const bool upstream = m_grid->config()->get_string("stress_balance.vertical_velocity_approximation") == "upstream";
+      if (status == SIAFD_B200_OK) {
+        status = siafd_b200_compute_vertical_velocity(h, upstream ? 1 : 0, inputs.basal_melt_rate ? 1 : 0);
+      }
+      if (status == SIAFD_B200_OK) {
+        status = siafd_b200_download(h, SIAFD_B200_F_W, m_w.get_array());
+      }
+      if (status != SIAFD_B200_OK) {
+        throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(h));
+      }
+    }
+  }
+  const IceModelVec3 &velocity_u() const { return m_modifier->velocity_u(); }
+  const IceModelVec3 &velocity_v() const { return m_modifier->velocity_v(); }
+  const IceModelVec3 &velocity_w() const { return m_w; }
+  const IceModelVec2Stag &diffusive_flux() { return m_modifier->diffusive_flux(); }
+  double max_diffusivity() const { return m_modifier->max_diffusivity(); }
+  const SIAFD_B200 *modifier() const { return m_modifier; }
+
+private:
+  IceGrid::ConstPtr m_grid;
+  SIAFD_B200 *m_modifier;
+  IceModelVec2V m_zero_sliding;
+  IceModelVec3 m_w;
+};
+
 } // namespace stressbalance
 } // namespace pism

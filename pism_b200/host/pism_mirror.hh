@@ -82,7 +82,9 @@ public:
              {"time.eemian_end", -114500.0 * secpera},
              {"time.holocene_start", -11000.0 * secpera},
              {"geometry.ice_free_thickness_standard", 0.01}};
-    m_str = {{"stress_balance.sia.flow_law", "gpbld"}, {"stress_balance.sia.surface_gradient_method", "haseloff"}};
+    m_str = {{"stress_balance.sia.flow_law", "gpbld"},
+             {"stress_balance.sia.surface_gradient_method", "haseloff"},
+             {"stress_balance.vertical_velocity_approximation", "centered"}};
     m_flag = {{"stress_balance.sia.limit_diffusivity", false},
               {"stress_balance.sia.grain_size_age_coupling", false},
               {"stress_balance.sia.e_age_coupling", false},
@@ -310,9 +312,10 @@ namespace stressbalance {
 // StressBalance.hh:41-65 (only the members SIAFD reads)
 class Inputs {
 public:
-  Inputs() : geometry(NULL), new_bed_elevation(true), enthalpy(NULL), age(NULL) {} // StressBalance.cc:36-46
+  Inputs() : geometry(NULL), new_bed_elevation(true), basal_melt_rate(NULL), enthalpy(NULL), age(NULL) {} // StressBalance.cc:36-46
   const Geometry *geometry;
   bool new_bed_elevation;
+  const IceModelVec2S *basal_melt_rate; // WITHOUT_GHOSTS; may be NULL
   const IceModelVec3 *enthalpy;
   const IceModelVec3 *age;
 };

@@ -224,6 +224,21 @@ class SIAFD(SSB_Modifier):
             self.m_u, self.m_v = arrs["u"], arrs["v"]
         self._check(status)
 
+    # -- the next consumer of u, v (a StressBalance member in the reference) --------------
+    def compute_vertical_velocity(self, basal_melt_rate=None, upstream=False):
+        """StressBalance::compute_vertical_velocity (StressBalance.cc:283-424) from the u, v, mask of the last
+        full update (still resident on the device, ghosts valid).  basal_melt_rate: owned points [ym, xm] or
+        None.  Returns w on the owned points, [ym, xm, Mz] (WITHOUT_GHOSTS, StressBalance.cc:142)."""
+        if basal_melt_rate is not None:
+            self.upload("basal_melt", basal_melt_rate)
+        self._check(lib.siafd_b200_compute_vertical_velocity(self._h, 1 if upstream else 0,
+                                                             0 if basal_melt_rate is None else 1))
+        self.m_w = self.download("w")
+        return self.m_w
+
+    def velocity_w(self):
+        return getattr(self, "m_w", None)
+
     # SIAFD.cc:963-977
     def surface_gradient_x(self):
         return self.m_h_x

@@ -64,10 +64,11 @@ void setInitStateF(const IceGrid &grid, IceModelVec2S &bed, IceModelVec2CellType
   enthalpy.update_ghosts();
 }
 
-// siafd_test.cc:105-151 (u and v only: the vertical velocity is outside this path)
+// siafd_test.cc:105-151
 void computeSurfaceVelocityErrors(const IceGrid &grid, const IceModelVec2S &ice_thickness, const IceModelVec3 &u3,
-                                  const IceModelVec3 &v3, double &gmaxUerr, double &gavUerr) {
-  double maxUerr = 0.0, avUerr = 0.0;
+                                  const IceModelVec3 &v3, const IceModelVec3 &w3, double &gmaxUerr, double &gavUerr,
+                                  double &gmaxWerr, double &gavWerr) {
+  double maxUerr = 0.0, avUerr = 0.0, maxWerr = 0.0, avWerr = 0.0;
   const double LforFG = 750000;
   for (int j = 0; j < grid.ym(); ++j) {
     for (int i = 0; i < grid.xm(); ++i) {
@@ -80,11 +81,16 @@ void computeSurfaceVelocityErrors(const IceGrid &grid, const IceModelVec2S &ice_
         const double Uerr = sqrt(du * du + dv * dv);
         maxUerr = std::max(maxUerr, Uerr);
         avUerr += Uerr;
+        const double Werr = fabs(w3.getValZ(i, j, H) - F.w[0]);
+        maxWerr = std::max(maxWerr, Werr);
+        avWerr += Werr;
       }
     }
   }
   gmaxUerr = maxUerr;
   gavUerr = avUerr / (grid.Mx() * grid.My());
+  gmaxWerr = maxWerr;
+  gavWerr = avWerr / (grid.Mx() * grid.My());
 }
 
 } // namespace
@@ -112,7 +118,10 @@ int main(int argc, char *argv[]) {
     Geometry geometry(grid);
     geometry.sea_level_elevation.set(0.0);
 
-    SIAFD_B200 sia(grid);
+    // stress_balance de-allocates sia (siafd_test.cc:340-346: StressBalance(grid, ZeroSliding, SIAFD))
+    SIAFD_B200 *sia_p = new SIAFD_B200(grid);
+    StressBalance_B200 stress_balance(grid, sia_p);
+    SIAFD_B200 &sia = *sia_p;
     IceModelVec2V no_sliding(grid, "velbar", WITH_GHOSTS, 1); // ZeroSliding: identically zero
     no_sliding.set(0.0);
 
@@ -126,19 +135,20 @@ int main(int argc, char *argv[]) {
         geometry.cell_type(i, j) = geometry.ice_thickness(i, j) > H_min ? MASK_GROUNDED : MASK_ICE_FREE_BEDROCK;
     geometry.cell_type.update_ghosts();
 
-    sia.init();
+    stress_balance.init();
     Inputs inputs;
     inputs.geometry = &geometry;
     inputs.enthalpy = &enthalpy;
     inputs.age = NULL;
 
-    sia.update(no_sliding, inputs, true);
+    stress_balance.update(inputs, true);
 
-    double maxUerr, avUerr;
-    computeSurfaceVelocityErrors(*grid, geometry.ice_thickness, sia.velocity_u(), sia.velocity_v(), maxUerr, avUerr);
+    double maxUerr, avUerr, maxWerr, avWerr;
+    computeSurfaceVelocityErrors(*grid, geometry.ice_thickness, stress_balance.velocity_u(), stress_balance.velocity_v(),
+                                 stress_balance.velocity_w(), maxUerr, avUerr, maxWerr, avWerr);
     const double secpera = 365.242198781 * 86400.0;
-    printf("surf vels :     maxUvec      avUvec\n");
-    printf("           %12.6f%12.6f\n", maxUerr * secpera, avUerr * secpera);
+    printf("surf vels :     maxUvec      avUvec        maxW         avW\n");
+    printf("           %12.6f%12.6f%12.6f%12.6f\n", maxUerr * secpera, avUerr * secpera, maxWerr * secpera, avWerr * secpera);
     double sumD = 0.0, sumQ = 0.0, sumU = 0.0;
     for (int j = 0; j < grid->ym(); ++j)
       for (int i = 0; i < grid->xm(); ++i) {

@@ -101,6 +101,7 @@ def lib():
         L.orc_siafd_flux_velocity.argtypes = [PP, FP, C.c_int]
         L.orc_siafd_update_single.argtypes = [PP, FP, C.c_int]
         L.orc_siafd_update_many.argtypes = [C.c_int, PP, FP, C.c_int, C.c_int]
+        L.orc_vertical_velocity.argtypes = [PP, _pd, _pd, _pd, _pd, C.c_int, _pd]
         _lib = L
     return _lib
 

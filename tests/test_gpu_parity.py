@@ -91,6 +91,35 @@ def test_nonzero_sliding_velocity(name, w_sliding):
         assert free.any() and np.array_equal(u[free], np.repeat(ub[free][:, None], grid.Mz, axis=1))
 
 
+@pytest.mark.parametrize("name,upstream,melt", [("C2", False, False), ("C4s", False, True), ("C4s", True, True),
+                                                ("dome_96_31", True, False), ("dome_33_13", False, True),
+                                                ("dome_64_41_quadratic", False, False)])
+def test_vertical_velocity_matches_oracle(name, upstream, melt):
+    """SURVEY 8(f) N2: StressBalance::compute_vertical_velocity (StressBalance.cc:283-424) on the u, v of a full
+    update, against the oracle run on the oracle's own u, v: centered and upstream differences, one-sided at ice
+    margins (all four mask values in C4s), with and without a basal melt rate, unequal dz."""
+    grid, cfg, inputs, gb = cases.case(name)
+    run = cases.oracle_run(grid, cfg, inputs, gb, full=True)
+    assert run.status == 0
+    p = run.p
+    for a in (run.a["u"], run.a["v"]):  # the ghost exchange of SIAFD.cc:946-947
+        O.lib().orc_wrap_ghosts(grid.Mx, grid.My, cfg.w_uv, grid.Mz, O.dptr(a))
+    bmr = None
+    if melt:
+        jj, ii = np.meshgrid(np.arange(grid.My), np.arange(grid.Mx), indexing="ij")
+        bmr = np.ascontiguousarray(1e-9 * (1.0 + np.sin(0.3 * ii) * np.cos(0.2 * jj)))
+    w_o = np.zeros((grid.My, grid.Mx, grid.Mz))
+    st = O.lib().orc_vertical_velocity(C.byref(p), O.dptr(run.a["mask"]), O.dptr(run.a["u"]), O.dptr(run.a["v"]),
+                                       O.dptr(bmr) if melt else None, 1 if upstream else 0, O.dptr(w_o))
+    assert st == 0
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, True)
+    w_g = sia.compute_vertical_velocity(bmr, upstream)
+    assert np.max(np.abs(w_o)) > 0
+    assert cases.rel_max(w_g, w_o) <= U.TOL
+    assert np.array_equal(w_g[..., 0], -bmr if melt else np.zeros((grid.My, grid.Mx)))  # w at the base, exactly
+
+
 def test_age_coupling_matches_oracle():
     """e_age_coupling and grain_size_age_coupling (SIAFD.cc:649-675) with the gk law."""
     grid, cfg, inputs, gb = cases.case("dome_64_31_gk")
