@@ -175,6 +175,20 @@ int orc_vertical_velocity(const orc_params *p, const double *mask, const double 
                           const double *basal_melt_rate, int use_upstream_fd, double *w);
 int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, int nthreads);
 
+/* SURVEY.md 8(f) N1 / N3 (mass_oracle.cc): GeometryEvolution::flow_step + apply_flux_divergence
+ * (geometry/GeometryEvolution.cc:241-350), source_term_step + apply_mass_fluxes (:327-390, :1005-1076) and the CFL
+ * reductions (stressbalance/timestepping.cc:42-153).  Array conventions in mass_oracle.cc. */
+int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, const double *bed, double *thickness,
+                       const double *velocity, const double *velocity_bc_mask, const double *thickness_bc_mask,
+                       const double *Q, double *flux_divergence, double *thickness_change,
+                       double *conservation_error);
+int orc_mass_source_step(const orc_params *p, double dt, double ice_density, int use_bmr, double *thickness,
+                         const double *mask, const double *thickness_bc_mask, const double *smb_flux,
+                         const double *basal_melt_rate, double *effective_SMB, double *effective_BMB);
+int orc_cfl_3d(const orc_params *p, double max_dt_seconds, const double *thickness, const double *mask,
+               const double *u3, const double *v3, const double *w3, double *out);
+int orc_cfl_2d(const orc_params *p, double max_dt_seconds, const double *mask, const double *velocity, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,8 +19,9 @@ def exactC(t, r):
     n, H0, R0 = 3.0, 3600.0, 750000.0
     lam, alpha, beta = 5.0, -1.0, 2.0
     t0 = 15208.0 * SperA
+    t = np.float64(t)  # t = 0: pow(0, -beta) = inf as in C, and r < Rmargin = 0 is false everywhere
     Rmargin = R0 * (t / t0) ** beta
-    with np.errstate(invalid="ignore"):
+    with np.errstate(all="ignore"):
         inner = 1.0 - ((t / t0) ** (-beta) * (r / R0)) ** ((n + 1) / n)
         H = np.where(r < Rmargin, H0 * (t / t0) ** (-alpha) * np.where(inner > 0, inner, 0.0) ** (n / (2 * n + 1)), 0.0)
     if t > 0.1 * SperA:
@@ -29,6 +30,20 @@ def exactC(t, r):
         Rm = R0 * (0.1 * SperA / t0) ** beta
         M = np.where(r < Rm, 5 * H0 / t0, 0.0)
     return H, M
+
+
+def exactB(t, r):
+    """H(t, r), M = 0 of Test B, the Halfar solution (exactTestsABCD.c:63-85). t in seconds."""
+    r = np.asarray(r, dtype=np.float64)
+    n, H0, R0 = 3.0, 3600.0, 750000.0
+    alpha, beta = 1.0 / 9.0, 1.0 / 18.0
+    t0 = 422.45 * SperA
+    t = np.float64(t)
+    Rmargin = R0 * (t / t0) ** beta
+    with np.errstate(all="ignore"):
+        inner = 1.0 - ((t / t0) ** (-beta) * (r / R0)) ** ((n + 1) / n)
+        H = np.where(r < Rmargin, H0 * (t / t0) ** (-alpha) * np.where(inner > 0, inner, 0.0) ** (n / (2 * n + 1)), 0.0)
+    return H, np.zeros_like(H)
 
 
 def _p3(x):

@@ -60,7 +60,10 @@ def case(name, patch=None):
     gb = None
     if name.startswith("C1"):  # pismv -test C: pismv.cc:96-102, iceCompModel.cc:65-124
         size = 61 if "_" not in name or not name.split("_")[-1].isdigit() else int(name.split("_")[-1])
-        grid = G.Grid(size, size, 31, 1000e3, 1000e3, 4000.0)
+        # pismv's default levels are QUADRATIC: pismv_grid_defaults sets EQUAL (pismv.cc:82) but
+        # vertical_grid_from_options (pismv.cc:155, IceGrid.cc:1289-1296) recomputes them with the configuration's
+        # grid.ice_vertical_spacing = "quadratic", lambda = 4 (the golden rows of test_15.sh only reproduce this way)
+        grid = G.Grid(size, size, 31, 1000e3, 1000e3, 4000.0, spacing="equal" if "equal" in name else "quadratic")
         grad = "haseloff"
         for g in ("mahaffy", "eta", "haseloff"):
             if g in name:
@@ -70,7 +73,8 @@ def case(name, patch=None):
         inputs = S.test_C_state(grid, patch or grid.whole(), cfg)
     elif name.startswith("C2"):  # pismv -test G: pismv.cc:103-110; arr; cold converter
         M = {"C2": (121, 61), "C2s": (41, 31), "C2t": (31, 21)}[name.split("_")[0]]
-        grid = G.Grid(M[0], M[0], M[1], 900e3, 900e3, 4000.0)
+        # full-size C2 uses pismv's quadratic levels (see C1); the scaled-down C2s / C2t keep equal ones (frozen fixture)
+        grid = G.Grid(M[0], M[0], M[1], 900e3, 900e3, 4000.0, spacing="quadratic" if name.split("_")[0] == "C2" else "equal")
         cfg = Cfg(flow_law="arr", smoother_range=0.0, fl_e=1.0, dry_simulation=1, **cold_converter())
         inputs = S.test_FG_state(grid, patch or grid.whole(), cfg, t_years=500.0, Cp=200.0)
     elif name.startswith("F"):  # siafd_test.cc: Test F, Lx = Ly = 900 km, Lz = 4000, arr, cold converter

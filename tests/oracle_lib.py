@@ -58,8 +58,8 @@ class Fields(C.Structure):
 
 
 def build(force=False):
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(
-            os.path.join(ORACLE_DIR, "siafd_oracle.cc")):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("siafd_oracle.cc", "mass_oracle.cc", "siafd_oracle.h")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL)
     return LIB
 
@@ -102,6 +102,10 @@ def lib():
         L.orc_siafd_update_single.argtypes = [PP, FP, C.c_int]
         L.orc_siafd_update_many.argtypes = [C.c_int, PP, FP, C.c_int, C.c_int]
         L.orc_vertical_velocity.argtypes = [PP, _pd, _pd, _pd, _pd, C.c_int, _pd]
+        L.orc_mass_flow_step.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
+        L.orc_mass_source_step.argtypes = [PP, _f64, _f64, C.c_int, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
+        L.orc_cfl_3d.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd]
+        L.orc_cfl_2d.argtypes = [PP, _f64, _pd, _pd, _pd]
         _lib = L
     return _lib
 
