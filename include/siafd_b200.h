@@ -20,6 +20,12 @@
  *   SSB_Modifier::diffusive_flux / velocity_u / velocity_v     output pointers of siafd_b200_update
  *   SIAFD::surface_gradient_x/y, diffusivity  SIAFD.cc:963-973 output pointers (h_x, h_y, D)
  *   GeometryCalculator::compute  util/Mask.hh:96-133           siafd_b200_geometry_compute
+ *   StressBalance::compute_vertical_velocity  StressBalance.cc:283-424   siafd_b200_compute_vertical_velocity
+ *   max_timestep_cfl_3d / _2d  stressbalance/timestepping.cc:42-153      siafd_b200_cfl
+ *   GeometryEvolution::flow_step + apply_flux_divergence  geometry/GeometryEvolution.cc:241-350
+ *                                                              siafd_b200_mass_flow_step
+ *   GeometryEvolution::source_term_step + apply_mass_fluxes  :327-390    siafd_b200_mass_source_step
+ *   Geometry::ensure_consistency  geometry/Geometry.cc:121-187 siafd_b200_ensure_consistency
  *
  * Array layout is PISM's DMDA local (ghosted) layout, unchanged: [j][i][dof] with dof
  * fastest (util/IceModelVec_inline.hh:28-40); a 3D field is dof = Mz (util/iceModelVec3.cc:85);
@@ -95,7 +101,17 @@ enum {
   SIAFD_B200_F_W_J = 21, /* scratch 2D, w_geom: haseloff weights / eta */
   SIAFD_B200_F_W = 22,          /* vertical velocity, 3D, no ghosts (StressBalance.cc:142) */
   SIAFD_B200_F_BASAL_MELT = 23, /* basal melt rate (Inputs::basal_melt_rate), 2D, no ghosts */
-  SIAFD_B200_F_COUNT = 24
+  /* 24..32: the mass-continuity consumer, geometry/GeometryEvolution.cc */
+  SIAFD_B200_F_SEA_LEVEL = 24,   /* Geometry::sea_level_elevation, 2D, w_geom (never uploaded = 0) */
+  SIAFD_B200_F_SMB = 25,         /* surface mass balance rate [kg m-2 s-1], 2D, no ghosts */
+  SIAFD_B200_F_THK_CHANGE = 26,  /* GeometryEvolution::thickness_change_due_to_flow, 2D, no ghosts */
+  SIAFD_B200_F_FLUX_DIV = 27,    /* GeometryEvolution::flux_divergence, 2D, no ghosts */
+  SIAFD_B200_F_CONS_ERR = 28,    /* GeometryEvolution::conservation_error, 2D, no ghosts */
+  SIAFD_B200_F_EFF_SMB = 29,     /* GeometryEvolution::top_surface_mass_balance [m], 2D, no ghosts */
+  SIAFD_B200_F_EFF_BMB = 30,     /* GeometryEvolution::bottom_surface_mass_balance [m], 2D, no ghosts */
+  SIAFD_B200_F_VEL_BC_MASK = 31, /* velocity Dirichlet B.C. mask, 2D, w_geom (never uploaded = 0) */
+  SIAFD_B200_F_THK_BC_MASK = 32, /* thickness Dirichlet B.C. mask, 2D, w_geom (never uploaded = 0) */
+  SIAFD_B200_F_COUNT = 33
 };
 
 /* Everything SIAFD's constructor and update() read from Config/IceGrid
@@ -242,6 +258,29 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update,
  * Reads the handle's mask, u, v (ghosts valid, i.e. after the wrap / exchange of SIAFD.cc:946-947) and, if
  * use_basal_melt, SIAFD_B200_F_BASAL_MELT; writes SIAFD_B200_F_W.  Asynchronous on the handle's stream. */
 int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int use_basal_melt);
+
+/* SURVEY.md 8(f) N1 -- the consumer of diffusive_flux(): GeometryEvolution (geometry/GeometryEvolution.cc), default
+ * configuration (geometry.part_grid.enabled = no).  All asynchronous on the handle's stream, device-resident:
+ *   mass_flow_step  = flow_step(geometry, dt, advective_velocity, diffusive_flux, bc masks) :241-324 followed by
+ *                     apply_flux_divergence :347-350.  Reads THICKNESS, BED, [SEA_LEVEL] (ghosts valid), FLUX (ghosts
+ *                     valid: SIAFD computes it on owned + 1), SLIDING as the advective velocity (ghost width >= 1 with
+ *                     valid ghosts, else it must be all zero = ZeroSliding), [VEL_BC_MASK], [THK_BC_MASK]; writes
+ *                     FLUX_DIV, THK_CHANGE, CONS_ERR and updates THICKNESS on the owned points.
+ *   mass_source_step = source_term_step :327-343 + apply_mass_fluxes :360-390.  Reads MASK, SMB, [BASAL_MELT if
+ *                     use_basal_melt], [THK_BC_MASK]; writes EFF_SMB, EFF_BMB, updates THICKNESS on the owned points.
+ *   ensure_consistency = Geometry::ensure_consistency (geometry/Geometry.cc:121-187) with the handle's
+ *                     ice_free_thickness: MASK and SURFACE from THICKNESS, BED, [SEA_LEVEL] on every local point.
+ *                     wrap_thickness = 1 first fills THICKNESS's ghosts by periodic self-wrap (single rank); a
+ *                     multi-rank caller exchanges them itself and passes 0.  H < 0 raises
+ *                     SIAFD_B200_ERR_NEGATIVE_THICKNESS at the next siafd_b200_finish. */
+int siafd_b200_mass_flow_step(siafd_b200_handle *h, double dt);
+int siafd_b200_mass_source_step(siafd_b200_handle *h, double dt, double ice_density, int use_basal_melt);
+int siafd_b200_ensure_consistency(siafd_b200_handle *h, int wrap_thickness);
+/* SURVEY.md 8(f) N3 (CFL part) -- max_timestep_cfl_3d / _2d (stressbalance/timestepping.cc:42-101, :113-153) on the
+ * handle's THICKNESS, MASK, U, V, W and SLIDING.  out[0..3] = {dt_max, u_max, v_max, w_max} of the 3D criterion (only
+ * if do_3d), out[4..7] = {dt_max, u_max, v_max, 0} of the 2D one; local values: multi-rank callers reduce them
+ * (min, max, max, max).  max_dt_seconds = time_stepping.maximum_time_step.  Synchronises the stream. */
+int siafd_b200_cfl(siafd_b200_handle *h, double max_dt_seconds, int do_3d, double *out8);
 
 /* Waits for the stream, then evaluates the reference's error conditions; returns the status
  * (collective callers reduce it over ranks before acting on it, cf. ParallelSection). */

@@ -29,6 +29,7 @@ struct siafd_b200_handle {
   double *d_z = nullptr;
   unsigned *d_err = nullptr;
   unsigned long long *d_dmax = nullptr;
+  unsigned long long *d_cfl = nullptr, *h_cfl = nullptr; // 8 maxima of siafd_b200_cfl and their pinned mirror
   int *d_hdc = nullptr;
   // pinned host mirror of {err, hdc, dmax}
   struct Result {
@@ -110,6 +111,9 @@ FieldMeta meta(const siafd_b200_config &c, int f) {
   case SIAFD_B200_F_THETA:
   case SIAFD_B200_F_W_I:
   case SIAFD_B200_F_W_J:
+  case SIAFD_B200_F_SEA_LEVEL:
+  case SIAFD_B200_F_VEL_BC_MASK:
+  case SIAFD_B200_F_THK_BC_MASK:
     return {c.w_geom, 1};
   case SIAFD_B200_F_ENTHALPY:
   case SIAFD_B200_F_AGE:
@@ -127,6 +131,12 @@ FieldMeta meta(const siafd_b200_config &c, int f) {
   case SIAFD_B200_F_W:
     return {0, c.Mz};
   case SIAFD_B200_F_BASAL_MELT:
+  case SIAFD_B200_F_SMB:
+  case SIAFD_B200_F_THK_CHANGE:
+  case SIAFD_B200_F_FLUX_DIV:
+  case SIAFD_B200_F_CONS_ERR:
+  case SIAFD_B200_F_EFF_SMB:
+  case SIAFD_B200_F_EFF_BMB:
     return {0, 1};
   default:
     return {-1, 0};
@@ -315,6 +325,9 @@ int fetch_result(siafd_b200_handle *h) {
     CU(h, cudaMemcpyAsync(&h->h_res->dmax, h->d_dmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(&h->h_res->err, h->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(&h->h_res->hdc, h->d_hdc, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    // error bits are sticky on the device until they have been read: an error raised by a call that follows an
+    // update (ensure_consistency, cfl) is reported by the next finish, not erased by the next update
+    CU(h, cudaMemsetAsync(h->d_err, 0, sizeof(unsigned), h->stream));
     h->result_pending = false;
   }
   CU(h, cudaStreamSynchronize(h->stream));
@@ -476,6 +489,8 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   cudaFree(h->d_err);
   cudaFree(h->d_dmax);
   cudaFree(h->d_hdc);
+  cudaFree(h->d_cfl);
+  if (h->h_cfl) cudaFreeHost(h->h_cfl);
   cudaFree(h->d_global_bed);
   for (void *p : h->ipc_mapped) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_pad);
@@ -878,7 +893,6 @@ static int flux_velocity_prepare(siafd_b200_handle *h, int full_update, double c
   }
   h->P.current_time = current_time;
   const Fields F = fields_of(h);
-  CU(h, cudaMemsetAsync(h->d_err, 0, sizeof(unsigned), h->stream));
   CU(h, cudaMemsetAsync(h->d_dmax, 0, sizeof(unsigned long long), h->stream));
   CU(h, cudaMemsetAsync(h->d_hdc, 0, sizeof(int), h->stream));
   h->launches += launch_prep2d(h->P, F, h->stream); // sia/SIAFD.cc:580-582
@@ -932,6 +946,107 @@ int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int
                                           use_basal_melt ? (const double *)h->buf[SIAFD_B200_F_BASAL_MELT] : nullptr,
                                           upstream, h->d_z, (double *)h->buf[SIAFD_B200_F_W], h->stream);
   CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+// ---- GeometryEvolution on device ----------------------------------------------------------
+int siafd_b200_mass_flow_step(siafd_b200_handle *h, double dt) {
+  CU(h, cudaSetDevice(h->device));
+  const int need[] = {SIAFD_B200_F_THICKNESS,  SIAFD_B200_F_BED,      SIAFD_B200_F_FLUX,
+                      SIAFD_B200_F_THK_CHANGE, SIAFD_B200_F_FLUX_DIV, SIAFD_B200_F_CONS_ERR};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  // the advective velocity needs its neighbours: without ghosts only ZeroSliding (no field / all zero) is possible
+  const double *vel = (h->cfg.w_sliding >= 1) ? D(SIAFD_B200_F_SLIDING) : nullptr;
+  h->launches += launch_mass_flow(h->P, dt, D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_BED), D(SIAFD_B200_F_SEA_LEVEL),
+                                  vel, D(SIAFD_B200_F_VEL_BC_MASK), D(SIAFD_B200_F_THK_BC_MASK), D(SIAFD_B200_F_FLUX),
+                                  D(SIAFD_B200_F_FLUX_DIV), D(SIAFD_B200_F_THK_CHANGE), D(SIAFD_B200_F_CONS_ERR),
+                                  h->stream);
+  h->launches += launch_mass_apply(h->P, D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_THK_CHANGE), h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_mass_source_step(siafd_b200_handle *h, double dt, double ice_density, int use_basal_melt) {
+  CU(h, cudaSetDevice(h->device));
+  const int need[] = {SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK, SIAFD_B200_F_SMB, SIAFD_B200_F_EFF_SMB,
+                      SIAFD_B200_F_EFF_BMB};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  if (use_basal_melt) {
+    int st = ensure(h, SIAFD_B200_F_BASAL_MELT);
+    if (st) return st;
+  }
+  if (!(ice_density > 0.0)) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "ice_density must be positive");
+  }
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  h->launches += launch_mass_source(h->P, dt, ice_density, use_basal_melt, D(SIAFD_B200_F_THICKNESS),
+                                    D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_THK_BC_MASK), D(SIAFD_B200_F_SMB),
+                                    D(SIAFD_B200_F_BASAL_MELT), D(SIAFD_B200_F_EFF_SMB), D(SIAFD_B200_F_EFF_BMB),
+                                    h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_ensure_consistency(siafd_b200_handle *h, int wrap_thickness) {
+  CU(h, cudaSetDevice(h->device));
+  const int need[] = {SIAFD_B200_F_THICKNESS, SIAFD_B200_F_BED, SIAFD_B200_F_MASK, SIAFD_B200_F_SURFACE};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  if (wrap_thickness) {
+    const int f = SIAFD_B200_F_THICKNESS;
+    int st = siafd_b200_wrap_ghosts_many(h, 1, &f);
+    if (st) return st;
+  }
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  h->launches += launch_consistency(h->P, (long)siafd_b200_field_size(h, SIAFD_B200_F_THICKNESS),
+                                    D(SIAFD_B200_F_SEA_LEVEL), D(SIAFD_B200_F_BED), D(SIAFD_B200_F_THICKNESS),
+                                    D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_SURFACE), h->d_err, h->stream);
+  CU(h, cudaGetLastError());
+  h->result_pending = true;
+  return SIAFD_B200_OK;
+}
+
+// ---- SURVEY.md 8(f) N3 (CFL part) ----------------------------------------------------------------------------
+int siafd_b200_cfl(siafd_b200_handle *h, double max_dt_seconds, int do_3d, double *out8) {
+  CU(h, cudaSetDevice(h->device));
+  if (!out8) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "out8 is NULL");
+  int st;
+  if ((st = ensure(h, SIAFD_B200_F_THICKNESS)) || (st = ensure(h, SIAFD_B200_F_MASK))) return st;
+  if (do_3d) {
+    const int need[] = {SIAFD_B200_F_U, SIAFD_B200_F_V, SIAFD_B200_F_W};
+    for (int f : need) {
+      if ((st = ensure(h, f))) return st;
+    }
+  }
+  if (!h->d_cfl) {
+    CU(h, cudaMalloc(&h->d_cfl, 8 * sizeof(unsigned long long)));
+    CU(h, cudaMallocHost(&h->h_cfl, 8 * sizeof(unsigned long long)));
+  }
+  CU(h, cudaMemsetAsync(h->d_cfl, 0, 8 * sizeof(unsigned long long), h->stream));
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  h->launches += launch_cfl(h->P, do_3d != 0, D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_U),
+                            D(SIAFD_B200_F_V), D(SIAFD_B200_F_W), h->d_z, D(SIAFD_B200_F_SLIDING), h->d_cfl, h->d_err,
+                            h->stream);
+  CU(h, cudaGetLastError());
+  h->result_pending = true;
+  CU(h, cudaMemcpyAsync(h->h_cfl, h->d_cfl, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  double m[8];
+  std::memcpy(m, h->h_cfl, sizeof(m));
+  // dt_max = min(max_dt, min_k 1 / denom_k) = min(max_dt, 1 / max_k denom_k): timestepping.cc:79-83, :139-142
+  out8[0] = (m[0] > 0.0) ? std::min(max_dt_seconds, 1.0 / m[0]) : max_dt_seconds;
+  out8[1] = m[1], out8[2] = m[2], out8[3] = m[3];
+  out8[4] = (m[4] > 0.0) ? std::min(max_dt_seconds, 1.0 / m[4]) : max_dt_seconds;
+  out8[5] = m[5], out8[6] = m[6], out8[7] = 0.0;
   return SIAFD_B200_OK;
 }
 

@@ -63,6 +63,20 @@ int launch_halo_wait(const unsigned long long *slots8, unsigned long long value,
 // StressBalance::compute_vertical_velocity (stressbalance/StressBalance.cc:283-424)
 int launch_vertical_velocity(const DP &P, const double *mask, const double *u, const double *v, const double *bmr,
                              int upstream, const double *z, double *w, cudaStream_t s);
+// SURVEY.md 8(f) N1 / N3-CFL (siafd_mass.cu): GeometryEvolution flow and source steps, Geometry::ensure_consistency,
+// max_timestep_cfl_3d / _2d.  NULL for an optional field means "all zero".
+int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,
+                     const double *vel_bc, const double *thk_bc, const double *Q, double *flux_div, double *dH,
+                     double *cons_err, cudaStream_t s);
+int launch_mass_apply(const DP &P, double *H, const double *dH, cudaStream_t s);
+int launch_mass_source(const DP &P, double dt, double ice_density, int use_bmr, double *H, const double *mask,
+                       const double *thk_bc, const double *smb, const double *bmr, double *eff_smb, double *eff_bmb,
+                       cudaStream_t s);
+int launch_consistency(const DP &P, long n, const double *sea, const double *bed, const double *thk, double *mask_out,
+                       double *surf_out, unsigned *err, cudaStream_t s);
+int launch_cfl(const DP &P, bool do3d, const double *thk, const double *mask, const double *u, const double *v,
+               const double *w, const double *z, const double *vel, unsigned long long *out, unsigned *err,
+               cudaStream_t s);
 int launch_geometry(const DP &P, long n, const double *sea_level, const double *bed, const double *thk, double *mask_out,
                     double *surf_out, cudaStream_t s);
 int launch_flow_n(const DP &P, long n, const double *stress, const double *E, const double *p, const double *gs,

