@@ -30,6 +30,10 @@ struct siafd_b200_handle {
   unsigned *d_err = nullptr;
   unsigned long long *d_dmax = nullptr;
   unsigned long long *d_cfl = nullptr, *h_cfl = nullptr; // 8 maxima of siafd_b200_cfl and their pinned mirror
+  bool cfl3_fresh = false; // slots 0..3 hold the maxima the last vertical-velocity launch took on the current fields
+  int vvel_rows = 64;      // rows one CTA of the marching vertical-velocity kernels takes
+  int vvel_kind = 0;       // 0: k_vvel_slab (shared memory, z sweep in registers); 1: k_vvel_march (lanes across z)
+  int vvel_wz = 16;        // z ranges per column of k_vvel_slab
   int *d_hdc = nullptr;
   // pinned host mirror of {err, hdc, dmax}
   struct Result {
@@ -432,6 +436,9 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   if (const char *e = getenv("SIAFD_B200_PIPELINE")) h->tuning.pipeline_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_BAND")) h->tuning.pipeline_band = atoi(e);
   if (const char *e = getenv("SIAFD_B200_WZ")) h->tuning.wz = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_VVEL_KIND")) h->vvel_kind = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_VVEL_WZ")) h->vvel_wz = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_VVEL_ROWS")) h->vvel_rows = atoi(e) > 0 ? atoi(e) : 64;
   if (const char *e = getenv("SIAFD_B200_ROWS")) h->tuning.rows_per_cta = atoi(e) > 0 ? atoi(e) : 64;
   {
     const double Lz = cfg->z[cfg->Mz - 1] - cfg->z[0], dz = Lz / (cfg->Mz - 1);
@@ -520,6 +527,7 @@ int siafd_b200_field_width(const siafd_b200_handle *h, int f) { return meta(h->c
 int siafd_b200_field_dof(const siafd_b200_handle *h, int f) { return meta(h->cfg, f).dof; }
 
 int siafd_b200_bind(siafd_b200_handle *h, int f, void *device_ptr) {
+  h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   if (f < 0 || f >= SIAFD_B200_F_COUNT) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad field id %d", f);
   }
@@ -552,6 +560,7 @@ int siafd_b200_set_stream(siafd_b200_handle *h, void *cuda_stream) {
 }
 
 int siafd_b200_upload(siafd_b200_handle *h, int f, const double *host) {
+  h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   int st = ensure(h, f);
   if (st) return st;
@@ -925,14 +934,24 @@ static int flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0,
 }
 
 int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, double current_time) {
+  h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   int st = flux_velocity_prepare(h, full_update, current_time);
   if (st) return st;
   return flux_velocity_launch(h, full_update, 0, -1);
 }
 
+static int ensure_cfl(siafd_b200_handle *h) {
+  if (!h->d_cfl) {
+    CU(h, cudaMalloc(&h->d_cfl, 8 * sizeof(unsigned long long)));
+    CU(h, cudaMallocHost(&h->h_cfl, 8 * sizeof(unsigned long long)));
+    CU(h, cudaMemsetAsync(h->d_cfl, 0, 8 * sizeof(unsigned long long), h->stream));
+  }
+  return SIAFD_B200_OK;
+}
+
 int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int use_basal_melt) {
   CU(h, cudaSetDevice(h->device));
-  const int need[] = {SIAFD_B200_F_MASK, SIAFD_B200_F_U, SIAFD_B200_F_V, SIAFD_B200_F_W};
+  const int need[] = {SIAFD_B200_F_MASK, SIAFD_B200_F_THICKNESS, SIAFD_B200_F_U, SIAFD_B200_F_V, SIAFD_B200_F_W};
   for (int f : need) {
     int st = ensure(h, f);
     if (st) return st;
@@ -941,16 +960,34 @@ int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int
     int st = ensure(h, SIAFD_B200_F_BASAL_MELT);
     if (st) return st;
   }
-  h->launches += launch_vertical_velocity(h->P, (const double *)h->buf[SIAFD_B200_F_MASK], (const double *)h->buf[SIAFD_B200_F_U],
-                                          (const double *)h->buf[SIAFD_B200_F_V],
-                                          use_basal_melt ? (const double *)h->buf[SIAFD_B200_F_BASAL_MELT] : nullptr,
-                                          upstream, h->d_z, (double *)h->buf[SIAFD_B200_F_W], h->stream);
+  int st = ensure_cfl(h);
+  if (st) return st;
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  const double *bmr = use_basal_melt ? D(SIAFD_B200_F_BASAL_MELT) : nullptr;
+  // the marching kernel also takes the 3D CFL maxima (StressBalance.cc:186-200 evaluates them right after w)
+  CU(h, cudaMemsetAsync(h->d_cfl, 0, 4 * sizeof(unsigned long long), h->stream));
+  int n = 0;
+  if (h->vvel_kind == 0) { // shared-memory kernel (z sweep in registers); 0 launches = does not apply
+    n = launch_vvel_slab(h->P, D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_U), D(SIAFD_B200_F_V), bmr,
+                         upstream, h->d_z, D(SIAFD_B200_F_W), h->d_cfl, h->d_err, h->vvel_rows, h->vvel_wz,
+                         (long)siafd_b200_field_size(h, SIAFD_B200_F_U), h->inv_dz, h->stream);
+  }
+  if (n == 0) n = launch_vvel_march(h->P, D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_U), D(SIAFD_B200_F_V),
+                            bmr, upstream, h->d_z, D(SIAFD_B200_F_W), h->d_cfl, h->d_err, h->vvel_rows, h->stream);
+  h->cfl3_fresh = n > 0;
+  if (n == 0) { // more than 256 levels: generic warp-per-column kernel
+    n = launch_vertical_velocity(h->P, D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_U), D(SIAFD_B200_F_V), bmr, upstream, h->d_z,
+                                 D(SIAFD_B200_F_W), h->stream);
+  }
+  h->launches += n;
+  h->result_pending = true;
   CU(h, cudaGetLastError());
   return SIAFD_B200_OK;
 }
 
 // ---- GeometryEvolution on device ----------------------------------------------------------
 int siafd_b200_mass_flow_step(siafd_b200_handle *h, double dt) {
+  h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_THICKNESS,  SIAFD_B200_F_BED,      SIAFD_B200_F_FLUX,
                       SIAFD_B200_F_THK_CHANGE, SIAFD_B200_F_FLUX_DIV, SIAFD_B200_F_CONS_ERR};
@@ -971,6 +1008,7 @@ int siafd_b200_mass_flow_step(siafd_b200_handle *h, double dt) {
 }
 
 int siafd_b200_mass_source_step(siafd_b200_handle *h, double dt, double ice_density, int use_basal_melt) {
+  h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK, SIAFD_B200_F_SMB, SIAFD_B200_F_EFF_SMB,
                       SIAFD_B200_F_EFF_BMB};
@@ -995,6 +1033,7 @@ int siafd_b200_mass_source_step(siafd_b200_handle *h, double dt, double ice_dens
 }
 
 int siafd_b200_ensure_consistency(siafd_b200_handle *h, int wrap_thickness) {
+  h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_THICKNESS, SIAFD_B200_F_BED, SIAFD_B200_F_MASK, SIAFD_B200_F_SURFACE};
   for (int f : need) {
@@ -1027,13 +1066,12 @@ int siafd_b200_cfl(siafd_b200_handle *h, double max_dt_seconds, int do_3d, doubl
       if ((st = ensure(h, f))) return st;
     }
   }
-  if (!h->d_cfl) {
-    CU(h, cudaMalloc(&h->d_cfl, 8 * sizeof(unsigned long long)));
-    CU(h, cudaMallocHost(&h->h_cfl, 8 * sizeof(unsigned long long)));
-  }
-  CU(h, cudaMemsetAsync(h->d_cfl, 0, 8 * sizeof(unsigned long long), h->stream));
+  if ((st = ensure_cfl(h))) return st;
+  // the 3D maxima may already be there: the vertical-velocity kernel takes them on the fly
+  const bool run_3d = do_3d && !h->cfl3_fresh;
+  CU(h, cudaMemsetAsync(h->d_cfl + (run_3d ? 0 : 4), 0, (run_3d ? 8 : 4) * sizeof(unsigned long long), h->stream));
   auto D = [&](int f) { return (double *)h->buf[f]; };
-  h->launches += launch_cfl(h->P, do_3d != 0, D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_U),
+  h->launches += launch_cfl(h->P, run_3d, D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_U),
                             D(SIAFD_B200_F_V), D(SIAFD_B200_F_W), h->d_z, D(SIAFD_B200_F_SLIDING), h->d_cfl, h->d_err,
                             h->stream);
   CU(h, cudaGetLastError());
@@ -1199,6 +1237,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
 }
 
 int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out, int full_update) {
+  h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   if (!h || !in || !out) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "null argument");
   }

@@ -63,6 +63,13 @@ int launch_halo_wait(const unsigned long long *slots8, unsigned long long value,
 // StressBalance::compute_vertical_velocity (stressbalance/StressBalance.cc:283-424)
 int launch_vertical_velocity(const DP &P, const double *mask, const double *u, const double *v, const double *bmr,
                              int upstream, const double *z, double *w, cudaStream_t s);
+// the marching kernel with the 3D CFL maxima fused in (siafd_mass.cu); 0 = not applicable (Mz > 256)
+int launch_vvel_march(const DP &P, const double *mask, const double *thk, const double *u, const double *v,
+                      const double *bmr, int upstream, const double *z, double *w, unsigned long long *cfl,
+                      unsigned *err, int rows_per_cta, cudaStream_t s);
+int launch_vvel_slab(const DP &P, const double *mask, const double *thk, const double *u, const double *v,
+                     const double *bmr, int upstream, const double *z, double *w, unsigned long long *cfl,
+                     unsigned *err, int rows_per_cta, int wz, long nUV, double inv_dz, cudaStream_t s);
 // SURVEY.md 8(f) N1 / N3-CFL (siafd_mass.cu): GeometryEvolution flow and source steps, Geometry::ensure_consistency,
 // max_timestep_cfl_3d / _2d.  NULL for an optional field means "all zero".
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,

@@ -12,6 +12,7 @@
 // Every expression whose rounding the reference fixes is written with explicit __dadd_rn / __dmul_rn so that nvcc
 // cannot contract it into an FMA: thickness, masks and the CFL scalars are BIT-EXACT against the oracle.
 #include "siafd_kernels.cuh"
+#include "siafd_math.cuh"
 
 #define FULLMASK 0xffffffffu
 
@@ -265,6 +266,506 @@ __global__ void k_cfl_2d(const __grid_constant__ DP P, const double *__restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// StressBalance::compute_vertical_velocity (stressbalance/StressBalance.cc:283-424) fused with max_timestep_cfl_3d
+// (stressbalance/timestepping.cc:42-101), which the reference evaluates right after it on the same fields
+// (StressBalance.cc:186-200).  SURVEY.md 8(f) N2 + N3-CFL.
+//
+// One warp per column, lanes across z (NCH chunks of 32 levels held in registers), marching up the rows of a row
+// segment: the v columns of rows j-1 and j stay in registers while row j+1 is loaded, so v is read once per row
+// (plus two rows per segment) instead of three times; the three u columns of a row are adjacent in memory and the
+// eight warps of a CTA take eight adjacent columns, so the neighbours' u comes from L1.  Per row a warp has 4 NCH
+// independent loads in flight.  The running integral w[k] = w[k-1] - dz/2 (s[k] + s[k-1]) is a warp scan with a
+// carry between chunks.  The CFL maxima (max denom, |u|, |v|, |w| over icy columns below the surface) are taken on
+// the values already in registers: no second pass over u, v, w.
+// HBM-bound: 24 Mz bytes per column (u, v read, w written).
+// ---------------------------------------------------------------------------------------------
+// inclusive warp scan step: t += (value of lane - d), only where that lane exists.  shfl.up returns the in-range
+// predicate itself, so a step is two SHFL and one predicated DADD (no compare / select).
+__device__ __forceinline__ double scan_step(double t, int d) {
+  int lo = __double2loint(t), hi = __double2hiint(t);
+  double r;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 ylo, yhi;\n"
+      ".reg .f64 y, tt;\n"
+      "shfl.sync.up.b32 ylo|p, %1, %3, 0, 0xffffffff;\n"
+      "shfl.sync.up.b32 yhi, %2, %3, 0, 0xffffffff;\n"
+      "mov.b64 y, {ylo, yhi};\n"
+      "mov.b64 tt, {%1, %2};\n"
+      "@p add.f64 tt, tt, y;\n"
+      "mov.f64 %0, tt;\n"
+      "}\n"
+      : "=d"(r)
+      : "r"(lo), "r"(hi), "r"(d));
+  return r;
+}
+
+template <int NCH>
+struct VvelRow { // everything a warp keeps while it marches up its column
+  double hdz[NCH], zk[NCH]; // 0.5 (z[k] - z[k-1]) and z[k] of this lane's levels (k = 32 c + lane)
+  int koff[NCH];            // min(k, Mz - 1): loads past the top re-read the top level instead of branching
+  double ztop;              // z[Mz - 1]
+};
+
+// one row of one column; (vs, vc, vn) = v of rows j - 1, j, j + 1 at this lane's levels (vn is loaded here)
+template <int NCH>
+__device__ __forceinline__ void vvel_row(const DP &P, const VvelRow<NCH> &R, int lane, int Mz, int upstream, bool cfl,
+                                         const double *__restrict__ mask, const double *__restrict__ thk,
+                                         const double *__restrict__ bmr, long g, long o2, long rowuv,
+                                         const double *__restrict__ uc_p, const double *__restrict__ vc_p,
+                                         double *__restrict__ w_p, const double (&vs)[NCH], const double (&vc)[NCH],
+                                         double (&vn)[NCH], int Ms, int M0, int Mn, double &dmax, double &umax,
+                                         double &vmax, double &wmax, unsigned *err) {
+  double uw[NCH], uc[NCH], ue[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int k = R.koff[c];
+    vn[c] = vc_p[k + rowuv];
+    uw[c] = uc_p[k - Mz];
+    uc[c] = uc_p[k];
+    ue[c] = uc_p[k + Mz];
+  }
+  const int Me = mask_int(mask[g + 1]), Mw = mask_int(mask[g - 1]);
+  double west = 1.0, east = 1.0, south = 1.0, north = 1.0;
+  if (upstream) { // :336-350, :372-386 (basal velocities decide the direction)
+    const double uw0 = __shfl_sync(FULLMASK, uw[0], 0), uc0 = __shfl_sync(FULLMASK, uc[0], 0),
+                 ue0 = __shfl_sync(FULLMASK, ue[0], 0), vs0 = __shfl_sync(FULLMASK, vs[0], 0),
+                 vc0 = __shfl_sync(FULLMASK, vc[0], 0), vn0 = __shfl_sync(FULLMASK, vn[0], 0);
+    const double uwf = 0.5 * (uw0 + uc0), uef = 0.5 * (uc0 + ue0);
+    if (uwf > 0.0 && uef >= 0.0) {
+      west = 1.0, east = 0.0;
+    } else if (uwf <= 0.0 && uef < 0.0) {
+      west = 0.0, east = 1.0;
+    }
+    const double vsf = 0.5 * (vs0 + vc0), vnf = 0.5 * (vc0 + vn0);
+    if (vsf > 0.0 && vnf >= 0.0) {
+      south = 1.0, north = 0.0;
+    } else if (vsf <= 0.0 && vnf < 0.0) {
+      south = 0.0, north = 1.0;
+    }
+  }
+  // one-sided differences at ice margins (:352-357, :388-393)
+  const bool icy0 = m_icy(M0);
+  if (icy0 != m_icy(Me)) east = 0;
+  if (icy0 != m_icy(Mw)) west = 0;
+  if (icy0 != m_icy(Mn)) north = 0;
+  if (icy0 != m_icy(Ms)) south = 0;
+  // 1 / (dx (east + west)) with east + west in {0, 1, 2}: RN(1 / dx) and exactly half of it, no division
+  const double D_x = (east + west > 1.5) ? 0.5 * P.inv_dx : ((east + west > 0) ? P.inv_dx : 0.0);
+  const double D_y = (north + south > 1.5) ? 0.5 * P.inv_dy : ((north + south > 0) ? P.inv_dy : 0.0);
+  // fold the weights into four coefficients: u_x = a_e (u_e - u) + a_w (u - u_w), likewise v_y
+  const double a_e = D_x * east, a_w = D_x * west, a_n = D_y * north, a_s = D_y * south;
+  double wacc = (bmr != nullptr) ? -bmr[o2] : 0.0; // w at the base (:409-413)
+  double carry = 0.0;                              // s at the level below the chunk
+  double wk[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const double u_x = a_w * (uc[c] - uw[c]) + a_e * (ue[c] - uc[c]);
+    const double v_y = a_s * (vc[c] - vs[c]) + a_n * (vn[c] - vc[c]);
+    const double sk = u_x + v_y;
+    double sprev = __shfl_up_sync(FULLMASK, sk, 1);
+    if (lane == 0) sprev = carry;
+    double t = -R.hdz[c] * (sk + sprev); // w[k] - w[k-1] (:418-422); hdz = 0 at k = 0 and past the top
+    t = scan_step(t, 1);
+    t = scan_step(t, 2);
+    t = scan_step(t, 4);
+    t = scan_step(t, 8);
+    t = scan_step(t, 16);
+    wk[c] = wacc + t;
+    if (c * 32 + lane < Mz) w_p[c * 32 + lane] = wk[c];
+    if (c + 1 < NCH) {
+      wacc = __shfl_sync(FULLMASK, wk[c], 31);
+      carry = __shfl_sync(FULLMASK, sk, 31);
+    }
+  }
+  if (cfl && icy0) { // max_timestep_cfl_3d, timestepping.cc:62-87: icy columns, levels 0 .. ks (warp-uniform branch)
+    // IceGrid::kBelowHeight (util/IceGrid.cc:427-440): the levels are sorted, so the largest k with z[k] <= H is a
+    // count; clamped to [0, Mz - 2] like GSL's bsearch
+    const double H = thk[g];
+    if (H < 0.0 - 1.0e-6) {
+      if (lane == 0) atomicOr(err, EB_BELOW);
+    } else if (H > R.ztop + 1.0e-6) {
+      if (lane == 0) atomicOr(err, EB_ABOVE);
+    } else {
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) cnt += __popc(__ballot_sync(FULLMASK, (c * 32 + lane < Mz) && R.zk[c] <= H));
+      const int ks = min(max(cnt - 1, 0), Mz - 2);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c * 32 + lane <= ks) {
+          const double ua = fabs(uc[c]), va = fabs(vc[c]);
+          umax = fmax(umax, ua);
+          vmax = fmax(vmax, va);
+          dmax = fmax(dmax, __dadd_rn(fabs(__dmul_rn(ua, P.inv_dx)), fabs(__dmul_rn(va, P.inv_dy))));
+          wmax = fmax(wmax, fabs(wk[c]));
+        }
+      }
+    }
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 4) ? 2 : 1)
+    k_vvel_march(const __grid_constant__ DP P, const double *__restrict__ mask, const double *__restrict__ thk,
+                 const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ bmr,
+                 int upstream, const double *__restrict__ z, double *__restrict__ w, int RS, unsigned long long *cfl,
+                 unsigned *err) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = P.xs + blockIdx.x * 8 + wid;
+  const int j0 = P.ys + blockIdx.y * RS, j1 = min(j0 + RS, P.ys + P.ym);
+  double dmax = 0.0, umax = 0.0, vmax = 0.0, wmax = 0.0;
+  if (i < P.xs + P.xm) {
+    const int Mz = P.Mz;
+    VvelRow<NCH> R;
+    R.ztop = z[Mz - 1];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int k = c * 32 + lane;
+      R.koff[c] = min(k, Mz - 1);
+      R.zk[c] = z[R.koff[c]];
+      R.hdz[c] = (k > 0 && k < Mz) ? 0.5 * (z[k] - z[k - 1]) : 0.0;
+    }
+    const long rowuv = (long)(P.xm + 2 * P.wuv) * Mz, roww = (long)P.xm * Mz, rowg = P.xm + 2 * P.wg;
+    const double *uc_p = u + idx2(P, i, j0, P.wuv) * Mz, *vc_p = v + idx2(P, i, j0, P.wuv) * Mz;
+    long o2 = (long)(j0 - P.ys) * P.xm + (i - P.xs);
+    double *w_p = w + o2 * Mz;
+    double va[NCH], vb[NCH], vcc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      va[c] = vc_p[R.koff[c] - rowuv];
+      vb[c] = vc_p[R.koff[c]];
+    }
+    long g = idx2(P, i, j0, P.wg);
+    int Ms = mask_int(mask[g - rowg]), M0 = mask_int(mask[g]);
+    const bool docfl = cfl != nullptr;
+    // the three v rows rotate through (va, vb, vcc) by unrolling the row loop three times: no register moves
+#define VVEL_ROW(S_, C_, N_)                                                                                           \
+  {                                                                                                                    \
+    const int Mn = mask_int(mask[g + rowg]);                                                                           \
+    vvel_row<NCH>(P, R, lane, Mz, upstream, docfl, mask, thk, bmr, g, o2, rowuv, uc_p, vc_p, w_p, S_, C_, N_, Ms, M0,  \
+                  Mn, dmax, umax, vmax, wmax, err);                                                                    \
+    Ms = M0, M0 = Mn;                                                                                                  \
+    uc_p += rowuv, vc_p += rowuv, w_p += roww, g += rowg, o2 += P.xm;                                                  \
+  }
+    int j = j0;
+    while (j < j1) {
+      VVEL_ROW(va, vb, vcc);
+      if (++j >= j1) break;
+      VVEL_ROW(vb, vcc, va);
+      if (++j >= j1) break;
+      VVEL_ROW(vcc, va, vb);
+      ++j;
+    }
+#undef VVEL_ROW
+  }
+  if (cfl != nullptr) {
+    dmax = warp_max(dmax), umax = warp_max(umax), vmax = warp_max(vmax), wmax = warp_max(wmax);
+    __shared__ double sm[4][8];
+    if (lane == 0) sm[0][wid] = dmax, sm[1][wid] = umax, sm[2][wid] = vmax, sm[3][wid] = wmax;
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double m = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m = fmax(m, sm[threadIdx.x][q]);
+      // most CTAs find the running maximum already above theirs: a plain load spares the atomic
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+      if (m > 0.0 && bits > *(volatile unsigned long long *)(cfl + threadIdx.x)) atomicMax(cfl + threadIdx.x, bits);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_vvel_slab: the same computation (w + fused 3D CFL maxima) with the z sweep in registers.
+//
+// k_vvel_march keeps lanes across z; every access is coalesced but the running integral becomes warp scans and the
+// kernel is issue-bound: 560 warp instructions per column, 45 % of the HBM roofline
+// (profiles/ncu_r01_vvel_march_2048_summary.txt).  Here a CTA takes a strip of NC = 16 columns and marches up the
+// rows of a row segment, transposing through shared memory like k_sia_slab:
+//   * loads: per row one mbarrier-tracked group of two cp.async.bulk copies (the u row, NC + 2 columns, and the v row
+//     two rows ahead, NC columns: both contiguous in PISM's layout), issued one row ahead by one thread into a
+//     2-slot (u) / 4-slot (v) ring; the per-column scalars (5 masks, thickness, basal melt) of the next row are
+//     prefetched into registers by the q = 0 threads during the sweep;
+//   * sweep: thread = (column c, z range q of Lq = ceil(Mz / WZ) levels).  Shared-memory columns are Mz doubles
+//     apart (odd), so the 16 columns of a half-warp fall into 16 different 8-byte banks.  The thread forms
+//     s = u_x + v_y level by level and the running integral of its range (one add per level), leaves the range-local
+//     w and the range total in shared memory, and takes the |u|, |v|, denominator maxima of the CFL criterion;
+//   * fix-up and store: the thread adds w(0) and the totals of the ranges below to its levels (and takes max |w|
+//     below the surface); the finished row (NC columns, contiguous in w) leaves by ONE bulk store from shared memory
+//     (cp.async.bulk.global.shared::cta), double-buffered so that it overlaps the next row's sweep.
+// Two barriers per row.  Shared memory 112 KB at Mz = 101: 2 CTAs per SM.  HBM-bound: 24 Mz bytes per column.
+// Needs an odd Mz (bank layout) -- otherwise the caller falls back to k_vvel_march.
+// ---------------------------------------------------------------------------------------------
+constexpr int VNC = 16;
+
+struct VvelArgs {
+  const double *mask, *thk, *u, *v, *bmr, *z;
+  double *w;
+  unsigned long long *cfl;
+  unsigned *err;
+  int upstream, RS, WZ, Lq;
+  long nUV; // doubles in the u / v arrays (bulk copies are clamped to it)
+  double inv_dz;
+};
+
+__host__ __device__ inline int vvel_su(int Mz) { return ((VNC + 2) * Mz + 2 + 1) & ~1; }
+__host__ __device__ inline int vvel_sv(int Mz) { return (VNC * Mz + 2 + 1) & ~1; }
+__host__ __device__ inline int vvel_sw(int Mz) { return (VNC * Mz + 2 + 1) & ~1; }
+__host__ inline size_t vvel_smem_bytes(int Mz) {
+  const size_t d = 2 * (size_t)vvel_su(Mz) + 4 * (size_t)vvel_sv(Mz) + 2 * (size_t)vvel_sw(Mz) +
+                   2 * (size_t)((Mz + 1) & ~1) + VNC * 16 + 4 * VNC;
+  return d * 8 + 2 * 8 + (2 * VNC + 2 * VNC * 5) * 4 + 16;
+}
+
+// IceGrid::kBelowHeight (util/IceGrid.cc:427-440) on the levels in shared memory
+__device__ __forceinline__ int k_below_height_s(const double *zz, int Mz, double height, double inv_dz, unsigned *err) {
+  if (height < 0.0 - 1.0e-6) {
+    atomicOr(err, EB_BELOW);
+    return 0;
+  }
+  if (height > zz[Mz - 1] + 1.0e-6) {
+    atomicOr(err, EB_ABOVE);
+    return 0;
+  }
+  if (inv_dz > 0.0) { // equally spaced levels: guess, then correct against the table
+    int k = min(max((int)(height * inv_dz), 0), Mz - 2);
+    while (k < Mz - 2 && zz[k + 1] <= height) ++k;
+    while (k > 0 && zz[k] > height) --k;
+    return k;
+  }
+  int ilo = 0, ihi = Mz - 1;
+  while (ihi > ilo + 1) {
+    const int m = (ihi + ilo) >> 1;
+    if (zz[m] > height) {
+      ihi = m;
+    } else {
+      ilo = m;
+    }
+  }
+  return ilo;
+}
+
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 2) k_vvel_slab(const __grid_constant__ DP P, const VvelArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int Mz = P.Mz, WZ = A.WZ, Lq = A.Lq, T = blockDim.x, tid = threadIdx.x;
+  const int SU = vvel_su(Mz), SV = vvel_sv(Mz), SW = vvel_sw(Mz), MzE = (Mz + 1) & ~1;
+  double *su = smem;                 // [2][SU]   u rows (slot = r & 1); data starts 0 or 1 double into the slot
+  double *sv = su + 2 * SU;          // [4][SV]   v rows (slot = (rv + 1) & 3, rv = row - j0 = -1 ..)
+  double *sw = sv + 4 * SV;          // [2][SW]   w of the row (slot = r & 1), same 0 / 1 shift as its place in w
+  double *shz = sw + 2 * SW;         // [Mz]      0.5 (z[k] - z[k-1]), 0 at k = 0
+  double *szz = shz + MzE;           // [Mz]      z[k]
+  double *stot = szz + MzE;          // [16][VNC] range totals
+  double *sthk = stot + VNC * 16;    // [2][VNC]  thickness (slot = r & 1)
+  double *sbmr = sthk + 2 * VNC;     // [2][VNC]  basal melt rate
+  unsigned long long *bars = (unsigned long long *)(sbmr + 2 * VNC); // [2]
+  int *sks = (int *)(bars + 2);      // [2][VNC]  ks of icy columns, -1 otherwise
+  int *smk = sks + 2 * VNC;          // [2][VNC][5] masks: centre, east, west, north, south
+
+  const int i0 = P.xs + blockIdx.x * VNC, ncol = min(VNC, P.xs + P.xm - i0);
+  const int j0 = P.ys + blockIdx.y * A.RS, nrows = min(A.RS, P.ys + P.ym - j0);
+  const int c = tid % VNC, q = tid / VNC; // q < WZ
+  const long rowuv = (long)(P.xm + 2 * P.wuv) * Mz, rowg = P.xm + 2 * P.wg, roww = (long)P.xm * Mz;
+  const long gu0 = idx2(P, i0 - 1, j0, P.wuv) * Mz, gv0 = idx2(P, i0, j0, P.wuv) * Mz;
+  const long gw0 = ((long)(j0 - P.ys) * P.xm + (i0 - P.xs)) * Mz;
+  const int nu = (ncol + 2) * Mz, nv = ncol * Mz;
+  const bool docfl = A.cfl != nullptr;
+
+  for (int k = tid; k < Mz; k += T) {
+    shz[k] = (k > 0) ? 0.5 * (A.z[k] - A.z[k - 1]) : 0.0;
+    szz[k] = A.z[k];
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  // per-column scalars of a row: masks (centre, east, west, north, south), thickness, basal melt
+  auto load_scalars = [&](int j, int (&M)[5], double &H, double &B) {
+    const long g = idx2(P, i0 + c, j, P.wg);
+    M[0] = mask_int(A.mask[g]), M[1] = mask_int(A.mask[g + 1]), M[2] = mask_int(A.mask[g - 1]);
+    M[3] = mask_int(A.mask[g + rowg]), M[4] = mask_int(A.mask[g - rowg]);
+    H = A.thk[g];
+    B = (A.bmr != nullptr) ? A.bmr[(long)(j - P.ys) * P.xm + (i0 + c - P.xs)] : 0.0;
+  };
+  auto store_scalars = [&](int slot, const int (&M)[5], double H, double B) {
+    int *mk = smk + (slot * VNC + c) * 5;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) mk[e] = M[e];
+    sthk[slot * VNC + c] = H;
+    sbmr[slot * VNC + c] = B;
+    sks[slot * VNC + c] = (docfl && m_icy(M[0])) ? k_below_height_s(szz, Mz, H, A.inv_dz, A.err) : -1;
+  };
+  __syncthreads(); // tables and mbarrier init visible
+  // one bulk copy of n doubles starting at base[goff] into a slot; the copy runs on 16-byte boundaries, so the data
+  // lands (goff & 1) doubles into the slot
+  auto copy_bytes = [&](long goff, int n) {
+    const long a0 = goff & ~1L;
+    long a1 = (goff + n + 1) & ~1L;
+    if (a1 > A.nUV) a1 -= 2;
+    return (unsigned)((a1 - a0) * 8);
+  };
+  auto copy_issue = [&](const double *base, long goff, int n, double *slot, unsigned long long *bar) {
+    const long a0 = goff & ~1L;
+    long a1 = (goff + n + 1) & ~1L;
+    if (a1 > A.nUV) { // last row of the array and an odd end: fetch the last double separately
+      a1 -= 2;
+      slot[(goff - a0) + n - 1] = base[goff + n - 1];
+    }
+    bulk_g2s(slot, base + a0, (unsigned)((a1 - a0) * 8), bar);
+  };
+  if (tid == 0) { // rows j0 - 1, j0, j0 + 1 of v and row j0 of u: the group of row r = 0
+    unsigned bytes = copy_bytes(gu0, nu);
+    for (int rv = -1; rv <= 1; ++rv) bytes += copy_bytes(gv0 + rv * rowuv, nv);
+    mbar_expect_tx(&bars[0], bytes);
+    copy_issue(A.u, gu0, nu, su, &bars[0]);
+    for (int rv = -1; rv <= 1; ++rv) copy_issue(A.v, gv0 + rv * rowuv, nv, sv + ((rv + 1) & 3) * SV, &bars[0]);
+  }
+  if (q == 0 && c < ncol) {
+    int M[5];
+    double H, B;
+    load_scalars(j0, M, H, B);
+    store_scalars(0, M, H, B);
+  }
+  __syncthreads();
+
+  double dmax = 0.0, umax = 0.0, vmax = 0.0, wmax = 0.0;
+  for (int r = 0; r < nrows; ++r) {
+    const int j = j0 + r, sl = r & 1;
+    const bool more = r + 1 < nrows;
+    // ---- issue the loads of row r + 1: u row r + 1 and v row r + 2 -------------------------------------------------
+    if (tid == 0 && more) {
+      const long gu = gu0 + (long)(r + 1) * rowuv, gv = gv0 + (long)(r + 2) * rowuv;
+      unsigned long long *bar = &bars[(r + 1) & 1];
+      mbar_expect_tx(bar, copy_bytes(gu, nu) + copy_bytes(gv, nv));
+      copy_issue(A.u, gu, nu, su + ((r + 1) & 1) * SU, bar);
+      copy_issue(A.v, gv, nv, sv + ((r + 3) & 3) * SV, bar);
+    }
+    int Mnext[5];
+    double Hnext = 0.0, Bnext = 0.0;
+    const bool pre = more && q == 0 && c < ncol;
+    if (pre) load_scalars(j + 1, Mnext, Hnext, Bnext);
+    mbar_wait(&bars[sl], (r >> 1) & 1);
+    // ---- sweep: range-local running integral -----------------------------------------------------------------------
+    const long gw = gw0 + (long)r * roww;             // where this row's NC columns start in w
+    double *wc = sw + sl * SW + (gw & 1) + c * Mz;    // same parity in shared memory: aligned bulk store
+    const int k0 = q * Lq, k1 = min(k0 + Lq, Mz);
+    int ks = -1;
+    if (c < ncol) {
+      const int *mk = smk + (sl * VNC + c) * 5;
+      const int M0 = mk[0], Me = mk[1], Mw = mk[2], Mn = mk[3], Ms = mk[4];
+      const double *uw = su + sl * SU + ((gu0 + (long)r * rowuv) & 1) + c * Mz, *uc = uw + Mz, *ue = uc + Mz;
+      const double *vs = sv + ((r + 0) & 3) * SV + ((gv0 + (long)(r - 1) * rowuv) & 1) + c * Mz;
+      const double *vc = sv + ((r + 1) & 3) * SV + ((gv0 + (long)r * rowuv) & 1) + c * Mz;
+      const double *vn = sv + ((r + 2) & 3) * SV + ((gv0 + (long)(r + 1) * rowuv) & 1) + c * Mz;
+      double west = 1.0, east = 1.0, south = 1.0, north = 1.0;
+      if (A.upstream) { // :336-350, :372-386 (basal velocities decide the direction)
+        const double uwf = 0.5 * (uw[0] + uc[0]), uef = 0.5 * (uc[0] + ue[0]);
+        if (uwf > 0.0 && uef >= 0.0) {
+          west = 1.0, east = 0.0;
+        } else if (uwf <= 0.0 && uef < 0.0) {
+          west = 0.0, east = 1.0;
+        }
+        const double vsf = 0.5 * (vs[0] + vc[0]), vnf = 0.5 * (vc[0] + vn[0]);
+        if (vsf > 0.0 && vnf >= 0.0) {
+          south = 1.0, north = 0.0;
+        } else if (vsf <= 0.0 && vnf < 0.0) {
+          south = 0.0, north = 1.0;
+        }
+      }
+      // one-sided differences at ice margins (:352-357, :388-393)
+      const bool icy0 = m_icy(M0);
+      if (icy0 != m_icy(Me)) east = 0;
+      if (icy0 != m_icy(Mw)) west = 0;
+      if (icy0 != m_icy(Mn)) north = 0;
+      if (icy0 != m_icy(Ms)) south = 0;
+      // 1 / (dx (east + west)) with east + west in {0, 1, 2}: RN(1 / dx) and exactly half of it, no division
+      const double D_x = (east + west > 1.5) ? 0.5 * P.inv_dx : ((east + west > 0) ? P.inv_dx : 0.0);
+      const double D_y = (north + south > 1.5) ? 0.5 * P.inv_dy : ((north + south > 0) ? P.inv_dy : 0.0);
+      const double a_e = D_x * east, a_w = D_x * west, a_n = D_y * north, a_s = D_y * south;
+      ks = sks[sl * VNC + c];
+      auto s_at = [&](int k) {
+        const double u_x = a_w * (uc[k] - uw[k]) + a_e * (ue[k] - uc[k]);
+        const double v_y = a_s * (vc[k] - vs[k]) + a_n * (vn[k] - vc[k]);
+        return u_x + v_y;
+      };
+      double sprev = (k0 > 0 && k0 < Mz) ? s_at(k0 - 1) : 0.0, run = 0.0;
+#pragma unroll 2
+      for (int k = k0; k < k1; ++k) {
+        const double sk = s_at(k);
+        run -= shz[k] * (sk + sprev); // :418-422
+        sprev = sk;
+        wc[k] = run;
+      }
+      if (ks >= k0) { // timestepping.cc:68-83, levels k0 .. min(ks, k1 - 1) of this range
+        const int ke = min(ks + 1, k1);
+        for (int k = k0; k < ke; ++k) {
+          const double ua = fabs(uc[k]), va = fabs(vc[k]);
+          umax = fmax(umax, ua);
+          vmax = fmax(vmax, va);
+          dmax = fmax(dmax, __dadd_rn(fabs(__dmul_rn(ua, P.inv_dx)), fabs(__dmul_rn(va, P.inv_dy))));
+        }
+      }
+      stot[q * VNC + c] = run;
+    }
+    if (pre) store_scalars(sl ^ 1, Mnext, Hnext, Bnext);
+    __syncthreads();
+    // ---- add w(0) and the totals of the ranges below; the row then leaves by one bulk store ---------------------------
+    if (c < ncol) {
+      double off = -sbmr[sl * VNC + c]; // :409-413 (0 without a basal melt rate)
+      for (int e = 0; e < q; ++e) off += stot[e * VNC + c];
+      const int ke = min(ks + 1, k1);
+      for (int k = k0; k < k1; ++k) {
+        const double wk = off + wc[k];
+        wc[k] = wk;
+        if (k < ke) wmax = fmax(wmax, fabs(wk));
+      }
+    }
+    fence_proxy_async();                // this thread's shared-memory writes, for the bulk-copy engine
+    if (tid == 0) bulk_wait_read0();    // the store of row r - 1 has read its slot: the next sweep may overwrite it
+    __syncthreads();
+    if (tid == 0) {
+      const int n = ncol * Mz;
+      const long a0 = (gw + 1) & ~1L, a1 = (gw + n) & ~1L; // the 16-byte aligned middle
+      const double *src = sw + sl * SW + (gw & 1);
+      if (gw & 1) A.w[gw] = src[0];
+      if ((gw + n) & 1) A.w[gw + n - 1] = src[n - 1];
+      if (a1 > a0) {
+        bulk_s2g(A.w + a0, src + (a0 - gw), (unsigned)((a1 - a0) * 8));
+        bulk_commit();
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_read0();
+  if (docfl) {
+    dmax = warp_max(dmax), umax = warp_max(umax), vmax = warp_max(vmax), wmax = warp_max(wmax);
+    __syncthreads();
+    double *red = stot;
+    const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+    if (lane == 0) red[wid] = dmax, red[8 + wid] = umax, red[16 + wid] = vmax, red[24 + wid] = wmax;
+    __syncthreads();
+    if (tid < 4) {
+      double m = 0.0;
+      for (int e = 0; e < nw; ++e) m = fmax(m, red[tid * 8 + e]);
+      // most CTAs find the running maximum already above theirs: a plain load spares the atomic
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+      if (m > 0.0 && bits > *(volatile unsigned long long *)(A.cfl + tid)) atomicMax(A.cfl + tid, bits);
+    }
+  }
+}
+
 } // namespace
 
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,
@@ -311,4 +812,52 @@ int launch_cfl(const DP &P, bool do3d, const double *thk, const double *mask, co
   return n;
 }
 
+} // namespace siafd
+
+namespace siafd {
+// the shared-memory kernel; returns 0 when it does not apply (even Mz, or rows too long for shared memory)
+int launch_vvel_slab(const DP &P, const double *mask, const double *thk, const double *u, const double *v,
+                     const double *bmr, int upstream, const double *z, double *w, unsigned long long *cfl,
+                     unsigned *err, int rows_per_cta, int wz, long nUV, double inv_dz, cudaStream_t s) {
+  if (P.xm <= 0 || P.ym <= 0) return 0;
+  const int WZ = (wz == 2 || wz == 4 || wz == 8 || wz == 16) ? wz : 16;
+  const size_t smem = vvel_smem_bytes(P.Mz);
+  if ((P.Mz & 1) == 0 || smem > 113 * 1024 || P.Mz < 3 || P.wuv < 1) return 0;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(k_vvel_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    configured = smem;
+  }
+  const int RS = rows_per_cta > 0 ? rows_per_cta : 32;
+  VvelArgs A{mask, thk, u, v, bmr, z, w, cfl, err, upstream, RS, WZ, (P.Mz + WZ - 1) / WZ, nUV, inv_dz};
+  const dim3 grid((unsigned)((P.xm + VNC - 1) / VNC), (unsigned)((P.ym + RS - 1) / RS));
+  k_vvel_slab<<<grid, VNC * WZ, smem, s>>>(P, A);
+  return 1;
+}
+
+// returns the number of launches, or 0 when Mz has more than 8 chunks of 32 levels (the caller then uses the
+// generic kernel of siafd_kernels.cu and the stand-alone CFL kernel)
+int launch_vvel_march(const DP &P, const double *mask, const double *thk, const double *u, const double *v,
+                      const double *bmr, int upstream, const double *z, double *w, unsigned long long *cfl,
+                      unsigned *err, int rows_per_cta, cudaStream_t s) {
+  if (P.xm <= 0 || P.ym <= 0) return 0;
+  const int nch = (P.Mz + 31) / 32;
+  const int RS = rows_per_cta > 0 ? rows_per_cta : 32;
+  const dim3 grid((unsigned)((P.xm + 7) / 8), (unsigned)((P.ym + RS - 1) / RS));
+  if (nch <= 1) {
+    k_vvel_march<1><<<grid, 256, 0, s>>>(P, mask, thk, u, v, bmr, upstream, z, w, RS, cfl, err);
+  } else if (nch <= 2) {
+    k_vvel_march<2><<<grid, 256, 0, s>>>(P, mask, thk, u, v, bmr, upstream, z, w, RS, cfl, err);
+  } else if (nch <= 4) {
+    k_vvel_march<4><<<grid, 256, 0, s>>>(P, mask, thk, u, v, bmr, upstream, z, w, RS, cfl, err);
+  } else if (nch <= 8) {
+    k_vvel_march<8><<<grid, 256, 0, s>>>(P, mask, thk, u, v, bmr, upstream, z, w, RS, cfl, err);
+  } else {
+    return 0;
+  }
+  return 1;
+}
 } // namespace siafd

@@ -98,6 +98,31 @@ def test_mass_continuity_and_cfl_bit_exact(name, amp):
     assert (H[wg:-wg, wg:-wg] >= 0).all() and ((es < 0) & (H[wg:-wg, wg:-wg] == 0)).any()
 
 
+@pytest.mark.parametrize("name", ["C4s", "dome_64_21", "dome_40_9", "dome_33_130"])
+def test_fused_cfl_equals_standalone_and_oracle(name):
+    """The 3D CFL maxima the marching vertical-velocity kernel takes on the fly are the stand-alone kernel's (bit for
+    bit), and w itself matches the oracle; Mz = 9, 21, 130 exercise 1, 1 and 5 chunks of 32 levels."""
+    grid, cfg, inputs, gb = cases.case(name)
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, True)
+    max_dt = 60.0 * icemodel.SECONDS_PER_YEAR_UDUNITS
+    fused, alone = (C.c_double * 8)(), (C.c_double * 8)()
+    for upstream in (0, 1):
+        sia._check(lib.siafd_b200_compute_vertical_velocity(sia.handle, upstream, 0))
+        sia._check(lib.siafd_b200_cfl(sia.handle, max_dt, 1, fused))
+        w_gpu = sia.download("w")
+        sia.upload("w", w_gpu)  # any upload invalidates the fused maxima: the next call runs the stand-alone kernel
+        sia._check(lib.siafd_b200_cfl(sia.handle, max_dt, 1, alone))
+        assert list(fused) == list(alone)
+        assert fused[1] > 0 and fused[3] > 0
+        w_or = np.zeros((grid.My, grid.Mx, grid.Mz))
+        p = cfg.oracle_params(grid)
+        u, v = np.ascontiguousarray(sia.velocity_u()), np.ascontiguousarray(sia.velocity_v())
+        assert O.lib().orc_vertical_velocity(C.byref(p), O.dptr(np.ascontiguousarray(inputs["mask"])), O.dptr(u),
+                                             O.dptr(v), None, upstream, O.dptr(w_or)) == 0
+        assert cases.rel_max(w_gpu, w_or) < 1e-10
+
+
 def test_negative_thickness_is_reported_by_ensure_consistency():
     grid, cfg, inputs, gb = cases.case("dome_64_21")
     sia = U.make_sia(grid, cfg, gb)
