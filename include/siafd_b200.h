@@ -22,6 +22,7 @@
  *   GeometryCalculator::compute  util/Mask.hh:96-133           siafd_b200_geometry_compute
  *   StressBalance::compute_vertical_velocity  StressBalance.cc:283-424   siafd_b200_compute_vertical_velocity
  *   max_timestep_cfl_3d / _2d  stressbalance/timestepping.cc:42-153      siafd_b200_cfl
+ *   StressBalance::compute_volumetric_strain_heating  StressBalance.cc:426-642  siafd_b200_compute_strain_heating
  *   GeometryEvolution::flow_step + apply_flux_divergence  geometry/GeometryEvolution.cc:241-350
  *                                                              siafd_b200_mass_flow_step
  *   GeometryEvolution::source_term_step + apply_mass_fluxes  :327-390    siafd_b200_mass_source_step
@@ -111,7 +112,8 @@ enum {
   SIAFD_B200_F_EFF_BMB = 30,     /* GeometryEvolution::bottom_surface_mass_balance [m], 2D, no ghosts */
   SIAFD_B200_F_VEL_BC_MASK = 31, /* velocity Dirichlet B.C. mask, 2D, w_geom (never uploaded = 0) */
   SIAFD_B200_F_THK_BC_MASK = 32, /* thickness Dirichlet B.C. mask, 2D, w_geom (never uploaded = 0) */
-  SIAFD_B200_F_COUNT = 33
+  SIAFD_B200_F_STRAIN_HEATING = 33, /* StressBalance::volumetric_strain_heating, 3D, no ghosts */
+  SIAFD_B200_F_COUNT = 34
 };
 
 /* Everything SIAFD's constructor and update() read from Config/IceGrid
@@ -258,6 +260,15 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update,
  * Reads the handle's mask, u, v (ghosts valid, i.e. after the wrap / exchange of SIAFD.cc:946-947) and, if
  * use_basal_melt, SIAFD_B200_F_BASAL_MELT; writes SIAFD_B200_F_W.  Asynchronous on the handle's stream. */
 int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int use_basal_melt);
+
+/* SURVEY.md 8(f) N3 -- StressBalance::compute_volumetric_strain_heating (stressbalance/StressBalance.cc:426-642):
+ * Sigma = 2 e^(-1/n) B(E, p) D2^((1/n + 1)/2) below the surface, 0 above, from the handle's THICKNESS, MASK, ENTHALPY,
+ * U, V (ghosts valid); writes STRAIN_HEATING.  The reference takes the flow law of the SHALLOW stress balance here
+ * (`stress_balance.ssa.flow_law`, `.Glen_exponent`, `.enhancement_factor`, even under ZeroSliding), so the law id,
+ * n and e are arguments; the Paterson-Budd / GPBLD / Hooke constants are the handle's.  gk has no softness
+ * (GoldsbyKohlstedt.cc:102-108): SIAFD_B200_ERR_BAD_CONFIG.  Asynchronous on the handle's stream. */
+int siafd_b200_compute_strain_heating(siafd_b200_handle *h, int flow_law, double glen_exponent,
+                                      double enhancement_factor);
 
 /* SURVEY.md 8(f) N1 -- the consumer of diffusive_flux(): GeometryEvolution (geometry/GeometryEvolution.cc), default
  * configuration (geometry.part_grid.enabled = no).  All asynchronous on the handle's stream, device-resident:

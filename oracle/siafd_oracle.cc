@@ -1342,4 +1342,108 @@ int orc_vertical_velocity(const orc_params *p, const double *mask, const double 
   return ORC_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// StressBalance::compute_volumetric_strain_heating  (src/stressbalance/StressBalance.cc:426-642)
+// SURVEY.md 8(f) N3.  p describes the flow law the reference takes here -- the SHALLOW stress balance's
+// (`stress_balance.ssa.` prefix even with ZeroSliding, ShallowStressBalance.cc / StressBalance.cc:508): its id,
+// Glen exponent fl_n and enhancement factor fl_e.  thickness, mask: 2D w_geom; enthalpy: 3D w_3d_in; u, v: 3D w_uv
+// with valid ghosts; Sigma: 3D owned only (WITHOUT_GHOSTS, StressBalance.cc:150).
+// ---------------------------------------------------------------------------------------
+int orc_strain_heating(const orc_params *p, const double *thickness, const double *mask, const double *enthalpy,
+                       const double *u, const double *v, double *Sigma_out) {
+  const Converter ec(*p);
+  std::unique_ptr<Law> law = make_law(*p, ec);
+  if (!law) {
+    return ORC_ERR_BAD_CONFIG;
+  }
+  const int Mz = p->Mz, wg = p->w_geom, wuv = p->w_uv, we = p->w_3d_in;
+  const long nxg = p->xm + 2 * wg, nxu = p->xm + 2 * wuv, nxe = p->xm + 2 * we;
+  const double *z = p->z;
+  auto M = [&](int i, int j) { return (int)floor(mask[(long)(j - (p->ys - wg)) * nxg + (i - (p->xs - wg))] + 0.5); };
+  auto icy = [&](int i, int j) { const int m = M(i, j); return m == 2 || m == 3; };
+  auto ice_free = [&](int i, int j) { return !icy(i, j); };
+  auto col = [&](const double *a, int i, int j) {
+    return a + ((long)(j - (p->ys - wuv)) * nxu + (i - (p->xs - wuv))) * Mz;
+  };
+  auto D2 = [](double u_x, double u_y, double u_z, double v_x, double v_y, double v_z) { // :446-448
+    return 0.5 * ((u_x + v_y) * (u_x + v_y) + u_x * u_x + v_y * v_y +
+                  0.5 * ((u_y + v_x) * (u_y + v_x) + u_z * u_z + v_z * v_z));
+  };
+  const double enhancement_factor = p->fl_e, n = law->exponent(), exponent = 0.5 * (1.0 / n + 1.0),
+               e_to_a_power = pow(enhancement_factor, -1.0 / n), hardness_power = -1.0 / n;
+  std::vector<double> depth(Mz), pressure(Mz), hardness(Mz);
+  for (int j = p->ys; j < p->ys + p->ym; ++j) {
+    for (int i = p->xs; i < p->xs + p->xm; ++i) {
+      const double H = thickness[(long)(j - (p->ys - wg)) * nxg + (i - (p->xs - wg))];
+      int status = ORC_OK;
+      const int ks = k_below_height(z, Mz, H, &status);
+      if (status != ORC_OK) {
+        return status;
+      }
+      double west = 1, east = 1, south = 1, north = 1, D_x = 0, D_y = 0;
+      {
+        if ((icy(i, j) and ice_free(i + 1, j)) or (ice_free(i, j) and icy(i + 1, j))) {
+          east = 0;
+        }
+        if ((icy(i, j) and ice_free(i - 1, j)) or (ice_free(i, j) and icy(i - 1, j))) {
+          west = 0;
+        }
+        if (east + west > 0) {
+          D_x = 1.0 / (p->dx * (east + west));
+        } else {
+          D_x = 0.0;
+        }
+      }
+      {
+        if ((icy(i, j) and ice_free(i, j + 1)) or (ice_free(i, j) and icy(i, j + 1))) {
+          north = 0;
+        }
+        if ((icy(i, j) and ice_free(i, j - 1)) or (ice_free(i, j) and icy(i, j - 1))) {
+          south = 0;
+        }
+        if (north + south > 0) {
+          D_y = 1.0 / (p->dy * (north + south));
+        } else {
+          D_y = 0.0;
+        }
+      }
+      const double *u_ij = col(u, i, j), *u_w = col(u, i - 1, j), *u_e = col(u, i + 1, j), *u_s = col(u, i, j - 1),
+                   *u_n = col(u, i, j + 1);
+      const double *v_ij = col(v, i, j), *v_w = col(v, i - 1, j), *v_e = col(v, i + 1, j), *v_s = col(v, i, j - 1),
+                   *v_n = col(v, i, j + 1);
+      const double *E_ij = enthalpy + ((long)(j - (p->ys - we)) * nxe + (i - (p->xs - we))) * Mz;
+      double *Sigma = Sigma_out + ((long)(j - p->ys) * p->xm + (i - p->xs)) * Mz;
+      for (int k = 0; k <= ks; ++k) {
+        depth[k] = H - z[k];
+      }
+      ec.pressure(depth, ks, pressure);
+      for (int k = 0; k <= ks; ++k) { // FlowLaw::hardness_n -> hardness_impl, FlowLaw.cc:135-144
+        hardness[k] = pow(law->softness(E_ij[k], pressure[k]), hardness_power);
+      }
+      for (int k = 0; k <= ks; ++k) {
+        double dz;
+        double u_z = 0.0, v_z = 0.0, u_x = D_x * (west * (u_ij[k] - u_w[k]) + east * (u_e[k] - u_ij[k])),
+               u_y = D_y * (south * (u_ij[k] - u_s[k]) + north * (u_n[k] - u_ij[k])),
+               v_x = D_x * (west * (v_ij[k] - v_w[k]) + east * (v_e[k] - v_ij[k])),
+               v_y = D_y * (south * (v_ij[k] - v_s[k]) + north * (v_n[k] - v_ij[k]));
+        if (k > 0) {
+          dz = z[k + 1] - z[k - 1];
+          u_z = (u_ij[k + 1] - u_ij[k - 1]) / dz;
+          v_z = (v_ij[k + 1] - v_ij[k - 1]) / dz;
+        } else {
+          dz = z[1] - z[0];
+          u_z = (u_ij[1] - u_ij[0]) / dz;
+          v_z = (v_ij[1] - v_ij[0]) / dz;
+        }
+        Sigma[k] = 2.0 * e_to_a_power * hardness[k] * pow(D2(u_x, u_y, u_z, v_x, v_y, v_z), exponent);
+      }
+      for (int k = ks + 1; k < Mz; ++k) {
+        Sigma[k] = 0.0;
+      }
+    }
+  }
+  return ORC_OK;
+}
+
 } // extern "C"

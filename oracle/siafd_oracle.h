@@ -174,6 +174,11 @@ int orc_siafd_update_single(const orc_params *p, orc_fields *f, int full);
 int orc_vertical_velocity(const orc_params *p, const double *mask, const double *u, const double *v,
                           const double *basal_melt_rate, int use_upstream_fd, double *w);
 int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, int nthreads);
+/* StressBalance::compute_volumetric_strain_heating (StressBalance.cc:426-642), SURVEY.md 8(f) N3: p carries the flow
+ * law of the SHALLOW stress balance (id, fl_n, fl_e); thickness, mask w_geom; enthalpy w_3d_in; u, v w_uv (ghosts
+ * valid); Sigma owned only. */
+int orc_strain_heating(const orc_params *p, const double *thickness, const double *mask, const double *enthalpy,
+                       const double *u, const double *v, double *Sigma_out);
 
 /* SURVEY.md 8(f) N1 / N3 (mass_oracle.cc): GeometryEvolution::flow_step + apply_flux_divergence
  * (geometry/GeometryEvolution.cc:241-350), source_term_step + apply_mass_fluxes (:327-390, :1005-1076) and the CFL

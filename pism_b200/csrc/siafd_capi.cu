@@ -133,6 +133,7 @@ FieldMeta meta(const siafd_b200_config &c, int f) {
   case SIAFD_B200_F_V:
     return {c.w_uv, c.Mz};
   case SIAFD_B200_F_W:
+  case SIAFD_B200_F_STRAIN_HEATING:
     return {0, c.Mz};
   case SIAFD_B200_F_BASAL_MELT:
   case SIAFD_B200_F_SMB:
@@ -978,6 +979,33 @@ int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int
   if (n == 0) { // more than 256 levels: generic warp-per-column kernel
     n = launch_vertical_velocity(h->P, D(SIAFD_B200_F_MASK), D(SIAFD_B200_F_U), D(SIAFD_B200_F_V), bmr, upstream, h->d_z,
                                  D(SIAFD_B200_F_W), h->stream);
+  }
+  h->launches += n;
+  h->result_pending = true;
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+// ---- volumetric strain heating -------------------------------------------------------------
+int siafd_b200_compute_strain_heating(siafd_b200_handle *h, int flow_law, double glen_exponent,
+                                      double enhancement_factor) {
+  CU(h, cudaSetDevice(h->device));
+  if (!(glen_exponent > 0.0) || !(enhancement_factor > 0.0)) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "Glen exponent and enhancement factor must be positive");
+  }
+  const int need[] = {SIAFD_B200_F_MASK, SIAFD_B200_F_THICKNESS, SIAFD_B200_F_ENTHALPY, SIAFD_B200_F_U, SIAFD_B200_F_V,
+                      SIAFD_B200_F_STRAIN_HEATING};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  const int n = launch_strain_heating(h->P, flow_law, glen_exponent, enhancement_factor, D(SIAFD_B200_F_MASK),
+                                      D(SIAFD_B200_F_THICKNESS), D(SIAFD_B200_F_ENTHALPY), D(SIAFD_B200_F_U),
+                                      D(SIAFD_B200_F_V), h->d_z, D(SIAFD_B200_F_STRAIN_HEATING), h->d_err, h->stream);
+  if (n < 0) {
+    return fail(h, SIAFD_B200_ERR_BAD_CONFIG,
+                "strain heating: flow law %d has no softness (gk: GoldsbyKohlstedt.cc:102-108) or Mz > 256", flow_law);
   }
   h->launches += n;
   h->result_pending = true;

@@ -70,6 +70,10 @@ int launch_vvel_march(const DP &P, const double *mask, const double *thk, const 
 int launch_vvel_slab(const DP &P, const double *mask, const double *thk, const double *u, const double *v,
                      const double *bmr, int upstream, const double *z, double *w, unsigned long long *cfl,
                      unsigned *err, int rows_per_cta, int wz, long nUV, double inv_dz, cudaStream_t s);
+// StressBalance::compute_volumetric_strain_heating; -1 = flow law without a softness (gk) or Mz > 256
+int launch_strain_heating(const DP &P, int law, double n, double e, const double *mask, const double *thk,
+                          const double *E, const double *u, const double *v, const double *z, double *sigma,
+                          unsigned *err, cudaStream_t s);
 // SURVEY.md 8(f) N1 / N3-CFL (siafd_mass.cu): GeometryEvolution flow and source steps, Geometry::ensure_consistency,
 // max_timestep_cfl_3d / _2d.  NULL for an optional field means "all zero".
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,

@@ -766,6 +766,126 @@ __global__ void __launch_bounds__(256, 2) k_vvel_slab(const __grid_constant__ DP
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// StressBalance::compute_volumetric_strain_heating (stressbalance/StressBalance.cc:426-642), SURVEY.md 8(f) N3.
+// Sigma = 2 e^(-1/n) B(E, p) D2^((1/n + 1)/2) on levels 0 .. ks, zero above; B = softness^(-1/n) (FlowLaw.cc:142-144)
+// of the SHALLOW stress balance's flow law (law id, n, e are arguments, not the handle's SIA law).
+// One warp per column, lanes across z, the eight warps of a CTA on eight adjacent columns, marching up the rows of a
+// row segment: every level is independent, the stencil neighbours (x: adjacent in memory; y: the rows the walk has
+// just read / reads next; z: levels k +- 1) come from L1 / L2.  For n = 3 the two powers are cube roots (x^(-1/3) = 1 / cbrt x,
+// x^(2/3) = cbrt(x)^2: two ~40-instruction calls instead of two ~150-instruction pow); other n use pow.
+// FP64-bound where there is ice (one exp, two cbrt per level), write-bound (8 Mz bytes) where there is none.
+// ---------------------------------------------------------------------------------------------
+template <int LAW> __device__ __forceinline__ double softness_eval(const DP &P, double E, double p) {
+  // literal restatements of softness_impl: the pressure-adjusted temperature is T - T_m + T_melting
+  // (util/EnthalpyConverter.cc:196-198), not the T + beta p of flow_from_temp
+  if (LAW == LAW_ISO) {
+    return P.iso_A; // rheology/IsothermalGlen.cc:41-43
+  }
+  const double T_m = ec_melting_temperature(P, p);
+  const double T_pa = ec_temperature(P, E, p) - T_m + P.T_melting;
+  if (LAW == LAW_PB) return softness_paterson_budd(P, T_pa);           // PatersonBudd.cc:41-45
+  if (LAW == LAW_ARR) return P.A_cold * exp(-P.Q_cold / (P.R * T_pa)); // PatersonBuddCold.cc:43-45
+  if (LAW == LAW_ARRWARM) return P.A_warm * exp(-P.Q_warm / (P.R * T_pa));
+  if (LAW == LAW_HOOKE) return P.hk_A * exp(-P.hk_Q / (P.R * T_pa) + 3.0 * P.hk_C * pow(P.hk_Tr - T_pa, -P.hk_K));
+  if (LAW == LAW_GPBLD) { // GPBLD.cc:49-61
+    const double E_s = P.c_i * (T_m - P.T_0);
+    if (E < E_s) return softness_paterson_budd(P, T_pa);
+    double omega = (E - E_s) / ec_L(P, T_m);
+    omega = fmin(omega, P.gp_limit);
+    return P.gp_softness_T0 * (1.0 + P.gp_coeff * omega);
+  }
+  return __longlong_as_double(0x7ff8000000000000LL); // gk: the reference throws (GoldsbyKohlstedt.cc:102-108)
+}
+
+struct HeatArgs {
+  const double *mask, *thk, *E, *u, *v, *z;
+  double *sigma;
+  unsigned *err;
+  double n, two_e_pow; // Glen exponent; 2 e^(-1/n)
+  int RS;
+};
+
+template <int LAW>
+__global__ void __launch_bounds__(256, 2) k_strain_heating(const __grid_constant__ DP P, const HeatArgs A) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = P.xs + blockIdx.x * 8 + wid;
+  if (i >= P.xs + P.xm) return;
+  const int j0 = P.ys + blockIdx.y * A.RS, j1 = min(j0 + A.RS, P.ys + P.ym);
+  const int Mz = P.Mz, nch = (Mz + 31) >> 5;
+  const bool n3 = (A.n == 3.0);
+  const double hardness_power = -1.0 / A.n, exponent = 0.5 * (1.0 / A.n + 1.0);
+  const double *__restrict__ z = A.z;
+  const double ztop = z[Mz - 1];
+  const long rowuv = (long)(P.xm + 2 * P.wuv) * Mz, rowe = (long)(P.xm + 2 * P.we) * Mz, rowg = P.xm + 2 * P.wg;
+  const double *uc_p = A.u + idx2(P, i, j0, P.wuv) * Mz, *vc_p = A.v + idx2(P, i, j0, P.wuv) * Mz;
+  const double *e_p = A.E + idx2(P, i, j0, P.we) * Mz;
+  double *s_p = A.sigma + ((long)(j0 - P.ys) * P.xm + (i - P.xs)) * Mz;
+  long g = idx2(P, i, j0, P.wg);
+  for (int j = j0; j < j1; ++j) {
+    const double H = A.thk[g];
+    // IceGrid::kBelowHeight (util/IceGrid.cc:427-440), for EVERY column, icy or not (StressBalance.cc:540): the levels
+    // are sorted, so the largest k with z[k] <= H is a count; clamped to [0, Mz - 2] like GSL's bsearch
+    int ks = 0;
+    if (H < 0.0 - 1.0e-6) {
+      if (lane == 0) atomicOr(A.err, EB_BELOW);
+    } else if (H > ztop + 1.0e-6) {
+      if (lane == 0) atomicOr(A.err, EB_ABOVE);
+    } else {
+      int cnt = 0;
+      for (int c = 0; c < nch; ++c) {
+        const int k = c * 32 + lane;
+        cnt += __popc(__ballot_sync(FULLMASK, (k < Mz) && z[min(k, Mz - 1)] <= H));
+      }
+      ks = min(max(cnt - 1, 0), Mz - 2);
+    }
+    const int M0 = mask_int(A.mask[g]), Me = mask_int(A.mask[g + 1]), Mw = mask_int(A.mask[g - 1]),
+              Mn = mask_int(A.mask[g + rowg]), Ms = mask_int(A.mask[g - rowg]);
+    const bool icy0 = m_icy(M0);
+    double west = 1.0, east = 1.0, south = 1.0, north = 1.0;
+    if (icy0 != m_icy(Me)) east = 0;
+    if (icy0 != m_icy(Mw)) west = 0;
+    if (icy0 != m_icy(Mn)) north = 0;
+    if (icy0 != m_icy(Ms)) south = 0;
+    // 1 / (dx (east + west)) with east + west in {0, 1, 2}: RN(1 / dx) and exactly half of it, no division
+    const double D_x = (east + west > 1.5) ? 0.5 * P.inv_dx : ((east + west > 0) ? P.inv_dx : 0.0);
+    const double D_y = (north + south > 1.5) ? 0.5 * P.inv_dy : ((north + south > 0) ? P.inv_dy : 0.0);
+    const double a_e = D_x * east, a_w = D_x * west, a_n = D_y * north, a_s = D_y * south;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      const int k = c * 32 + lane;
+      double sig = 0.0;
+      if (c * 32 <= ks && k <= ks) { // (chunks wholly above the ice skip the arithmetic warp-uniformly)
+        const double uc = uc_p[k], vc = vc_p[k];
+        const double u_x = a_w * (uc - uc_p[k - Mz]) + a_e * (uc_p[k + Mz] - uc);
+        const double v_x = a_w * (vc - vc_p[k - Mz]) + a_e * (vc_p[k + Mz] - vc);
+        const double u_y = a_s * (uc - uc_p[k - rowuv]) + a_n * (uc_p[k + rowuv] - uc);
+        const double v_y = a_s * (vc - vc_p[k - rowuv]) + a_n * (vc_p[k + rowuv] - vc);
+        const int kp = k + 1, km = max(k - 1, 0); // k <= ks <= Mz - 2: level k + 1 exists; one-sided at the base
+        const double dz = z[kp] - z[km];
+        const double u_z = (uc_p[kp] - uc_p[km]) / dz, v_z = (vc_p[kp] - vc_p[km]) / dz;
+        const double d2 = 0.5 * ((u_x + v_y) * (u_x + v_y) + u_x * u_x + v_y * v_y +
+                                 0.5 * ((u_y + v_x) * (u_y + v_x) + u_z * u_z + v_z * v_z));
+        const double pr = P.p_air + P.rg * (H - z[k]); // EnthalpyConverter.cc:137-152 (no depth clamp)
+        const double soft = softness_eval<LAW>(P, e_p[k], pr);
+        double hard, dpow;
+        if (n3) {
+          hard = 1.0 / cbrt(soft);
+          const double cr = cbrt(d2);
+          dpow = cr * cr;
+        } else {
+          hard = pow(soft, hardness_power);
+          dpow = pow(d2, exponent);
+        }
+        sig = A.two_e_pow * hard * dpow;
+      }
+      if (k < Mz) s_p[k] = sig;
+    }
+    uc_p += rowuv, vc_p += rowuv, e_p += rowe, s_p += (long)P.xm * Mz, g += rowg;
+  }
+}
+
 } // namespace
 
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,
@@ -859,5 +979,38 @@ int launch_vvel_march(const DP &P, const double *mask, const double *thk, const 
     return 0;
   }
   return 1;
+}
+} // namespace siafd
+
+namespace siafd {
+template <int LAW>
+static int launch_heat_law(const DP &P, const HeatArgs &A, cudaStream_t s) {
+  const dim3 grid((unsigned)((P.xm + 7) / 8), (unsigned)((P.ym + A.RS - 1) / A.RS));
+  k_strain_heating<LAW><<<grid, 256, 0, s>>>(P, A);
+  return 1;
+}
+
+// returns launches, or -1: law not supported here (gk has no softness, GoldsbyKohlstedt.cc:102-108)
+int launch_strain_heating(const DP &P, int law, double n, double e, const double *mask, const double *thk,
+                          const double *E, const double *u, const double *v, const double *z, double *sigma,
+                          unsigned *err, cudaStream_t s) {
+  if (P.xm <= 0 || P.ym <= 0) return 0;
+  HeatArgs A{mask, thk, E, u, v, z, sigma, err, n, 2.0 * pow(e, -1.0 / n), 32};
+  switch (law) {
+  case LAW_ISO:
+    return launch_heat_law<LAW_ISO>(P, A, s);
+  case LAW_PB:
+    return launch_heat_law<LAW_PB>(P, A, s);
+  case LAW_GPBLD:
+    return launch_heat_law<LAW_GPBLD>(P, A, s);
+  case LAW_HOOKE:
+    return launch_heat_law<LAW_HOOKE>(P, A, s);
+  case LAW_ARR:
+    return launch_heat_law<LAW_ARR>(P, A, s);
+  case LAW_ARRWARM:
+    return launch_heat_law<LAW_ARRWARM>(P, A, s);
+  default:
+    return -1;
+  }
 }
 } // namespace siafd

@@ -236,6 +236,21 @@ class SIAFD(SSB_Modifier):
         self.m_w = self.download("w")
         return self.m_w
 
+    # -- SURVEY.md 8(f) N3 (a StressBalance member in the reference) -------------------------------------------
+    def compute_volumetric_strain_heating(self, flow_law="gpbld", glen_exponent=3.0, enhancement_factor=1.0):
+        """StressBalance::compute_volumetric_strain_heating (StressBalance.cc:426-642) from the thickness, mask,
+        enthalpy, u, v of the last full update (resident on the device).  flow_law / glen_exponent /
+        enhancement_factor: the SHALLOW stress balance's (`stress_balance.ssa.*`), as in the reference.
+        Returns Sigma on the owned points, [ym, xm, Mz]."""
+        law = capi.FLOW_LAWS[flow_law] if isinstance(flow_law, str) else int(flow_law)
+        self._check(lib.siafd_b200_compute_strain_heating(self._h, law, glen_exponent, enhancement_factor))
+        self._check(lib.siafd_b200_finish(self._h))
+        self.m_strain_heating = self.download("strain_heating")
+        return self.m_strain_heating
+
+    def volumetric_strain_heating(self):
+        return getattr(self, "m_strain_heating", None)
+
     def velocity_w(self):
         return getattr(self, "m_w", None)
 

@@ -102,6 +102,7 @@ def lib():
         L.orc_siafd_update_single.argtypes = [PP, FP, C.c_int]
         L.orc_siafd_update_many.argtypes = [C.c_int, PP, FP, C.c_int, C.c_int]
         L.orc_vertical_velocity.argtypes = [PP, _pd, _pd, _pd, _pd, C.c_int, _pd]
+        L.orc_strain_heating.argtypes = [PP, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_mass_flow_step.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_mass_source_step.argtypes = [PP, _f64, _f64, C.c_int, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_cfl_3d.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd]

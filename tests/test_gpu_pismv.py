@@ -123,6 +123,37 @@ def test_fused_cfl_equals_standalone_and_oracle(name):
         assert cases.rel_max(w_gpu, w_or) < 1e-10
 
 
+@pytest.mark.parametrize("name,law,n,e", [("C4s", "gpbld", 3.0, 1.0), ("C4s", "pb", 3.0, 0.6), ("Fs", "arr", 3.0, 1.0),
+                                          ("dome_64_21", "gpbld", 4.0, 2.0), ("dome_33_130", "hooke", 3.0, 1.0),
+                                          ("C1_31", "isothermal_glen", 3.0, 1.0), ("dome_40_9", "arrwarm", 3.0, 3.0)])
+def test_strain_heating_matches_oracle(name, law, n, e):
+    """Sigma within 1e-10 (max-norm relative) of the oracle, exact zeros above the ice and in ice-free
+    columns, for every flow law that has a softness; the flow law is the shallow stress balance's, not SIAFD's."""
+    grid, cfg, inputs, gb = cases.case(name)
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, True)
+    sig = sia.compute_volumetric_strain_heating(law, n, e)
+    p = cfg.oracle_params(grid)
+    p.flow_law, p.fl_n, p.fl_e = O.FLOW_LAWS[law], n, e
+    u, v = np.ascontiguousarray(sia.velocity_u()), np.ascontiguousarray(sia.velocity_v())
+    ref = np.zeros((grid.My, grid.Mx, grid.Mz))
+    assert O.lib().orc_strain_heating(C.byref(p), O.dptr(np.ascontiguousarray(inputs["thickness"])),
+                                      O.dptr(np.ascontiguousarray(inputs["mask"])),
+                                      O.dptr(np.ascontiguousarray(inputs["enthalpy"])), O.dptr(u), O.dptr(v),
+                                      O.dptr(ref)) == 0
+    assert ref.max() > 0
+    assert cases.rel_max(sig, ref) < 1e-10, cases.rel_max(sig, ref)
+    assert np.array_equal(sig == 0.0, ref == 0.0)
+
+
+def test_strain_heating_rejects_gk():
+    from pism_b200 import capi
+    grid, cfg, inputs, gb = cases.case("dome_40_9")
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, True)
+    assert lib.siafd_b200_compute_strain_heating(sia.handle, capi.FLOW_LAWS["gk"], 3.0, 1.0) == capi.ERR_BAD_CONFIG
+
+
 def test_negative_thickness_is_reported_by_ensure_consistency():
     grid, cfg, inputs, gb = cases.case("dome_64_21")
     sia = U.make_sia(grid, cfg, gb)

@@ -178,3 +178,44 @@ def test_semantics_gotchas():
     cfg.limit_diffusivity = 0
     run4 = cases.oracle_run(grid, cfg, inputs, full=False)
     assert run4.status == 5
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_EXACT), reason="oracle/_ref not built (needs /root/reference)")
+def test_strain_heating_against_exact_solution_F():
+    """the oracle's volumetric strain heating on the test-F state against the reference's exact
+    Sigma (exactTestsFG.cc, compiled unmodified): the reference reports maxSig / avSig errors of this size for
+    `pismv -test F` on a 61^3 grid (a second-order scheme on a 30 km grid: a few per cent away from the margin)."""
+    import cases
+    grid, cfg, inputs, _ = cases.case("F")
+    run = cases.oracle_run(grid, cfg, inputs, None, full=True)
+    assert run.status == 0
+    p = cfg.oracle_params(grid)
+    p.flow_law, p.fl_n, p.fl_e = O.FLOW_LAWS["arr"], 3.0, 1.0
+    sig = np.zeros((grid.My, grid.Mx, grid.Mz))
+    a = run.a
+    assert O.lib().orc_strain_heating(C.byref(p), O.dptr(a["thickness"]), O.dptr(a["mask"]), O.dptr(a["enthalpy"]),
+                                      O.dptr(a["u"]), O.dptr(a["v"]), O.dptr(sig)) == 0
+    ref = C.CDLL(O.REF_EXACT)
+    ref.ref_exactFG.argtypes = [C.c_double, C.c_double, C.c_int] + [C.POINTER(C.c_double)] + [C.c_double] + \
+        [C.POINTER(C.c_double)] * 7
+    Mz = grid.Mz
+    z = np.ascontiguousarray(grid.z)
+    worst, n, errs = 0.0, 0, []
+    for j in range(grid.My):
+        for i in range(grid.Mx):
+            r = float(np.hypot(grid.x[i], grid.y[j]))
+            if not (100e3 < r < 600e3):  # away from the dome (Sigma -> 0) and from the margin (one-sided stencils)
+                continue
+            H, M = C.c_double(), C.c_double()
+            outs = [np.zeros(Mz) for _ in range(5)]
+            assert ref.ref_exactFG(0.0, r, Mz, O.dptr(z), 0.0, C.byref(H), C.byref(M), *[O.dptr(o) for o in outs]) == 0
+            exact = outs[3] * (910.0 * 2009.0)  # K s-1 -> W m-3, as compute_strain_heating_errors does (iCMthermo.cc:412)
+            ks = grid.k_below_height(H.value)
+            k = slice(1, max(ks - 1, 2))  # the base level uses a one-sided (first-order) u_z: ~15 % low there
+            scale = np.abs(exact[k]).max()
+            errs.append(np.abs(sig[j, i, k] - exact[k]).max() / scale)
+            worst = max(worst, errs[-1])
+            n += 1
+    assert n > 500
+    print("strain heating vs exact F: worst %.4f mean %.4f" % (worst, np.mean(errs)))
+    assert worst < 0.05 and np.mean(errs) < 0.03, (worst, np.mean(errs))
