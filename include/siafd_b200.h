@@ -23,6 +23,8 @@
  *   StressBalance::compute_vertical_velocity  StressBalance.cc:283-424   siafd_b200_compute_vertical_velocity
  *   max_timestep_cfl_3d / _2d  stressbalance/timestepping.cc:42-153      siafd_b200_cfl
  *   StressBalance::compute_volumetric_strain_heating  StressBalance.cc:426-642  siafd_b200_compute_strain_heating
+ *   SIAFD_Regional::compute_surface_gradient  regional/SIAFD_Regional.cc:46-116
+ *                                               siafd_b200_compute_gradient_no_model + _apply_no_model_gradient
  *   GeometryEvolution::flow_step + apply_flux_divergence  geometry/GeometryEvolution.cc:241-350
  *                                                              siafd_b200_mass_flow_step
  *   GeometryEvolution::source_term_step + apply_mass_fluxes  :327-390    siafd_b200_mass_source_step
@@ -113,7 +115,12 @@ enum {
   SIAFD_B200_F_VEL_BC_MASK = 31, /* velocity Dirichlet B.C. mask, 2D, w_geom (never uploaded = 0) */
   SIAFD_B200_F_THK_BC_MASK = 32, /* thickness Dirichlet B.C. mask, 2D, w_geom (never uploaded = 0) */
   SIAFD_B200_F_STRAIN_HEATING = 33, /* StressBalance::volumetric_strain_heating, 3D, no ghosts */
-  SIAFD_B200_F_COUNT = 34
+  /* 34..37: SIAFD_Regional (regional/SIAFD_Regional.cc), SURVEY.md 8(f) N4 */
+  SIAFD_B200_F_NO_MODEL_MASK = 34,    /* Inputs::no_model_mask, 2D, w_geom */
+  SIAFD_B200_F_NO_MODEL_SURFACE = 35, /* Inputs::no_model_surface_elevation, 2D, w_geom */
+  SIAFD_B200_F_H_X_NO_MODEL = 36,
+  SIAFD_B200_F_H_Y_NO_MODEL = 37,     /* Stag, w_stag: SIAFD_Regional::m_h_x_no_model / m_h_y_no_model */
+  SIAFD_B200_F_COUNT = 38
 };
 
 /* Everything SIAFD's constructor and update() read from Config/IceGrid
@@ -260,6 +267,14 @@ int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update,
  * Reads the handle's mask, u, v (ghosts valid, i.e. after the wrap / exchange of SIAFD.cc:946-947) and, if
  * use_basal_melt, SIAFD_B200_F_BASAL_MELT; writes SIAFD_B200_F_W.  Asynchronous on the handle's stream. */
 int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int use_basal_melt);
+
+/* SURVEY.md 8(f) N4 -- SIAFD_Regional::compute_surface_gradient (regional/SIAFD_Regional.cc:46-116), the regional
+ * model's override of the protected phase SIAFD.hh:72-75.  After siafd_b200_compute_gradient and the wrap / exchange
+ * of H_X, H_Y:  _compute_gradient_no_model = surface_gradient_haseloff on NO_MODEL_SURFACE (always haseloff, whatever
+ * the configured method) into H_X_NO_MODEL / H_Y_NO_MODEL; the caller wraps / exchanges those two (width 1); then
+ * _apply_no_model_gradient overrides H_X, H_Y next to NO_MODEL_MASK cells on owned + 1.  Asynchronous. */
+int siafd_b200_compute_gradient_no_model(siafd_b200_handle *h);
+int siafd_b200_apply_no_model_gradient(siafd_b200_handle *h);
 
 /* SURVEY.md 8(f) N3 -- StressBalance::compute_volumetric_strain_heating (stressbalance/StressBalance.cc:426-642):
  * Sigma = 2 e^(-1/n) B(E, p) D2^((1/n + 1)/2) below the surface, 0 above, from the handle's THICKNESS, MASK, ENTHALPY,

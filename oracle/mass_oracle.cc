@@ -294,4 +294,54 @@ int orc_cfl_2d(const orc_params *p, double max_dt_seconds, const double *mask, c
   return ORC_OK;
 }
 
+
+// SIAFD_Regional::compute_surface_gradient, the override loop (src/regional/SIAFD_Regional.cc:63-116), SURVEY.md 8(f)
+// N4.  no_model: the no_model_mask (2D w_geom, ghosts valid); hx_nm / hy_nm: the haseloff gradient of
+// no_model_surface_elevation (Stag w_stag, ghosts valid; the caller computes it with orc_siafd_gradient on a
+// field set whose surface is the stored one and whose method is haseloff, SIAFD_Regional.cc:52-55); h_x, h_y:
+// the regular gradient, overridden in place on owned + 1.
+int orc_regional_gradient_override(const orc_params *p, const double *no_model, const double *hx_nm,
+                                   const double *hy_nm, double *h_x, double *h_y) {
+  const int wg = p->w_geom, ws = p->w_stag, Mx = p->Mx, My = p->My;
+  const long nxg = p->xm + 2 * wg, nxs = p->xm + 2 * ws;
+  auto NM = [&](int i, int j) { return (int)floor(no_model[(long)(j - (p->ys - wg)) * nxg + (i - (p->xs - wg))] + 0.5); };
+  auto S = [&](int i, int j, int o) { return ((long)(j - (p->ys - ws)) * nxs + (i - (p->xs - ws))) * 2 + o; };
+  for (int j = p->ys - 1; j < p->ys + p->ym + 1; ++j) {
+    for (int i = p->xs - 1; i < p->xs + p->xm + 1; ++i) {
+      // BoxStencil (iceModelVec.hh:54-57): ij, n, nw, w, sw, s, se, e, ne
+      const int ij = NM(i, j), n = NM(i, j + 1), nw = NM(i - 1, j + 1), w = NM(i - 1, j), s = NM(i, j - 1),
+                se = NM(i + 1, j - 1), e = NM(i + 1, j), ne = NM(i + 1, j + 1);
+      if (ij > 0.5 or e > 0.5) { // x-component, i-offset
+        if (i < 0 or i + 1 > Mx - 1) {
+          h_x[S(i, j, 0)] = 0.0;
+        } else {
+          h_x[S(i, j, 0)] = hx_nm[S(i, j, 0)];
+        }
+      }
+      if (nw > 0.5 or ne > 0.5 or w > 0.5 or e > 0.5) { // x-component, j-offset
+        if (i - 1 < 0 or j + 1 > My - 1 or i + 1 > Mx - 1) {
+          h_x[S(i, j, 1)] = 0.0;
+        } else {
+          h_x[S(i, j, 1)] = hx_nm[S(i, j, 1)];
+        }
+      }
+      if (n > 0.5 or ne > 0.5 or s > 0.5 or se > 0.5) { // y-component, i-offset
+        if (i < 0 or j + 1 > My - 1 or i + 1 > Mx - 1 or j - 1 < 0) {
+          h_y[S(i, j, 0)] = 0.0;
+        } else {
+          h_y[S(i, j, 0)] = hy_nm[S(i, j, 0)];
+        }
+      }
+      if (ij > 0.5 or n > 0.5) { // y-component, j-offset
+        if (j < 0 or j + 1 > My - 1) {
+          h_y[S(i, j, 1)] = 0.0;
+        } else {
+          h_y[S(i, j, 1)] = hy_nm[S(i, j, 1)];
+        }
+      }
+    }
+  }
+  return ORC_OK;
+}
+
 } // extern "C"

@@ -193,6 +193,9 @@ int orc_mass_source_step(const orc_params *p, double dt, double ice_density, int
 int orc_cfl_3d(const orc_params *p, double max_dt_seconds, const double *thickness, const double *mask,
                const double *u3, const double *v3, const double *w3, double *out);
 int orc_cfl_2d(const orc_params *p, double max_dt_seconds, const double *mask, const double *velocity, double *out);
+/* SIAFD_Regional::compute_surface_gradient's override loop (regional/SIAFD_Regional.cc:63-116), SURVEY.md 8(f) N4. */
+int orc_regional_gradient_override(const orc_params *p, const double *no_model, const double *hx_nm,
+                                   const double *hy_nm, double *h_x, double *h_y);
 
 #ifdef __cplusplus
 }

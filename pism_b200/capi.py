@@ -13,7 +13,8 @@ ERR_DIFFUSIVITY, ERR_BAD_CONFIG, ERR_CUDA, ERR_BAD_ARGUMENT = 5, 6, 7, 8
 
 FIELDS = ["surface", "thickness", "mask", "bed", "enthalpy", "age", "sliding", "topgsmooth", "maxtl", "C2", "C3",
           "C4", "h_x", "h_y", "D", "flux", "u", "v", "thk_smooth", "theta", "w_i", "w_j", "w", "basal_melt",
-          "sea_level", "smb", "thk_change", "flux_div", "cons_err", "eff_smb", "eff_bmb", "vel_bc_mask", "thk_bc_mask", "strain_heating"]
+          "sea_level", "smb", "thk_change", "flux_div", "cons_err", "eff_smb", "eff_bmb", "vel_bc_mask", "thk_bc_mask", "strain_heating",
+          "no_model_mask", "no_model_surface", "h_x_no_model", "h_y_no_model"]
 F = {name: i for i, name in enumerate(FIELDS)}
 
 _i32, _f64, _pd = C.c_int32, C.c_double, C.POINTER(C.c_double)
@@ -95,6 +96,8 @@ def _load():
         "siafd_b200_compute_gradient": (C.c_int, [vp]),
         "siafd_b200_compute_flux_velocity": (C.c_int, [vp, C.c_int, C.c_double]),
         "siafd_b200_compute_vertical_velocity": (C.c_int, [vp, C.c_int, C.c_int]),
+        "siafd_b200_compute_gradient_no_model": (C.c_int, [vp]),
+        "siafd_b200_apply_no_model_gradient": (C.c_int, [vp]),
         "siafd_b200_compute_strain_heating": (C.c_int, [vp, C.c_int, C.c_double, C.c_double]),
         "siafd_b200_mass_flow_step": (C.c_int, [vp, C.c_double]),
         "siafd_b200_mass_source_step": (C.c_int, [vp, C.c_double, C.c_double, C.c_int]),

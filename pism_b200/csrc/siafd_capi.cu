@@ -116,6 +116,8 @@ FieldMeta meta(const siafd_b200_config &c, int f) {
   case SIAFD_B200_F_W_I:
   case SIAFD_B200_F_W_J:
   case SIAFD_B200_F_SEA_LEVEL:
+  case SIAFD_B200_F_NO_MODEL_MASK:
+  case SIAFD_B200_F_NO_MODEL_SURFACE:
   case SIAFD_B200_F_VEL_BC_MASK:
   case SIAFD_B200_F_THK_BC_MASK:
     return {c.w_geom, 1};
@@ -128,6 +130,8 @@ FieldMeta meta(const siafd_b200_config &c, int f) {
   case SIAFD_B200_F_H_Y:
   case SIAFD_B200_F_D:
   case SIAFD_B200_F_FLUX:
+  case SIAFD_B200_F_H_X_NO_MODEL:
+  case SIAFD_B200_F_H_Y_NO_MODEL:
     return {c.w_stag, 2};
   case SIAFD_B200_F_U:
   case SIAFD_B200_F_V:
@@ -982,6 +986,43 @@ int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int
   }
   h->launches += n;
   h->result_pending = true;
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+// ---- SIAFD_Regional::compute_surface_gradient -------------------------------------------------
+int siafd_b200_compute_gradient_no_model(siafd_b200_handle *h) {
+  CU(h, cudaSetDevice(h->device));
+  const int need[] = {SIAFD_B200_F_NO_MODEL_SURFACE, SIAFD_B200_F_MASK,  SIAFD_B200_F_H_X_NO_MODEL,
+                      SIAFD_B200_F_H_Y_NO_MODEL,     SIAFD_B200_F_W_I,   SIAFD_B200_F_W_J,
+                      SIAFD_B200_F_THICKNESS,        SIAFD_B200_F_BED};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  Fields F = fields_of(h);
+  F.h = (const double *)h->buf[SIAFD_B200_F_NO_MODEL_SURFACE];
+  F.h_x = (double *)h->buf[SIAFD_B200_F_H_X_NO_MODEL];
+  F.h_y = (double *)h->buf[SIAFD_B200_F_H_Y_NO_MODEL];
+  DP P = h->P;
+  P.grad = SIAFD_B200_GRAD_HASELOFF; // regional/SIAFD_Regional.cc:52-55 calls surface_gradient_haseloff directly
+  h->launches += launch_gradient(P, F, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_apply_no_model_gradient(siafd_b200_handle *h) {
+  CU(h, cudaSetDevice(h->device));
+  const int need[] = {SIAFD_B200_F_NO_MODEL_MASK, SIAFD_B200_F_H_X_NO_MODEL, SIAFD_B200_F_H_Y_NO_MODEL,
+                      SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
+  for (int f : need) {
+    int st = ensure(h, f);
+    if (st) return st;
+  }
+  auto D = [&](int f) { return (double *)h->buf[f]; };
+  h->launches += launch_regional_override(h->P, D(SIAFD_B200_F_NO_MODEL_MASK), D(SIAFD_B200_F_H_X_NO_MODEL),
+                                          D(SIAFD_B200_F_H_Y_NO_MODEL), D(SIAFD_B200_F_H_X), D(SIAFD_B200_F_H_Y),
+                                          h->stream);
   CU(h, cudaGetLastError());
   return SIAFD_B200_OK;
 }

@@ -74,6 +74,8 @@ int launch_vvel_slab(const DP &P, const double *mask, const double *thk, const d
 int launch_strain_heating(const DP &P, int law, double n, double e, const double *mask, const double *thk,
                           const double *E, const double *u, const double *v, const double *z, double *sigma,
                           unsigned *err, cudaStream_t s);
+int launch_regional_override(const DP &P, const double *no_model, const double *hx_nm, const double *hy_nm, double *h_x,
+                             double *h_y, cudaStream_t s);
 // SURVEY.md 8(f) N1 / N3-CFL (siafd_mass.cu): GeometryEvolution flow and source steps, Geometry::ensure_consistency,
 // max_timestep_cfl_3d / _2d.  NULL for an optional field means "all zero".
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,

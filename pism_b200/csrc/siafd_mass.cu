@@ -886,6 +886,28 @@ __global__ void __launch_bounds__(256, 2) k_strain_heating(const __grid_constant
   }
 }
 
+
+// SIAFD_Regional::compute_surface_gradient, the override loop (regional/SIAFD_Regional.cc:63-116), SURVEY.md 8(f) N4:
+// next to no_model cells the gradient of the stored surface (haseloff, computed beforehand into hx_nm / hy_nm with
+// valid ghosts) replaces the regular one; zero where the stencil leaves the domain.  On owned + 1.
+__global__ void k_regional_override(const __grid_constant__ DP P, const double *__restrict__ no_model,
+                                    const double *__restrict__ hx_nm, const double *__restrict__ hy_nm,
+                                    double *__restrict__ h_x, double *__restrict__ h_y) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nx = P.xm + 2;
+  if (q >= (long)nx * (P.ym + 2)) return;
+  const int i = P.xs - 1 + (int)(q % nx), j = P.ys - 1 + (int)(q / nx);
+  auto NM = [&](int ii, int jj) { return mask_int(no_model[idx2(P, ii, jj, P.wg)]) >= 1; };
+  const bool ij = NM(i, j), n = NM(i, j + 1), nw = NM(i - 1, j + 1), w = NM(i - 1, j), s = NM(i, j - 1),
+             se = NM(i + 1, j - 1), e = NM(i + 1, j), ne = NM(i + 1, j + 1);
+  const long o = idx2(P, i, j, P.wst) * 2;
+  const int Mx = P.Mx, My = P.My;
+  if (ij || e) h_x[o] = (i < 0 || i + 1 > Mx - 1) ? 0.0 : hx_nm[o];
+  if (nw || ne || w || e) h_x[o + 1] = (i - 1 < 0 || j + 1 > My - 1 || i + 1 > Mx - 1) ? 0.0 : hx_nm[o + 1];
+  if (n || ne || s || se) h_y[o] = (i < 0 || j + 1 > My - 1 || i + 1 > Mx - 1 || j - 1 < 0) ? 0.0 : hy_nm[o];
+  if (ij || n) h_y[o + 1] = (j < 0 || j + 1 > My - 1) ? 0.0 : hy_nm[o + 1];
+}
+
 } // namespace
 
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,
@@ -1012,5 +1034,14 @@ int launch_strain_heating(const DP &P, int law, double n, double e, const double
   default:
     return -1;
   }
+}
+} // namespace siafd
+
+namespace siafd {
+int launch_regional_override(const DP &P, const double *no_model, const double *hx_nm, const double *hy_nm, double *h_x,
+                             double *h_y, cudaStream_t s) {
+  const long n = (long)(P.xm + 2) * (P.ym + 2);
+  k_regional_override<<<nblk_(n, 256), 256, 0, s>>>(P, no_model, hx_nm, hy_nm, h_x, h_y);
+  return 1;
 }
 } // namespace siafd

@@ -62,11 +62,15 @@ class Geometry:
 class Inputs:
     """stressbalance::Inputs (StressBalance.hh:41-65): only the members SIAFD reads."""
 
-    def __init__(self, geometry=None, enthalpy=None, age=None, new_bed_elevation=True):
+    def __init__(self, geometry=None, enthalpy=None, age=None, new_bed_elevation=True, no_model_mask=None,
+                 no_model_surface_elevation=None):
         self.geometry = geometry
         self.new_bed_elevation = new_bed_elevation  # default true, StressBalance.cc:40
         self.enthalpy = enthalpy
         self.age = age
+        # regional models only (StressBalance.hh:59-62)
+        self.no_model_mask = no_model_mask
+        self.no_model_surface_elevation = no_model_surface_elevation
 
 
 class SSB_Modifier:
@@ -266,3 +270,48 @@ class SIAFD(SSB_Modifier):
 
     def high_diffusivity_count(self):
         return lib.siafd_b200_high_diffusivity_count(self._h)
+
+
+class SIAFD_Regional(SIAFD):
+    """stressbalance::SIAFD_Regional (src/regional/SIAFD_Regional.cc): SIAFD whose surface gradient next to
+    `no_model_mask` cells is that of the stored `no_model_surface_elevation`.  Single rank,
+    host arrays; runs the update through the split form of the C ABI because the override sits between the
+    gradient and the flux (SIAFD.cc:137-141)."""
+
+    def init(self):
+        super().init()
+
+    def update(self, sliding_velocity, inputs, full_update):
+        geo = inputs.geometry
+        if inputs.no_model_mask is None or inputs.no_model_surface_elevation is None:
+            raise PISMRuntimeError(capi.ERR_BAD_ARGUMENT, "SIAFD_Regional needs no_model_mask and "
+                                                          "no_model_surface_elevation (StressBalance.hh:59-62)")
+        if inputs.new_bed_elevation and self.config.smoother_range > 0.0:
+            self.preprocess_bed(self._global_bed)
+        h = self._h
+        for name, a in (("surface", geo.ice_surface_elevation), ("thickness", geo.ice_thickness),
+                        ("mask", geo.cell_type), ("bed", geo.bed_elevation), ("enthalpy", inputs.enthalpy),
+                        ("age", inputs.age), ("sliding", sliding_velocity), ("no_model_mask", inputs.no_model_mask),
+                        ("no_model_surface", inputs.no_model_surface_elevation)):
+            if a is not None:
+                self.upload(name, a)
+
+        def wrap(*names):
+            ids = (C.c_int * len(names))(*[F[n] for n in names])
+            self._check(lib.siafd_b200_wrap_ghosts_many(h, len(names), ids))
+
+        self._check(lib.siafd_b200_compute_gradient(h))            # SIAFD::compute_surface_gradient
+        wrap("h_x", "h_y")
+        self._check(lib.siafd_b200_compute_gradient_no_model(h))   # SIAFD_Regional.cc:52-55
+        wrap("h_x_no_model", "h_y_no_model")
+        self._check(lib.siafd_b200_apply_no_model_gradient(h))     # SIAFD_Regional.cc:63-116
+        self._check(lib.siafd_b200_compute_flux_velocity(h, 1 if full_update else 0, self.current_time))
+        if full_update:
+            wrap("u", "v")
+        status = lib.siafd_b200_finish(h)
+        self.m_D_max = lib.siafd_b200_max_diffusivity(h)
+        self.m_h_x, self.m_h_y, self.m_D = self.download("h_x"), self.download("h_y"), self.download("D")
+        self.m_diffusive_flux = self.download("flux")
+        if full_update:
+            self.m_u, self.m_v = self.download("u"), self.download("v")
+        self._check(status)

@@ -107,6 +107,7 @@ def lib():
         L.orc_mass_source_step.argtypes = [PP, _f64, _f64, C.c_int, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_cfl_3d.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_cfl_2d.argtypes = [PP, _f64, _pd, _pd, _pd]
+        L.orc_regional_gradient_override.argtypes = [PP, _pd, _pd, _pd, _pd, _pd]
         _lib = L
     return _lib
 

@@ -154,6 +154,55 @@ def test_strain_heating_rejects_gk():
     assert lib.siafd_b200_compute_strain_heating(sia.handle, capi.FLOW_LAWS["gk"], 3.0, 1.0) == capi.ERR_BAD_CONFIG
 
 
+@pytest.mark.parametrize("name", ["C4s_nosmooth", "dome_64_21_mahaffy"])
+def test_siafd_regional_gradient_override(name):
+    """SIAFD_Regional -- the gradient next to no_model cells is the stored surface's (haseloff, whatever
+    the configured method), zero where the stencil leaves the domain; gradients bit-exact, D / Q / u / v to 1e-10."""
+    from pism_b200.sia import SIAFD_Regional, Geometry, Inputs
+    grid, cfg, inputs, gb = cases.case(name)
+    w = cfg.w_geom
+    no_model = np.zeros_like(inputs["mask"])
+    strip = 5
+    no_model[w:w + strip, :] = 1
+    no_model[-w - strip:-w, :] = 1
+    no_model[:, w:w + strip] = 1
+    no_model[:, -w - strip:-w] = 1
+    no_model[w + 20:w + 24, w + 20:w + 26] = 1  # and an island inside
+    G.wrap_ghosts(no_model, w)
+    usurf_stored = np.ascontiguousarray(inputs["surface"] * 0.97 + 5.0)
+    # oracle: regular gradient, gradient of the stored surface (haseloff), override, then flux + velocity
+    p = cfg.oracle_params(grid)
+    run = O.Run(p, inputs)
+    assert run.gradient() == 0
+    for k in ("h_x", "h_y"):
+        G.wrap_ghosts(run.a[k], cfg.w_stag)
+    p_nm = cfg.oracle_params(grid)
+    p_nm.gradient_method = O.GRADIENTS["haseloff"]
+    nm_inputs = dict(inputs)
+    nm_inputs["surface"] = usurf_stored
+    run_nm = O.Run(p_nm, nm_inputs)
+    assert run_nm.gradient() == 0
+    for k in ("h_x", "h_y"):
+        G.wrap_ghosts(run_nm.a[k], cfg.w_stag)
+    assert O.lib().orc_regional_gradient_override(C.byref(p), O.dptr(no_model), O.dptr(run_nm.a["h_x"]),
+                                                  O.dptr(run_nm.a["h_y"]), O.dptr(run.a["h_x"]),
+                                                  O.dptr(run.a["h_y"])) == 0
+    assert run.flux_velocity(True) == 0
+    for k in ("u", "v"):
+        G.wrap_ghosts(run.a[k], cfg.w_uv)
+
+    sia = SIAFD_Regional(grid, global_bed=gb, **cfg.overrides())
+    geo = Geometry(inputs["bed"], inputs["thickness"], inputs["surface"], inputs["mask"])
+    sia.update(inputs["sliding"], Inputs(geo, inputs["enthalpy"], no_model_mask=no_model,
+                                         no_model_surface_elevation=usurf_stored), True)
+    assert np.array_equal(sia.surface_gradient_x(), run.a["h_x"])
+    assert np.array_equal(sia.surface_gradient_y(), run.a["h_y"])
+    assert not np.array_equal(run.a["h_x"], O.Run(p, inputs).a["h_x"])
+    for a, b in ((sia.diffusivity(), run.a["D"]), (sia.diffusive_flux(), run.a["Q"]), (sia.velocity_u(), run.a["u"]),
+                 (sia.velocity_v(), run.a["v"])):
+        assert cases.rel_max(a, b) < 1e-10
+
+
 def test_negative_thickness_is_reported_by_ensure_consistency():
     grid, cfg, inputs, gb = cases.case("dome_64_21")
     sia = U.make_sia(grid, cfg, gb)
