@@ -349,7 +349,7 @@ def main():
             check(lib.siafd_b200_compute_vertical_velocity(sia.handle, 0, 0))
         ms_w, _ = timed(w_step, args.steps, 3)
         bw = 24 * Mz  # read u, v once, write w
-        vertical = {"kernel": "k_vvel_march (w + fused 3D CFL maxima)", "ms": ms_w / args.steps,
+        vertical = {"kernel": "k_vvel_slab (w + fused 3D CFL maxima)", "ms": ms_w / args.steps,
                     "algorithmic_bytes_per_column": bw,
                     "achieved_GBps": bw * cols_total / (ms_w / args.steps / 1e3) / 1e9,
                     "frac": bw * cols_total / (ms_w / args.steps / 1e3) / 1e9 / peak}
@@ -369,7 +369,17 @@ def main():
             check(lib.siafd_b200_mass_source_step(sia.handle, 0.0, 910.0, 0))
             check(lib.siafd_b200_ensure_consistency(sia.handle, 1))
         ms_m, _ = timed(mass_step, args.steps, 3)
+        def heat_step():
+            check(lib.siafd_b200_compute_strain_heating(sia.handle, 2, 3.0, 1.0))  # gpbld, n = 3, e = 1 (ssa defaults)
+        ms_h, _ = timed(heat_step, args.steps, 3)
+        bh = 32 * Mz  # read E, u, v, write Sigma
         consumers = {"vertical_velocity_plus_cfl_ms": ms_cf / args.steps, "cfl3d_dt_s": out8[0],
+                     "strain_heating": {"kernel": "k_strain_heating<gpbld>", "ms": ms_h / args.steps,
+                                        "algorithmic_bytes_per_column": bh,
+                                        "achieved_GBps": bh * cols_total / (ms_h / args.steps / 1e3) / 1e9,
+                                        "frac": bh * cols_total / (ms_h / args.steps / 1e3) / 1e9 / peak,
+                                        "note": "FP64-bound where there is ice (exp + 2 cbrt per level), "
+                                                "write-bound elsewhere"},
                      "mass_continuity_step_ms": ms_m / args.steps,
                      "mass_continuity_launches": 8,
                      "note": "flow step + ensure_consistency + source step + ensure_consistency (2D fields only)"}

@@ -799,6 +799,8 @@ template <int LAW> __device__ __forceinline__ double softness_eval(const DP &P, 
   return __longlong_as_double(0x7ff8000000000000LL); // gk: the reference throws (GoldsbyKohlstedt.cc:102-108)
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
+
 struct HeatArgs {
   const double *mask, *thk, *E, *u, *v, *z;
   double *sigma;
@@ -808,7 +810,7 @@ struct HeatArgs {
 };
 
 template <int LAW>
-__global__ void __launch_bounds__(256, 2) k_strain_heating(const __grid_constant__ DP P, const HeatArgs A) {
+__global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant__ DP P, const HeatArgs A) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i = P.xs + blockIdx.x * 8 + wid;
   if (i >= P.xs + P.xm) return;
@@ -824,6 +826,19 @@ __global__ void __launch_bounds__(256, 2) k_strain_heating(const __grid_constant
   double *s_p = A.sigma + ((long)(j0 - P.ys) * P.xm + (i - P.xs)) * Mz;
   long g = idx2(P, i, j0, P.wg);
   for (int j = j0; j < j1; ++j) {
+    // the rows the next iteration misses in cache (u, v two rows up; enthalpy one row up) are requested now, so that
+    // their DRAM latency overlaps this row's arithmetic instead of stalling the next row's
+    {
+      const bool uv_ok = j + 2 < P.ys + P.ym + P.wuv, e_ok = j + 1 < j1; // rows inside the arrays
+      for (int c = 0; c < nch; ++c) {
+        const int k = min(c * 32 + lane, Mz - 1);
+        if (uv_ok) {
+          prefetch_l1(uc_p + k + 2 * rowuv);
+          prefetch_l1(vc_p + k + 2 * rowuv);
+        }
+        if (e_ok) prefetch_l1(e_p + k + rowe);
+      }
+    }
     const double H = A.thk[g];
     // IceGrid::kBelowHeight (util/IceGrid.cc:427-440), for EVERY column, icy or not (StressBalance.cc:540): the levels
     // are sorted, so the largest k with z[k] <= H is a count; clamped to [0, Mz - 2] like GSL's bsearch
@@ -852,7 +867,7 @@ __global__ void __launch_bounds__(256, 2) k_strain_heating(const __grid_constant
     const double D_x = (east + west > 1.5) ? 0.5 * P.inv_dx : ((east + west > 0) ? P.inv_dx : 0.0);
     const double D_y = (north + south > 1.5) ? 0.5 * P.inv_dy : ((north + south > 0) ? P.inv_dy : 0.0);
     const double a_e = D_x * east, a_w = D_x * west, a_n = D_y * north, a_s = D_y * south;
-#pragma unroll 1
+#pragma unroll 2
     for (int c = 0; c < nch; ++c) {
       const int k = c * 32 + lane;
       double sig = 0.0;

@@ -12,6 +12,6 @@ import json, sys
 r = sys.argv[1]
 d = json.loads(open("gpurun_out/bench_consumers_%s.json" % r).read())
 v = d["vertical_velocity"]
-print("kind_wz_rows", r, "step ms", round(d["ms_per_step"], 3), "slab frac", round(d["roofline"]["frac"], 3), "| w ms", round(v["ms"], 3), "frac", round(v["frac"], 3), "| w+cfl ms", round(d["consumers"]["vertical_velocity_plus_cfl_ms"], 3), "mass step ms", round(d["consumers"]["mass_continuity_step_ms"], 3))
+print("kind_wz_rows", r, "step ms", round(d["ms_per_step"], 3), "slab frac", round(d["roofline"]["frac"], 3), "| w ms", round(v["ms"], 3), "frac", round(v["frac"], 3), "| w+cfl ms", round(d["consumers"]["vertical_velocity_plus_cfl_ms"], 3), "mass step ms", round(d["consumers"]["mass_continuity_step_ms"], 3), "| heat ms", round(d["consumers"]["strain_heating"]["ms"], 3), "frac", round(d["consumers"]["strain_heating"]["frac"], 3))
 PY
 done
