@@ -143,19 +143,20 @@ public:
   const IceModelVec2Stag &diffusivity() const { return m_D; }
   siafd_b200_handle *handle() { return m_handle; }
 
-private:
-  // status code -> RuntimeError, with the message the reference would have thrown
-  void check(int status) {
-    if (status != SIAFD_B200_OK) {
-      throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(m_handle));
-    }
-  }
   // rheology/FlowLawFactory.cc:71-87
   static int flow_law_id(const std::string &name) {
     const char *names[] = {"isothermal_glen", "pb", "gpbld", "hooke", "arr", "arrwarm", "gk"};
     for (int k = 0; k < 7; ++k)
       if (name == names[k]) return k;
     throw RuntimeError::formatted(SIAFD_B200_ERR_BAD_CONFIG, "Selected ice flow law \"%s\" is not available", name.c_str());
+  }
+
+private:
+  // status code -> RuntimeError, with the message the reference would have thrown
+  void check(int status) {
+    if (status != SIAFD_B200_OK) {
+      throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(m_handle));
+    }
   }
   // SIAFD.cc:197-220
   static int gradient_id(const std::string &name) {
@@ -170,50 +171,82 @@ private:
   IceModelVec2Stag m_h_x, m_h_y, m_D;
 };
 
+// stressbalance/timestepping.hh: what max_timestep_cfl_2d / _3d return
+struct CFLData {
+  CFLData() : dt_max(0.0), u_max(0.0), v_max(0.0), w_max(0.0) {}
+  double dt_max, u_max, v_max, w_max;
+};
+
 // The SIA-only StressBalance container (stressbalance/StressBalance.cc:140-212 with ZeroSliding as the shallow
 // stress balance, factory.cc:59-64): update() runs the modifier and, on a full update, the vertical velocity
-// from incompressibility (StressBalance.cc:283-424) on the device fields the modifier left
-// there.  Strain heating and the CFL reductions (8(f) N3) are not part of it yet.
+// from incompressibility (StressBalance.cc:283-424), the volumetric strain heating (:426-642,
+// N3) and the CFL reductions (timestepping.cc:42-153, N3) on the device fields the modifier left there.
 class StressBalance_B200 {
 public:
   StressBalance_B200(IceGrid::ConstPtr g, SIAFD_B200 *modifier)
-      : m_grid(g), m_modifier(modifier), m_zero_sliding(g, "velbar", WITH_GHOSTS, 1), m_w(g, "wvel_rel", WITHOUT_GHOSTS) {
+      : m_grid(g), m_modifier(modifier), m_zero_sliding(g, "velbar", WITH_GHOSTS, 1), m_w(g, "wvel_rel", WITHOUT_GHOSTS),
+        m_strain_heating(g, "strain_heating", WITHOUT_GHOSTS) {
     m_zero_sliding.set(0.0); // ZeroSliding
   }
   ~StressBalance_B200() { delete m_modifier; } // StressBalance.cc:157-160
   void init() { m_modifier->init(); }
   void update(const Inputs &inputs, bool full_update) {
     m_modifier->update(m_zero_sliding, inputs, full_update);
+    siafd_b200_handle *h = m_modifier->handle();
+    const Config &cf = *m_grid->config();
+    int status = SIAFD_B200_OK;
     if (full_update) {
-      siafd_b200_handle *h = m_modifier->handle();
-      int status = SIAFD_B200_OK;
       if (inputs.basal_melt_rate) {
         status = siafd_b200_upload(h, SIAFD_B200_F_BASAL_MELT, inputs.basal_melt_rate->get_array());
       }
-      const bool upstream = m_grid->config()->get_string("stress_balance.vertical_velocity_approximation") == "upstream";
+      const bool upstream = cf.get_string("stress_balance.vertical_velocity_approximation") == "upstream";
       if (status == SIAFD_B200_OK) {
         status = siafd_b200_compute_vertical_velocity(h, upstream ? 1 : 0, inputs.basal_melt_rate ? 1 : 0);
       }
       if (status == SIAFD_B200_OK) {
         status = siafd_b200_download(h, SIAFD_B200_F_W, m_w.get_array());
       }
-      if (status != SIAFD_B200_OK) {
-        throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(h));
+      if (status == SIAFD_B200_OK) { // the SHALLOW stress balance's flow law (StressBalance.cc:508-524)
+        status = siafd_b200_compute_strain_heating(h, SIAFD_B200::flow_law_id(cf.get_string("stress_balance.ssa.flow_law")),
+                                                   cf.get_number("stress_balance.ssa.Glen_exponent"),
+                                                   cf.get_number("stress_balance.ssa.enhancement_factor"));
+      }
+      if (status == SIAFD_B200_OK) {
+        status = siafd_b200_download(h, SIAFD_B200_F_STRAIN_HEATING, m_strain_heating.get_array());
       }
     }
+    if (status == SIAFD_B200_OK) { // StressBalance.cc:196-205
+      double out[8];
+      status = siafd_b200_cfl(h, cf.get_number("time_stepping.maximum_time_step") * seconds_per_year_udunits(),
+                              full_update ? 1 : 0, out);
+      if (status == SIAFD_B200_OK) {
+        if (full_update) m_cfl_3d.dt_max = out[0], m_cfl_3d.u_max = out[1], m_cfl_3d.v_max = out[2], m_cfl_3d.w_max = out[3];
+        m_cfl_2d.dt_max = out[4], m_cfl_2d.u_max = out[5], m_cfl_2d.v_max = out[6], m_cfl_2d.w_max = 0.0;
+      }
+    }
+    if (status != SIAFD_B200_OK) {
+      throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(h));
+    }
   }
+  static double seconds_per_year_udunits() { return 365.242198781 * 86400.0; } // convert(sys, 1, "year", "seconds")
   const IceModelVec3 &velocity_u() const { return m_modifier->velocity_u(); }
   const IceModelVec3 &velocity_v() const { return m_modifier->velocity_v(); }
   const IceModelVec3 &velocity_w() const { return m_w; }
+  const IceModelVec3 &volumetric_strain_heating() const { return m_strain_heating; }
+  const IceModelVec2V &advective_velocity() const { return m_zero_sliding; }
   const IceModelVec2Stag &diffusive_flux() { return m_modifier->diffusive_flux(); }
   double max_diffusivity() const { return m_modifier->max_diffusivity(); }
+  CFLData max_timestep_cfl_2d() const { return m_cfl_2d; }
+  CFLData max_timestep_cfl_3d() const { return m_cfl_3d; }
   const SIAFD_B200 *modifier() const { return m_modifier; }
+  SIAFD_B200 *modifier() { return m_modifier; }
 
 private:
   IceGrid::ConstPtr m_grid;
   SIAFD_B200 *m_modifier;
   IceModelVec2V m_zero_sliding;
-  IceModelVec3 m_w;
+  IceModelVec3 m_w, m_strain_heating;
+  CFLData m_cfl_2d, m_cfl_3d;
 };
 
 } // namespace stressbalance

@@ -81,14 +81,20 @@ public:
              {"time.eemian_start", -132000.0 * secpera},
              {"time.eemian_end", -114500.0 * secpera},
              {"time.holocene_start", -11000.0 * secpera},
-             {"geometry.ice_free_thickness_standard", 0.01}};
+             {"geometry.ice_free_thickness_standard", 0.01},
+             {"stress_balance.ssa.Glen_exponent", 3.0},
+             {"stress_balance.ssa.enhancement_factor", 1.0},
+             {"time_stepping.maximum_time_step", 60.0}, // years (pism_config.cdl:2626)
+             {"time_stepping.adaptive_ratio", 0.12}};
     m_str = {{"stress_balance.sia.flow_law", "gpbld"},
              {"stress_balance.sia.surface_gradient_method", "haseloff"},
+             {"stress_balance.ssa.flow_law", "gpbld"},
              {"stress_balance.vertical_velocity_approximation", "centered"}};
     m_flag = {{"stress_balance.sia.limit_diffusivity", false},
               {"stress_balance.sia.grain_size_age_coupling", false},
               {"stress_balance.sia.e_age_coupling", false},
               {"ocean.always_grounded", false},
+              {"geometry.update.use_basal_melt_rate", true},
               {"enthalpy_converter.cold_mode", false}}; // ColdEnthalpyConverter (EnthalpyConverter.cc:287-296)
   }
   double get_number(const std::string &name) const { return find(m_num, name); }
@@ -303,6 +309,35 @@ public:
         cell_type(grid, "mask", WITH_GHOSTS, w(grid)) {}
   IceModelVec2S bed_elevation, sea_level_elevation, ice_thickness, ice_surface_elevation;
   IceModelVec2CellType cell_type;
+
+  // Geometry::ensure_consistency (geometry/Geometry.cc:121-187) with GeometryCalculator::compute (util/Mask.hh:96-133);
+  // under PISM this is PISM's own host code -- the device version is siafd_b200_ensure_consistency
+  void ensure_consistency(double ice_free_thickness_threshold) {
+    IceGrid::ConstPtr grid = ice_thickness.grid();
+    const Config &config = *grid->config();
+    const double alpha = 1 - config.get_number("constants.ice.density") / config.get_number("constants.sea_water.density");
+    const bool is_dry_simulation = config.get_flag("ocean.always_grounded");
+    for (int j = 0; j < grid->ym(); ++j) {
+      for (int i = 0; i < grid->xm(); ++i) {
+        const double thickness = ice_thickness(i, j);
+        if (thickness < 0.0) {
+          throw RuntimeError::formatted(1, "Thickness is negative at point i=%d, j=%d", i, j);
+        }
+        const double hgrounded = bed_elevation(i, j) + thickness, hfloating = sea_level_elevation(i, j) + alpha * thickness;
+        const bool is_floating = (hfloating > hgrounded), ice_free = (thickness <= ice_free_thickness_threshold);
+        if (is_floating && (not is_dry_simulation)) {
+          ice_surface_elevation(i, j) = hfloating;
+          cell_type(i, j) = ice_free ? MASK_ICE_FREE_OCEAN : MASK_FLOATING;
+        } else {
+          ice_surface_elevation(i, j) = hgrounded;
+          cell_type(i, j) = ice_free ? MASK_ICE_FREE_BEDROCK : MASK_GROUNDED;
+        }
+      }
+    }
+    ice_thickness.update_ghosts();
+    cell_type.update_ghosts();
+    ice_surface_elevation.update_ghosts();
+  }
 
 private:
   static int w(IceGrid::ConstPtr grid) { return (int)grid->config()->get_number("grid.max_stencil_width"); }

@@ -1,0 +1,142 @@
+// pismv_test_C.cc -- `pismv -test C` (isothermal SIA with a time-dependent surface mass balance, BASELINE configs[0])
+// through the C++ host classes: the time step of IceModel::step (src/icemodel/IceModel.cc:388-640) with
+// StressBalance_B200 (SIAFD_B200 + vertical velocity + strain heating + CFL) and GeometryEvolution_B200 over the C ABI.
+// Prints the reference's report (src/verification/iceCompModel.cc:661-667), which test/regression/test_15.sh diffs
+// against its golden rows.  TEST CODE: the exact solution comes from the reference's own exactTestsABCD.c compiled
+// into oracle/_ref/libpism_exact.so.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../pism_b200/host/GeometryEvolution_B200.hh"
+
+extern "C" int ref_exactC(double t, double r, double *H, double *M);
+
+using namespace pism;
+
+int main(int argc, char *argv[]) {
+  using namespace pism::stressbalance;
+  int Mx = 31, My = 31, Mz = 31;
+  double run_length_years = 5000.0;
+  for (int a = 1; a + 1 < argc; a += 2) {
+    if (!strcmp(argv[a], "-Mx")) Mx = atoi(argv[a + 1]);
+    if (!strcmp(argv[a], "-My")) My = atoi(argv[a + 1]);
+    if (!strcmp(argv[a], "-Mz")) Mz = atoi(argv[a + 1]);
+    if (!strcmp(argv[a], "-y")) run_length_years = atof(argv[a + 1]);
+  }
+  try {
+    const double year = StressBalance_B200::seconds_per_year_udunits(); // calendar "none", pismv.cc:51
+    Config::Ptr config(new Config());
+    // IceCompModel::IceCompModel for test C, iceCompModel.cc:60-135
+    config->set_number("stress_balance.sia.enhancement_factor", 1.0);
+    config->set_number("stress_balance.sia.bed_smoother.range", 0.0);
+    config->set_flag("geometry.update.use_basal_melt_rate", false);
+    config->set_string("stress_balance.sia.flow_law", "isothermal_glen");
+    config->set_number("flow_law.isothermal_Glen.ice_softness", 1.0e-16 / year);
+    config->set_flag("ocean.always_grounded", true);
+    config->set_flag("enthalpy_converter.cold_mode", true); // pismv.cc:61
+    // pismv_grid_defaults + vertical_grid_from_options: 2000 km x 2000 km x 4000 m, QUADRATIC levels (pismv.cc:96-102, :155)
+    IceGrid::Ptr grid(new IceGrid(config, Mx, My, 1000e3, 1000e3, IceGrid::compute_vertical_levels(4000.0, Mz, QUADRATIC)));
+    const int WIDE_STENCIL = (int)config->get_number("grid.max_stencil_width");
+    const double ice_density = config->get_number("constants.ice.density");
+    const double ice_free_thickness = config->get_number("geometry.ice_free_thickness_standard");
+
+    Geometry geometry(grid);
+    IceModelVec3 enthalpy(grid, "enthalpy", WITH_GHOSTS, WIDE_STENCIL);
+    enthalpy.set(config->get_number("constants.ice.specific_heat_capacity") * (263.15 - config->get_number("enthalpy_converter.T_reference")));
+    IceModelVec2S mass_flux(grid, "climatic_mass_balance", WITHOUT_GHOSTS);
+    geometry.bed_elevation.set(0.0);
+    geometry.sea_level_elevation.set(0.0);
+
+    double time = 0.0;
+    const double run_end = run_length_years * year;
+    // initTestABCDH, iceCompModel.cc:301-356
+    for (int j = 0; j < grid->ym(); ++j)
+      for (int i = 0; i < grid->xm(); ++i) {
+        double H, M;
+        ref_exactC(time, radius(*grid, i, j), &H, &M);
+        geometry.ice_thickness(i, j) = H;
+      }
+    geometry.ice_thickness.update_ghosts();
+
+    StressBalance_B200 stress_balance(grid, new SIAFD_B200(grid));
+    stress_balance.init();
+    GeometryEvolution_B200 geometry_evolution(grid, stress_balance.modifier()->handle());
+
+    Inputs inputs;
+    inputs.geometry = &geometry;
+    inputs.enthalpy = &enthalpy;
+    inputs.new_bed_elevation = false;
+
+    geometry.ensure_consistency(ice_free_thickness); // IceModel::run, IceModel.cc:763
+    const double max_dt = config->get_number("time_stepping.maximum_time_step") * year;
+    int steps = 0;
+    while (time < run_end) { // IceModel::run :790 / IceModel::step
+      grid->set_current_time(time);
+      stress_balance.update(inputs, true);
+      // IceModel::max_timestep, icemodel/timestepping.cc:111-232 (hit_multiples = 0, skip off)
+      std::vector<std::pair<double, std::string> > restrictions;
+      restrictions.push_back(std::make_pair(stress_balance.max_timestep_cfl_3d().dt_max, "energy")); // EnergyModel.cc:314-324
+      restrictions.push_back(std::make_pair(max_dt, "max"));
+      if (run_end - time > 0.0) restrictions.push_back(std::make_pair(run_end - time, "end of the run"));
+      restrictions.push_back(std::make_pair(stress_balance.max_timestep_cfl_2d().dt_max, "2D CFL"));
+      const double D_max = stress_balance.max_diffusivity();
+      if (D_max > 0.0) { // :52-68
+        const double dx = grid->dx(), dy = grid->dy(), grid_factor = 1.0 / (dx * dx) + 1.0 / (dy * dy);
+        restrictions.push_back(std::make_pair(config->get_number("time_stepping.adaptive_ratio") * 2.0 / (D_max * grid_factor), "diffusivity"));
+      } else {
+        restrictions.push_back(std::make_pair(max_dt, "max time step"));
+      }
+      std::sort(restrictions.begin(), restrictions.end());
+      const double dt = restrictions[0].first;
+
+      geometry_evolution.flow_step(geometry, dt, stress_balance.advective_velocity(), stress_balance.diffusive_flux(), NULL, NULL);
+      geometry_evolution.apply_flux_divergence(geometry);
+      geometry.ensure_consistency(ice_free_thickness);
+      // surface::Verification::update_ABCDH at the start-of-step time, PSVerification.cc:165-224
+      for (int j = 0; j < grid->ym(); ++j)
+        for (int i = 0; i < grid->xm(); ++i) {
+          double H, M;
+          ref_exactC(time, radius(*grid, i, j), &H, &M);
+          mass_flux(i, j) = M * ice_density;
+        }
+      geometry_evolution.source_term_step(geometry, dt, NULL, mass_flux, NULL);
+      geometry_evolution.apply_mass_fluxes(geometry);
+      geometry.ensure_consistency(ice_free_thickness);
+      time += dt; // Time::step, Time.cc:206-215
+      if (run_end > time && run_end - time < 1e-3) time = run_end;
+      steps += 1;
+    }
+
+    // IceCompModel::computeGeometryErrors + reportErrors, iceCompModel.cc:442-583, :661-667
+    const double a = grid->dx() * grid->dy() * 1e-3 * 1e-3, m = (2.0 * 3.0 + 2.0) / 3.0;
+    double vol = 0, volexact = 0, Herr = 0, avHerr = 0, etaerr = 0, domeHexact = 0;
+    for (int j = 0; j < grid->ym(); ++j)
+      for (int i = 0; i < grid->xm(); ++i) {
+        double Hexact, M;
+        ref_exactC(time, radius(*grid, i, j), &Hexact, &M);
+        const double H = geometry.ice_thickness(i, j);
+        if (H > 0) vol += a * H * 1e-3;
+        if (Hexact > 0) volexact += a * Hexact * 1e-3;
+        if (i == ((int)grid->Mx() - 1) / 2 and j == ((int)grid->My() - 1) / 2) domeHexact = Hexact;
+        Herr = std::max(Herr, fabs(H - Hexact));
+        etaerr = std::max(etaerr, fabs(pow(H, m) - pow(Hexact, m)));
+        avHerr += fabs(H - Hexact);
+      }
+    printf("NUMERICAL ERRORS evaluated at final time (relative to exact solution):\n");
+    printf("geometry  :    prcntVOL        maxH         avH   relmaxETA\n");
+    printf("           %12.6f%12.6f%12.6f%12.6f\n", 100 * fabs(vol - volexact) / volexact, Herr, avHerr / (grid->Mx() * grid->My()),
+           etaerr / pow(domeHexact, m));
+    printf("NUM ERRORS DONE\n");
+    printf("steps %d\n", steps);
+  } catch (RuntimeError &e) {
+    fprintf(stderr, "PISM ERROR: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

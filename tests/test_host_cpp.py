@@ -18,7 +18,7 @@ EXE = os.path.join(DIR, "siafd_test")
 def build():
     if not os.path.exists(os.path.join(HERE, "..", "oracle", "_ref", "libpism_exact.so")):
         pytest.skip("oracle/_ref/libpism_exact.so (the reference's exact solutions) has not been built")
-    subprocess.run(["make", "-C", DIR], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", DIR, "all"], check=True, stdout=subprocess.DEVNULL)
 
 
 def test_host_class_compiles_and_fails_loudly_without_a_gpu():
@@ -59,3 +59,30 @@ def test_siafd_test_F_through_the_cpp_class():
     assert abs(D.sum() - vals["sum_D"]) <= 1e-11 * vals["sum_D"]
     u = cases.interior(sia.velocity_u(), cfg.w_uv)
     assert abs(np.abs(u[:, :, grid.Mz // 2]).sum() - vals["sum_absU_mid"]) <= 1e-11 * vals["sum_absU_mid"]
+
+
+@pytest.mark.gpu
+def test_pismv_test_C_through_the_cpp_classes_reproduces_test_15():
+    """`pismv -test C` time-stepped in C++ (tests/host_cpp/pismv_test_C.cc: IceModel::step over StressBalance_B200 and
+    GeometryEvolution_B200, host arrays in and out of the C ABI every step, like a drop-in under PISM) prints the
+    reference's golden rows of test/regression/test_15.sh."""
+    build()
+    import pismv_oracle as PO
+    for M, golden in PO.TEST_15_GOLDEN.items():
+        r = subprocess.run([os.path.join(DIR, "pismv_test_C"), "-Mx", str(M), "-My", str(M)], capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.splitlines()
+        assert lines[0] == "NUMERICAL ERRORS evaluated at final time (relative to exact solution):"
+        assert lines[1] == "geometry  :    prcntVOL        maxH         avH   relmaxETA"
+        assert lines[2] == "           " + golden, (lines[2], golden)
+        assert lines[3] == "NUM ERRORS DONE" and lines[4] == "steps 84"
+
+
+def test_pismv_test_C_cpp_fails_loudly_without_a_gpu():
+    build()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; covered by the gpu test")
+    r = subprocess.run([os.path.join(DIR, "pismv_test_C")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
