@@ -805,9 +805,32 @@ struct HeatArgs {
   const double *mask, *thk, *E, *u, *v, *z;
   double *sigma;
   unsigned *err;
-  double n, two_e_pow; // Glen exponent; 2 e^(-1/n)
+  double n, two_e_pow;         // Glen exponent; 2 e^(-1/n)
+  double inv_n, iso_hardness;  // 1 / n; iso_A^(-1/n)
   int RS;
 };
+
+// hardness B = softness^(-1/n) (FlowLaw.cc:142-144).  Where the softness is an Arrhenius factor A exp(-Q / (R T)) the
+// power is taken inside the exponential, B = exp((Q / (R T) - ln A) / n): one exp instead of an exp and a pow
+// (relative difference to pow(softness, -1/n): a few 1e-15).  The temperate branch of gpbld and hooke take the
+// literal softness and one cbrt (n = 3) or pow.
+template <int LAW>
+__device__ __forceinline__ double hardness_eval(const DP &P, double E, double p, double n, double inv_n, double iso_hardness) {
+  if (LAW == LAW_ISO) {
+    return iso_hardness;
+  }
+  if (LAW == LAW_PB || LAW == LAW_ARR || LAW == LAW_ARRWARM || LAW == LAW_GPBLD) {
+    const double T_m = ec_melting_temperature(P, p);
+    if (LAW != LAW_GPBLD || E < P.c_i * (T_m - P.T_0)) {
+      const double T_pa = ec_temperature(P, E, p) - T_m + P.T_melting; // EnthalpyConverter.cc:196-198
+      const bool cold = (LAW == LAW_ARR) || (LAW != LAW_ARRWARM && T_pa < P.T_crit);
+      const double lnA = cold ? P.lnA_cold : P.lnA_warm, QoR = cold ? P.QoR_cold : P.QoR_warm;
+      return exp_fast((QoR * rcp_fast(T_pa) - lnA) * inv_n);
+    }
+  }
+  const double soft = softness_eval<LAW>(P, E, p);
+  return (n == 3.0) ? 1.0 / cbrt(soft) : pow(soft, -inv_n);
+}
 
 template <int LAW>
 __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant__ DP P, const HeatArgs A) {
@@ -817,7 +840,7 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
   const int j0 = P.ys + blockIdx.y * A.RS, j1 = min(j0 + A.RS, P.ys + P.ym);
   const int Mz = P.Mz, nch = (Mz + 31) >> 5;
   const bool n3 = (A.n == 3.0);
-  const double hardness_power = -1.0 / A.n, exponent = 0.5 * (1.0 / A.n + 1.0);
+  const double exponent = 0.5 * (1.0 / A.n + 1.0);
   const double *__restrict__ z = A.z;
   const double ztop = z[Mz - 1];
   const long rowuv = (long)(P.xm + 2 * P.wuv) * Mz, rowe = (long)(P.xm + 2 * P.we) * Mz, rowg = P.xm + 2 * P.wg;
@@ -883,14 +906,12 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
         const double d2 = 0.5 * ((u_x + v_y) * (u_x + v_y) + u_x * u_x + v_y * v_y +
                                  0.5 * ((u_y + v_x) * (u_y + v_x) + u_z * u_z + v_z * v_z));
         const double pr = P.p_air + P.rg * (H - z[k]); // EnthalpyConverter.cc:137-152 (no depth clamp)
-        const double soft = softness_eval<LAW>(P, e_p[k], pr);
-        double hard, dpow;
+        const double hard = hardness_eval<LAW>(P, e_p[k], pr, A.n, A.inv_n, A.iso_hardness);
+        double dpow;
         if (n3) {
-          hard = 1.0 / cbrt(soft);
           const double cr = cbrt(d2);
           dpow = cr * cr;
         } else {
-          hard = pow(soft, hardness_power);
           dpow = pow(d2, exponent);
         }
         sig = A.two_e_pow * hard * dpow;
@@ -1032,7 +1053,7 @@ int launch_strain_heating(const DP &P, int law, double n, double e, const double
                           const double *E, const double *u, const double *v, const double *z, double *sigma,
                           unsigned *err, cudaStream_t s) {
   if (P.xm <= 0 || P.ym <= 0) return 0;
-  HeatArgs A{mask, thk, E, u, v, z, sigma, err, n, 2.0 * pow(e, -1.0 / n), 32};
+  HeatArgs A{mask, thk, E, u, v, z, sigma, err, n, 2.0 * pow(e, -1.0 / n), 1.0 / n, pow(P.iso_A, -1.0 / n), 32};
   switch (law) {
   case LAW_ISO:
     return launch_heat_law<LAW_ISO>(P, A, s);
