@@ -95,5 +95,8 @@ def pismv_model(testname, M, start_year=0.0, run_length_years=5000.0, max_dt_yea
 
 
 # the reference's golden output: test/regression/test_15.sh:19-28 (pismv -test C -Mbz 1 -Mz 31 -y 5000, Mx = My = 31, 41)
-TEST_15_GOLDEN = {31: "   80.824124  503.131175    3.114691    0.820828",
-                  41: "   32.783573  193.022555    1.330304    0.405692"}
+import json as _json
+import os as _os
+
+with open(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "reference_kats.json")) as _f:
+    TEST_15_GOLDEN = {int(k): v for k, v in _json.load(_f)["pismv_test_C"]["rows"].items()}

@@ -54,3 +54,63 @@ def test_gpu_matches_fixture(name):
                       (sia.velocity_u(), outs["u"]), (sia.velocity_v(), outs["v"])):
         assert cases.rel_max(got, want) <= 1e-10
     assert abs(sia.max_diffusivity() - float(outs["D_max"])) <= 1e-10 * float(outs["D_max"])
+
+
+# ---- SURVEY 8(f) rows on the frozen C4s update (tests/golden/oracle_consumers_C4s.npz, tools/make_golden.py) -------
+def _consumers():
+    return np.load(os.path.join(HERE, "golden", "oracle_consumers_C4s.npz"))
+
+
+def test_oracle_reproduces_consumer_fixture_bitwise():
+    import subprocess
+    import sys
+    import tempfile
+    d = _consumers()
+    # regenerate into a scratch copy of the tree's golden directory and compare array by array
+    sys.path.insert(0, os.path.join(HERE, "..", "tools"))
+    import make_golden
+    old_root = make_golden.ROOT
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "tests", "golden"))
+        make_golden.ROOT = tmp
+        try:
+            make_golden.consumers()
+        finally:
+            make_golden.ROOT = old_root
+        new = np.load(os.path.join(tmp, "tests", "golden", "oracle_consumers_C4s.npz"))
+        for k in d.files:
+            assert np.array_equal(d[k], new[k]), k
+
+
+@pytest.mark.gpu
+def test_gpu_consumers_match_fixture():
+    """w, CFL scalars, strain heating, flow step, masks, source step on the B200 against committed vectors: no oracle at
+    run time.  Thickness, divergence, masks bit-exact when fed the stored flux; w, Sigma within 1e-10."""
+    import ctypes as C
+    import gpu_util as U
+    from pism_b200.capi import lib
+    d = _consumers()
+    grid, cfg, _, _ = cases.case("C4s")
+    inputs, outs, gb = load("C4s")
+    sia = U.make_sia(grid, cfg, gb)
+    U.gpu_update(sia, inputs, True)
+    for f, k in (("flux", "Q"), ("u", "u"), ("v", "v")):  # the stored update, so that later differences are the consumers'
+        sia.upload(f, outs[k])
+    w = sia.compute_vertical_velocity()
+    assert cases.rel_max(w, d["w"]) <= 1e-10
+    sia.upload("w", d["w"])
+    out = (C.c_double * 8)()
+    sia._check(lib.siafd_b200_cfl(sia.handle, float(d["max_dt"]), 1, out))
+    assert list(out[0:4]) == list(d["cfl3d"]) and list(out[4:7]) == list(d["cfl2d"][0:3])
+    sig = sia.compute_volumetric_strain_heating("gpbld", 3.0, 1.0)
+    assert cases.rel_max(sig, d["sigma"]) <= 1e-10
+    sia._check(lib.siafd_b200_mass_flow_step(sia.handle, float(d["dt"])))
+    wg = cfg.w_geom
+    assert np.array_equal(sia.download("flux_div"), d["flux_div"])
+    assert np.array_equal(sia.download("thk_change"), d["thk_change"])
+    assert np.array_equal(sia.download("thickness")[wg:-wg, wg:-wg], d["H_after_flow"])
+    sia._check(lib.siafd_b200_ensure_consistency(sia.handle, 1))
+    assert np.array_equal(sia.download("mask"), d["mask_after_flow"])
+    sia.upload("smb", d["smb"])
+    sia._check(lib.siafd_b200_mass_source_step(sia.handle, float(d["dt2"]), 910.0, 0))
+    assert np.array_equal(sia.download("thickness")[wg:-wg, wg:-wg], d["H_after_source"])

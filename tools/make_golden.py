@@ -35,5 +35,52 @@ def main():
         print(path, os.path.getsize(path) // 1024, "KiB")
 
 
+def consumers(name="C4s", dt_years=0.5, dt2_years=200.0):
+    """oracle_consumers_<case>.npz: the SURVEY 8(f) rows on the frozen update of oracle_fixture_<case>.npz -- vertical
+    velocity, 3D / 2D CFL scalars, strain heating (gpbld, n = 3, e = 1), one flow step and one source step."""
+    import ctypes as C
+    import oracle_lib as O
+    sec = 365.242198781 * 86400.0
+    grid, cfg, inputs, gb = cases.case(name)
+    run = cases.oracle_run(grid, cfg, inputs, gb, full=True)
+    p, a, L = run.p, run.a, O.lib()
+    n = (grid.My, grid.Mx)
+    d = {}
+    d["w"] = np.zeros(n + (grid.Mz,))
+    assert L.orc_vertical_velocity(C.byref(p), O.dptr(a["mask"]), O.dptr(a["u"]), O.dptr(a["v"]), None, 0, O.dptr(d["w"])) == 0
+    c3, c2 = (C.c_double * 4)(), (C.c_double * 4)()
+    max_dt = 60.0 * sec
+    assert L.orc_cfl_3d(C.byref(p), max_dt, O.dptr(a["thickness"]), O.dptr(a["mask"]), O.dptr(a["u"]), O.dptr(a["v"]),
+                        O.dptr(d["w"]), c3) == 0
+    assert L.orc_cfl_2d(C.byref(p), max_dt, O.dptr(a["mask"]), O.dptr(a["sliding"]), c2) == 0
+    d["cfl3d"], d["cfl2d"] = np.array(list(c3)), np.array(list(c2))
+    ph = cfg.oracle_params(grid)
+    ph.flow_law, ph.fl_n, ph.fl_e = O.FLOW_LAWS["gpbld"], 3.0, 1.0
+    d["sigma"] = np.zeros(n + (grid.Mz,))
+    assert L.orc_strain_heating(C.byref(ph), O.dptr(a["thickness"]), O.dptr(a["mask"]), O.dptr(a["enthalpy"]),
+                                O.dptr(a["u"]), O.dptr(a["v"]), O.dptr(d["sigma"])) == 0
+    H = a["thickness"].copy()
+    d["flux_div"], d["thk_change"], ce = np.zeros(n), np.zeros(n), np.zeros(n)
+    assert L.orc_mass_flow_step(C.byref(p), dt_years * sec, None, O.dptr(a["bed"]), O.dptr(H), None, None, None,
+                                O.dptr(a["Q"]), O.dptr(d["flux_div"]), O.dptr(d["thk_change"]), O.dptr(ce)) == 0
+    w = cfg.w_geom
+    d["H_after_flow"] = H[w:-w, w:-w].copy()
+    from pism_b200 import grid as G
+    G.wrap_ghosts(H, w)
+    mask, surf = np.zeros_like(H), np.zeros_like(H)
+    L.orc_geometry_compute(C.byref(p), H.size, O.dptr(np.zeros_like(H)), O.dptr(a["bed"]), O.dptr(H), O.dptr(mask), O.dptr(surf))
+    d["mask_after_flow"] = mask
+    d["smb"] = (np.random.default_rng(0).random(n) - 0.6) * 3e-3
+    es, eb = np.zeros(n), np.zeros(n)
+    assert L.orc_mass_source_step(C.byref(p), dt2_years * sec, 910.0, 0, O.dptr(H), O.dptr(mask), None, O.dptr(d["smb"]), None,
+                                  O.dptr(es), O.dptr(eb)) == 0
+    d["H_after_source"] = H[w:-w, w:-w].copy()
+    d["dt"], d["dt2"], d["max_dt"] = np.array(dt_years * sec), np.array(dt2_years * sec), np.array(max_dt)
+    path = os.path.join(ROOT, "tests", "golden", "oracle_consumers_%s.npz" % name)
+    np.savez_compressed(path, **d)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     main()
+    consumers()
