@@ -42,9 +42,11 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--rows-per-cta", type=int, default=0)
     ap.add_argument("--bulk", type=int, default=-1)
-    ap.add_argument("--with-w", action="store_true",
-                    help="also time StressBalance::compute_vertical_velocity (SURVEY 8f N2) after the update; "
-                         "reported under 'vertical_velocity', not part of the metric")
+    ap.add_argument("--with-w", action="store_true", help="(default at N = 1) kept for compatibility")
+    ap.add_argument("--no-consumers", action="store_true",
+                    help="skip timing the consumers of the update (SURVEY 8f: vertical velocity + CFL, strain heating, "
+                         "mass-continuity step); they are reported under 'vertical_velocity' / 'consumers', after the "
+                         "metric's timed region and not part of it")
     ap.add_argument("--no-input-exchange", action="store_true",
                     help="skip the per-step width-2 exchange of the inputs' ghosts (N > 1)")
     return ap.parse_args()
@@ -344,7 +346,7 @@ def main():
 
     vertical = None
     consumers = None
-    if args.with_w and full and not multi:
+    if (args.with_w or not args.no_consumers) and full and not multi:
         def w_step():
             check(lib.siafd_b200_compute_vertical_velocity(sia.handle, 0, 0))
         ms_w, _ = timed(w_step, args.steps, 3)

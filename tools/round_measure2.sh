@@ -2,10 +2,9 @@
 # default bench command: the JSON line, then the ncu launch list of the SAME command (one pass, no replay)
 mkdir -p gpurun_out
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01_final.json 2> gpurun_out/bench_r01_final.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r01_default.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 2000 --csv --log-file gpurun_out/launches_r01_default.csv \
   python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_default.log 2>&1
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r01_reference.json 2>> gpurun_out/bench_r01_final.err
-tail -c 400 gpurun_out/bench_r01_reference.json
+python __graft_entry__.py smoke 2>&1 | tail -2
 python - <<'PY'
 import csv, collections
 rows = list(csv.reader(open("gpurun_out/launches_r01_default.csv")))
