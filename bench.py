@@ -47,6 +47,8 @@ def parse():
                     help="skip timing the consumers of the update (SURVEY 8f: vertical velocity + CFL, strain heating, "
                          "mass-continuity step); they are reported under 'vertical_velocity' / 'consumers', after the "
                          "metric's timed region and not part of it")
+    ap.add_argument("--regime", default="dome", choices=["dome", "icefree"],
+                    help="icefree: zero thickness everywhere (the write-only regime of the fused kernel; diagnostic)")
     ap.add_argument("--no-input-exchange", action="store_true",
                     help="skip the per-step width-2 exchange of the inputs' ghosts (N > 1)")
     return ap.parse_args()
@@ -254,6 +256,10 @@ def main():
         if name in inp:
             fields[name].copy_(inp[name])
     del inp
+    if args.regime == "icefree":
+        fields["thickness"].zero_()
+        fields["mask"].zero_()
+        fields["surface"].copy_(fields["bed"])
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
 

@@ -549,15 +549,6 @@ __device__ __forceinline__ int k_below_height_s(const double *zz, int Mz, double
   return ilo;
 }
 
-__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 __global__ void __launch_bounds__(256, 2) k_vvel_slab(const __grid_constant__ DP P, const VvelArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int Mz = P.Mz, WZ = A.WZ, Lq = A.Lq, T = blockDim.x, tid = threadIdx.x;

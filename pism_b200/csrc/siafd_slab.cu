@@ -279,6 +279,9 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   // logical state of the I arrays (CTA-uniform): bit set = materialised in shared memory, else "all zero".
   // bit 0, 1: I1 slots; bit 2: I0
   unsigned ivalid = 0;
+  // the write-only regime (no ice in the strip, zero sliding velocity): I0_s holds zeros that the bulk-copy engine
+  // stores as whole rows of u and v; zero_inflight = such a store may still be reading I0_s
+  bool zero_ready = false, zero_inflight = false;
 
   for (int r = r0; r < rb; ++r) {
     const int it = r - r0;
@@ -302,6 +305,12 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     double Dsum = 0.0, hx = 0.0, hy = 0.0;
     bool act = false;
     if (row_active) {
+      if (FULL && zero_inflight) { // CTA-uniform: stage A is about to overwrite the zeros a bulk store may still read
+        if (tid == 0) bulk_wait_read0();
+        __syncthreads();
+        zero_inflight = false;
+      }
+      zero_ready = false;
       // ---------------- stage A: integrate z range w of staggered point pt of lane column c ------------
       if (pending) { // CTA-uniform
         if (A.use_bulk) {
@@ -542,7 +551,38 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
         __syncthreads(); // #3: I0, I1, cf final
       }
       // ---------------- stage B: u, v of the regular columns, sia/SIAFD.cc:904-943 ----------------
-      if (r >= rbase && r < rend) { // CTA-uniform
+      // Write-only rows (no ice at any staggered point of this and the previous row, G9) whose sliding velocity is zero
+      // everywhere in the strip: u = v = 0 on every level.  The owned columns of a row are contiguous in memory, so
+      // each field's row leaves as ONE bulk store from a block of zeros (measured: 5.2 -> 5.9 TB/s in this regime).
+      bool row_done = false;
+      if (A.use_bulk && !any_valid && r >= rbase && r < rend) { // CTA-uniform
+        if (__syncthreads_and(sv.x == 0.0 && sv.y == 0.0)) {
+          if (!zero_ready) {
+            for (int e = tid; e < NC * S; e += NT) I0_s[e] = 0.0;
+            fence_proxy_async();
+            __syncthreads();
+            zero_ready = true;
+          }
+          if (tid == 0) {
+            const int i_first = max(ca + 1, P.xs), i_last = min(ca + NC - 1, P.xs + P.xm - 1);
+            const long n = (long)(i_last - i_first + 1) * Mz;
+            if (n > 0) {
+              const long g0 = ((long)(r - (P.ys - P.wuv)) * (P.xm + 2 * P.wuv) + (i_first - P.xs + P.wuv)) * Mz;
+              const long a0 = (g0 + 1) & ~1L, a1 = (g0 + n) & ~1L; // the 16-byte aligned middle
+              if (g0 & 1) F.u[g0] = 0.0, F.v[g0] = 0.0;
+              if ((g0 + n) & 1) F.u[g0 + n - 1] = 0.0, F.v[g0 + n - 1] = 0.0;
+              if (a1 > a0) {
+                bulk_s2g(F.u + a0, I0_s, (unsigned)((a1 - a0) * 8));
+                bulk_s2g(F.v + a0, I0_s, (unsigned)((a1 - a0) * 8));
+                bulk_commit();
+              }
+            }
+          }
+          zero_inflight = true;
+          row_done = true;
+        }
+      }
+      if (!row_done && r >= rbase && r < rend) { // CTA-uniform
         const bool south = (ivalid & (1u << s_nxt)) != 0;
 #pragma unroll
         for (int p = 0; p < NPASS; ++p) {
@@ -594,6 +634,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     }
   }
 
+  if (FULL && zero_inflight && tid == 0) bulk_wait_read0(); // shared memory must outlive the stores that read it
   // ---- D_max / counter reduction: warp shuffle -> shared -> one atomic per CTA ----
   {
     unsigned long long m = (unsigned long long)__double_as_longlong(dmax_local);
