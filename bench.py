@@ -47,6 +47,10 @@ def parse():
                     help="skip timing the consumers of the update (SURVEY 8f: vertical velocity + CFL, strain heating, "
                          "mass-continuity step); they are reported under 'vertical_velocity' / 'consumers', after the "
                          "metric's timed region and not part of it")
+    ap.add_argument("--uniform", action="store_true",
+                    help="N > 1: PISM's default (equal) ownership ranges instead of the load-balanced -procs_x / -procs_y")
+    ap.add_argument("--procs-x", default="", help="PISM's -procs_x: comma-separated ownership ranges in x")
+    ap.add_argument("--procs-y", default="", help="PISM's -procs_y: comma-separated ownership ranges in y")
     ap.add_argument("--regime", default="dome", choices=["dome", "icefree"],
                     help="icefree: zero thickness everywhere (the write-only regime of the fused kernel; diagnostic)")
     ap.add_argument("--no-input-exchange", action="store_true",
@@ -230,7 +234,25 @@ def main():
     M, Mz = args.size, args.mz
     L = (M - 1) / 2.0 * 5000.0
     grid = G.Grid(M, M, Mz, L, L, 4000.0)
-    patches = G.decompose(M, M, N)
+    # PISM's processor grid (IceGrid.cc:443-484).  Ownership ranges: what a PISM user passes as -procs_x / -procs_y
+    # (IceGrid.cc:549-580) to balance the work -- here derived from the ice cover of the synthetic dome with the
+    # measured cost ratio of an icy to an ice-free column -- or PISM's default equal ranges with --uniform.
+    Nx_, Ny_ = G.compute_nprocs(M, M, N)
+    procs_x = [int(v) for v in args.procs_x.split(",")] if args.procs_x else None
+    procs_y = [int(v) for v in args.procs_y.split(",")] if args.procs_y else None
+    ranges_note = "PISM DMDA rule"
+    if N > 1 and not args.uniform and procs_x is None and procs_y is None:
+        xs_ = torch.as_tensor(grid.x, dtype=torch.float64)
+        icy = S.dome_2d(grid, capi.default_config(), xs_, torch.as_tensor(grid.y, dtype=torch.float64))["thickness"] > 0
+        cost = np.where(icy.numpy(), 2.7, 1.0)  # 1.16 vs 3.2 G column-updates/s in the two regimes
+        procs_x, procs_y = G.balanced_ownership_ranges(cost, Nx_, Ny_)
+        del icy, cost
+    if procs_x is not None or procs_y is not None:
+        ranges_note = "PISM DMDA, -procs_x %s -procs_y %s" % (",".join(map(str, procs_x or G.ownership_ranges(M, Nx_))),
+                                                             ",".join(map(str, procs_y or G.ownership_ranges(M, Ny_))))
+        if not (args.procs_x or args.procs_y):
+            ranges_note += " (balanced by ice cover)"
+    patches = G.decompose(M, M, N, Nx_, Ny_, procs_x, procs_y)
     patch = patches[rank]
     cfg = capi.default_config()
     cfg.smoother_range = 0.0
@@ -329,6 +351,17 @@ def main():
     check(lib.siafd_b200_kernel_timing(sia.handle, 0))
     cols_total = M * M
     value = cols_total * args.steps / (ms / 1e3)
+
+    # decomposition check: sums over the OWNED points of |u|, |v| and |Q| (whatever the ranks and their ranges, these
+    # agree to rounding of the summation order; D_max agrees exactly)
+    checksum = None
+    if full:
+        wuv, wst = sia.config.w_uv, sia.config.w_stag
+        parts = torch.stack([fields["u"][wuv:-wuv, wuv:-wuv].abs().sum(), fields["v"][wuv:-wuv, wuv:-wuv].abs().sum(),
+                             fields["flux"][wst:-wst, wst:-wst].abs().sum()])
+        if multi:
+            dist.all_reduce(parts, op=dist.ReduceOp.SUM)
+        checksum = {"sum_abs_u": float(parts[0]), "sum_abs_v": float(parts[1]), "sum_abs_flux": float(parts[2])}
 
     # roofline of the dominant (fused) kernel on this rank; report the slowest rank's
     B = algorithmic_bytes_per_column(Mz, full)
@@ -451,9 +484,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, "%dx%d (PISM DMDA rule)" % (patch.Nx, patch.Ny)),
+            "config": workload_config(args, "%dx%d (%s)" % (patch.Nx, patch.Ny, ranges_note)),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "D_max": dmax, "vertical_velocity": vertical, "consumers": consumers, "halo_bytes_per_step_per_rank": (halo.bytes_sent // max(args.steps + W + 1, 1)) if halo else 0,
+            "clocks": clocks, "D_max": dmax, "checksum": checksum, "vertical_velocity": vertical, "consumers": consumers, "halo_bytes_per_step_per_rank": (halo.bytes_sent // max(args.steps + W + 1, 1)) if halo else 0,
             "halo_transport": "direct stores into CUDA-IPC-mapped neighbour arrays (NVLink), 3 phases/step" if halo else None,
             "input_generation_s": t_gen,
         }

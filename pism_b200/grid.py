@@ -79,18 +79,85 @@ class Patch:
         return ((self.px + dx) % self.Nx) + self.Nx * ((self.py + dy) % self.Ny)
 
 
-def decompose(Mx, My, size, Nx=None, Ny=None):
-    """All patches of a `size`-rank run, rank = px + Nx * py (DMDA ordering)."""
+def decompose(Mx, My, size, Nx=None, Ny=None, procs_x=None, procs_y=None):
+    """All patches of a `size`-rank run, rank = px + Nx * py (DMDA ordering).
+
+    Nx, Ny: PISM's -Nx / -Ny (default: compute_nprocs).  procs_x, procs_y: PISM's -procs_x / -procs_y, explicit
+    ownership ranges (IceGrid.cc:519-586; they must have Nx / Ny entries and sum to Mx / My, :1327-1333); default:
+    the uniform ranges of ownership_ranges()."""
     if Nx is None or Ny is None:
         Nx, Ny = compute_nprocs(Mx, My, size)
-    lx, ly = ownership_ranges(Mx, Nx), ownership_ranges(My, Ny)
+    if Nx * Ny != size:
+        raise ValueError("Nx * Ny has to be equal to %d." % size)
+    lx = list(procs_x) if procs_x is not None else ownership_ranges(Mx, Nx)
+    ly = list(procs_y) if procs_y is not None else ownership_ranges(My, Ny)
+    if len(lx) != Nx:
+        raise ValueError("-Nx has to be equal to the -procs_x size.")
+    if len(ly) != Ny:
+        raise ValueError("-Ny has to be equal to the -procs_y size.")
+    if sum(lx) != Mx:
+        raise ValueError("procs_x don't sum up to Mx")
+    if sum(ly) != My:
+        raise ValueError("procs_y don't sum up to My")
     x0 = np.concatenate([[0], np.cumsum(lx)])
     y0 = np.concatenate([[0], np.cumsum(ly)])
     out = []
     for py in range(Ny):
         for px in range(Nx):
-            out.append(Patch(px + Nx * py, px, py, Nx, Ny, int(x0[px]), lx[px], int(y0[py]), ly[py]))
+            out.append(Patch(px + Nx * py, px, py, Nx, Ny, int(x0[px]), int(lx[px]), int(y0[py]), int(ly[py])))
     return out
+
+
+def _min_bottleneck_cuts(block_costs, parts, min_len=2):
+    """Cut the rows of block_costs[n_rows, n_blocks] into `parts` consecutive groups so that the largest
+    (group, block) sum is as small as possible: bisection on the bottleneck, greedy sweep for feasibility."""
+    n = block_costs.shape[0]
+    cum = np.vstack([np.zeros((1, block_costs.shape[1])), np.cumsum(block_costs, axis=0)])
+
+    def sweep(limit):
+        cuts, start = [], 0
+        for g in range(parts):
+            remaining = parts - g - 1
+            lo, hi = start + min_len, n - remaining * min_len
+            if g == parts - 1:
+                end = n
+            else:
+                # the furthest end whose block sums stay below the limit (sums are monotone in end)
+                seg = (cum[lo:hi + 1] - cum[start]).max(axis=1)
+                ok = np.nonzero(seg <= limit)[0]
+                end = lo + (int(ok[-1]) if len(ok) else 0)
+            if (cum[end] - cum[start]).max() > limit:
+                return None
+            cuts.append(end - start)
+            start = end
+        return cuts
+
+    lo, hi = float(block_costs.sum(axis=0).max()) / parts, float(block_costs.sum(axis=0).max())
+    best = sweep(hi)
+    for _ in range(50):
+        mid = 0.5 * (lo + hi)
+        c = sweep(mid)
+        if c is None:
+            lo = mid
+        else:
+            best, hi = c, mid
+    return best
+
+
+def balanced_ownership_ranges(cost, Nx, Ny, sweeps=3):
+    """Ownership ranges (procs_x, procs_y) of an Nx x Ny tensor-product decomposition that balance a per-column cost
+    map cost[My, Mx] (e.g. 1 for an ice-free column, ~2.5 for an icy one): what a PISM user passes as -procs_x /
+    -procs_y.  Alternates 1D minimum-bottleneck cuts in y (given the x blocks) and in x (given the y blocks)."""
+    My, Mx = cost.shape
+    lx, ly = ownership_ranges(Mx, Nx), ownership_ranges(My, Ny)
+    for _ in range(sweeps):
+        xe = np.concatenate([[0], np.cumsum(lx)])
+        rows_by_xblock = np.stack([cost[:, xe[b]:xe[b + 1]].sum(axis=1) for b in range(Nx)], axis=1)
+        ly = _min_bottleneck_cuts(rows_by_xblock, Ny)
+        ye = np.concatenate([[0], np.cumsum(ly)])
+        cols_by_yblock = np.stack([cost[ye[b]:ye[b + 1], :].sum(axis=0) for b in range(Ny)], axis=1)
+        lx = _min_bottleneck_cuts(cols_by_yblock, Nx)
+    return [int(v) for v in lx], [int(v) for v in ly]
 
 
 class Grid:

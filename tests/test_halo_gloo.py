@@ -25,13 +25,13 @@ def _free_port():
     return port
 
 
-def _worker_exchange(rank, world, port, Mx, My, q):
+def _worker_exchange(rank, world, port, Mx, My, q, procs=None):
     try:
         os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
         from pism_b200 import grid as G
         from pism_b200.halo import HaloExchanger, global_max
-        patches = G.decompose(Mx, My, world)
+        patches = G.decompose(Mx, My, world, **(procs or {}))
         pt = patches[rank]
         ex = HaloExchanger(pt)
         rng = np.random.RandomState(7)
@@ -55,12 +55,15 @@ def _worker_exchange(rank, world, port, Mx, My, q):
             dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,Mx,My", [(2, 12, 16), (2, 16, 9), (4, 13, 11), (3, 30, 7)])
-def test_halo_exchange_matches_periodic_box_ghosts(world, Mx, My):
+@pytest.mark.parametrize("world,Mx,My,ranges", [(2, 12, 16, None), (2, 16, 9, None), (4, 13, 11, None), (3, 30, 7, None),
+                                                 # PISM's -Nx / -Ny / -procs_x / -procs_y: unequal ownership ranges
+                                                 (4, 13, 11, dict(Nx=2, Ny=2, procs_x=[9, 4], procs_y=[3, 8])),
+                                                 (3, 9, 20, dict(Nx=1, Ny=3, procs_y=[11, 2, 7]))])
+def test_halo_exchange_matches_periodic_box_ghosts(world, Mx, My, ranges):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_exchange, args=(r, world, port, Mx, My, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker_exchange, args=(r, world, port, Mx, My, q, ranges)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
