@@ -334,6 +334,11 @@ int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev,
 int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_copy, int skip_ice_free_rows);
 /* Number of kernel launches issued by this handle since create (bench.py's gpu_launches). */
 int64_t siafd_b200_launch_count(const siafd_b200_handle *h);
+/* Bytes the host-pointer calls (upload / download / update with host arrays) have moved over PCIe since create.
+ * siafd_b200_update with host arrays moves only the parts of the 3D arrays within 3 cells of ice (no enthalpy is read
+ * and u = v = sliding velocity elsewhere, SIAFD.cc:631-637, :935-942: those parts of u, v are filled on the host);
+ * afterwards the DEVICE copy of the enthalpy is only current in those parts. */
+int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t *d2h);
 /* CUDA-event timing of the fused kernel alone, on the handle's stream (bench.py's roofline):
  * enable, run updates (<= 256), then read the accumulated milliseconds and launch count. */
 int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable);

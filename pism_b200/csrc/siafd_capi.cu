@@ -13,7 +13,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
+#include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace siafd;
@@ -31,6 +37,8 @@ struct siafd_b200_handle {
   unsigned long long *d_dmax = nullptr;
   unsigned long long *d_cfl = nullptr, *h_cfl = nullptr; // 8 maxima of siafd_b200_cfl and their pinned mirror
   bool cfl3_fresh = false; // slots 0..3 hold the maxima the last vertical-velocity launch took on the current fields
+  int fill_threads = 8;    // host threads that fill the ice-free parts of u, v in the sparse host path
+  int64_t bytes_h2d = 0, bytes_d2h = 0; // bytes the host-path calls moved over PCIe since create
   int vvel_rows = 64;      // rows one CTA of the marching vertical-velocity kernels takes
   int vvel_kind = 0;       // 0: k_vvel_slab (shared memory, z sweep in registers); 1: k_vvel_march (lanes across z)
   int vvel_wz = 16;        // z ranges per column of k_vvel_slab
@@ -440,6 +448,9 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.wz = 4;
   h->tuning.pipeline_host = 1;
   h->tuning.pipeline_band = 4;
+  h->tuning.sparse_host = 1;
+  if (const char *e = getenv("SIAFD_B200_SPARSE")) h->tuning.sparse_host = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_FILL_THREADS")) h->fill_threads = std::max(1, atoi(e));
   if (const char *e = getenv("SIAFD_B200_PIPELINE")) h->tuning.pipeline_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_BAND")) h->tuning.pipeline_band = atoi(e);
   if (const char *e = getenv("SIAFD_B200_WZ")) h->tuning.wz = atoi(e);
@@ -573,6 +584,7 @@ int siafd_b200_upload(siafd_b200_handle *h, int f, const double *host) {
   if (st) return st;
   const size_t bytes = (size_t)siafd_b200_field_size(h, f) * sizeof(double);
   CU(h, cudaMemcpyAsync(h->buf[f], host, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)bytes;
   return SIAFD_B200_OK;
 }
 
@@ -583,6 +595,7 @@ int siafd_b200_download(siafd_b200_handle *h, int f, double *host) {
   const size_t bytes = (size_t)siafd_b200_field_size(h, f) * sizeof(double);
   CU(h, cudaMemcpyAsync(host, h->buf[f], bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  h->bytes_d2h += (int64_t)bytes;
   return SIAFD_B200_OK;
 }
 
@@ -1200,6 +1213,112 @@ int siafd_b200_high_diffusivity_count(siafd_b200_handle *h) {
 // enthalpy, the fused kernel, device->host copy of u and v -- run as a pipeline over bands of rows on three streams
 // (PCIe is full duplex), instead of one after the other.  The bands are whole row segments of the fused kernel, and
 // every array is contiguous in rows, so each leg of a band is one cudaMemcpyAsync / one launch.
+// Where there is no ice the fused kernel reads no enthalpy and writes u = v = sliding velocity on every level
+// (SIAFD.cc:631-637, :935-942), so those parts of the 3D arrays need not cross PCIe: per band of rows only the
+// rectangle of columns within 3 cells of ice goes up (enthalpy) and comes down (u, v); the rest of u, v is filled in
+// place on the host by a few threads while the copies run.  The host arrays end up bit-identical to a full transfer.
+struct IceExtent {
+  std::vector<int> lo, hi; // per owned row: columns [lo, hi] to transfer (lo > hi: none; lo < 0: the whole row)
+};
+
+static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E) {
+  const int xm = c.xm, ym = c.ym, wg = c.w_geom, margin = 3;
+  const long pitch = xm + 2 * wg;
+  std::vector<int> l0(ym), h0(ym);
+  for (int j = 0; j < ym; ++j) {
+    const double *row = H + (long)(j + wg) * pitch + wg;
+    int a = 0, b = xm - 1;
+    while (a < xm && row[a] == 0.0) ++a;
+    while (b >= a && row[b] == 0.0) --b;
+    l0[j] = a, h0[j] = b; // a > b: no ice in this row
+  }
+  E.lo.assign(ym, xm), E.hi.assign(ym, -1);
+  for (int j = 0; j < ym; ++j) {
+    int lo = xm, hi = -1;
+    for (int d = -margin; d <= margin; ++d) { // rows wrap periodically, like the ghosts
+      const int jj = ((j + d) % ym + ym) % ym;
+      if (l0[jj] <= h0[jj]) lo = std::min(lo, l0[jj]), hi = std::max(hi, h0[jj]);
+    }
+    if (hi >= lo) {
+      lo -= margin, hi += margin;
+      if (lo < margin || hi > xm - 1 - margin) lo = -1, hi = xm; // ice near the edge of the domain: whole rows
+    }
+    E.lo[j] = lo, E.hi[j] = hi;
+  }
+}
+
+// rectangle of the owned rows [j0, j1) (wrapped into [0, ym)): returns false when there is nothing to transfer
+static bool band_extent(const IceExtent &E, int ym, int j0, int j1, int *lo, int *hi, bool *whole) {
+  int a = 1 << 30, b = -1;
+  *whole = false;
+  for (int j = j0; j < j1; ++j) {
+    const int jj = ((j % ym) + ym) % ym;
+    if (E.hi[jj] < E.lo[jj]) continue;
+    if (E.lo[jj] < 0) *whole = true;
+    a = std::min(a, E.lo[jj]), b = std::max(b, E.hi[jj]);
+  }
+  *lo = a, *hi = b;
+  return b >= a || *whole;
+}
+
+// n doubles starting at p set to `value` with non-temporal stores where the ISA has them: the filled parts of u, v
+// (gigabytes) are not read again by this call, and a regular store would first read every cache line it overwrites,
+// doubling the DRAM traffic that competes with the PCIe copies landing in the same arrays
+static void fill_stream(double *p, size_t n, double value) {
+#if defined(__x86_64__) || defined(_M_X64)
+  size_t k = 0;
+  while (k < n && (reinterpret_cast<uintptr_t>(p + k) & 15u)) p[k++] = value;
+  const __m128d v = _mm_set1_pd(value);
+  for (; k + 8 <= n; k += 8) {
+    _mm_stream_pd(p + k, v);
+    _mm_stream_pd(p + k + 2, v);
+    _mm_stream_pd(p + k + 4, v);
+    _mm_stream_pd(p + k + 6, v);
+  }
+  for (; k + 2 <= n; k += 2) _mm_stream_pd(p + k, v);
+  for (; k < n; ++k) p[k] = value;
+#else
+  std::fill(p, p + n, value);
+#endif
+}
+
+struct FillTask {
+  int j, c0, c1; // owned row, local columns [c0, c1) of the u / v arrays (ghost columns included)
+};
+
+// u, v of ice-free columns: the sliding velocity on every level (zero when there is no sliding field)
+static void fill_rows(const siafd_b200_config &c, const double *sliding, double *u, double *v, const FillTask *tasks,
+                      size_t n, size_t first, size_t stride) {
+  const int wuv = c.w_uv, wsl = c.w_sliding, Mz = c.Mz, xm = c.xm;
+  const long rowUV = (long)(xm + 2 * wuv) * Mz, pitchS = (long)(xm + 2 * wsl) * 2;
+  for (size_t t = first; t < n; t += stride) {
+    const FillTask &T = tasks[t];
+    double *ur = u + (long)(T.j + wuv) * rowUV, *vr = v + (long)(T.j + wuv) * rowUV;
+    bool zero = true;
+    if (sliding) {
+      const double *sr = sliding + (long)(T.j + wsl) * pitchS + 2L * wsl;
+      for (int cc = T.c0; cc < T.c1 && zero; ++cc) {
+        const int i = ((cc - wuv) % xm + xm) % xm; // ghost columns wrap periodically
+        zero = (sr[2L * i] == 0.0 && sr[2L * i + 1] == 0.0);
+      }
+      if (!zero) {
+        for (int cc = T.c0; cc < T.c1; ++cc) {
+          const int i = ((cc - wuv) % xm + xm) % xm;
+          fill_stream(ur + (long)cc * Mz, (size_t)Mz, sr[2L * i]);
+          fill_stream(vr + (long)cc * Mz, (size_t)Mz, sr[2L * i + 1]);
+        }
+      }
+    }
+    if (zero) {
+      fill_stream(ur + (long)T.c0 * Mz, (size_t)(T.c1 - T.c0) * Mz, 0.0);
+      fill_stream(vr + (long)T.c0 * Mz, (size_t)(T.c1 - T.c0) * Mz, 0.0);
+    }
+  }
+#if defined(__x86_64__) || defined(_M_X64)
+  _mm_sfence(); // the streamed stores are globally visible before the thread is joined
+#endif
+}
+
 static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out) {
   const siafd_b200_config &c = h->cfg;
   int st;
@@ -1220,6 +1339,53 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   for (int f : outs_f) {
     if ((st = ensure(h, f))) return st;
   }
+  const int we = c.w_3d_in, wuv = c.w_uv;
+  const long rowsE = c.ym + 2 * we, rowE = (long)(c.xm + 2 * we) * c.Mz;
+  const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
+  // ---- which parts of the 3D arrays have to move at all (sparse = 0 moves everything) ----
+  const bool sparse = h->tuning.sparse_host != 0;
+  IceExtent ext;
+  if (sparse) ice_extent(c, in->thickness, ext);
+  // the host fills what is not downloaded; the tasks are known up front, so the threads start before the copies
+  std::vector<FillTask> fills;
+  std::vector<std::thread> workers;
+  struct Rect {
+    int o0, o1, c0, c1; // owned rows [o0, o1), local columns [c0, c1) of u / v to download (c0 >= c1: none)
+  };
+  std::vector<Rect> down(NB);
+  for (int b = 0; b < NB; ++b) {
+    const int s0 = b * band, s1 = std::min(nseg, (b + 1) * band);
+    Rect R{std::max(0, s0 * RS - 1), std::min(c.ym, s1 * RS - 1), 0, c.xm + 2 * wuv};
+    if (sparse && R.o1 > R.o0) {
+      int lo, hi;
+      bool whole;
+      const bool any = band_extent(ext, c.ym, R.o0, R.o1, &lo, &hi, &whole);
+      if (!any) {
+        R.c0 = R.c1 = 0;
+      } else if (!whole) {
+        R.c0 = lo + wuv, R.c1 = hi + 1 + wuv;
+      }
+      for (int j = R.o0; j < R.o1; ++j) {
+        if (R.c0 > 0 || R.c0 >= R.c1) fills.push_back({j, 0, R.c0 >= R.c1 ? c.xm + 2 * wuv : R.c0});
+        if (R.c0 < R.c1 && R.c1 < c.xm + 2 * wuv) fills.push_back({j, R.c1, c.xm + 2 * wuv});
+      }
+    }
+    down[b] = R;
+  }
+  if (!fills.empty() && !getenv("SIAFD_B200_NOFILL")) { // (NOFILL: timing diagnostic only, leaves u, v incomplete)
+    const size_t nt = std::min<size_t>(std::max(1u, std::min((unsigned)h->fill_threads, std::thread::hardware_concurrency())), fills.size());
+    for (size_t t = 0; t < nt; ++t) {
+      workers.emplace_back(fill_rows, std::cref(c), in->sliding, out->u, out->v, fills.data(), fills.size(), t, nt);
+    }
+  }
+  struct Joiner { // the workers are joined on every way out of this function
+    std::vector<std::thread> &w;
+    ~Joiner() {
+      for (auto &t : w)
+        if (t.joinable()) t.join();
+    }
+  } joiner{workers};
+
   cudaEvent_t ev_start = h->ev_pipe[2 * NB];
   CU(h, cudaEventRecord(ev_start, h->stream)); // earlier work on the handle's stream (fresh buffers' zero-fill)
   CU(h, cudaStreamWaitEvent(h->s_up, ev_start, 0));
@@ -1234,21 +1400,30 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     if (q.p && (st = siafd_b200_upload(h, q.f, q.p))) return st;
   }
   // enthalpy bands on the upload stream: band b reads local rows below (b + 1) band RS + w_3d_in (+1 of slack)
-  const int we = c.w_3d_in, wuv = c.w_uv;
-  const long rowsE = c.ym + 2 * we, rowE = (long)(c.xm + 2 * we) * c.Mz;
+  double *E_dev = (double *)h->buf[SIAFD_B200_F_ENTHALPY];
+  auto upload_rows = [&](long r0, long r1) -> int { // local rows [r0, r1) of the enthalpy array
+    if (r1 <= r0) return SIAFD_B200_OK;
+    int lo = 0, hi = 0;
+    bool whole = true;
+    if (sparse && !band_extent(ext, c.ym, (int)r0 - we, (int)r1 - we, &lo, &hi, &whole)) return SIAFD_B200_OK; // no ice
+    if (!sparse || whole) {
+      CU(h, cudaMemcpyAsync(E_dev + r0 * rowE, in->enthalpy + r0 * rowE, (size_t)(r1 - r0) * rowE * sizeof(double),
+                            cudaMemcpyHostToDevice, h->s_up));
+      h->bytes_h2d += (int64_t)(r1 - r0) * rowE * 8;
+    } else {
+      h->bytes_h2d += (int64_t)(hi - lo + 1) * c.Mz * 8 * (r1 - r0);
+      const long off = r0 * rowE + (long)(lo + we) * c.Mz;
+      CU(h, cudaMemcpy2DAsync(E_dev + off, (size_t)rowE * sizeof(double), in->enthalpy + off, (size_t)rowE * sizeof(double),
+                              (size_t)(hi - lo + 1) * c.Mz * sizeof(double), (size_t)(r1 - r0), cudaMemcpyHostToDevice,
+                              h->s_up));
+    }
+    return SIAFD_B200_OK;
+  };
   long up0 = 0;
   for (int b = 0; b < NB; ++b) {
-    const long up1 = std::min<long>(rowsE, (long)std::min(nseg, (b + 1) * band) * RS + we + 1);
-    if (up1 > up0) {
-      CU(h, cudaMemcpyAsync((double *)h->buf[SIAFD_B200_F_ENTHALPY] + up0 * rowE, in->enthalpy + up0 * rowE,
-                            (size_t)(up1 - up0) * rowE * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
-      up0 = up1;
-    }
-    if (b == NB - 1 && up0 < rowsE) {
-      CU(h, cudaMemcpyAsync((double *)h->buf[SIAFD_B200_F_ENTHALPY] + up0 * rowE, in->enthalpy + up0 * rowE,
-                            (size_t)(rowsE - up0) * rowE * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
-      up0 = rowsE;
-    }
+    const long up1 = (b == NB - 1) ? rowsE : std::min<long>(rowsE, (long)std::min(nseg, (b + 1) * band) * RS + we + 1);
+    if ((st = upload_rows(up0, up1))) return st;
+    up0 = std::max(up0, up1);
     CU(h, cudaEventRecord(h->ev_pipe[b], h->s_up));
   }
   // gradient and 2D preparation while the first band is in flight
@@ -1258,7 +1433,6 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
   }
   if ((st = flux_velocity_prepare(h, 1, in->current_time))) return st;
-  const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
   const int uvf[2] = {SIAFD_B200_F_U, SIAFD_B200_F_V};
   double *uvh[2] = {out->u, out->v};
   for (int b = 0; b < NB; ++b) {
@@ -1266,7 +1440,8 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_pipe[b], 0));
     if ((st = flux_velocity_launch(h, 1, s0, s1 - s0))) return st;
     // owned rows of this band (extended row e = ys - 1 + s RS ... ; owned rows are ys .. ys + ym - 1)
-    const int o0 = std::max(0, s0 * RS - 1), o1 = std::min(c.ym, s1 * RS - 1);
+    const Rect &R = down[b];
+    const int o0 = R.o0, o1 = R.o1;
     if (o1 > o0) {
       for (int q = 0; q < 2; ++q) { // periodic wrap in x of the band's rows (SIAFD.cc:946-947), then download
         double *a = (double *)h->buf[uvf[q]];
@@ -1277,10 +1452,17 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
       }
       CU(h, cudaEventRecord(h->ev_pipe[NB + b], h->stream));
       CU(h, cudaStreamWaitEvent(h->s_dn, h->ev_pipe[NB + b], 0));
-      for (int q = 0; q < 2; ++q) {
-        const long off = (long)(wuv + o0) * rowUV;
-        CU(h, cudaMemcpyAsync(uvh[q] + off, (double *)h->buf[uvf[q]] + off, (size_t)(o1 - o0) * rowUV * sizeof(double),
-                              cudaMemcpyDeviceToHost, h->s_dn));
+      for (int q = 0; q < 2 && R.c1 > R.c0; ++q) {
+        const long off = (long)(wuv + o0) * rowUV + (long)R.c0 * c.Mz;
+        h->bytes_d2h += (int64_t)(R.c1 - R.c0) * c.Mz * 8 * (o1 - o0);
+        if (R.c0 == 0 && R.c1 == c.xm + 2 * wuv) {
+          CU(h, cudaMemcpyAsync(uvh[q] + off, (double *)h->buf[uvf[q]] + off, (size_t)(o1 - o0) * rowUV * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->s_dn));
+        } else {
+          CU(h, cudaMemcpy2DAsync(uvh[q] + off, (size_t)rowUV * sizeof(double), (double *)h->buf[uvf[q]] + off,
+                                  (size_t)rowUV * sizeof(double), (size_t)(R.c1 - R.c0) * c.Mz * sizeof(double),
+                                  (size_t)(o1 - o0), cudaMemcpyDeviceToHost, h->s_dn));
+        }
       }
     }
   }
@@ -1289,6 +1471,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     if ((st = wrap_dir(h, uvf[q], 1))) return st;
     double *a = (double *)h->buf[uvf[q]];
     CU(h, cudaMemcpyAsync(uvh[q], a, (size_t)wuv * rowUV * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->bytes_d2h += 2 * (int64_t)wuv * rowUV * 8;
     const long off = (long)(wuv + c.ym) * rowUV;
     CU(h, cudaMemcpyAsync(uvh[q] + off, a + off, (size_t)wuv * rowUV * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
@@ -1300,6 +1483,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     if (!q.p) continue;
     CU(h, cudaMemcpyAsync(q.p, h->buf[q.f], (size_t)siafd_b200_field_size(h, q.f) * sizeof(double), cudaMemcpyDeviceToHost,
                           h->stream));
+    h->bytes_d2h += (int64_t)siafd_b200_field_size(h, q.f) * 8;
   }
   st = siafd_b200_finish(h);
   CU(h, cudaStreamSynchronize(h->s_dn));
@@ -1412,6 +1596,12 @@ int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_c
 }
 
 int64_t siafd_b200_launch_count(const siafd_b200_handle *h) { return h->launches; }
+
+int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t *d2h) {
+  if (h2d) *h2d = h->bytes_h2d;
+  if (d2h) *d2h = h->bytes_d2h;
+  return SIAFD_B200_OK;
+}
 
 int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable) {
   CU(h, cudaSetDevice(h->device));

@@ -23,6 +23,7 @@ struct Tuning {
   int wz;            // z ranges per column (2, 4 or 8)
   int pipeline_host; // 1: siafd_b200_update with host arrays overlaps upload, kernel and download over row bands
   int pipeline_band; // row segments per band of that pipeline
+  int sparse_host;   // 1: that pipeline moves only the parts of the 3D arrays that are within 3 cells of ice
 };
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
