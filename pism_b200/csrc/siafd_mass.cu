@@ -762,8 +762,8 @@ __global__ void __launch_bounds__(256, 2) k_vvel_slab(const __grid_constant__ DP
 // StressBalance::compute_volumetric_strain_heating (stressbalance/StressBalance.cc:426-642), SURVEY.md 8(f) N3.
 // Sigma = 2 e^(-1/n) B(E, p) D2^((1/n + 1)/2) on levels 0 .. ks, zero above; B = softness^(-1/n) (FlowLaw.cc:142-144)
 // of the SHALLOW stress balance's flow law (law id, n, e are arguments, not the handle's SIA law).
-// One warp per column, lanes across z, the eight warps of a CTA on eight adjacent columns, marching up the rows of a
-// row segment: every level is independent, the stencil neighbours (x: adjacent in memory; y: the rows the walk has
+// A half-warp per column, lanes across z, the eight warps of a CTA on sixteen adjacent columns, marching up the rows
+// of a row segment: every level is independent, the stencil neighbours (x: adjacent in memory; y: the rows the walk has
 // just read / reads next; z: levels k +- 1) come from L1 / L2.  For n = 3 the two powers are cube roots (x^(-1/3) = 1 / cbrt x,
 // x^(2/3) = cbrt(x)^2: two ~40-instruction calls instead of two ~150-instruction pow); other n use pow.
 // FP64-bound where there is ice (one exp, two cbrt per level), write-bound (8 Mz bytes) where there is none.
@@ -825,11 +825,14 @@ __device__ __forceinline__ double hardness_eval(const DP &P, double E, double p,
 
 template <int LAW>
 __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant__ DP P, const HeatArgs A) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int i = P.xs + blockIdx.x * 8 + wid;
-  if (i >= P.xs + P.xm) return;
+  // a half-warp per column (16 lanes across z: 128-byte pieces; Mz = 101 fills 7 x 16 lanes to 90 %, 4 x 32 to 79 %,
+  // and the part of a column above the ice wastes at most 15 lanes), two adjacent columns per warp
+  const int lane = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1, wid = threadIdx.x >> 5;
+  const int i_raw = P.xs + blockIdx.x * 16 + wid * 2 + half;
+  const bool live = i_raw < P.xs + P.xm; // (an idle half still takes part in the warp's ballots)
+  const int i = live ? i_raw : P.xs + P.xm - 1;
   const int j0 = P.ys + blockIdx.y * A.RS, j1 = min(j0 + A.RS, P.ys + P.ym);
-  const int Mz = P.Mz, nch = (Mz + 31) >> 5;
+  const int Mz = P.Mz, nch = (Mz + 15) >> 4;
   const bool n3 = (A.n == 3.0);
   const double exponent = 0.5 * (1.0 / A.n + 1.0);
   const double *__restrict__ z = A.z;
@@ -845,7 +848,7 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
     {
       const bool uv_ok = j + 2 < P.ys + P.ym + P.wuv, e_ok = j + 1 < j1; // rows inside the arrays
       for (int c = 0; c < nch; ++c) {
-        const int k = min(c * 32 + lane, Mz - 1);
+        const int k = min(c * 16 + lane, Mz - 1);
         if (uv_ok) {
           prefetch_l1(uc_p + k + 2 * rowuv);
           prefetch_l1(vc_p + k + 2 * rowuv);
@@ -857,17 +860,20 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
     // IceGrid::kBelowHeight (util/IceGrid.cc:427-440), for EVERY column, icy or not (StressBalance.cc:540): the levels
     // are sorted, so the largest k with z[k] <= H is a count; clamped to [0, Mz - 2] like GSL's bsearch
     int ks = 0;
-    if (H < 0.0 - 1.0e-6) {
-      if (lane == 0) atomicOr(A.err, EB_BELOW);
-    } else if (H > ztop + 1.0e-6) {
-      if (lane == 0) atomicOr(A.err, EB_ABOVE);
-    } else {
-      int cnt = 0;
+    {
+      int cnt = 0; // (the ballots are taken by the whole warp: the two halves hold different columns)
       for (int c = 0; c < nch; ++c) {
-        const int k = c * 32 + lane;
-        cnt += __popc(__ballot_sync(FULLMASK, (k < Mz) && z[min(k, Mz - 1)] <= H));
+        const int k = c * 16 + lane;
+        const unsigned b = __ballot_sync(FULLMASK, (k < Mz) && z[min(k, Mz - 1)] <= H);
+        cnt += __popc((b >> (half * 16)) & 0xffffu);
       }
-      ks = min(max(cnt - 1, 0), Mz - 2);
+      if (H < 0.0 - 1.0e-6) {
+        if (lane == 0) atomicOr(A.err, EB_BELOW);
+      } else if (H > ztop + 1.0e-6) {
+        if (lane == 0) atomicOr(A.err, EB_ABOVE);
+      } else {
+        ks = min(max(cnt - 1, 0), Mz - 2);
+      }
     }
     const int M0 = mask_int(A.mask[g]), Me = mask_int(A.mask[g + 1]), Mw = mask_int(A.mask[g - 1]),
               Mn = mask_int(A.mask[g + rowg]), Ms = mask_int(A.mask[g - rowg]);
@@ -883,9 +889,9 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
     const double a_e = D_x * east, a_w = D_x * west, a_n = D_y * north, a_s = D_y * south;
 #pragma unroll 2
     for (int c = 0; c < nch; ++c) {
-      const int k = c * 32 + lane;
+      const int k = c * 16 + lane;
       double sig = 0.0;
-      if (c * 32 <= ks && k <= ks) { // (chunks wholly above the ice skip the arithmetic warp-uniformly)
+      if (k <= ks) { // (chunks wholly above the ice skip the arithmetic warp-uniformly)
         const double uc = uc_p[k], vc = vc_p[k];
         const double u_x = a_w * (uc - uc_p[k - Mz]) + a_e * (uc_p[k + Mz] - uc);
         const double v_x = a_w * (vc - vc_p[k - Mz]) + a_e * (vc_p[k + Mz] - vc);
@@ -907,7 +913,7 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
         }
         sig = A.two_e_pow * hard * dpow;
       }
-      if (k < Mz) s_p[k] = sig;
+      if (live && k < Mz) s_p[k] = sig;
     }
     uc_p += rowuv, vc_p += rowuv, e_p += rowe, s_p += (long)P.xm * Mz, g += rowg;
   }
@@ -1034,7 +1040,7 @@ int launch_vvel_march(const DP &P, const double *mask, const double *thk, const 
 namespace siafd {
 template <int LAW>
 static int launch_heat_law(const DP &P, const HeatArgs &A, cudaStream_t s) {
-  const dim3 grid((unsigned)((P.xm + 7) / 8), (unsigned)((P.ym + A.RS - 1) / A.RS));
+  const dim3 grid((unsigned)((P.xm + 15) / 16), (unsigned)((P.ym + A.RS - 1) / A.RS));
   k_strain_heating<LAW><<<grid, 256, 0, s>>>(P, A);
   return 1;
 }
