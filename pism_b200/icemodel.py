@@ -12,10 +12,10 @@ energy / age / bed deformation / calving, explicit mass continuity.  Every array
 *backend* object (the device backend below drives libsiafd_b200.so through the C ABI and keeps all state in HBM;
 the tests drive the same loop with the CPU oracle), so nothing in this file computes physics on fields.
 
-Backend protocol (whole-domain, single rank):
-    set_thickness(H_owned[My, Mx]); thickness() -> H_owned; ensure_consistency()
-    stress_balance_update(full_update) -> dict(D_max=..., cfl3d_dt=..., cfl2d_dt=...)   [max_dt passed at init]
-    flow_step(dt); source_step(dt, smb_owned[My, Mx] in kg m-2 s-1)
+Backend protocol (global [My, Mx] arrays in and out; a backend of a multi-rank run keeps its own patch of them):
+    set_thickness(H); thickness() -> H; ensure_consistency()
+    stress_balance_update(full_update) -> dict(D_max=..., cfl3d_dt=..., cfl2d_dt=...), reduced over ranks
+    flow_step(dt); source_step(dt, smb in kg m-2 s-1)
 """
 import ctypes as C
 
@@ -164,55 +164,114 @@ class IceCompModel:
         return "%12.6f%12.6f%12.6f%12.6f" % self.geometry_errors()
 
 
+class Ranks:
+    """What a backend needs from a parallel run (one process per GPU / patch): its patch of PISM's decomposition and
+    the reductions the reference does with GlobalMax / GlobalMin (src/util/pism_utilities.cc:140-160).  Serial when
+    torch.distributed is not initialised."""
+
+    def __init__(self, grid, patches=None, rank=0, group=None):
+        self.grid = grid
+        self.patches = patches or [grid.whole()]
+        self.rank, self.group = rank, group
+        self.patch = self.patches[rank]
+        self.size = len(self.patches)
+
+    def _reduce(self, x, op):
+        if self.size == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op, group=self.group)
+        return float(t.item())
+
+    def global_max(self, x):
+        import torch.distributed as dist
+        return self._reduce(x, dist.ReduceOp.MAX) if self.size > 1 else x
+
+    def global_min(self, x):
+        import torch.distributed as dist
+        return self._reduce(x, dist.ReduceOp.MIN) if self.size > 1 else x
+
+    def gather_owned(self, owned):
+        """Global [My, Mx] array from every rank's owned part (reports only: small grids)."""
+        if self.size == 1:
+            return owned
+        import torch.distributed as dist
+        parts = [None] * self.size
+        dist.all_gather_object(parts, np.ascontiguousarray(owned), group=self.group)
+        out = np.zeros((self.grid.My, self.grid.Mx))
+        for pt, a in zip(self.patches, parts):
+            out[pt.ys:pt.ys + pt.ym, pt.xs:pt.xs + pt.xm] = a
+        return out
+
+    def owned(self, a_global):
+        p = self.patch
+        return np.ascontiguousarray(a_global[p.ys:p.ys + p.ym, p.xs:p.xs + p.xm])
+
+
 class DeviceBackend:
     """The backend that runs on the B200: all fields stay in the handle's device buffers; per step only D_max,
-    the CFL scalars and the (2D) surface mass flux cross PCIe.  `sia` is a pism_b200.sia.SIAFD."""
+    the CFL scalars and the (2D) surface mass flux cross PCIe.  `sia` is a pism_b200.sia.SIAFD built for this rank's
+    patch.  On several ranks (`ranks`, one process per GPU) the ghost updates where the reference has them
+    (Geometry.cc:172, SIAFD.cc:498-499, :946-947) go through `halo` (pism_b200.halo.PeerHalo: direct stores into the
+    neighbours' arrays over NVLink) and D_max / the CFL scalars are reduced over ranks."""
 
-    def __init__(self, sia, inputs, max_dt_seconds, ice_density=ICE_DENSITY):
+    def __init__(self, sia, inputs, max_dt_seconds, ice_density=ICE_DENSITY, ranks=None, halo=None):
         from .capi import F, lib
         self.sia, self.lib, self.F = sia, lib, F
         self.max_dt, self.ice_density = max_dt_seconds, ice_density
         self.w = sia.config.w_geom
+        self.ranks = ranks or Ranks(sia.grid)
+        self.halo = halo
+        assert (self.ranks.size == 1) == (halo is None)
         for name in ("bed", "thickness", "enthalpy", "sliding"):
-            sia.upload(name, inputs[name])
-        self._wrapH = (C.c_int * 1)(F["thickness"])
+            sia.upload(name, inputs[name])  # this patch's local arrays, ghosts included
 
     def _check(self, status):
         self.sia._check(status)
 
-    def set_thickness(self, H_owned):
-        g, w = self.sia.grid, self.w
-        a = np.zeros((g.My + 2 * w, g.Mx + 2 * w))
-        a[w:-w, w:-w] = H_owned
-        self.sia.upload("thickness", a)
+    def _ghosts(self, names_widths, phase):
+        """IceModelVec::update_ghosts of fields on the device."""
+        if self.halo is not None:
+            self.halo.exchange(names_widths, phase)
+        else:
+            ids = (C.c_int * len(names_widths))(*[self.F[n] for n, _ in names_widths])
+            self._check(self.lib.siafd_b200_wrap_ghosts_many(self.sia.handle, len(names_widths), ids))
+
+    def set_thickness(self, H_global):
+        from . import grid as G
+        self.sia.upload("thickness", G.global_to_local(np.ascontiguousarray(H_global), self.ranks.patch, self.w))
 
     def thickness(self):
         w = self.w
-        return self.sia.download("thickness")[w:-w, w:-w]
+        return self.ranks.gather_owned(self.sia.download("thickness")[w:-w, w:-w])
 
     def ensure_consistency(self):
-        self._check(self.lib.siafd_b200_ensure_consistency(self.sia.handle, 1))
+        self._ghosts([("thickness", self.w)], 0)
+        self._check(self.lib.siafd_b200_ensure_consistency(self.sia.handle, 0))
 
     def stress_balance_update(self, full_update):
         h, lib = self.sia.handle, self.lib
         self._check(lib.siafd_b200_compute_gradient(h))
-        names = (C.c_int * 2)(self.F["h_x"], self.F["h_y"])
-        self._check(lib.siafd_b200_wrap_ghosts_many(h, 2, names))
+        self._ghosts([("h_x", 1), ("h_y", 1)], 1)
         self._check(lib.siafd_b200_compute_flux_velocity(h, 1 if full_update else 0, self.sia.current_time))
         out = (C.c_double * 8)()
         if full_update:
-            names = (C.c_int * 2)(self.F["u"], self.F["v"])
-            self._check(lib.siafd_b200_wrap_ghosts_many(h, 2, names))
+            self._ghosts([("u", 1), ("v", 1)], 2)
             self._check(lib.siafd_b200_compute_vertical_velocity(h, 0, 0))
         self._check(lib.siafd_b200_cfl(h, self.max_dt, 1 if full_update else 0, out))
         self._check(lib.siafd_b200_finish(h))
+        R = self.ranks
         if full_update:
-            self._cfl3d = out[0]
-        return dict(D_max=lib.siafd_b200_max_diffusivity(h), cfl3d_dt=self._cfl3d, cfl2d_dt=out[4])
+            self._cfl3d = R.global_min(out[0])
+        return dict(D_max=R.global_max(lib.siafd_b200_max_diffusivity(h)), cfl3d_dt=self._cfl3d,
+                    cfl2d_dt=R.global_min(out[4]))
 
     def flow_step(self, dt):
         self._check(self.lib.siafd_b200_mass_flow_step(self.sia.handle, dt))
 
-    def source_step(self, dt, smb_owned):
-        self.sia.upload("smb", smb_owned)
+    def source_step(self, dt, smb_global):
+        self.sia.upload("smb", self.ranks.owned(smb_global))
         self._check(self.lib.siafd_b200_mass_source_step(self.sia.handle, dt, self.ice_density, 0))
