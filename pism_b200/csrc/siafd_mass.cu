@@ -843,17 +843,20 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
   double *s_p = A.sigma + ((long)(j0 - P.ys) * P.xm + (i - P.xs)) * Mz;
   long g = idx2(P, i, j0, P.wg);
   for (int j = j0; j < j1; ++j) {
-    // the rows the next iteration misses in cache (u, v two rows up; enthalpy one row up) are requested now, so that
-    // their DRAM latency overlaps this row's arithmetic instead of stalling the next row's
+    // the rows the next iterations miss in cache (u, v two rows up; enthalpy one row up) are requested now, so that
+    // their DRAM latency overlaps this row's arithmetic -- but only the levels that will be read: those at or below
+    // the ice surface of that row's column, plus one (u_z, v_z look one level up)
     {
       const bool uv_ok = j + 2 < P.ys + P.ym + P.wuv, e_ok = j + 1 < j1; // rows inside the arrays
+      const double H1 = e_ok ? A.thk[g + rowg] : -1.0, H2 = (uv_ok && j + 2 <= P.ys + P.ym + P.wg - 1) ? A.thk[g + 2 * rowg] : -1.0;
       for (int c = 0; c < nch; ++c) {
         const int k = min(c * 16 + lane, Mz - 1);
-        if (uv_ok) {
+        const double zb = z[max(k - 1, 0)];
+        if (H2 > 0.0 && zb <= H2) {
           prefetch_l1(uc_p + k + 2 * rowuv);
           prefetch_l1(vc_p + k + 2 * rowuv);
         }
-        if (e_ok) prefetch_l1(e_p + k + rowe);
+        if (H1 > 0.0 && zb <= H1) prefetch_l1(e_p + k + rowe);
       }
     }
     const double H = A.thk[g];
