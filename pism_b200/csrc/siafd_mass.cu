@@ -1001,13 +1001,10 @@ int launch_vvel_slab(const DP &P, const double *mask, const double *thk, const d
   const int WZ = (wz == 2 || wz == 4 || wz == 8 || wz == 16) ? wz : 16;
   const size_t smem = vvel_smem_bytes(P.Mz);
   if ((P.Mz & 1) == 0 || smem > 113 * 1024 || P.Mz < 3 || P.wuv < 1) return 0;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(k_vvel_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      cudaGetLastError();
-      return 0;
-    }
-    configured = smem;
+  // (set on every launch: the attribute is per device and a process may hold handles on several)
+  if (cudaFuncSetAttribute(k_vvel_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
   }
   const int RS = rows_per_cta > 0 ? rows_per_cta : 32;
   VvelArgs A{mask, thk, u, v, bmr, z, w, cfl, err, upstream, RS, WZ, (P.Mz + WZ - 1) / WZ, nUV, inv_dz};

@@ -681,13 +681,16 @@ template <int LAW, bool FULL, int NC, int WZ>
 static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaStream_t s) {
   const size_t smem = slab_smem_bytes(P, FULL, NC, WZ, A.use_bulk != 0);
   if (smem > (size_t)227 * 1024) return -1;
-  static size_t configured = 0; // per instantiation
-  if (smem > configured) {
+  static size_t configured[64] = {}; // per instantiation and per device (the attribute is a per-device setting)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  const int slot = dev & 63;
+  if (smem > configured[slot]) {
     if (cudaFuncSetAttribute(k_sia_slab<LAW, FULL, NC, WZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess) {
       return -1;
     }
-    configured = smem;
+    configured[slot] = smem;
   }
   dim3 grid((unsigned)((P.xm + 1 + (NC - 2)) / (NC - 1)), (unsigned)A.nseg);
   k_sia_slab<LAW, FULL, NC, WZ><<<grid, 2 * NC * WZ, smem, s>>>(P, F, A);
