@@ -1372,7 +1372,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     }
     down[b] = R;
   }
-  if (!fills.empty() && !getenv("SIAFD_B200_NOFILL")) { // (NOFILL: timing diagnostic only, leaves u, v incomplete)
+  if (!fills.empty()) {
     const size_t nt = std::min<size_t>(std::max(1u, std::min((unsigned)h->fill_threads, std::thread::hardware_concurrency())), fills.size());
     for (size_t t = 0; t < nt; ++t) {
       workers.emplace_back(fill_rows, std::cref(c), in->sliding, out->u, out->v, fills.data(), fills.size(), t, nt);
