@@ -30,6 +30,14 @@ def test_library_exports_every_declared_symbol():
     assert capi.lib.siafd_b200_abi_version() == 1
 
 
+def test_field_ids_of_the_python_binding_match_the_header():
+    text = open(os.path.join(ROOT, "include", "siafd_b200.h")).read()
+    ids = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"SIAFD_B200_F_([A-Z0-9_]+)\s*=\s*(\d+)", text)}
+    count = ids.pop("count")
+    assert count == len(capi.FIELDS) == len(ids)
+    assert ids == {k.lower(): v for k, v in capi.F.items()}  # ("C2".."C4", "D" keep their reference spelling)
+
+
 def test_config_struct_matches_oracle_params_and_defaults():
     """Same member list on both sides, and the defaults are pism_config.cdl's."""
     assert [n for n, _ in capi.CONFIG_FIELDS] == [n for n, _ in O.PARAM_FIELDS]
