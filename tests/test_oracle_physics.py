@@ -219,3 +219,38 @@ def test_strain_heating_against_exact_solution_F():
     assert n > 500
     print("strain heating vs exact F: worst %.4f mean %.4f" % (worst, np.mean(errs)))
     assert worst < 0.05 and np.mean(errs) < 0.03, (worst, np.mean(errs))
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_EXACT), reason="oracle/_ref not built (needs /root/reference)")
+def test_vertical_velocity_against_exact_solution_F():
+    """the oracle's w from incompressibility on the test-F state against the reference's exact w(z)
+    (exactTestsFG.cc, compiled unmodified).  Test F is steady: w balances the accumulation; the reference's own golden
+    surface error for Test G after 1000 a on a coarser grid is 0.028 m/a (maxW, test_17.sh)."""
+    import cases
+    grid, cfg, inputs, _ = cases.case("F")
+    run = cases.oracle_run(grid, cfg, inputs, None, full=True)
+    assert run.status == 0
+    p, a = run.p, run.a
+    w = np.zeros((grid.My, grid.Mx, grid.Mz))
+    assert O.lib().orc_vertical_velocity(C.byref(p), O.dptr(a["mask"]), O.dptr(a["u"]), O.dptr(a["v"]), None, 0,
+                                         O.dptr(w)) == 0
+    ref = C.CDLL(O.REF_EXACT)
+    ref.ref_exactFG.argtypes = [C.c_double, C.c_double, C.c_int] + [C.POINTER(C.c_double)] + [C.c_double] + \
+        [C.POINTER(C.c_double)] * 7
+    Mz, z = grid.Mz, np.ascontiguousarray(grid.z)
+    secpera = 31556926.0
+    errs = []
+    for j in range(grid.My):
+        for i in range(grid.Mx):
+            r = float(np.hypot(grid.x[i], grid.y[j]))
+            if not (100e3 < r < 600e3):
+                continue
+            H, M = C.c_double(), C.c_double()
+            outs = [np.zeros(Mz) for _ in range(5)]
+            assert ref.ref_exactFG(0.0, r, Mz, O.dptr(z), 0.0, C.byref(H), C.byref(M), *[O.dptr(o) for o in outs]) == 0
+            ks = grid.k_below_height(H.value)
+            errs.append(np.abs(w[j, i, :ks + 1] - outs[2][:ks + 1]).max() * secpera)
+    errs = np.array(errs)
+    print("w vs exact F: worst %.4f m/a mean %.4f m/a (|w| up to %.2f m/a)" % (errs.max(), errs.mean(),
+                                                                                 np.abs(w).max() * secpera))
+    assert len(errs) > 500 and errs.max() < 0.002 and errs.mean() < 0.001
