@@ -29,6 +29,8 @@
  *                                                              siafd_b200_mass_flow_step
  *   GeometryEvolution::source_term_step + apply_mass_fluxes  :327-390    siafd_b200_mass_source_step
  *   Geometry::ensure_consistency  geometry/Geometry.cc:121-187 siafd_b200_ensure_consistency
+ *   IceModelVec3::getSurfaceValues / getHorSlice  util/iceModelVec3.cc:209-240
+ *                                               siafd_b200_surface_values / siafd_b200_hor_slice
  *
  * Array layout is PISM's DMDA local (ghosted) layout, unchanged: [j][i][dof] with dof
  * fastest (util/IceModelVec_inline.hh:28-40); a 3D field is dof = Mz (util/iceModelVec3.cc:85);
@@ -284,6 +286,18 @@ int siafd_b200_apply_no_model_gradient(siafd_b200_handle *h);
  * (GoldsbyKohlstedt.cc:102-108): SIAFD_B200_ERR_BAD_CONFIG.  Asynchronous on the handle's stream. */
 int siafd_b200_compute_strain_heating(siafd_b200_handle *h, int flow_law, double glen_exponent,
                                       double enhancement_factor);
+
+/* IceModelVec3::getSurfaceValues (util/iceModelVec3.cc:226-240) and ::getHorSlice (:209-223), the reads of the
+ * path's 3D outputs that its callers make: PISM.sia.computeSIASurfaceVelocities (site-packages/PISM/sia.py:63-72,
+ * SURVEY.md 3.4) and siafd_test's surface-speed errors (sia/siafd_test.cc:105-151) take u, v at z = H; the velsurf /
+ * velbase diagnostics take the same.  Per owned column: IceModelVec3D::getValZ (:153-182), i.e. the end levels
+ * outside [z_0, z_{Mz-1}], else linear interpolation between the levels around the height, in the reference's
+ * expression order (bit-identical to the CPU's).  field3d is one of ENTHALPY, AGE, U, V, W, STRAIN_HEATING;
+ * _surface_values evaluates at the handle's THICKNESS, _hor_slice at the constant height z.  out_dev: DEVICE pointer
+ * to ym * xm doubles, [j][i] without ghosts (an IceModelVec2S created WITHOUT_GHOSTS).  Asynchronous on the handle's
+ * stream. */
+int siafd_b200_surface_values(siafd_b200_handle *h, int field3d, double *out_dev);
+int siafd_b200_hor_slice(siafd_b200_handle *h, int field3d, double z, double *out_dev);
 
 /* SURVEY.md 8(f) N1 -- the consumer of diffusive_flux(): GeometryEvolution (geometry/GeometryEvolution.cc), default
  * configuration (geometry.part_grid.enabled = no).  All asynchronous on the handle's stream, device-resident:

@@ -1247,6 +1247,36 @@ int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, i
 }
 
 // ---------------------------------------------------------------------------------------
+// IceModelVec3D::getValZ (src/util/iceModelVec3.cc:153-182), IceModelVec3::getSurfaceValues (:226-240) and
+// ::getHorSlice (:209-223).  a: 3D field of ghost width wa; heights: 2D field of ghost width wh (the ice thickness
+// for getSurfaceValues) or NULL for the constant height z0; out: owned points only ([ym][xm]).
+// ---------------------------------------------------------------------------------------
+static double get_val_z(const double *column, const double *z, int Mz, double height) {
+  if (height >= z[Mz - 1]) {
+    return column[Mz - 1];
+  } else if (height <= z[0]) {
+    return column[0];
+  }
+  const int mcurr = gsl_style_find(z, Mz, height); // gsl_interp_accel_find
+  const double incr = (height - z[mcurr]) / (z[mcurr + 1] - z[mcurr]);
+  const double valm = column[mcurr];
+  return valm + incr * (column[mcurr + 1] - valm);
+}
+
+void orc_value_at_height(const orc_params *p, const double *a, int wa, const double *heights, int wh, double z0,
+                         double *out) {
+  const int Mz = p->Mz;
+  const long nxa = p->xm + 2 * wa, nxh = p->xm + 2 * wh;
+  for (int j = p->ys; j < p->ys + p->ym; ++j) {
+    for (int i = p->xs; i < p->xs + p->xm; ++i) {
+      const double *column = a + ((long)(j - (p->ys - wa)) * nxa + (i - (p->xs - wa))) * Mz;
+      const double height = heights ? heights[(long)(j - (p->ys - wh)) * nxh + (i - (p->xs - wh))] : z0;
+      out[(long)(j - p->ys) * p->xm + (i - p->xs)] = get_val_z(column, p->z, Mz, height);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // StressBalance::compute_vertical_velocity  (src/stressbalance/StressBalance.cc:283-424)
 // the next consumer of u, v.  mask: 2D, ghost width w_geom; u, v: 3D, ghost
 // width w_uv with valid ghosts; basal_melt_rate: owned points only ([ym][xm]) or NULL; w: 3D,

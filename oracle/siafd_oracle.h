@@ -173,6 +173,10 @@ int orc_siafd_update_single(const orc_params *p, orc_fields *f, int full);
  * basal_melt_rate owned-only or NULL, w owned-only. */
 int orc_vertical_velocity(const orc_params *p, const double *mask, const double *u, const double *v,
                           const double *basal_melt_rate, int use_upstream_fd, double *w);
+/* IceModelVec3::getSurfaceValues / getHorSlice (util/iceModelVec3.cc:153-240): a (3D, ghost width wa) at the heights
+ * in `heights` (2D, ghost width wh) or, with heights == NULL, at z0; out owned-only. */
+void orc_value_at_height(const orc_params *p, const double *a, int wa, const double *heights, int wh, double z0,
+                         double *out);
 int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, int nthreads);
 /* StressBalance::compute_volumetric_strain_heating (StressBalance.cc:426-642), SURVEY.md 8(f) N3: p carries the flow
  * law of the SHALLOW stress balance (id, fl_n, fl_e); thickness, mask w_geom; enthalpy w_3d_in; u, v w_uv (ghosts

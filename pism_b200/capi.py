@@ -99,6 +99,8 @@ def _load():
         "siafd_b200_compute_gradient_no_model": (C.c_int, [vp]),
         "siafd_b200_apply_no_model_gradient": (C.c_int, [vp]),
         "siafd_b200_compute_strain_heating": (C.c_int, [vp, C.c_int, C.c_double, C.c_double]),
+        "siafd_b200_surface_values": (C.c_int, [vp, C.c_int, vp]),
+        "siafd_b200_hor_slice": (C.c_int, [vp, C.c_int, C.c_double, vp]),
         "siafd_b200_mass_flow_step": (C.c_int, [vp, C.c_double]),
         "siafd_b200_mass_source_step": (C.c_int, [vp, C.c_double, C.c_double, C.c_int]),
         "siafd_b200_ensure_consistency": (C.c_int, [vp, C.c_int]),

@@ -1042,6 +1042,43 @@ int siafd_b200_apply_no_model_gradient(siafd_b200_handle *h) {
   return SIAFD_B200_OK;
 }
 
+// ---- IceModelVec3::getSurfaceValues / getHorSlice (util/iceModelVec3.cc:209-240) ----------------------------------
+static int value_at_height(siafd_b200_handle *h, int field3d, bool at_surface, double z, double *out_dev) {
+  CU(h, cudaSetDevice(h->device));
+  switch (field3d) {
+  case SIAFD_B200_F_ENTHALPY:
+  case SIAFD_B200_F_AGE:
+  case SIAFD_B200_F_U:
+  case SIAFD_B200_F_V:
+  case SIAFD_B200_F_W:
+  case SIAFD_B200_F_STRAIN_HEATING:
+    break;
+  default:
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "field %d is not a 3D field", field3d);
+  }
+  if (!out_dev) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "out_dev is NULL");
+  if (!h->buf[field3d]) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "field %d has not been computed, uploaded or bound yet", field3d);
+  }
+  if (at_surface) {
+    int st = ensure(h, SIAFD_B200_F_THICKNESS);
+    if (st) return st;
+  }
+  h->launches += launch_value_at_height(h->P, (const double *)h->buf[field3d], meta(h->cfg, field3d).width,
+                                        at_surface ? (const double *)h->buf[SIAFD_B200_F_THICKNESS] : nullptr,
+                                        h->cfg.w_geom, z, h->d_z, out_dev, h->stream);
+  CU(h, cudaGetLastError());
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_surface_values(siafd_b200_handle *h, int field3d, double *out_dev) {
+  return value_at_height(h, field3d, true, 0.0, out_dev);
+}
+
+int siafd_b200_hor_slice(siafd_b200_handle *h, int field3d, double z, double *out_dev) {
+  return value_at_height(h, field3d, false, z, out_dev);
+}
+
 // ---- volumetric strain heating -------------------------------------------------------------
 int siafd_b200_compute_strain_heating(siafd_b200_handle *h, int flow_law, double glen_exponent,
                                       double enhancement_factor) {

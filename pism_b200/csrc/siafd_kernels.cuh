@@ -77,6 +77,10 @@ int launch_strain_heating(const DP &P, int law, double n, double e, const double
                           unsigned *err, cudaStream_t s);
 int launch_regional_override(const DP &P, const double *no_model, const double *hx_nm, const double *hy_nm, double *h_x,
                              double *h_y, cudaStream_t s);
+// IceModelVec3::getSurfaceValues / getHorSlice (util/iceModelVec3.cc:153-240): a 3D field (ghost width wa) at the
+// height zq[i,j] (2D, ghost width wz) or, with zq == NULL, at the height z0; out is [ym][xm] without ghosts
+int launch_value_at_height(const DP &P, const double *a, int wa, const double *zq, int wz, double z0, const double *z,
+                           double *out, cudaStream_t s);
 // SURVEY.md 8(f) N1 / N3-CFL (siafd_mass.cu): GeometryEvolution flow and source steps, Geometry::ensure_consistency,
 // max_timestep_cfl_3d / _2d.  NULL for an optional field means "all zero".
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,

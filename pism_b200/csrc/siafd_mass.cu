@@ -944,6 +944,43 @@ __global__ void k_regional_override(const __grid_constant__ DP P, const double *
   if (ij || n) h_y[o + 1] = (j < 0 || j + 1 > My - 1) ? 0.0 : hy_nm[o + 1];
 }
 
+// IceModelVec3D::getValZ (util/iceModelVec3.cc:153-182) for every owned column: the value of a 3D field at height
+// zq[i,j] (IceModelVec3::getSurfaceValues, :226-240, zq = ice thickness) or at one height z0 (getHorSlice, :209-223).
+// Linear interpolation between the two levels around the height, the end levels outside [z_0, z_Mz-1]; expression
+// order and roundings of the reference (no contraction), so the result is bit-identical to the CPU's.  One thread
+// per column: two 8-byte reads of a column that is 8 Mz bytes long, so the field is touched at 64 of its 8 Mz
+// bytes per column (sector granularity) and the launch is bound by those sectors, not by the 3D field's size.
+__global__ void k_value_at_height(const __grid_constant__ DP P, const double *__restrict__ a, int wa,
+                                  const double *__restrict__ zq, int wz, double z0, const double *__restrict__ z,
+                                  double *__restrict__ out) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long)P.xm * P.ym) return;
+  const int i = P.xs + (int)(q % P.xm), j = P.ys + (int)(q / P.xm);
+  const double height = zq ? zq[idx2(P, i, j, wz)] : z0;
+  const double *col = a + idx2(P, i, j, wa) * P.Mz;
+  const int Mz = P.Mz;
+  double r;
+  if (height >= z[Mz - 1]) {
+    r = col[Mz - 1];
+  } else if (height <= z[0]) {
+    r = col[0];
+  } else {
+    int ilo = 0, ihi = Mz - 1; // gsl_interp_accel_find: largest m in [0, Mz - 2] with z[m] <= height
+    while (ihi > ilo + 1) {
+      const int m = (ihi + ilo) >> 1;
+      if (z[m] > height) {
+        ihi = m;
+      } else {
+        ilo = m;
+      }
+    }
+    const double incr = __ddiv_rn(__dsub_rn(height, z[ilo]), __dsub_rn(z[ilo + 1], z[ilo]));
+    const double valm = col[ilo];
+    r = __dadd_rn(valm, __dmul_rn(incr, __dsub_rn(col[ilo + 1], valm)));
+  }
+  out[q] = r;
+}
+
 } // namespace
 
 int launch_mass_flow(const DP &P, double dt, const double *H, const double *bed, const double *sea, const double *vel,
@@ -1075,6 +1112,12 @@ int launch_regional_override(const DP &P, const double *no_model, const double *
                              double *h_y, cudaStream_t s) {
   const long n = (long)(P.xm + 2) * (P.ym + 2);
   k_regional_override<<<nblk_(n, 256), 256, 0, s>>>(P, no_model, hx_nm, hy_nm, h_x, h_y);
+  return 1;
+}
+
+int launch_value_at_height(const DP &P, const double *a, int wa, const double *zq, int wz, double z0, const double *z,
+                           double *out, cudaStream_t s) {
+  k_value_at_height<<<nblk_((long)P.xm * P.ym, 256), 256, 0, s>>>(P, a, wa, zq, wz, z0, z, out);
   return 1;
 }
 } // namespace siafd

@@ -122,6 +122,7 @@ class SIAFD(SSB_Modifier):
         self.config = cfg
         self.current_time = current_time
         self._global_bed = global_bed
+        self._device = device
         self._h = C.c_void_p()
         status = lib.siafd_b200_create(C.byref(cfg), device, C.byref(self._h))
         if status != capi.OK:
@@ -252,6 +253,28 @@ class SIAFD(SSB_Modifier):
         self.m_strain_heating = self.download("strain_heating")
         return self.m_strain_heating
 
+    # -- reads of the 3D outputs (util/iceModelVec3.cc:153-240) ------------------------------------------------
+    def _value_at_height(self, name, z=None):
+        import torch
+        dev = self._device if self._device >= 0 else torch.cuda.current_device()
+        out = torch.empty((self.patch.ym, self.patch.xm), dtype=torch.float64, device="cuda:%d" % dev)
+        if z is None:
+            self._check(lib.siafd_b200_surface_values(self._h, F[name], out.data_ptr()))
+        else:
+            self._check(lib.siafd_b200_hor_slice(self._h, F[name], float(z), out.data_ptr()))
+        torch.cuda.synchronize(dev)  # the kernel ran on the handle's stream, not torch's
+        return out.cpu().numpy()
+
+    def getSurfaceValues(self, name):
+        """IceModelVec3::getSurfaceValues (iceModelVec3.cc:226-240): the 3D field `name` ("u", "v", "w", "enthalpy",
+        "age", "strain_heating") at z = ice thickness of the last update, on the owned points [ym, xm]; evaluated
+        on the device from the resident fields (two values per column are read, nothing 3D crosses PCIe)."""
+        return self._value_at_height(name)
+
+    def getHorSlice(self, name, z):
+        """IceModelVec3::getHorSlice (iceModelVec3.cc:209-223): the field at the constant height z."""
+        return self._value_at_height(name, z)
+
     def volumetric_strain_heating(self):
         return getattr(self, "m_strain_heating", None)
 
@@ -315,3 +338,35 @@ class SIAFD_Regional(SIAFD):
         if full_update:
             self.m_u, self.m_v = self.download("u"), self.download("v")
         self._check(status)
+
+
+def computeSIASurfaceVelocities(grid, thk, topg, enthalpy, siasolver=SIAFD, config=None, **overrides):
+    """PISM.sia.computeSIASurfaceVelocities (site-packages/PISM/sia.py:24-74): surface horizontal velocities of the
+    SIA with zero basal sliding.  `thk`, `topg`: ghosted [ym + 2w, xm + 2w] arrays (w = w_geom, ghosts valid, the
+    reference's md.vecs.thk / .topg); `enthalpy`: ghosted [.., Mz].  Sea level 0 and Geometry::ensure_consistency
+    with geometry.ice_free_thickness_standard (the configuration's), as there (sia.py:40-45), by the library's mask
+    kernel.
+    Returns (u_surface, v_surface) on the owned points (the reference's vel_sia components)."""
+    import torch
+    thk = np.ascontiguousarray(thk, dtype=np.float64)
+    topg = np.ascontiguousarray(topg, dtype=np.float64)
+    if "global_bed" not in overrides and "patch" not in overrides:
+        # one patch = the whole domain: the bed smoother's global bed (BedSmoother.cc:99-153) is topg's interior
+        wb = (topg.shape[0] - grid.My) // 2
+        overrides["global_bed"] = topg[wb:topg.shape[0] - wb, wb:topg.shape[1] - wb]
+    sia = siasolver(grid, config=config, **overrides)
+    sia.init()
+    dev = "cuda:%d" % torch.cuda.current_device()
+    d_thk, d_bed = torch.from_numpy(thk).to(dev), torch.from_numpy(topg).to(dev)
+    d_sea = torch.zeros_like(d_thk)
+    d_mask, d_surf = torch.empty_like(d_thk), torch.empty_like(d_thk)
+    torch.cuda.synchronize()  # the copies above went through torch's stream, the kernel runs on the handle's
+    sia._check(lib.siafd_b200_geometry_compute(sia.handle, thk.size, d_sea.data_ptr(), d_bed.data_ptr(),
+                                               d_thk.data_ptr(), d_mask.data_ptr(), d_surf.data_ptr()))
+    torch.cuda.synchronize()
+    geometry = Geometry(topg, thk, d_surf.cpu().numpy(), d_mask.cpu().numpy())
+    inputs = Inputs(geometry, np.ascontiguousarray(enthalpy, dtype=np.float64), None)
+    ws = sia.config.w_sliding
+    sliding = np.zeros((sia.patch.ym + 2 * ws, sia.patch.xm + 2 * ws, 2))
+    sia.update(sliding, inputs, True)
+    return sia.getSurfaceValues("u"), sia.getSurfaceValues("v")

@@ -102,6 +102,8 @@ def lib():
         L.orc_siafd_update_single.argtypes = [PP, FP, C.c_int]
         L.orc_siafd_update_many.argtypes = [C.c_int, PP, FP, C.c_int, C.c_int]
         L.orc_vertical_velocity.argtypes = [PP, _pd, _pd, _pd, _pd, C.c_int, _pd]
+        L.orc_value_at_height.restype = None
+        L.orc_value_at_height.argtypes = [PP, _pd, C.c_int, _pd, C.c_int, _f64, _pd]
         L.orc_strain_heating.argtypes = [PP, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_mass_flow_step.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_mass_source_step.argtypes = [PP, _f64, _f64, C.c_int, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
@@ -182,6 +184,20 @@ class Run:
     @property
     def D_max(self):
         return self.f.D_max
+
+
+def value_at_height(p, a, wa, heights=None, wh=0, z0=0.0):
+    """orc_value_at_height: IceModelVec3::getSurfaceValues (heights = thickness) / getHorSlice (heights None)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert a.shape == shape(p, wa, p.Mz), (a.shape, shape(p, wa, p.Mz))
+    out = np.zeros((p.ym, p.xm))
+    hp = None
+    if heights is not None:
+        heights = np.ascontiguousarray(heights, dtype=np.float64)
+        assert heights.shape == shape(p, wh)
+        hp = dptr(heights)
+    lib().orc_value_at_height(C.byref(p), dptr(a), wa, hp, wh, z0, dptr(out))
+    return out
 
 
 def preprocess_bed(p, topg_global):

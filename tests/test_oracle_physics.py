@@ -254,3 +254,49 @@ def test_vertical_velocity_against_exact_solution_F():
     print("w vs exact F: worst %.4f m/a mean %.4f m/a (|w| up to %.2f m/a)" % (errs.max(), errs.mean(),
                                                                                  np.abs(w).max() * secpera))
     assert len(errs) > 500 and errs.max() < 0.002 and errs.mean() < 0.001
+
+
+def test_surface_values_and_horizontal_slices():
+    """IceModelVec3::getSurfaceValues / getHorSlice (util/iceModelVec3.cc:153-240), the reads
+    PISM.sia.computeSIASurfaceVelocities (site-packages/PISM/sia.py:63-72) and siafd_test.cc:105-151 make of u, v:
+    the restatement against getValZ written out literally, its end-level rules, and -- the pin -- the surface speeds
+    of one update on the Test F state against exactFG, the check siafd_test itself makes."""
+    import oracle_lib as O
+    grid, cfg, inputs, _ = cases.case("Fs")
+    run = cases.oracle_run(grid, cfg, inputs, full=True)
+    assert run.status == 0
+    p, w, wuv, z = run.p, cfg.w_geom, cfg.w_uv, grid.z
+    us = O.value_at_height(p, run.a["u"], wuv, inputs["thickness"], w)
+    vs = O.value_at_height(p, run.a["v"], wuv, inputs["thickness"], w)
+    u, H = cases.interior(run.a["u"], wuv), cases.interior(inputs["thickness"], w)
+    for j in range(grid.My):
+        for i in range(grid.Mx):
+            h = H[j, i]
+            if h >= z[-1]:
+                lit = u[j, i, -1]
+            elif h <= z[0]:
+                lit = u[j, i, 0]
+            else:
+                k = grid.k_below_height(h)
+                incr = (h - z[k]) / (z[k + 1] - z[k])
+                lit = u[j, i, k] + incr * (u[j, i, k + 1] - u[j, i, k])
+            assert us[j, i] == lit, (i, j)
+    # end levels, a height exactly on a level, and one between two levels
+    E = inputs["enthalpy"]
+    Ei = cases.interior(E, cfg.w_3d_in)
+    assert np.array_equal(O.value_at_height(p, E, cfg.w_3d_in, z0=-5.0), Ei[:, :, 0])
+    assert np.array_equal(O.value_at_height(p, E, cfg.w_3d_in, z0=0.0), Ei[:, :, 0])
+    assert np.array_equal(O.value_at_height(p, E, cfg.w_3d_in, z0=z[-1]), Ei[:, :, -1])
+    assert np.array_equal(O.value_at_height(p, E, cfg.w_3d_in, z0=z[-1] + 1.0), Ei[:, :, -1])
+    assert np.array_equal(O.value_at_height(p, E, cfg.w_3d_in, z0=z[7]), Ei[:, :, 7])
+    zm = 0.25 * z[7] + 0.75 * z[8]
+    mid = O.value_at_height(p, E, cfg.w_3d_in, z0=zm)
+    assert np.allclose(mid, 0.25 * Ei[:, :, 7] + 0.75 * Ei[:, :, 8], rtol=1e-14, atol=0.0)
+    # siafd_test.cc:105-151: max error of the surface velocity vector against exactFG on 1 m <= r <= L - 1 m
+    Uex, r = cases.interior(inputs["exact_surface_speed"], w), cases.interior(inputs["radius"], w)
+    X, Y = np.meshgrid(grid.x, grid.y)
+    sel = (r >= 1.0) & (r <= 750000.0 - 1.0) & (H > 0)
+    rr = np.where(sel, r, 1.0)
+    err = np.hypot(us - X / rr * Uex, vs - Y / rr * Uex)[sel]
+    assert sel.sum() > 300 and err.max() * V.SperA < 1.0 and err.max() < 0.2 * Uex.max(), err.max() * V.SperA
+
