@@ -37,7 +37,8 @@ struct siafd_b200_handle {
   unsigned long long *d_dmax = nullptr;
   unsigned long long *d_cfl = nullptr, *h_cfl = nullptr; // 8 maxima of siafd_b200_cfl and their pinned mirror
   bool cfl3_fresh = false; // slots 0..3 hold the maxima the last vertical-velocity launch took on the current fields
-  int fill_threads = 8;    // host threads that fill the ice-free parts of u, v in the sparse host path
+  int fill_threads = 4;    // host threads that fill the ice-free parts of u, v in the sparse host path (more of them
+                           // only compete with the PCIe copies for host DRAM: 4096^2, 4 / 8 threads: 362 / 368 ms)
   int64_t bytes_h2d = 0, bytes_d2h = 0; // bytes the host-path calls moved over PCIe since create
   int vvel_rows = 64;      // rows one CTA of the marching vertical-velocity kernels takes
   int vvel_kind = 0;       // 0: k_vvel_slab (shared memory, z sweep in registers); 1: k_vvel_march (lanes across z)
@@ -447,7 +448,7 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.skip_ice_free = 1;
   h->tuning.wz = 4;
   h->tuning.pipeline_host = 1;
-  h->tuning.pipeline_band = 4;
+  h->tuning.pipeline_band = 1; // 4096^2, segments per band 1 / 2 / 4 / 8: 368 / 375 / 386 / 411 ms (tools/e2e_sweep.py)
   h->tuning.sparse_host = 1;
   if (const char *e = getenv("SIAFD_B200_SPARSE")) h->tuning.sparse_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_FILL_THREADS")) h->fill_threads = std::max(1, atoi(e));
