@@ -3,8 +3,10 @@
 // CPU restatement of the consumers of SIAFD's outputs, SURVEY.md 8(f) rows N1 and N3 (CFL part):
 //   * GeometryEvolution::flow_step / apply_flux_divergence   src/geometry/GeometryEvolution.cc:241-350
 //       compute_interface_fluxes :535-654, limit_diffusive_flux :462-525, limit_advective_velocity :395-457,
-//       compute_flux_divergence :660-688, update_in_place :716-771 (part_grid off, the default
-//       geometry.part_grid.enabled = no), ensure_nonnegativity :960-1000
+//       compute_flux_divergence :644-669, update_in_place :689-771 (part_grid off, the default
+//       geometry.part_grid.enabled = no), ensure_nonnegativity :960-1000; and, for pinning only, the same step with
+//       part_grid on (orc_mass_flow_step_part_grid: residual redistribution :777-944,
+//       part_grid_threshold_thickness.cc) against the golden numbers of test/mass_transport.py
 //   * GeometryEvolution::source_term_step / apply_mass_fluxes  :327-343, :360-390, effective_change :1005-1011,
 //       compute_surface_and_basal_mass_balance :1028-1076
 //   * max_timestep_cfl_3d / max_timestep_cfl_2d                src/stressbalance/timestepping.cc:42-101, :113-153
@@ -90,10 +92,12 @@ extern "C" {
 // it on owned + 1).  Outputs (owned points only, [ym][xm]): flux_divergence, thickness_change (after
 // ensure_nonnegativity), conservation_error; thickness is updated in place on the owned points
 // (H_old + thickness_change, GeometryEvolution.cc:347-350); the caller refreshes its ghosts.
-int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, const double *bed, double *thickness,
-                       const double *velocity, const double *velocity_bc_mask, const double *thickness_bc_mask,
-                       const double *Q, double *flux_divergence, double *thickness_change,
-                       double *conservation_error) {
+// The first half of flow_step (:247-282): gc.compute on the ghosted copies, compute_interface_fluxes,
+// compute_flux_divergence.  cell_type (w_geom, every local point) and flux_divergence (owned) are outputs.
+static int flow_step_flux_divergence(const orc_params *p, const double *sea_level, const double *bed,
+                                     const double *thickness, const double *velocity, const double *velocity_bc_mask,
+                                     const double *thickness_bc_mask, const double *Q, std::vector<double> &cell_type,
+                                     double *flux_divergence) {
   const int wg = p->w_geom, ws = p->w_stag, wv = p->w_sliding;
   const long nxg = p->xm + 2 * wg, nyg = p->ym + 2 * wg, nxs = p->xm + 2 * ws, nxv = p->xm + 2 * wv;
   if (velocity != NULL and wv < 1) return ORC_ERR_BAD_CONFIG;
@@ -103,7 +107,8 @@ int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, 
     return velocity ? velocity[((long)(j - (p->ys - wv)) * nxv + (i - (p->xs - wv))) * 2 + c] : 0.0;
   };
   // :262-266 gc.compute on the ghosted copies (pointwise; ghosts of the result = result on the ghosts)
-  std::vector<double> cell_type(nxg * nyg), zero;
+  std::vector<double> zero;
+  cell_type.assign(nxg * nyg, 0.0);
   if (sea_level == NULL) {
     zero.assign(nxg * nyg, 0.0);
     sea_level = zero.data();
@@ -157,8 +162,7 @@ int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, 
       }
     }
   }
-  // compute_flux_divergence (:660-688), update_in_place (:716-771, no part_grid), compute changes (:295-300),
-  // ensure_nonnegativity (:960-1000), apply_flux_divergence (:347-350)
+  // compute_flux_divergence (:644-669)
   const double dx = p->dx, dy = p->dy;
   for (int j = p->ys; j < p->ys + p->ym; ++j) {
     for (int i = p->xs; i < p->xs + p->xm; ++i) {
@@ -171,6 +175,28 @@ int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, 
         divQ = (Qe - Qw) / dx + (Qn - Qs) / dy;
       }
       flux_divergence[o] = divQ;
+    }
+  }
+  return ORC_OK;
+}
+
+int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, const double *bed, double *thickness,
+                       const double *velocity, const double *velocity_bc_mask, const double *thickness_bc_mask,
+                       const double *Q, double *flux_divergence, double *thickness_change,
+                       double *conservation_error) {
+  const int wg = p->w_geom;
+  const long nxg = p->xm + 2 * wg;
+  auto G = [&](int i, int j) { return (long)(j - (p->ys - wg)) * nxg + (i - (p->xs - wg)); };
+  std::vector<double> cell_type;
+  const int status = flow_step_flux_divergence(p, sea_level, bed, thickness, velocity, velocity_bc_mask,
+                                               thickness_bc_mask, Q, cell_type, flux_divergence);
+  if (status != ORC_OK) return status;
+  // update_in_place (:689-771, no part_grid), compute changes (:295-300), ensure_nonnegativity (:960-1000),
+  // apply_flux_divergence (:347-350)
+  for (int j = p->ys; j < p->ys + p->ym; ++j) {
+    for (int i = p->xs; i < p->xs + p->xm; ++i) {
+      const long o = (long)(j - p->ys) * p->xm + (i - p->xs);
+      const double divQ = flux_divergence[o];
       const double H_old = thickness[G(i, j)];
       double H_new = H_old;
       H_new += -dt * divQ;
@@ -189,6 +215,191 @@ int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, 
       thickness[G(i, j)] = thickness[G(i, j)] + 1.0 * thickness_change[(long)(j - p->ys) * p->xm + (i - p->xs)];
     }
   }
+  return ORC_OK;
+}
+
+// geometry/part_grid_threshold_thickness.cc:33-70; star stencils as {ij, e, w, n, s}
+static double part_grid_threshold_thickness(const int M[5], const double H[5], const double h[5],
+                                            double bed_elevation) {
+  double H_average = 0.0, h_average = 0.0, H_threshold = 0.0;
+  int N = 0;
+  const int dirs[] = {3, 1, 4, 2}; // North, East, South, West
+  for (int n = 0; n < 4; ++n) {
+    const int d = dirs[n];
+    if (m_icy(M[d])) {
+      H_average += H[d];
+      h_average += h[d];
+      N++;
+    }
+  }
+  if (N == 0) {
+    return 0.0;
+  }
+  H_average = H_average / N;
+  h_average = h_average / N;
+  if (bed_elevation + H_average > h_average) {
+    H_threshold = h_average - bed_elevation;
+  } else {
+    H_threshold = H_average;
+  }
+  return std::max(H_threshold, 0.0);
+}
+
+// flow_step + apply_flux_divergence WITH geometry.part_grid.enabled (GeometryEvolution.cc:241-357, update_in_place
+// :689-816, residual_redistribution_iteration :819-944).  The CUDA path implements the default (part_grid off); this
+// variant exists so that the restated interface fluxes (advective part, bc masks, flux divergence) -- shared with
+// orc_mass_flow_step -- can be pinned against the golden numbers of the reference's test/mass_transport.py:169-173,
+// which runs with part_grid on.  One patch covering the whole domain (ghost updates are periodic self-wraps).
+// thickness, area_specific_volume: w_geom, ghosts valid, updated in place (H_old + thickness_change etc., ghosts
+// wrapped); outputs owned-only.
+int orc_mass_flow_step_part_grid(const orc_params *p, double dt, const double *sea_level, const double *bed,
+                                 double *thickness, double *area_specific_volume, const double *velocity,
+                                 const double *velocity_bc_mask, const double *thickness_bc_mask, const double *Q,
+                                 int max_iterations, double *flux_divergence, double *thickness_change,
+                                 double *area_specific_volume_change, double *conservation_error) {
+  if (p->xm != p->Mx or p->ym != p->My or p->xs != 0 or p->ys != 0) return ORC_ERR_BAD_CONFIG;
+  const int wg = p->w_geom, xm = p->xm, ym = p->ym;
+  if (wg < 1) return ORC_ERR_BAD_CONFIG;
+  const long nxg = xm + 2 * wg, nyg = ym + 2 * wg, n_all = nxg * nyg;
+  auto G = [&](int i, int j) { return (long)(j + wg) * nxg + (i + wg); };
+  std::vector<double> zero;
+  if (sea_level == NULL) {
+    zero.assign(n_all, 0.0);
+    sea_level = zero.data();
+  }
+  // :247-256 ghosted copies
+  std::vector<double> H(thickness, thickness + n_all), V(area_specific_volume, area_specific_volume + n_all);
+  std::vector<double> cell_type, surface(n_all), residual(n_all, 0.0), H_copy;
+  int status = flow_step_flux_divergence(p, sea_level, bed, H.data(), velocity, velocity_bc_mask, thickness_bc_mask, Q,
+                                         cell_type, flux_divergence);
+  if (status != ORC_OK) return status;
+  auto M = [&](int i, int j) { return (int)floor(cell_type[G(i, j)] + 0.5); };
+  auto threshold_at = [&](int i, int j) {
+    const int Ms[5] = {M(i, j), M(i + 1, j), M(i - 1, j), M(i, j + 1), M(i, j - 1)};
+    const double Hs[5] = {H_copy[G(i, j)], H_copy[G(i + 1, j)], H_copy[G(i - 1, j)], H_copy[G(i, j + 1)],
+                          H_copy[G(i, j - 1)]};
+    const double hs[5] = {surface[G(i, j)], surface[G(i + 1, j)], surface[G(i - 1, j)], surface[G(i, j + 1)],
+                          surface[G(i, j - 1)]};
+    return part_grid_threshold_thickness(Ms, Hs, hs, bed[G(i, j)]);
+  };
+  // ---- update_in_place :689-771 ----
+  orc_geometry_compute(p, (int)n_all, sea_level, bed, H.data(), cell_type.data(), surface.data());
+  H_copy = H;
+  for (int j = 0; j < ym; ++j) {
+    for (int i = 0; i < xm; ++i) {
+      double divQ = flux_divergence[(long)j * xm + i];
+      const long g = G(i, j);
+      const bool next_to_ice = m_icy(M(i + 1, j)) or m_icy(M(i - 1, j)) or m_icy(M(i, j + 1)) or m_icy(M(i, j - 1));
+      if (ice_free_ocean(M(i, j)) and next_to_ice) {
+        V[g] += -divQ * dt;
+        double threshold = threshold_at(i, j);
+        if (threshold == 0.0) {
+          threshold = V[g];
+        }
+        if (V[g] >= threshold) {
+          H[g] += threshold;
+          residual[g] = V[g] - threshold;
+          V[g] = 0.0;
+        }
+        divQ = 0.0;
+      }
+      H[g] += -dt * divQ;
+    }
+  }
+  orc_wrap_ghosts(xm, ym, wg, 1, H.data());
+  orc_geometry_compute(p, (int)n_all, sea_level, bed, H.data(), cell_type.data(), NULL); // compute_mask :770
+  // ---- residual redistribution :777-815 ----
+  bool done = false;
+  for (int it = 0; it < max_iterations and not done; ++it) {
+    // residual_redistribution_iteration :819-944
+    orc_geometry_compute(p, (int)n_all, sea_level, bed, H.data(), cell_type.data(), NULL);
+    for (int j = 0; j < ym; ++j) {
+      for (int i = 0; i < xm; ++i) {
+        const long g = G(i, j);
+        if (residual[g] <= 0.0) {
+          continue;
+        }
+        const int nb[4] = {M(i, j + 1), M(i + 1, j), M(i, j - 1), M(i - 1, j)};
+        int N = 0;
+        for (int n = 0; n < 4; ++n) {
+          if (ice_free_ocean(nb[n])) {
+            N++;
+          }
+        }
+        if (N > 0) {
+          residual[g] /= N;
+        } else {
+          H[g] += residual[g];
+          residual[g] = 0.0;
+        }
+      }
+    }
+    orc_wrap_ghosts(xm, ym, wg, 1, residual.data());
+    for (int j = 0; j < ym; ++j) {
+      for (int i = 0; i < xm; ++i) {
+        if (ice_free_ocean(M(i, j))) {
+          V[G(i, j)] += (residual[G(i + 1, j)] + residual[G(i - 1, j)] + residual[G(i, j + 1)] + residual[G(i, j - 1)]);
+        }
+      }
+    }
+    std::fill(residual.begin(), residual.end(), 0.0);
+    orc_wrap_ghosts(xm, ym, wg, 1, H.data());
+    H_copy = H;
+    orc_geometry_compute(p, (int)n_all, sea_level, bed, H.data(), cell_type.data(), surface.data());
+    double remaining_residual = 0.0;
+    for (int j = 0; j < ym; ++j) {
+      for (int i = 0; i < xm; ++i) {
+        const long g = G(i, j);
+        if (V[g] <= 0.0) {
+          continue;
+        }
+        double threshold = threshold_at(i, j);
+        if (threshold == 0.0) {
+          threshold = V[g];
+        }
+        if (V[g] >= threshold) {
+          H[g] += threshold;
+          residual[g] = V[g] - threshold;
+          V[g] = 0.0;
+          remaining_residual += residual[g];
+        }
+      }
+    }
+    done = not(remaining_residual > 0.0);
+    orc_wrap_ghosts(xm, ym, wg, 1, H.data());
+  }
+  if (not done and max_iterations > 0) {
+    for (long g = 0; g < n_all; ++g) {
+      H[g] = H[g] + 1.0 * residual[g];
+    }
+  }
+  // ---- changes :293-300, ensure_nonnegativity :960-1000, apply_flux_divergence :347-357 ----
+  for (int j = 0; j < ym; ++j) {
+    for (int i = 0; i < xm; ++i) {
+      const long g = G(i, j), o = (long)j * xm + i;
+      double dH = H[g] + (-1.0) * thickness[g], dV = V[g] + (-1.0) * area_specific_volume[g];
+      conservation_error[o] = 0.0;
+      if (thickness[g] + dH < 0.0) {
+        conservation_error[o] += -(thickness[g] + dH);
+        dH = thickness[g];
+      }
+      if (area_specific_volume[g] + dV < 0.0) {
+        conservation_error[o] += -(area_specific_volume[g] + dV);
+        dV = area_specific_volume[g];
+      }
+      thickness_change[o] = dH;
+      area_specific_volume_change[o] = dV;
+    }
+  }
+  for (int j = 0; j < ym; ++j) {
+    for (int i = 0; i < xm; ++i) {
+      const long g = G(i, j), o = (long)j * xm + i;
+      thickness[g] = thickness[g] + 1.0 * thickness_change[o];
+      area_specific_volume[g] = area_specific_volume[g] + 1.0 * area_specific_volume_change[o];
+    }
+  }
+  orc_wrap_ghosts(xm, ym, wg, 1, thickness);
+  orc_wrap_ghosts(xm, ym, wg, 1, area_specific_volume);
   return ORC_OK;
 }
 

@@ -191,6 +191,13 @@ int orc_mass_flow_step(const orc_params *p, double dt, const double *sea_level, 
                        const double *velocity, const double *velocity_bc_mask, const double *thickness_bc_mask,
                        const double *Q, double *flux_divergence, double *thickness_change,
                        double *conservation_error);
+/* The same step with geometry.part_grid.enabled (GeometryEvolution.cc:689-944, part_grid_threshold_thickness.cc): used
+ * only to pin the shared interface-flux code against test/mass_transport.py's golden numbers.  Whole-domain patch. */
+int orc_mass_flow_step_part_grid(const orc_params *p, double dt, const double *sea_level, const double *bed,
+                                 double *thickness, double *area_specific_volume, const double *velocity,
+                                 const double *velocity_bc_mask, const double *thickness_bc_mask, const double *Q,
+                                 int max_iterations, double *flux_divergence, double *thickness_change,
+                                 double *area_specific_volume_change, double *conservation_error);
 int orc_mass_source_step(const orc_params *p, double dt, double ice_density, int use_bmr, double *thickness,
                          const double *mask, const double *thickness_bc_mask, const double *smb_flux,
                          const double *basal_melt_rate, double *effective_SMB, double *effective_BMB);

@@ -106,6 +106,8 @@ def lib():
         L.orc_value_at_height.argtypes = [PP, _pd, C.c_int, _pd, C.c_int, _f64, _pd]
         L.orc_strain_heating.argtypes = [PP, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_mass_flow_step.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
+        L.orc_mass_flow_step_part_grid.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, C.c_int, _pd, _pd,
+                                                   _pd, _pd]
         L.orc_mass_source_step.argtypes = [PP, _f64, _f64, C.c_int, _pd, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_cfl_3d.argtypes = [PP, _f64, _pd, _pd, _pd, _pd, _pd, _pd]
         L.orc_cfl_2d.argtypes = [PP, _f64, _pd, _pd, _pd]
