@@ -59,11 +59,12 @@ class Time:
 
 
 class IceCompModel:
-    """`pismv -test B|C` as far as the SIAFD path and its mass-continuity consumer go."""
+    """`pismv -test B|C|L` as far as the SIAFD path and its mass-continuity consumer go.  Test L (steady state on a
+    non-flat bed, iceCompModel.cc:372-423): the backend must have been given exactL's bed."""
 
     def __init__(self, backend, grid, testname="C", start_year=0.0, run_length_years=1000.0, max_dt_years=60.0,
                  adaptive_ratio=0.12):
-        assert testname in ("B", "C")
+        assert testname in ("B", "C", "L")
         self.backend, self.grid, self.testname = backend, grid, testname
         self.time = Time(start_year, run_length_years)
         # config->get_number("time_stepping.maximum_time_step", "seconds") converts with UDUNITS
@@ -74,12 +75,20 @@ class IceCompModel:
         self.steps = 0
         self.dt_history = []
         self.r = verification.radius(grid)
+        if testname == "L":
+            # initTestL (iceCompModel.cc:372-423): thickness from the ODE solution, kept as m_HexactL; accumulation of
+            # Verification::update_L (PSVerification.cc:99-126): a0 converted by UDUNITS, not exactL's own SperA
+            self.m_HexactL, _, _ = verification.exactL(self.r)
+            a0 = 0.3 / SECONDS_PER_YEAR_UDUNITS
+            self.m_mass_flux_L = a0 * (1.0 - (2.0 * self.r * self.r / (750e3 * 750e3)))
         self.initialize_2d()
 
     # iceCompModel.cc:301-356
     def exact(self, t):
         if self.testname == "C":
             return verification.exactC(t, self.r)
+        if self.testname == "L":
+            return self.m_HexactL, self.m_mass_flux_L
         return verification.exactB(t, self.r)
 
     def initialize_2d(self):

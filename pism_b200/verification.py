@@ -1,4 +1,4 @@
-"""Exact solutions used by pismv tests C and F/G, restated in numpy.
+"""Exact solutions used by pismv tests B, C, L and F/G, restated in numpy.
 
 Reference sources (compiled unmodified into oracle/_ref/libpism_exact.so where the reference
 tree is mounted; tests/test_exact_solutions.py checks these restatements against that build):
@@ -96,6 +96,46 @@ def exactFG(t, r, z, Cp):
                   _p3(mu * H) * np.exp(mu * H) - _p3(0.0))
     U = omega * I3
     return {"H": float(H), "T": T, "U": U}
+
+
+def exactL(r):
+    """H(r), b(r), a(r) of Test L, the steady isothermal sheet on a non-flat bed
+    (src/verification/tests/exactTestL.cc:35-178): u = H^(8/3) solves
+        du/dr = -(8/3) b'(r) u^(5/8) - (a0 r (L^2 - r^2) / (2 L^2 Gamma~))^(1/3),   u(L) = 0,
+    integrated inward from the margin.  The reference integrates with GSL's rk8pd at EPS_ABS = 1e-12 (GSL is not in
+    this image: `gsl_odeiv2` cannot be built here); this restatement uses scipy's DOP853 at tolerances tight enough
+    that the two agree far below the six decimals of the golden rows of test/regression/test_16.sh, which is what
+    pins it (tests/test_oracle_pismv.py).  r: array of any shape, metres."""
+    from scipy.integrate import solve_ivp
+    r = np.asarray(r, dtype=np.float64)
+    L, b0, z0, g, rho, n = 750.0e3, 500.0, 1.2, 9.81, 910.0, 3.0
+    Lsqr = L * L
+    a0 = 0.3 / SperA
+    A = 1.0e-16 / SperA
+    Gamma = 2 * (rho * g) ** n * A / (n + 2)
+    tilGamma = Gamma * n ** n / (2.0 * n + 2.0) ** n
+    Cc = a0 / (2.0 * Lsqr * tilGamma)
+    freq = z0 * np.pi / L
+
+    def funcL(rr, u):
+        if 0.0 <= rr <= L:
+            bprime = b0 * freq * np.sin(freq * rr)
+            return [-(8.0 / 3.0) * bprime * max(u[0], 0.0) ** (5.0 / 8.0) - (Cc * rr * (Lsqr - rr * rr)) ** (1.0 / 3.0)]
+        return [0.0]
+
+    flat = r.ravel()
+    inside = np.unique(flat[flat < L])[::-1]  # decreasing radii, like the sorted list of iceCompModel.cc:372-401
+    u_of = {}
+    if inside.size:
+        sol = solve_ivp(funcL, (L, float(inside[-1])), [0.0], method="DOP853", t_eval=inside, rtol=1e-13, atol=1e-10,
+                        first_step=1.0)
+        assert sol.success, sol.message
+        u_of = dict(zip(inside.tolist(), sol.y[0].tolist()))
+    u = np.array([u_of.get(x, 0.0) for x in flat.tolist()]).reshape(r.shape)
+    H = np.maximum(u, 0.0) ** (3.0 / 8.0)
+    b = -b0 * np.cos(z0 * np.pi * r / L)
+    a = a0 * (1.0 - (2.0 * r * r / Lsqr))
+    return H, b, a
 
 
 def radius(grid):

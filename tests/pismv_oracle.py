@@ -101,7 +101,7 @@ class OracleBackend:
 
 def pismv_model(testname, M, start_year=0.0, run_length_years=5000.0, max_dt_years=60.0, backend_factory=None,
                 ranks=None):
-    """`pismv -test B|C -Mx M -My M -Mz 31 -ys .. -y .. [-max_dt ..]` on the oracle (or, with backend_factory(grid,
+    """`pismv -test B|C|L -Mx M -My M -Mz 31 -ys .. -y .. [-max_dt ..]` on the oracle (or, with backend_factory(grid,
     cfg, inputs, max_dt_seconds[, ranks]), on the GPU).  Test B shares test C's set-up except the domain half-width
     (pismv.cc:88-102).  `ranks`: a pism_b200.icemodel.Ranks for a multi-rank run (this rank gets its patch)."""
     from pism_b200 import icemodel
@@ -109,8 +109,16 @@ def pismv_model(testname, M, start_year=0.0, run_length_years=5000.0, max_dt_yea
     if testname == "B":
         grid = G.Grid(M, M, 31, 1200e3, 1200e3, 4000.0, spacing="quadratic")
     patch = ranks.patch if ranks is not None and ranks.size > 1 else None
-    _, _, inputs, _ = cases.case("C1_%d" % M, patch=patch)
+    if testname == "L":  # pismv.cc:103-110: the 1800 km box of tests F, G, L
+        grid = G.Grid(M, M, 31, 900e3, 900e3, 4000.0, spacing="quadratic")
+        from pism_b200 import synthetic as S, verification as V
+        inputs = cases.to_numpy(S.test_C_state(grid, patch or grid.whole(), cfg))
+    else:
+        _, _, inputs, _ = cases.case("C1_%d" % M, patch=patch)
     inputs = {k: np.array(v, dtype=np.float64, copy=True) for k, v in inputs.items()}
+    if testname == "L":  # initTestL (iceCompModel.cc:372-423): the bed of exactL; the thickness follows in initialize_2d
+        _, bed, _ = V.exactL(V.radius(grid))
+        inputs["bed"] = np.ascontiguousarray(G.global_to_local(bed, patch or grid.whole(), cfg.w_geom))
     max_dt = max_dt_years * icemodel.SECONDS_PER_YEAR_UDUNITS
     kw = {} if ranks is None else {"ranks": ranks}
     backend = (backend_factory or OracleBackend)(grid, cfg, inputs, max_dt, **kw)
@@ -122,4 +130,7 @@ import json as _json
 import os as _os
 
 with open(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "reference_kats.json")) as _f:
-    TEST_15_GOLDEN = {int(k): v for k, v in _json.load(_f)["pismv_test_C"]["rows"].items()}
+    _kats = _json.load(_f)
+    TEST_15_GOLDEN = {int(k): v for k, v in _kats["pismv_test_C"]["rows"].items()}
+    # test/regression/test_16.sh:17-28 (pismv -test L -Mbz 1 -Mz 31 -y 1000, Mx = My = 21, 31)
+    TEST_16_GOLDEN = {int(k): v for k, v in _kats["pismv_test_L"]["rows"].items()}

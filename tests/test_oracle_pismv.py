@@ -1,5 +1,6 @@
-"""Pins the oracle against the reference's OWN golden output: `pismv -test C` (test/regression/test_15.sh) and the
-mass-conservation criterion of `pismv -test B` (test/regression/test_12.sh).
+"""Pins the oracle against the reference's OWN golden output: `pismv -test C` (test/regression/test_15.sh), `pismv -test L`
+(test/regression/test_16.sh: non-flat bed) and the mass-conservation criterion of `pismv -test B`
+(test/regression/test_12.sh).
 
 The run goes through every function of the hot path -- haseloff gradient, compute_diffusivity on pismv's quadratic
 levels, diffusive flux, D_max, 3D velocities (through the 3D CFL restriction) -- plus the mass-continuity consumer
@@ -18,6 +19,21 @@ def test_pismv_test_C_golden_rows_of_test_15():
         m.run()
         assert m.steps == 84  # 83 steps of 60 years ("max") and the remainder ("end of the run")
         assert m.report() == golden, (M, m.report(), golden)
+
+
+def test_pismv_test_L_golden_rows_of_test_16():
+    """test/regression/test_16.sh, "isothermal SIA with non-flat bed": 1000 years from the steady state of exactL on
+    the bed b(r) = -500 cos(1.2 pi r / L), Mx = My = 21 and 31.  The bed enters the path through the surface elevation
+    (haseloff gradient), through thk_smooth = max(usurf - topgsmooth, 0) (BedSmoother.cc:306-320, smoother off) and
+    through the mask; the steps are limited by the diffusivity (timestepping.cc:52-68), so D_max is pinned too.  The
+    four printed numbers come out digit for digit.  (exactL needs an ODE solve; the reference's uses GSL, this one
+    scipy: pism_b200/verification.py::exactL.)"""
+    for M, golden in P.TEST_16_GOLDEN.items():
+        m = P.pismv_model("L", M, run_length_years=1000.0)
+        m.run()
+        assert m.report() == golden, (M, m.report(), golden)
+        assert "diffusivity" in m.m_adaptive_timestep_reason or "end of the run" in m.m_adaptive_timestep_reason
+        assert m.steps > 1000.0 / 60.0 + 1  # i.e. not the 60-year steps of test C
 
 
 def test_pismv_test_C_restrictions():
