@@ -196,7 +196,9 @@ int siafd_b200_abi_version(void);
 void siafd_b200_default_config(siafd_b200_config *cfg);
 const char *siafd_b200_status_string(int status);
 
-/* device < 0: use the current CUDA device.  Fails with SIAFD_B200_ERR_CUDA when no GPU. */
+/* device < 0: use the current CUDA device.  Fails with SIAFD_B200_ERR_CUDA when no GPU; *out is NULL then.
+ * Every other entry point accepts a NULL handle and reports it: status-returning calls give
+ * SIAFD_B200_ERR_BAD_ARGUMENT (text through siafd_b200_last_error(NULL)), getters -1 / NaN / NULL. */
 int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handle **out);
 void siafd_b200_destroy(siafd_b200_handle *h);
 const char *siafd_b200_last_error(const siafd_b200_handle *h);

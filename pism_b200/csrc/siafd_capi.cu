@@ -95,6 +95,10 @@ int fail(siafd_b200_handle *h, int code, const char *fmt, ...) {
   return code;
 }
 
+// every entry point tolerates a NULL handle (e.g. after a failed siafd_b200_create): status codes report
+// ERR_BAD_ARGUMENT (message through siafd_b200_last_error(NULL)), getters return -1 / NAN / NULL
+int null_handle() { return fail(nullptr, SIAFD_B200_ERR_BAD_ARGUMENT, "NULL handle"); }
+
 #define CU(h, call)                                                                                                    \
   do {                                                                                                                 \
     cudaError_t e_ = (call);                                                                                           \
@@ -539,13 +543,17 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
 const char *siafd_b200_last_error(const siafd_b200_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t siafd_b200_field_size(const siafd_b200_handle *h, int f) {
+  if (!h) return -1;
   const FieldMeta m = meta(h->cfg, f);
   return m.width < 0 ? -1 : field_cells(h->cfg, m.width) * m.dof;
 }
-int siafd_b200_field_width(const siafd_b200_handle *h, int f) { return meta(h->cfg, f).width; }
-int siafd_b200_field_dof(const siafd_b200_handle *h, int f) { return meta(h->cfg, f).dof; }
+int siafd_b200_field_width(const siafd_b200_handle *h, int f) {
+  if (!h) return -1; return meta(h->cfg, f).width; }
+int siafd_b200_field_dof(const siafd_b200_handle *h, int f) {
+  if (!h) return -1; return meta(h->cfg, f).dof; }
 
 int siafd_b200_bind(siafd_b200_handle *h, int f, void *device_ptr) {
+  if (!h) return null_handle();
   h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   if (f < 0 || f >= SIAFD_B200_F_COUNT) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad field id %d", f);
@@ -567,6 +575,7 @@ int siafd_b200_bind(siafd_b200_handle *h, int f, void *device_ptr) {
 }
 
 void *siafd_b200_device_ptr(siafd_b200_handle *h, int f) {
+  if (!h) return nullptr;
   if (cudaSetDevice(h->device) != cudaSuccess || ensure(h, f) != SIAFD_B200_OK) {
     return nullptr;
   }
@@ -574,11 +583,13 @@ void *siafd_b200_device_ptr(siafd_b200_handle *h, int f) {
 }
 
 int siafd_b200_set_stream(siafd_b200_handle *h, void *cuda_stream) {
+  if (!h) return null_handle();
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
   return SIAFD_B200_OK;
 }
 
 int siafd_b200_upload(siafd_b200_handle *h, int f, const double *host) {
+  if (!h) return null_handle();
   h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   int st = ensure(h, f);
@@ -590,6 +601,7 @@ int siafd_b200_upload(siafd_b200_handle *h, int f, const double *host) {
 }
 
 int siafd_b200_download(siafd_b200_handle *h, int f, double *host) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   int st = ensure(h, f);
   if (st) return st;
@@ -601,6 +613,7 @@ int siafd_b200_download(siafd_b200_handle *h, int f, double *host) {
 }
 
 int siafd_b200_wrap_ghosts(siafd_b200_handle *h, int f) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   int st = ensure(h, f);
   if (st) return st;
@@ -610,6 +623,7 @@ int siafd_b200_wrap_ghosts(siafd_b200_handle *h, int f) {
 }
 
 int siafd_b200_wrap_ghosts_dir(siafd_b200_handle *h, int f, int dir) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   int st = ensure(h, f);
   if (st) return st;
@@ -647,6 +661,7 @@ static bool halo_rect(const siafd_b200_handle *h, int f, int dir_x, int dir_y, i
 }
 
 int64_t siafd_b200_halo_count(const siafd_b200_handle *h, int f, int dir_x, int dir_y, int width) {
+  if (!h) return -1;
   int i0, j0, wc, hc;
   if (!halo_rect(h, f, dir_x, dir_y, width, false, &i0, &j0, &wc, &hc)) {
     return -1;
@@ -655,6 +670,7 @@ int64_t siafd_b200_halo_count(const siafd_b200_handle *h, int f, int dir_x, int 
 }
 
 int siafd_b200_halo_pack(siafd_b200_handle *h, int f, int dir_x, int dir_y, int width, double *device_buf) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   int st = ensure(h, f);
   if (st) return st;
@@ -670,6 +686,7 @@ int siafd_b200_halo_pack(siafd_b200_handle *h, int f, int dir_x, int dir_y, int 
 }
 
 int siafd_b200_halo_unpack(siafd_b200_handle *h, int f, int dir_x, int dir_y, int width, const double *device_buf) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   int st = ensure(h, f);
   if (st) return st;
@@ -696,6 +713,7 @@ static int ensure_pad(siafd_b200_handle *h) {
 }
 
 int siafd_b200_ipc_export(siafd_b200_handle *h, int field, void *handle64) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
   void *p = nullptr;
@@ -718,6 +736,7 @@ int siafd_b200_ipc_export(siafd_b200_handle *h, int field, void *handle64) {
 }
 
 int siafd_b200_ipc_open(siafd_b200_handle *h, const void *handle64, void **peer_ptr) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   cudaIpcMemHandle_t mh;
   std::memcpy(&mh, handle64, sizeof(mh));
@@ -727,6 +746,7 @@ int siafd_b200_ipc_open(siafd_b200_handle *h, const void *handle64, void **peer_
 }
 
 int siafd_b200_halo_attach(siafd_b200_handle *h, int field, int dir, void *peer_base, int peer_xm, int peer_ym) {
+  if (!h) return null_handle();
   if (dir < 0 || dir > 7 || field >= SIAFD_B200_F_COUNT) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "bad halo attachment (field %d, dir %d)", field, dir);
   }
@@ -772,6 +792,7 @@ static int halo_descriptors(siafd_b200_handle *h, int f, int w, bool to_peers, H
 }
 
 int siafd_b200_wrap_ghosts_many(siafd_b200_handle *h, int n, const int *fields) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   const siafd_b200_config &c = h->cfg;
   if (c.xm != c.Mx || c.ym != c.My) {
@@ -791,6 +812,7 @@ int siafd_b200_wrap_ghosts_many(siafd_b200_handle *h, int n, const int *fields) 
 }
 
 int siafd_b200_halo_push(siafd_b200_handle *h, int n, const int *fields, const int *widths, int phase) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   if (phase < 0 || phase > 3 || n < 1 || n > 6) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_push: phase in 0..3 and 1..6 fields");
@@ -813,6 +835,7 @@ int siafd_b200_halo_push(siafd_b200_handle *h, int n, const int *fields, const i
 }
 
 int siafd_b200_halo_wait(siafd_b200_handle *h, int phase) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   if (phase < 0 || phase > 3 || !h->d_pad) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "halo_wait: nothing was pushed");
   h->launches += launch_halo_wait(h->d_pad + phase * 8, h->halo_step[phase], h->stream);
@@ -821,6 +844,7 @@ int siafd_b200_halo_wait(siafd_b200_handle *h, int phase) {
 }
 
 int siafd_b200_preprocess_bed(siafd_b200_handle *h, const double *global_bed_host) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   const siafd_b200_config &c = h->cfg;
   const int five[5] = {SIAFD_B200_F_TOPGSMOOTH, SIAFD_B200_F_MAXTL, SIAFD_B200_F_C2, SIAFD_B200_F_C3, SIAFD_B200_F_C4};
@@ -862,6 +886,7 @@ int siafd_b200_preprocess_bed(siafd_b200_handle *h, const double *global_bed_hos
 
 int siafd_b200_set_smoothed_bed(siafd_b200_handle *h, const double *topgsmooth, const double *maxtl, const double *C2,
                                 const double *C3, const double *C4, int smoother_active) {
+  if (!h) return null_handle();
   int st;
   if ((st = siafd_b200_upload(h, SIAFD_B200_F_TOPGSMOOTH, topgsmooth))) return st;
   if ((st = siafd_b200_upload(h, SIAFD_B200_F_MAXTL, maxtl))) return st;
@@ -875,6 +900,7 @@ int siafd_b200_set_smoothed_bed(siafd_b200_handle *h, const double *topgsmooth, 
 }
 
 int siafd_b200_compute_gradient(siafd_b200_handle *h) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_SURFACE, SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK, SIAFD_B200_F_BED,
                       SIAFD_B200_F_H_X,     SIAFD_B200_F_H_Y,       SIAFD_B200_F_W_I,  SIAFD_B200_F_W_J};
@@ -955,6 +981,7 @@ static int flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0,
 }
 
 int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, double current_time) {
+  if (!h) return null_handle();
   h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   int st = flux_velocity_prepare(h, full_update, current_time);
   if (st) return st;
@@ -971,6 +998,7 @@ static int ensure_cfl(siafd_b200_handle *h) {
 }
 
 int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int use_basal_melt) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_MASK, SIAFD_B200_F_THICKNESS, SIAFD_B200_F_U, SIAFD_B200_F_V, SIAFD_B200_F_W};
   for (int f : need) {
@@ -1008,6 +1036,7 @@ int siafd_b200_compute_vertical_velocity(siafd_b200_handle *h, int upstream, int
 
 // ---- SIAFD_Regional::compute_surface_gradient -------------------------------------------------
 int siafd_b200_compute_gradient_no_model(siafd_b200_handle *h) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_NO_MODEL_SURFACE, SIAFD_B200_F_MASK,  SIAFD_B200_F_H_X_NO_MODEL,
                       SIAFD_B200_F_H_Y_NO_MODEL,     SIAFD_B200_F_W_I,   SIAFD_B200_F_W_J,
@@ -1028,6 +1057,7 @@ int siafd_b200_compute_gradient_no_model(siafd_b200_handle *h) {
 }
 
 int siafd_b200_apply_no_model_gradient(siafd_b200_handle *h) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_NO_MODEL_MASK, SIAFD_B200_F_H_X_NO_MODEL, SIAFD_B200_F_H_Y_NO_MODEL,
                       SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
@@ -1073,16 +1103,19 @@ static int value_at_height(siafd_b200_handle *h, int field3d, bool at_surface, d
 }
 
 int siafd_b200_surface_values(siafd_b200_handle *h, int field3d, double *out_dev) {
+  if (!h) return null_handle();
   return value_at_height(h, field3d, true, 0.0, out_dev);
 }
 
 int siafd_b200_hor_slice(siafd_b200_handle *h, int field3d, double z, double *out_dev) {
+  if (!h) return null_handle();
   return value_at_height(h, field3d, false, z, out_dev);
 }
 
 // ---- volumetric strain heating -------------------------------------------------------------
 int siafd_b200_compute_strain_heating(siafd_b200_handle *h, int flow_law, double glen_exponent,
                                       double enhancement_factor) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   if (!(glen_exponent > 0.0) || !(enhancement_factor > 0.0)) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "Glen exponent and enhancement factor must be positive");
@@ -1109,6 +1142,7 @@ int siafd_b200_compute_strain_heating(siafd_b200_handle *h, int flow_law, double
 
 // ---- GeometryEvolution on device ----------------------------------------------------------
 int siafd_b200_mass_flow_step(siafd_b200_handle *h, double dt) {
+  if (!h) return null_handle();
   h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_THICKNESS,  SIAFD_B200_F_BED,      SIAFD_B200_F_FLUX,
@@ -1130,6 +1164,7 @@ int siafd_b200_mass_flow_step(siafd_b200_handle *h, double dt) {
 }
 
 int siafd_b200_mass_source_step(siafd_b200_handle *h, double dt, double ice_density, int use_basal_melt) {
+  if (!h) return null_handle();
   h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK, SIAFD_B200_F_SMB, SIAFD_B200_F_EFF_SMB,
@@ -1155,6 +1190,7 @@ int siafd_b200_mass_source_step(siafd_b200_handle *h, double dt, double ice_dens
 }
 
 int siafd_b200_ensure_consistency(siafd_b200_handle *h, int wrap_thickness) {
+  if (!h) return null_handle();
   h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   CU(h, cudaSetDevice(h->device));
   const int need[] = {SIAFD_B200_F_THICKNESS, SIAFD_B200_F_BED, SIAFD_B200_F_MASK, SIAFD_B200_F_SURFACE};
@@ -1178,6 +1214,7 @@ int siafd_b200_ensure_consistency(siafd_b200_handle *h, int wrap_thickness) {
 
 // ---- SURVEY.md 8(f) N3 (CFL part) ----------------------------------------------------------------------------
 int siafd_b200_cfl(siafd_b200_handle *h, double max_dt_seconds, int do_3d, double *out8) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   if (!out8) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "out8 is NULL");
   int st;
@@ -1211,6 +1248,7 @@ int siafd_b200_cfl(siafd_b200_handle *h, double max_dt_seconds, int do_3d, doubl
 }
 
 int siafd_b200_finish(siafd_b200_handle *h) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   int st = fetch_result(h);
   if (st) return st;
@@ -1232,6 +1270,7 @@ int siafd_b200_finish(siafd_b200_handle *h) {
 }
 
 double siafd_b200_max_diffusivity(siafd_b200_handle *h) {
+  if (!h) return NAN;
   if (cudaSetDevice(h->device) != cudaSuccess || fetch_result(h) != SIAFD_B200_OK) {
     return NAN;
   }
@@ -1241,6 +1280,7 @@ double siafd_b200_max_diffusivity(siafd_b200_handle *h) {
 }
 
 int siafd_b200_high_diffusivity_count(siafd_b200_handle *h) {
+  if (!h) return -1;
   if (cudaSetDevice(h->device) != cudaSuccess || fetch_result(h) != SIAFD_B200_OK) {
     return -1;
   }
@@ -1530,6 +1570,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
 }
 
 int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out, int full_update) {
+  if (!h) return null_handle();
   h->cfl3_fresh = false; // the fields the fused CFL maxima were taken on are about to change
   if (!h || !in || !out) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "null argument");
@@ -1606,6 +1647,7 @@ int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b
 
 int siafd_b200_geometry_compute(siafd_b200_handle *h, int64_t n, const double *sea_level_dev, const double *bed_dev,
                                 const double *thickness_dev, double *mask_out_dev, double *surface_out_dev) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   h->launches += launch_geometry(h->P, n, sea_level_dev, bed_dev, thickness_dev, mask_out_dev, surface_out_dev, h->stream);
   CU(h, cudaGetLastError());
@@ -1615,6 +1657,7 @@ int siafd_b200_geometry_compute(siafd_b200_handle *h, int64_t n, const double *s
 
 int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev, const double *enthalpy_dev,
                       const double *pressure_dev, const double *grainsize_dev, double *result_dev) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   const int k = launch_flow_n(h->P, n, stress_dev, enthalpy_dev, pressure_dev, grainsize_dev, result_dev, h->stream);
   if (k < 0) {
@@ -1627,21 +1670,25 @@ int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev,
 }
 
 int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_copy, int skip_ice_free_rows) {
+  if (!h) return null_handle();
   if (rows_per_cta > 0) h->tuning.rows_per_cta = rows_per_cta;
   if (use_bulk_copy >= 0) h->tuning.use_bulk_copy = use_bulk_copy ? 1 : 0;
   if (skip_ice_free_rows >= 0) h->tuning.skip_ice_free = skip_ice_free_rows ? 1 : 0;
   return SIAFD_B200_OK;
 }
 
-int64_t siafd_b200_launch_count(const siafd_b200_handle *h) { return h->launches; }
+int64_t siafd_b200_launch_count(const siafd_b200_handle *h) {
+  if (!h) return -1; return h->launches; }
 
 int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t *d2h) {
+  if (!h) return null_handle();
   if (h2d) *h2d = h->bytes_h2d;
   if (d2h) *d2h = h->bytes_d2h;
   return SIAFD_B200_OK;
 }
 
 int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable) {
+  if (!h) return null_handle();
   CU(h, cudaSetDevice(h->device));
   if (enable && h->ev_start.empty()) {
     h->ev_start.resize(256);
@@ -1657,6 +1704,7 @@ int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable) {
 }
 
 double siafd_b200_kernel_time_ms(siafd_b200_handle *h, int *launches_out) {
+  if (!h) return NAN;
   if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) {
     return -1.0;
   }

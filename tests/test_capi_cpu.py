@@ -107,3 +107,23 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"liboracle|siafd_oracle|oracle_lib|orc_siafd|/oracle/", text):
                         bad.append(os.path.join(dirpath, fn))
     assert not bad, bad
+
+
+def test_null_handle_is_an_error_not_a_crash():
+    """Every entry point tolerates the NULL handle a failed siafd_b200_create leaves behind: status calls return
+    ERR_BAD_ARGUMENT, getters -1 / NaN / NULL; nothing touches the GPU."""
+    L = capi.lib
+    out8, i64 = (C.c_double * 8)(), C.c_int64()
+    assert L.siafd_b200_update(None, None, None, 1) == capi.ERR_BAD_ARGUMENT
+    assert b"NULL handle" in L.siafd_b200_last_error(None)
+    for st in (L.siafd_b200_upload(None, 0, None), L.siafd_b200_download(None, 0, None), L.siafd_b200_finish(None),
+               L.siafd_b200_compute_gradient(None), L.siafd_b200_compute_flux_velocity(None, 1, 0.0),
+               L.siafd_b200_compute_vertical_velocity(None, 0, 0), L.siafd_b200_cfl(None, 1.0, 1, out8),
+               L.siafd_b200_mass_flow_step(None, 1.0), L.siafd_b200_ensure_consistency(None, 1),
+               L.siafd_b200_surface_values(None, capi.F["u"], None), L.siafd_b200_set_stream(None, None),
+               L.siafd_b200_transfer_bytes(None, C.byref(i64), C.byref(i64)), L.siafd_b200_bind(None, 0, None)):
+        assert st == capi.ERR_BAD_ARGUMENT
+    assert L.siafd_b200_field_size(None, 0) == -1 and L.siafd_b200_launch_count(None) == -1
+    assert L.siafd_b200_device_ptr(None, 0) is None
+    assert np.isnan(L.siafd_b200_max_diffusivity(None))
+    L.siafd_b200_destroy(None)
