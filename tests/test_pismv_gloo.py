@@ -24,7 +24,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, M, decomp, q):
+def _worker(rank, world, port, M, decomp, q, testname="C", years=5000.0):
     try:
         os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -32,9 +32,9 @@ def _worker(rank, world, port, M, decomp, q):
         from pism_b200 import grid as G
         from pism_b200 import icemodel
         import cases
-        grid, _, _, _ = cases.case("C1_%d" % M)
+        grid, _, _, _ = cases.case("C1_%d" % M)  # (only Mx, My matter to Ranks; pismv_model builds the test's own grid)
         ranks = icemodel.Ranks(grid, G.decompose(grid.Mx, grid.My, world, **decomp), rank)
-        m = PO.pismv_model("C", M, ranks=ranks)
+        m = PO.pismv_model(testname, M, run_length_years=years, ranks=ranks)
         m.run()
         q.put((rank, m.steps, m.report(), None))
     except Exception:  # pragma: no cover
@@ -61,3 +61,23 @@ def test_pismv_test_C_on_patches_prints_the_golden_rows(world, M, decomp):
         assert err is None, (rank, err)
         assert steps == 84
         assert report == PO.TEST_15_GOLDEN[M], (rank, report)
+
+
+def test_pismv_test_L_on_two_ranks_like_test_16():
+    """test/regression/test_16.sh runs `mpiexec -n 2 pismv -test L`: two patches (PISM's 1 x 2 split), non-flat bed,
+    diffusivity-limited steps from the GLOBAL D_max; both ranks print the golden rows."""
+    import pismv_oracle as PO
+    ctx = mp.get_context("spawn")
+    for M in (21, 31):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, M, {}, q, "L", 1000.0)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=600) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        for rank, steps, report, err in res:
+            assert err is None, (rank, err)
+            assert report == PO.TEST_16_GOLDEN[M], (M, rank, report)
+
