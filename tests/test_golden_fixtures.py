@@ -114,3 +114,25 @@ def test_gpu_consumers_match_fixture():
     sia.upload("smb", d["smb"])
     sia._check(lib.siafd_b200_mass_source_step(sia.handle, float(d["dt2"]), 910.0, 0))
     assert np.array_equal(sia.download("thickness")[wg:-wg, wg:-wg], d["H_after_source"])
+
+
+# ---- reads of the 3D outputs and the spreading-disc flow steps (tools/make_golden.py::reads_and_transport) ---------
+def test_oracle_reproduces_reads_and_mass_transport_fixtures_bitwise():
+    import oracle_lib as O
+    grid, cfg, _, _ = cases.case("C4s")
+    inputs, outs, gb = load("C4s")
+    d = np.load(os.path.join(HERE, "golden", "oracle_reads_C4s.npz"))
+    p = cfg.oracle_params(grid)
+    H, wg = inputs["thickness"], cfg.w_geom
+    assert np.array_equal(O.value_at_height(p, outs["u"], cfg.w_uv, H, wg), d["u_surface"])
+    assert np.array_equal(O.value_at_height(p, outs["v"], cfg.w_uv, H, wg), d["v_surface"])
+    assert np.array_equal(O.value_at_height(p, inputs["enthalpy"], cfg.w_3d_in, z0=float(d["z_slice"])),
+                          d["enthalpy_slice"])
+    assert np.abs(d["u_surface"]).max() > 0
+
+    from test_gpu_mass_transport import oracle_flow_steps, spreading_disc_setup
+    S = spreading_disc_setup(51)
+    oracle_flow_steps(S, 12)
+    m = np.load(os.path.join(HERE, "golden", "oracle_mass_transport_51.npz"))
+    assert np.array_equal(S["H"], m["thickness"]) and np.array_equal(S["mask"], m["mask"])
+    assert S["dt"] == float(m["dt_last"])

@@ -34,6 +34,10 @@ def test_surface_values_match_oracle(name):
         assert np.array_equal(got, O.value_at_height(run.p, sia.download(f), cfg.w_uv, H, wg)), f
         # and through the whole update: the tolerance of u, v
         assert cases.rel_max(got, O.value_at_height(run.p, run.a[f], cfg.w_uv, H, wg)) <= U.TOL, f
+        if name == "C4s":  # and against the frozen vectors of tools/make_golden.py
+            import os
+            d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_reads_C4s.npz"))
+            assert cases.rel_max(got, d[f + "_surface"]) <= U.TOL, f
 
 
 def test_horizontal_slices_and_the_other_3d_fields():

@@ -81,6 +81,34 @@ def consumers(name="C4s", dt_years=0.5, dt2_years=200.0):
     print(path, os.path.getsize(path) // 1024, "KiB")
 
 
+def reads_and_transport(name="C4s"):
+    """oracle_reads_<case>.npz: IceModelVec3::getSurfaceValues of u, v and a horizontal slice of the enthalpy on the
+    frozen update (util/iceModelVec3.cc:153-240); oracle_mass_transport_51.npz: the thickness after 12 CFL-limited
+    flow steps of the spreading disc of test/mass_transport.py (default variant, part_grid off; advective velocity,
+    both B.C. masks) -- the set-up of tests/test_gpu_mass_transport.py."""
+    import ctypes as C
+    import oracle_lib as O
+    from pism_b200 import grid as G
+    grid, cfg, inputs, gb = cases.case(name)
+    run = cases.oracle_run(grid, cfg, inputs, gb, full=True)
+    H, wg = inputs["thickness"], cfg.w_geom
+    d = {"u_surface": O.value_at_height(run.p, run.a["u"], cfg.w_uv, H, wg),
+         "v_surface": O.value_at_height(run.p, run.a["v"], cfg.w_uv, H, wg),
+         "z_slice": np.array(0.3 * grid.Lz + 1.0),
+         "enthalpy_slice": O.value_at_height(run.p, inputs["enthalpy"], cfg.w_3d_in, z0=0.3 * grid.Lz + 1.0)}
+    path = os.path.join(ROOT, "tests", "golden", "oracle_reads_%s.npz" % name)
+    np.savez_compressed(path, **d)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+    from test_gpu_mass_transport import spreading_disc_setup, oracle_flow_steps
+    S = spreading_disc_setup(51)
+    oracle_flow_steps(S, 12)
+    path = os.path.join(ROOT, "tests", "golden", "oracle_mass_transport_51.npz")
+    np.savez_compressed(path, thickness=S["H"], mask=S["mask"], dt_last=np.array(S["dt"]))
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     main()
     consumers()
+    reads_and_transport()
