@@ -51,7 +51,7 @@ def parse():
                     help="N > 1: PISM's default (equal) ownership ranges instead of the load-balanced -procs_x / -procs_y")
     ap.add_argument("--procs-x", default="", help="PISM's -procs_x: comma-separated ownership ranges in x")
     ap.add_argument("--procs-y", default="", help="PISM's -procs_y: comma-separated ownership ranges in y")
-    ap.add_argument("--regime", default="dome", choices=["dome", "icefree"],
+    ap.add_argument("--regime", default="dome", choices=["dome", "icefree", "allice"],
                     help="icefree: zero thickness everywhere (the write-only regime of the fused kernel; diagnostic)")
     ap.add_argument("--no-input-exchange", action="store_true",
                     help="skip the per-step width-2 exchange of the inputs' ghosts (N > 1)")
@@ -271,7 +271,7 @@ def main():
     t_gen = time.perf_counter()
     # the fields live in the handle's own device storage (exportable to the neighbours over CUDA IPC); torch
     # sees them as views
-    inp = S.dome(grid, patch, sia.config, device=dev)
+    inp = S.dome(grid, patch, sia.config, device=dev, Rfrac=1.5 if args.regime == "allice" else 0.75)
     fields = {}
     for name in ("surface", "thickness", "mask", "bed", "enthalpy", "sliding", "h_x", "h_y", "D", "flux", "u", "v"):
         fields[name] = device_view(sia, name, sia.field_shape(name), dev)

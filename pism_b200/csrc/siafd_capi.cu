@@ -275,6 +275,11 @@ void fill_dp(siafd_b200_handle *h) {
   P.T_crit = c.fl_T_crit, P.R = c.fl_R;
   P.QoR_cold = c.fl_Q_cold / c.fl_R, P.QoR_warm = c.fl_Q_warm / c.fl_R;
   P.lnA_cold = log(c.fl_A_cold), P.lnA_warm = log(c.fl_A_warm);
+  {
+    const double c16 = 16.0 / log(2.0);
+    P.lnA2_cold = P.lnA_cold * c16, P.lnA2_warm = P.lnA_warm * c16;
+    P.QoR2_cold = P.QoR_cold * c16, P.QoR2_warm = P.QoR_warm * c16;
+  }
   P.hic = 0.5 / c.ec_c_i;
   P.cts2_a = 2.0 * c.ec_c_i * (c.ec_T_melting - c.ec_T_0), P.cts2_b = 2.0 * c.ec_c_i * c.ec_beta;
   {

@@ -33,6 +33,7 @@ struct DP {
   // the same factor in the form exp(lnA - (Q/R) / T) (siafd_slab.cu): ln A; 0.5 / c_i; and the cold-ice test
   // E < E_cts(p) as (E_ij + E_offset) < cts2_a - cts2_b p, cts2_a = 2 c_i (T_melting - T_0), cts2_b = 2 c_i beta
   double lnA_cold, lnA_warm, hic, cts2_a, cts2_b;
+  double lnA2_cold, lnA2_warm, QoR2_cold, QoR2_warm; // ln A and Q / R times 16 / ln2 (exp2_tab16, siafd_math.cuh)
   double beta_ratio; // m_beta_CC_grad / (m_rho * m_g), rheology/PatersonBudd.cc:57
   double gp_T0, gp_coeff, gp_limit, gp_softness_T0; // rheology/GPBLD.cc:49-61
   double iso_A;

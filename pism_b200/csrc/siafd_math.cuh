@@ -150,6 +150,46 @@ __device__ __forceinline__ double exp_tab(double x, const double *tab) {
   return __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
 }
 
+// The same factor with the argument already in units of ln2 / 16: exp2_tab16(y) = 2^(y / 16).  The caller folds
+// 16 / ln2 into ln A and Q / R (DP::lnA2_*, QoR2_*), so the reduction is three exact additions (t = y + 1.5 2^52,
+// j = low word of t, r = y - (t - 1.5 2^52), |r| <= 1/2) instead of a multiply and a two-constant Cody-Waite
+// step, and the polynomial takes r with (ln2 / 16)^k / k! as coefficients (degree 6: truncation 4.4e-16).
+// 10 FP64 operations; error <= ~2 ulp.
+static __constant__ double EXP2C[8] = {
+    0.043321698784996581839,    // [0] ln2/16
+    0.00093838479280898715755,  // [1] (ln2/16)^2 / 2
+    0.000013550807779497456043, // [2] (ln2/16)^3 / 3!
+    1.4676100322919429263e-7,   // [3] (ln2/16)^4 / 4!
+    1.2715871950558131622e-9,   // [4] (ln2/16)^5 / 5!
+    9.1812195738444387641e-12,  // [5] (ln2/16)^6 / 6!
+    6755399441055744.0,         // [6] 1.5 * 2^52
+    0.0};
+__device__ __forceinline__ double exp2_tab16(double y, const double *tab) {
+  double t = y + EXP2C[6];
+  const int n = __double2loint(t);
+  t -= EXP2C[6];
+  const double r = y - t;
+  double p = EXP2C[5];
+  p = fma(p, r, EXP2C[4]);
+  p = fma(p, r, EXP2C[3]);
+  p = fma(p, r, EXP2C[2]);
+  p = fma(p, r, EXP2C[1]);
+  p = fma(p, r, EXP2C[0]);
+  p = fma(p, r, 1.0);
+  p *= tab[n & 15];
+  return __hiloint2double(__double2hiint(p) + (n & ~15) * 65536, __double2loint(p));
+}
+
+// 1 / a with one third-order step on the MUFU.RCP64H seed s (20 mantissa bits): e = 1 - a s, 1 / a = s (1 + e + e^2 +
+// ...), truncated after e^2: relative error e^3 <= 2^-60.  Three DFMA against the four of rcp_fast.
+__device__ __forceinline__ double rcp_cubic(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  const double e = fma(-a, r, 1.0);
+  const double f = fma(e, e, e);
+  return fma(r, f, r);
+}
+
 // A * exp(-Q / (R * T)) of FlowLaw::softness_paterson_budd (rheology/FlowLaw.cc:89-94) and the arr / arrwarm
 // variants (PatersonBuddCold.cc:43-46, PatersonBuddWarm.cc:42-45), T in (150 K, 400 K)
 __device__ __forceinline__ double arrhenius(double A, double Q_over_R, double T) {

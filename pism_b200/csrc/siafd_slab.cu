@@ -32,6 +32,8 @@
 // Newton reciprocal; sums over z are taken per z range and then added.
 #include "siafd_math.cuh"
 
+#include <type_traits>
+
 #ifndef SLAB_LZ
 #define SLAB_LZ 16 // lanes across z in stage B
 #endif
@@ -112,7 +114,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   double *sT = sL + 2 * WZ * NC;             // [2][WZ][NC] I increment over a range
   double *cf = sT + 2 * WZ * NC;             // [2][NC][4]  h_x, h_y of the o = 0 and o = 1 points, by row parity
   double *tab16 = cf + 2 * NC * 4;           // 2^(j/16), for exp_tab
-  unsigned long long *bars = (unsigned long long *)(tab16 + 16);
+  double2 *selAQ = (double2 *)(tab16 + 16);  // {ln A, Q / R} 16 / ln2 of the cold [0] and the warm [1] Paterson-Budd branch
+  unsigned long long *bars = (unsigned long long *)(tab16 + 20);
 
   const int ca = (P.xs - 1) + blockIdx.x * OWN;
   const int ilast = P.xs + P.xm; // last extended column
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     zz[k] = make_double2(zk, (k > 0) ? 0.5 * (zk - F.z[k - 1]) : 0.0);
   }
   if (tid < 16) tab16[tid] = EXPT[tid];
+  if (tid == 16) selAQ[0] = make_double2(P.lnA2_cold, P.QoR2_cold), selAQ[1] = make_double2(P.lnA2_warm, P.QoR2_warm);
   if (A.use_bulk && tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -337,7 +341,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       const int ks = act ? ks0 : -1;
       // levels per z range of this column: a function of the column alone, never of the CTA tiling, so that
       // the order of every sum -- and with it every bit of the result -- is independent of the decomposition
-      const int Lc = (ks0 + WZ) / WZ;
+      // (a multiple of the levels per trip of the Arrhenius loop, so that only the range the surface cuts has a short trip)
+      const int Lc = SLAB_NL * ((ks0 + WZ * SLAB_NL) / (WZ * SLAB_NL));
       const int k0 = w * Lc;
       const int ke = min(k0 + Lc - 1, ks); // last level of this thread (empty range: ke < k0)
       // sia/SIAFD.cc:686, :693-696
@@ -360,21 +365,27 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
         //   E = (E1 + E2) / 2 is kept as the sum s; T = s (0.5 / c_i) + T_0; the cold-ice test E < E_cts(p) is
         //   s < cts2_a - cts2_b p; T_pa = T - T_m + T_melting = T + beta p; A exp(-Q / (R T)) = exp(ln A - (Q/R) / T);
         //   delta = (e theta 2 alpha^2) p^3 softness;  (depth[k] + dz) delta[k-1] = depth[k-1] delta[k-1].
+        // NL levels per trip (NL independent Arrhenius chains in flight per thread).  The range is walked with
+        // stepped pointers and compile-time offsets: whole trips carry no predication at all, and only the trip
+        // that the ice surface cuts short (at most one per column: Lc is a multiple of NL) is predicated.
         const double K = c2c * (hx * hx + hy * hy);
         double gprev = 0.0; // depth[k-1] * delta[k-1]
-        // NL levels (k .. k + NL - 1) per trip: NL independent Arrhenius chains in flight per thread
         constexpr int NL = SLAB_NL;
-        for (int k = k0; k <= ke; k += NL) {
-          // (a short last trip evaluates the last level again in the unused slots; those copies are dropped)
+        const double *e1 = E1 + k0, *e2 = E2 + k0;
+        const double2 *zp = zz + k0;
+        double *ic = Ic + k0;
+        int left = ke - k0 + 1; // levels of this thread still to do
+        bool is_first = true;
+        const double2 *selAQw = selAQ + 1;
+        auto trip = [&](auto tail_tag) {
+          constexpr bool TAIL = decltype(tail_tag)::value; // fewer than NL levels left: slots >= left repeat the last one
           double2 zh[NL];
-          double s[NL], dep[NL], pr[NL], T[NL], lnA[NL], QoR[NL], soft[NL], cts2[NL], d[NL], g[NL];
-          bool in[NL];
+          double s[NL], dep[NL], pr[NL], T[NL], arg[NL], soft[NL], d[NL], g[NL];
 #pragma unroll
           for (int j = 0; j < NL; ++j) {
-            in[j] = (k + j <= ke);
-            const int kj = min(k + j, ke);
-            zh[j] = zz[kj];
-            s[j] = E1[kj] + E2[kj];
+            const int jj = TAIL ? min(j, left - 1) : j;
+            zh[j] = zp[jj];
+            s[j] = e1[jj] + e2[jj];
           }
 #pragma unroll
           for (int j = 0; j < NL; ++j) {
@@ -388,31 +399,37 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
               T[j] = fmin(Tc, T_m); // EnthalpyConverter::temperature, :180-188
               if (LAW == LAW_PB) T[j] = fma(P.beta_ratio, pr[j], T[j]); // rheology/PatersonBudd.cc:57
             }
+          }
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
+            // ln A - (Q / R) / T in units of ln2 / 16
+            const double rT = rcp_cubic(T[j]);
             if (LAW == LAW_ARR) {
-              lnA[j] = P.lnA_cold, QoR[j] = P.QoR_cold;
+              arg[j] = fma(-P.QoR2_cold, rT, P.lnA2_cold);
             } else if (LAW == LAW_ARRWARM) {
-              lnA[j] = P.lnA_warm, QoR[j] = P.QoR_warm;
+              arg[j] = fma(-P.QoR2_warm, rT, P.lnA2_warm);
             } else {
-              const bool cold = T[j] < P.T_crit; // rheology/FlowLaw.cc:89-94
-              lnA[j] = cold ? P.lnA_cold : P.lnA_warm, QoR[j] = cold ? P.QoR_cold : P.QoR_warm;
+              // rheology/FlowLaw.cc:89-94: {ln A, Q / R} of the cold or the warm branch, one 16-byte load
+              const double2 aq = *((T[j] < P.T_crit) ? selAQ : selAQw);
+              arg[j] = fma(-aq.y, rT, aq.x);
             }
           }
 #pragma unroll
-          for (int j = 0; j < NL; ++j) soft[j] = exp_tab(fma(-QoR[j], rcp_fast(T[j]), lnA[j]), tab16);
+          for (int j = 0; j < NL; ++j) soft[j] = exp2_tab16(arg[j], tab16);
           if (LAW == LAW_GPBLD) {
+            // temperate ice: E >= E_cts(p), i.e. E / c_i + T_0 + beta p >= T_melting (the flow law is continuous there,
+            // so a point within rounding of the CTS may take either branch)
             bool any_temperate = false;
 #pragma unroll
-            for (int j = 0; j < NL; ++j) {
-              cts2[j] = fma(-P.cts2_b, pr[j], P.cts2_a);
-              any_temperate |= !(s[j] < cts2[j]);
-            }
-            if (any_temperate) { // temperate ice, rheology/GPBLD.cc:55-60
+            for (int j = 0; j < NL; ++j) any_temperate |= !(T[j] < P.T_melting);
+            if (any_temperate) { // rheology/GPBLD.cc:55-60
 #pragma unroll
               for (int j = 0; j < NL; ++j) {
-                if (!(s[j] < cts2[j])) {
+                if (!(T[j] < P.T_melting)) {
+                  const double cts2 = fma(-P.cts2_b, pr[j], P.cts2_a);
                   const double T_m = fma(-P.ec_beta, pr[j], P.T_melting);
                   const double Lm = fma(P.c_w - P.c_i, T_m - 273.15, P.L0); // EnthalpyConverter::L, :365-367
-                  const double omega = fmin(0.5 * (s[j] - cts2[j]) * rcp_fast(Lm), P.gp_limit);
+                  const double omega = fmin(fmax(0.5 * (s[j] - cts2), 0.0) * rcp_fast(Lm), P.gp_limit);
                   soft[j] = P.gp_softness_T0 * fma(P.gp_coeff, omega, 1.0);
                 }
               }
@@ -423,17 +440,26 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
             d[j] = (K * (pr[j] * pr[j] * pr[j])) * soft[j];
             g[j] = dep[j] * d[j];
           }
-          const bool is_first = (k == k0);
           first = is_first ? d[0] : first;
 #pragma unroll
           for (int j = 0; j < NL; ++j) {
-            const double hz = (in[j] && !(j == 0 && is_first)) ? zh[j].y : 0.0;
+            // (the trapezoid ending at the first level of the range needs the range below: added after the loop;
+            // repeated slots of a short trip carry weight 0 and re-store the value of the last level)
+            double hz = zh[j].y;
+            if (j == 0) hz = is_first ? 0.0 : hz;
+            if (TAIL && j > 0) hz = (j < left) ? hz : 0.0;
             run = fma(hz, prev + d[j], run);
             dp = fma(hz, gprev + g[j], dp);
-            if (FULL && in[j]) Ic[k + j] = run;
-            prev = in[j] ? d[j] : prev, gprev = in[j] ? g[j] : gprev;
+            if (FULL) ic[TAIL ? min(j, left - 1) : j] = run;
+            prev = d[j], gprev = g[j];
           }
+        };
+        while (left >= NL) {
+          trip(std::false_type{});
+          e1 += NL, e2 += NL, zp += NL, ic += NL, left -= NL;
+          is_first = false;
         }
+        if (left > 0) trip(std::true_type{});
       } else
       for (int k = k0; k <= ke; ++k) {
         const double2 zh = zz[k];
@@ -673,7 +699,7 @@ static size_t slab_smem_bytes(const DP &P, bool full, int NC, int WZ, bool bulk)
   const long slotE = ((NC + 1) * S + 2 + 1) & ~1L;
   const long colI = (NC * S + 1) & ~1L;
   long d = 2 * Mz + 2 * slotE + (P.use_age ? 2 * slotE : 0) + 2 * AUX_N + (full ? 3 * colI : 0) + 2 * 2 * WZ * NC +
-           2 * NC * 4 + 16;
+           2 * NC * 4 + 16 + 4;
   return (size_t)d * 8 + 2 * 8 /* mbarriers */ + 16;
 }
 

@@ -101,17 +101,18 @@ def _enthalpy_rows(ec, z, H, r, R, rows, out):
     out[rows] = enthalpy_permissive(ec, T, omega, P)
 
 
-def dome(grid, patch, cfg, device="cpu", variant="flat", pin=False, row_chunk=64, with_3d=True):
-    """Config C5 (and its scaled-down versions): synthetic dome, gpbld-ready enthalpy."""
+def dome(grid, patch, cfg, device="cpu", variant="flat", pin=False, row_chunk=64, with_3d=True, Rfrac=0.75):
+    """Config C5 (and its scaled-down versions): synthetic dome, gpbld-ready enthalpy.  Rfrac = margin radius / Lx
+    (0.75: 44 % of the columns carry ice; >= sqrt(2): every column does, bench.py --regime allice)."""
     wg, we, ws = cfg.w_geom, cfg.w_3d_in, cfg.w_sliding
     ec = ec_constants(cfg)
     xg, yg = _coords(grid, patch, wg, device)
-    g2 = dome_2d(grid, cfg, xg, yg, variant)
+    g2 = dome_2d(grid, cfg, xg, yg, variant, Rfrac=Rfrac)
     out = {k: g2[k].contiguous() for k in ("surface", "thickness", "mask", "bed")}
     out["sliding"] = torch.zeros((patch.ym + 2 * ws, patch.xm + 2 * ws, 2), dtype=F64, device=device)
     if with_3d:
         xe, ye = _coords(grid, patch, we, device)
-        g3 = dome_2d(grid, cfg, xe, ye, variant)
+        g3 = dome_2d(grid, cfg, xe, ye, variant, Rfrac=Rfrac)
         z = torch.as_tensor(grid.z, dtype=F64, device=device)
         E = _alloc((patch.ym + 2 * we, patch.xm + 2 * we, grid.Mz), device, pin)
         nj = E.shape[0]
