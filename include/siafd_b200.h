@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define SIAFD_B200_ABI_VERSION 1
+#define SIAFD_B200_ABI_VERSION 2
 
 /* stress_balance.sia.flow_law keywords (pism_config.cdl:2093-2094, rheology/FlowLawFactory.cc:71-87) */
 enum {
@@ -77,7 +77,8 @@ enum {
   SIAFD_B200_ERR_DIFFUSIVITY = 5,        /* sia/SIAFD.cc:752-760 */
   SIAFD_B200_ERR_BAD_CONFIG = 6,         /* sia/SIAFD.cc:69-86,216-219; BedSmoother.cc:134-137 */
   SIAFD_B200_ERR_CUDA = 7,               /* any CUDA runtime failure, incl. "no device" */
-  SIAFD_B200_ERR_BAD_ARGUMENT = 8
+  SIAFD_B200_ERR_BAD_ARGUMENT = 8,
+  SIAFD_B200_ERR_COMM = 9 /* a peer never arrived at a ghost update of a decomposed run */
 };
 
 /* Field ids for upload / download / bind / device_ptr / wrap_ghosts / halo pack. */
@@ -250,6 +251,39 @@ int siafd_b200_ipc_open(siafd_b200_handle *h, const void *handle64, void **peer_
 int siafd_b200_halo_attach(siafd_b200_handle *h, int field, int dir, void *peer_base, int peer_xm, int peer_ym);
 int siafd_b200_halo_push(siafd_b200_handle *h, int n, const int *fields, const int *widths, int phase);
 int siafd_b200_halo_wait(siafd_b200_handle *h, int phase);
+
+/* Communicator of a decomposed run: one process per GPU of one NVLink node (or, for tests, several handles in one
+ * process), no MPI / NCCL underneath.  It replaces IceModelVec::update_ghosts (util/iceModelVec.cc:630-643:
+ * DMLocalToLocal on the periodic BOX-stencil DMDA, util/IceGrid.cc:863-885), GlobalMax / GlobalSum
+ * (util/pism_utilities.cc:140-167; SIAFD.cc:748-750) and ParallelSection (util/error_handling.cc:189-214) for this path.
+ *   comm_init: collective over the `size` ranks.  Every rank writes its patch and the CUDA IPC handles of its ghosted
+ *     fields (handle-owned storage; allocated here if they are not yet) and of its pad to `<prefix>.rank.<rank>`, reads
+ *     the others' files (any shared directory, e.g. /dev/shm; polls for up to timeout_seconds), maps its neighbours'
+ *     arrays and every rank's pad, and leaves when all ranks have done so.  Neighbours are found from the patches
+ *     (periodic in x and y); the decomposition must be a tensor product of 1D ranges, as PISM's is (IceGrid.cc:489-499).
+ *     The prefix must be unique to this communicator; the files are removed by siafd_b200_destroy.
+ *   comm_init_local: the same for `size` handles of ONE process (any devices with peer access; one device for tests).
+ *   comm_exchange: update_ghosts of 1..6 fields at once, ONE launch: the eight strips of every field are stored straight
+ *     into the neighbours' ghost cells (BOX corners included), the last CTA raises the neighbours' arrival counters and
+ *     waits for this rank's own.  Stream-ordered, no host synchronisation.  Collective: all ranks make the same calls.
+ *   comm_allreduce: max (op 0) / min (1) / sum in rank order (2) of 1..8 doubles over all ranks, through the pads;
+ *     values in / out on the host; synchronises the stream. */
+int siafd_b200_comm_init(siafd_b200_handle *h, int rank, int size, const char *rendezvous_prefix, double timeout_seconds);
+int siafd_b200_comm_init_local(siafd_b200_handle **handles, int size);
+int siafd_b200_comm_rank(const siafd_b200_handle *h);
+int siafd_b200_comm_size(const siafd_b200_handle *h);
+int siafd_b200_comm_exchange(siafd_b200_handle *h, int n, const int *fields, const int *widths);
+int siafd_b200_comm_allreduce(siafd_b200_handle *h, int op, int n, double *values);
+/* SIAFD::update (sia/SIAFD.cc:122-155) of one rank of a decomposed run on device-resident fields, every communication
+ * of the reference inside: [exchange_inputs: ghosts of surface, thickness, mask, bed, enthalpy (age) -- device-resident
+ * callers; under PISM the host arrays already carry them]; gradient, with the ghost update of h_x, h_y (:498-499) stored
+ * by the gradient kernel itself; thk_smooth / theta; the fused diffusivity / flux / velocity kernel, which also stores
+ * the rim of u, v into the neighbours' ghost cells (:946-947); one last single-CTA kernel that waits for the
+ * neighbours' u, v and reduces {D_max, error bits, high-diffusivity counter} over ALL ranks (:748-750) into pinned host
+ * memory.  4-6 launches, captured once as a CUDA graph and replayed.  Asynchronous; siafd_b200_finish waits and returns
+ * the status, which is the same on every rank (ParallelSection), as are siafd_b200_max_diffusivity and
+ * _high_diffusivity_count afterwards.  Works with a communicator of one rank (periodic self-wrap). */
+int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double current_time, int exchange_inputs);
 
 /* BedSmoother::preprocess_bed on the GLOBAL bed (Mx*My doubles, [j][i], no ghosts; host
  * pointer).  Every rank passes the same array and gets its own patch (+ghosts) of

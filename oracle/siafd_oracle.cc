@@ -1247,6 +1247,129 @@ int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, i
 }
 
 // ---------------------------------------------------------------------------------------
+// SIAFD::update on the n patches of ONE domain (PISM's DMDA decomposition, one patch per MPI rank in the reference;
+// here the patches share the address space and an OpenMP thread takes the place of a rank).  Same passes as the
+// reference; its two ghost updates (SIAFD.cc:498-499 h_x, h_y; :946-947 u, v; DMLocalToLocal on the periodic BOX
+// stencil) are copies from the owning patch, and D_max is the maximum over the patches (:748).  Used by bench.py's CPU
+// arm ("one domain split over all cores") and by the tests of the decomposed path.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct PatchMap {
+  std::vector<int> xo, yo; // global column / row -> index of its 1D range
+  std::vector<int> rank;   // [iy * nx + ix] -> patch
+  int nx = 0, ny = 0;
+};
+bool build_patch_map(int n, const orc_params *p, PatchMap &M) {
+  const int Mx = p[0].Mx, My = p[0].My;
+  M.xo.assign(Mx, -1), M.yo.assign(My, -1);
+  std::vector<int> xs_list, ys_list;
+  for (int q = 0; q < n; ++q) {
+    if (std::find(xs_list.begin(), xs_list.end(), p[q].xs) == xs_list.end()) xs_list.push_back(p[q].xs);
+    if (std::find(ys_list.begin(), ys_list.end(), p[q].ys) == ys_list.end()) ys_list.push_back(p[q].ys);
+  }
+  std::sort(xs_list.begin(), xs_list.end()), std::sort(ys_list.begin(), ys_list.end());
+  M.nx = (int)xs_list.size(), M.ny = (int)ys_list.size();
+  if (M.nx * M.ny != n) return false;
+  M.rank.assign(n, -1);
+  for (int q = 0; q < n; ++q) {
+    const int ix = (int)(std::find(xs_list.begin(), xs_list.end(), p[q].xs) - xs_list.begin());
+    const int iy = (int)(std::find(ys_list.begin(), ys_list.end(), p[q].ys) - ys_list.begin());
+    M.rank[iy * M.nx + ix] = q;
+    for (int i = p[q].xs; i < p[q].xs + p[q].xm; ++i) M.xo[i] = ix;
+    for (int j = p[q].ys; j < p[q].ys + p[q].ym; ++j) M.yo[j] = iy;
+  }
+  for (int v : M.xo) if (v < 0) return false;
+  for (int v : M.yo) if (v < 0) return false;
+  for (int v : M.rank) if (v < 0) return false;
+  return true;
+}
+// ghosts of width w of patch q's array a[q] (ghost width W, dof values per cell) from the owners' arrays
+void pull_ghosts(int q, const orc_params *p, const PatchMap &M, double *const *a, int W, int w, int dof) {
+  const orc_params &P = p[q];
+  const long rowc = P.xm + 2 * W;
+  for (int j = P.ys - w; j < P.ys + P.ym + w; ++j) {
+    const int gj = ((j % P.My) + P.My) % P.My;
+    const bool jown = j >= P.ys && j < P.ys + P.ym;
+    for (int i = P.xs - w; i < P.xs + P.xm + w; ++i) {
+      if (jown && i >= P.xs && i < P.xs + P.xm) {
+        i = P.xs + P.xm - 1; // skip the owned run
+        continue;
+      }
+      const int gi = ((i % P.Mx) + P.Mx) % P.Mx;
+      const int r = M.rank[M.yo[gj] * M.nx + M.xo[gi]];
+      const orc_params &R = p[r];
+      const double *src = a[r] + ((long)(gj - (R.ys - W)) * (R.xm + 2 * W) + (gi - (R.xs - W))) * dof;
+      double *dst = a[q] + ((long)(j - (P.ys - W)) * rowc + (i - (P.xs - W))) * dof;
+      std::memcpy(dst, src, sizeof(double) * dof);
+    }
+  }
+}
+} // namespace
+
+int orc_siafd_update_decomposed(int n, const orc_params *p, orc_fields *f, int full, int nthreads) {
+  PatchMap M;
+  if (n < 1 || !build_patch_map(n, p, M)) return ORC_ERR_BAD_CONFIG;
+  int worst = ORC_OK;
+  std::vector<double *> hx(n), hy(n), u(n), v(n);
+  for (int q = 0; q < n; ++q) hx[q] = f[q].h_x, hy[q] = f[q].h_y, u[q] = f[q].u, v[q] = f[q].v;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+  {
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+    for (int q = 0; q < n; ++q) {
+      const int st = orc_siafd_gradient(&p[q], &f[q]);
+      if (st != ORC_OK) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        worst = st;
+      }
+    }
+    if (p[0].gradient_method == ORC_GRAD_HASELOFF) { // SIAFD.cc:498-499
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+      for (int q = 0; q < n; ++q) {
+        pull_ghosts(q, p, M, hx.data(), p[q].w_stag, p[q].w_stag, 2);
+        pull_ghosts(q, p, M, hy.data(), p[q].w_stag, p[q].w_stag, 2);
+      }
+    }
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+    for (int q = 0; q < n; ++q) {
+      const int st = orc_siafd_flux_velocity(&p[q], &f[q], full);
+      if (st != ORC_OK) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        worst = st;
+      }
+    }
+    if (full) { // SIAFD.cc:946-947
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+      for (int q = 0; q < n; ++q) {
+        pull_ghosts(q, p, M, u.data(), p[q].w_uv, p[q].w_uv, p[q].Mz);
+        pull_ghosts(q, p, M, v.data(), p[q].w_uv, p[q].w_uv, p[q].Mz);
+      }
+    }
+  }
+  double dmax = 0.0; // SIAFD.cc:748
+  for (int q = 0; q < n; ++q) dmax = std::max(dmax, f[q].D_max);
+  for (int q = 0; q < n; ++q) f[q].D_max = dmax;
+  return worst;
+}
+
+// ---------------------------------------------------------------------------------------
 // IceModelVec3D::getValZ (src/util/iceModelVec3.cc:153-182), IceModelVec3::getSurfaceValues (:226-240) and
 // ::getHorSlice (:209-223).  a: 3D field of ghost width wa; heights: 2D field of ghost width wh (the ice thickness
 // for getSurfaceValues) or NULL for the constant height z0; out: owned points only ([ym][xm]).

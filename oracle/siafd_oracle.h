@@ -178,6 +178,10 @@ int orc_vertical_velocity(const orc_params *p, const double *mask, const double 
 void orc_value_at_height(const orc_params *p, const double *a, int wa, const double *heights, int wh, double z0,
                          double *out);
 int orc_siafd_update_many(int n, const orc_params *p, orc_fields *f, int full, int nthreads);
+/* SIAFD::update on the n patches of one domain (PISM's decomposition): the reference's passes, its two ghost updates
+ * (SIAFD.cc:498-499, :946-947) as copies from the owning patch, D_max over all patches (:748); one OpenMP thread per
+ * patch stands for one MPI rank. */
+int orc_siafd_update_decomposed(int n, const orc_params *p, orc_fields *f, int full, int nthreads);
 /* StressBalance::compute_volumetric_strain_heating (StressBalance.cc:426-642), SURVEY.md 8(f) N3: p carries the flow
  * law of the SHALLOW stress balance (id, fl_n, fl_e); thickness, mask w_geom; enthalpy w_3d_in; u, v w_uv (ghosts
  * valid); Sigma owned only. */

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libsiafd_b200.so")
 FLOW_LAWS = {"isothermal_glen": 0, "pb": 1, "gpbld": 2, "hooke": 3, "arr": 4, "arrwarm": 5, "gk": 6}
 GRADIENTS = {"haseloff": 0, "mahaffy": 1, "eta": 2}
 OK, ERR_NEGATIVE_THICKNESS, ERR_OMEGA_NEGATIVE, ERR_HEIGHT_BELOW_BASE, ERR_HEIGHT_ABOVE_TOP = 0, 1, 2, 3, 4
-ERR_DIFFUSIVITY, ERR_BAD_CONFIG, ERR_CUDA, ERR_BAD_ARGUMENT = 5, 6, 7, 8
+ERR_DIFFUSIVITY, ERR_BAD_CONFIG, ERR_CUDA, ERR_BAD_ARGUMENT, ERR_COMM = 5, 6, 7, 8, 9
 
 FIELDS = ["surface", "thickness", "mask", "bed", "enthalpy", "age", "sliding", "topgsmooth", "maxtl", "C2", "C3",
           "C4", "h_x", "h_y", "D", "flux", "u", "v", "thk_smooth", "theta", "w_i", "w_j", "w", "basal_melt",
@@ -91,6 +91,13 @@ def _load():
         "siafd_b200_halo_attach": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]),
         "siafd_b200_halo_push": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
         "siafd_b200_halo_wait": (C.c_int, [vp, C.c_int]),
+        "siafd_b200_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.c_double]),
+        "siafd_b200_comm_init_local": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "siafd_b200_comm_rank": (C.c_int, [vp]),
+        "siafd_b200_comm_size": (C.c_int, [vp]),
+        "siafd_b200_comm_exchange": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "siafd_b200_comm_allreduce": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+        "siafd_b200_update_decomposed": (C.c_int, [vp, C.c_int, C.c_double, C.c_int]),
         "siafd_b200_preprocess_bed": (C.c_int, [vp, vp]),
         "siafd_b200_set_smoothed_bed": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
         "siafd_b200_compute_gradient": (C.c_int, [vp]),

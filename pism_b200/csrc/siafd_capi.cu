@@ -4,8 +4,7 @@
 // local ghosted layout, one CUDA stream per handle, error flags and D_max reduced on device and
 // read back once per update.  No CPU fallback: without a CUDA device every entry point that
 // needs one fails with SIAFD_B200_ERR_CUDA.
-#include "../../include/siafd_b200.h"
-#include "siafd_kernels.cuh"
+#include "siafd_handle.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -24,60 +23,7 @@
 
 using namespace siafd;
 
-struct siafd_b200_handle {
-  siafd_b200_config cfg;
-  std::vector<double> z;
-  DP P;
-  int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  void *buf[SIAFD_B200_F_COUNT];
-  bool owned[SIAFD_B200_F_COUNT];
-  double *d_z = nullptr;
-  unsigned *d_err = nullptr;
-  unsigned long long *d_dmax = nullptr;
-  unsigned long long *d_cfl = nullptr, *h_cfl = nullptr; // 8 maxima of siafd_b200_cfl and their pinned mirror
-  bool cfl3_fresh = false; // slots 0..3 hold the maxima the last vertical-velocity launch took on the current fields
-  int fill_threads = 4;    // host threads that fill the ice-free parts of u, v in the sparse host path (more of them
-                           // only compete with the PCIe copies for host DRAM: 4096^2, 4 / 8 threads: 362 / 368 ms)
-  int64_t bytes_h2d = 0, bytes_d2h = 0; // bytes the host-path calls moved over PCIe since create
-  int vvel_rows = 64;      // rows one CTA of the marching vertical-velocity kernels takes
-  int vvel_kind = 0;       // 0: k_vvel_slab (shared memory, z sweep in registers); 1: k_vvel_march (lanes across z)
-  int vvel_wz = 16;        // z ranges per column of k_vvel_slab
-  int *d_hdc = nullptr;
-  // pinned host mirror of {err, hdc, dmax}
-  struct Result {
-    unsigned long long dmax;
-    unsigned err;
-    int hdc;
-  } *h_res = nullptr;
-  bool result_pending = false;
-  bool smoother_set = false;
-  int bedNx = -1, bedNy = -1;
-  double *d_global_bed = nullptr;
-  cudaStream_t s_up = nullptr, s_dn = nullptr; // upload / download legs of the pipelined host update
-  std::vector<cudaEvent_t> ev_pipe;
-  // peer halo exchange: per field and neighbour direction the mapped base of the neighbour's array (nullptr =
-  // this rank) and its patch size; the arrival-counter pad [4 phases][8 dirs] and the neighbours' pads
-  struct Peer {
-    double *base = nullptr;
-    int xm = 0, ym = 0;
-    bool attached = false;
-  } peers[SIAFD_B200_F_COUNT][8];
-  unsigned long long *d_pad = nullptr, *peer_pad[8] = {};
-  bool pad_attached[8] = {};
-  unsigned long long halo_step[4] = {0, 0, 0, 0};
-  std::vector<void *> ipc_mapped;
-  Tuning tuning;
-  double inv_dz = 0.0; // (Mz - 1) / Lz when the levels are equally spaced, else 0
-  int64_t launches = 0;
-  // CUDA-event pairs around the fused kernel (bench.py's roofline timing), a ring of 256
-  std::vector<cudaEvent_t> ev_start, ev_stop;
-  int ev_count = 0;
-  bool timing = false;
-  std::string err;
-};
-
-namespace {
+namespace siafd_host {
 
 thread_local std::string g_create_error;
 
@@ -98,20 +44,6 @@ int fail(siafd_b200_handle *h, int code, const char *fmt, ...) {
 // every entry point tolerates a NULL handle (e.g. after a failed siafd_b200_create): status codes report
 // ERR_BAD_ARGUMENT (message through siafd_b200_last_error(NULL)), getters return -1 / NAN / NULL
 int null_handle() { return fail(nullptr, SIAFD_B200_ERR_BAD_ARGUMENT, "NULL handle"); }
-
-#define CU(h, call)                                                                                                    \
-  do {                                                                                                                 \
-    cudaError_t e_ = (call);                                                                                           \
-    if (e_ != cudaSuccess) {                                                                                           \
-      return fail((h), SIAFD_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,          \
-                  __LINE__);                                                                                           \
-    }                                                                                                                  \
-  } while (0)
-
-struct FieldMeta {
-  int width;
-  int dof;
-};
 
 FieldMeta meta(const siafd_b200_config &c, int f) {
   switch (f) {
@@ -344,10 +276,25 @@ int status_from_bits(unsigned bits) {
   if (bits & EB_OMEGA) return SIAFD_B200_ERR_OMEGA_NEGATIVE;
   if (bits & EB_BELOW) return SIAFD_B200_ERR_HEIGHT_BELOW_BASE;
   if (bits & EB_ABOVE) return SIAFD_B200_ERR_HEIGHT_ABOVE_TOP;
+  if (bits & EB_COMM) return SIAFD_B200_ERR_COMM;
   return SIAFD_B200_OK;
 }
 
+void invalidate_graphs(siafd_b200_handle *h) {
+  for (int q = 0; q < 4; ++q) h->comm.graph_valid[q] = false;
+}
+
 int fetch_result(siafd_b200_handle *h) {
+  if (h->comm.result_from_comm && !h->result_pending) {
+    // siafd_b200_update_decomposed: the reduction over all ranks was written to pinned host memory by the last kernel
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->h_res->dmax = h->comm.h_res[0];
+    h->h_res->err = (unsigned)h->comm.h_res[1];
+    h->h_res->hdc = (int)h->comm.h_res[2];
+    h->comm.result_from_comm = false;
+    return SIAFD_B200_OK;
+  }
+  h->comm.result_from_comm = false;
   if (h->result_pending) {
     CU(h, cudaMemcpyAsync(&h->h_res->dmax, h->d_dmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(&h->h_res->err, h->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
@@ -361,7 +308,9 @@ int fetch_result(siafd_b200_handle *h) {
   return SIAFD_B200_OK;
 }
 
-} // namespace
+} // namespace siafd_host
+
+using namespace siafd_host;
 
 extern "C" {
 
@@ -411,6 +360,8 @@ const char *siafd_b200_status_string(int s) {
     return "CUDA failure";
   case SIAFD_B200_ERR_BAD_ARGUMENT:
     return "bad argument";
+  case SIAFD_B200_ERR_COMM:
+    return "a rank of the communicator did not arrive at a ghost update (timed out)";
   default:
     return "unknown status";
   }
@@ -459,6 +410,8 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.pipeline_host = 1;
   h->tuning.pipeline_band = 1; // 4096^2, segments per band 1 / 2 / 4 / 8: 368 / 375 / 386 / 411 ms (tools/e2e_sweep.py)
   h->tuning.sparse_host = 1;
+  h->tuning.graph_step = 1;
+  if (const char *e = getenv("SIAFD_B200_GRAPH")) h->tuning.graph_step = atoi(e);
   if (const char *e = getenv("SIAFD_B200_SPARSE")) h->tuning.sparse_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_FILL_THREADS")) h->fill_threads = std::max(1, atoi(e));
   if (const char *e = getenv("SIAFD_B200_PIPELINE")) h->tuning.pipeline_host = atoi(e);
@@ -527,6 +480,7 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   cudaFree(h->d_cfl);
   if (h->h_cfl) cudaFreeHost(h->h_cfl);
   cudaFree(h->d_global_bed);
+  comm_release(h);
   for (void *p : h->ipc_mapped) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_pad);
   if (h->h_res) {
@@ -576,6 +530,7 @@ int siafd_b200_bind(siafd_b200_handle *h, int f, void *device_ptr) {
   }
   h->buf[f] = device_ptr;
   h->owned[f] = false;
+  invalidate_graphs(h);
   return SIAFD_B200_OK;
 }
 
@@ -863,6 +818,7 @@ int siafd_b200_preprocess_bed(siafd_b200_handle *h, const double *global_bed_hos
     h->bedNx = h->bedNy = -1;
     h->P.smoother_active = 0;
     h->smoother_set = false;
+    invalidate_graphs(h);
     return SIAFD_B200_OK;
   }
   // sia/BedSmoother.cc:111-137
@@ -886,6 +842,7 @@ int siafd_b200_preprocess_bed(siafd_b200_handle *h, const double *global_bed_hos
   h->bedNx = Nx, h->bedNy = Ny;
   h->P.smoother_active = 1;
   h->smoother_set = true;
+  invalidate_graphs(h);
   return SIAFD_B200_OK;
 }
 
@@ -901,6 +858,7 @@ int siafd_b200_set_smoothed_bed(siafd_b200_handle *h, const double *topgsmooth, 
   CU(h, cudaStreamSynchronize(h->stream));
   h->P.smoother_active = smoother_active ? 1 : 0;
   h->smoother_set = true;
+  invalidate_graphs(h);
   return SIAFD_B200_OK;
 }
 
@@ -920,7 +878,8 @@ int siafd_b200_compute_gradient(siafd_b200_handle *h) {
 }
 
 // checks, scratch fields and the 2D preparation of SIAFD::compute_diffusivity (SIAFD.cc:555-582)
-static int flux_velocity_prepare(siafd_b200_handle *h, int full_update, double current_time) {
+extern "C++" {
+int siafd_host::flux_velocity_prepare(siafd_b200_handle *h, int full_update, double current_time) {
   CU(h, cudaSetDevice(h->device));
   const siafd_b200_config &c = h->cfg;
   const int need[] = {SIAFD_B200_F_SURFACE,    SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK,  SIAFD_B200_F_BED,
@@ -960,9 +919,11 @@ static int flux_velocity_prepare(siafd_b200_handle *h, int full_update, double c
   CU(h, cudaGetLastError());
   return SIAFD_B200_OK;
 }
+} // extern "C++"
 
 // the fused kernel on the row segments [seg0, seg0 + nseg) (nseg < 0: all)
-static int flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0, int nseg) {
+extern "C++" {
+int siafd_host::flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0, int nseg, const PeerPush *push) {
   const Fields F = fields_of(h);
   const Tuning T = h->tuning;
   const bool timed = h->timing && h->ev_count < (int)h->ev_start.size();
@@ -970,7 +931,7 @@ static int flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0,
     CU(h, cudaEventRecord(h->ev_start[h->ev_count], h->stream));
   }
   const int n = launch_slab(h->P, F, full_update != 0, T, (long)siafd_b200_field_size(h, SIAFD_B200_F_ENTHALPY),
-                            (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, seg0, nseg, h->stream);
+                            (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, seg0, nseg, h->stream, push);
   if (timed) {
     CU(h, cudaEventRecord(h->ev_stop[h->ev_count], h->stream));
     h->ev_count += 1;
@@ -984,6 +945,7 @@ static int flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0,
   h->result_pending = true;
   return SIAFD_B200_OK;
 }
+} // extern "C++"
 
 int siafd_b200_compute_flux_velocity(siafd_b200_handle *h, int full_update, double current_time) {
   if (!h) return null_handle();
@@ -1304,9 +1266,39 @@ struct IceExtent {
   std::vector<int> lo, hi; // per owned row: columns [lo, hi] to transfer (lo > hi: none; lo < 0: the whole row)
 };
 
-static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E) {
-  const int xm = c.xm, ym = c.ym, wg = c.w_geom, margin = 3;
+static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E, bool patch_mode) {
+  const int xm = c.xm, ym = c.ym, wg = c.w_geom;
   const long pitch = xm + 2 * wg;
+  if (patch_mode) {
+    // one patch of a decomposed domain: the ghost cells (width wg >= 2) are the neighbours' thickness, no wrap.  A
+    // column matters when there is ice within one cell of it (the staggered points around it); two cells are taken.
+    const int margin = 2, R = ym + 2 * wg;
+    std::vector<int> l0(R), h0(R); // per local row (ghost rows included): local columns [l0, h0] with ice, ghosts included
+    for (int r = 0; r < R; ++r) {
+      const double *row = H + (long)r * pitch;
+      int a = 0, b = (int)pitch - 1;
+      while (a < pitch && row[a] == 0.0) ++a;
+      while (b >= a && row[b] == 0.0) --b;
+      l0[r] = a, h0[r] = b;
+    }
+    E.lo.assign(ym, xm), E.hi.assign(ym, -1);
+    for (int j = 0; j < ym; ++j) {
+      int lo = 1 << 30, hi = -1;
+      for (int d = -margin; d <= margin; ++d) {
+        const int r = j + wg + d; // wg >= margin: always a row of the array
+        if (l0[r] <= h0[r]) lo = std::min(lo, l0[r]), hi = std::max(hi, h0[r]);
+      }
+      if (hi >= lo) {
+        lo = lo - wg - margin, hi = hi - wg + margin; // owned-column indices
+        if (lo < margin || hi > xm - 1 - margin) {
+          lo = -1, hi = xm; // ice near the edge of the patch: whole rows
+        }
+        E.lo[j] = lo, E.hi[j] = hi;
+      }
+    }
+    return;
+  }
+  const int margin = 3;
   std::vector<int> l0(ym), h0(ym);
   for (int j = 0; j < ym; ++j) {
     const double *row = H + (long)(j + wg) * pitch + wg;
@@ -1331,11 +1323,12 @@ static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E
 }
 
 // rectangle of the owned rows [j0, j1) (wrapped into [0, ym)): returns false when there is nothing to transfer
-static bool band_extent(const IceExtent &E, int ym, int j0, int j1, int *lo, int *hi, bool *whole) {
+static bool band_extent(const IceExtent &E, int ym, int j0, int j1, int *lo, int *hi, bool *whole, bool patch_mode = false) {
   int a = 1 << 30, b = -1;
   *whole = false;
   for (int j = j0; j < j1; ++j) {
-    const int jj = ((j % ym) + ym) % ym;
+    // (a patch: the ghost rows take the extent of the nearest owned row, which already looks two rows past the edge)
+    const int jj = patch_mode ? std::min(std::max(j, 0), ym - 1) : ((j % ym) + ym) % ym;
     if (E.hi[jj] < E.lo[jj]) continue;
     if (E.lo[jj] < 0) *whole = true;
     a = std::min(a, E.lo[jj]), b = std::max(b, E.hi[jj]);
@@ -1427,8 +1420,14 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
   // ---- which parts of the 3D arrays have to move at all (sparse = 0 moves everything) ----
   const bool sparse = h->tuning.sparse_host != 0;
+  // With a communicator (siafd_b200_comm_init*, one rank or many) the ghost updates of h_x, h_y and u, v are stores by
+  // the producing kernels into the neighbours' arrays (this rank's own where it is its own periodic neighbour), and the
+  // status / D_max are reduced over all ranks.  patch: the neighbours in x are other ranks, so the ghost columns of
+  // u, v arrive from them and are downloaded at the end, with the ghost rows.
+  const bool comm = h->comm.active;
+  const bool patch = comm && (c.xm != c.Mx || c.ym != c.My);
   IceExtent ext;
-  if (sparse) ice_extent(c, in->thickness, ext);
+  if (sparse) ice_extent(c, in->thickness, ext, patch);
   // the host fills what is not downloaded; the tasks are known up front, so the threads start before the copies
   std::vector<FillTask> fills;
   std::vector<std::thread> workers;
@@ -1438,19 +1437,26 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   std::vector<Rect> down(NB);
   for (int b = 0; b < NB; ++b) {
     const int s0 = b * band, s1 = std::min(nseg, (b + 1) * band);
-    Rect R{std::max(0, s0 * RS - 1), std::min(c.ym, s1 * RS - 1), 0, c.xm + 2 * wuv};
+    // (a patch: owned columns only -- the ghost columns are the neighbours' to fill and come down at the end)
+    Rect R{std::max(0, s0 * RS - 1), std::min(c.ym, s1 * RS - 1), patch ? wuv : 0, patch ? c.xm + wuv : c.xm + 2 * wuv};
     if (sparse && R.o1 > R.o0) {
       int lo, hi;
       bool whole;
-      const bool any = band_extent(ext, c.ym, R.o0, R.o1, &lo, &hi, &whole);
+      const bool any = band_extent(ext, c.ym, R.o0, R.o1, &lo, &hi, &whole, patch);
       if (!any) {
         R.c0 = R.c1 = 0;
       } else if (!whole) {
         R.c0 = lo + wuv, R.c1 = hi + 1 + wuv;
       }
+      // (a patch: the host fills owned columns only; the ghost columns come down from the device at the end)
+      const int f0 = patch ? wuv : 0, f1 = patch ? c.xm + wuv : c.xm + 2 * wuv;
       for (int j = R.o0; j < R.o1; ++j) {
-        if (R.c0 > 0 || R.c0 >= R.c1) fills.push_back({j, 0, R.c0 >= R.c1 ? c.xm + 2 * wuv : R.c0});
-        if (R.c0 < R.c1 && R.c1 < c.xm + 2 * wuv) fills.push_back({j, R.c1, c.xm + 2 * wuv});
+        if (R.c0 >= R.c1) {
+          fills.push_back({j, f0, f1});
+        } else {
+          if (R.c0 > f0) fills.push_back({j, f0, R.c0});
+          if (R.c1 < f1) fills.push_back({j, R.c1, f1});
+        }
       }
     }
     down[b] = R;
@@ -1488,7 +1494,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     if (r1 <= r0) return SIAFD_B200_OK;
     int lo = 0, hi = 0;
     bool whole = true;
-    if (sparse && !band_extent(ext, c.ym, (int)r0 - we, (int)r1 - we, &lo, &hi, &whole)) return SIAFD_B200_OK; // no ice
+    if (sparse && !band_extent(ext, c.ym, (int)r0 - we, (int)r1 - we, &lo, &hi, &whole, patch)) return SIAFD_B200_OK; // no ice
     if (!sparse || whole) {
       CU(h, cudaMemcpyAsync(E_dev + r0 * rowE, in->enthalpy + r0 * rowE, (size_t)(r1 - r0) * rowE * sizeof(double),
                             cudaMemcpyHostToDevice, h->s_up));
@@ -1510,10 +1516,25 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     CU(h, cudaEventRecord(h->ev_pipe[b], h->s_up));
   }
   // gradient and 2D preparation while the first band is in flight
-  if ((st = siafd_b200_compute_gradient(h))) return st;
-  if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
-    const int hxy[2] = {SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
-    if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
+  PeerPush PPu = PeerPush();
+  if (comm) {
+    const int more[] = {SIAFD_B200_F_W_I, SIAFD_B200_F_W_J};
+    for (int f : more) {
+      if ((st = ensure(h, f))) return st;
+    }
+    PeerPush PPg;
+    comm_make_push(h, SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y, c.w_stag, 1, PPg);
+    comm_make_push(h, SIAFD_B200_F_U, SIAFD_B200_F_V, c.w_uv, 1, PPu);
+    const bool haseloff = c.gradient_method == SIAFD_B200_GRAD_HASELOFF;
+    h->launches += launch_gradient(h->P, fields_of(h), h->stream, haseloff ? &PPg : nullptr); // SIAFD.cc:137, :498-499
+    CU(h, cudaGetLastError());
+    if (haseloff && h->comm.size > 1) h->launches += launch_comm_sync(h->comm.d_peers, 2, h->stream);
+  } else {
+    if ((st = siafd_b200_compute_gradient(h))) return st;
+    if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
+      const int hxy[2] = {SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
+      if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
+    }
   }
   if ((st = flux_velocity_prepare(h, 1, in->current_time))) return st;
   const int uvf[2] = {SIAFD_B200_F_U, SIAFD_B200_F_V};
@@ -1521,12 +1542,12 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   for (int b = 0; b < NB; ++b) {
     const int s0 = b * band, s1 = std::min(nseg, (b + 1) * band);
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_pipe[b], 0));
-    if ((st = flux_velocity_launch(h, 1, s0, s1 - s0))) return st;
+    if ((st = flux_velocity_launch(h, 1, s0, s1 - s0, comm ? &PPu : nullptr))) return st;
     // owned rows of this band (extended row e = ys - 1 + s RS ... ; owned rows are ys .. ys + ym - 1)
     const Rect &R = down[b];
     const int o0 = R.o0, o1 = R.o1;
     if (o1 > o0) {
-      for (int q = 0; q < 2; ++q) { // periodic wrap in x of the band's rows (SIAFD.cc:946-947), then download
+      for (int q = 0; q < 2 && !comm; ++q) { // periodic wrap in x of the band's rows (SIAFD.cc:946-947), then download
         double *a = (double *)h->buf[uvf[q]];
         h->launches += launch_copy_region(a, c.xm + 2 * wuv, 0, wuv + o0, a, c.xm + 2 * wuv, c.xm, wuv + o0, wuv, o1 - o0, c.Mz,
                                           h->stream);
@@ -1549,10 +1570,26 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
       }
     }
   }
-  // ghost rows of u, v (periodic wrap in y), the 2D outputs, D_max and the error flags
+  // ghost rows of u, v (periodic wrap in y / the neighbours' stores), the 2D outputs, D_max and the error flags
+  if (comm) {
+    // wait for the neighbours' u, v; {D_max, error bits, counter} over all ranks (SIAFD.cc:748-750)
+    h->launches += launch_comm_final(h->comm.d_peers, h->comm.size > 1 ? 3 : -1, h->d_dmax, h->d_err, h->d_hdc, h->comm.d_res,
+                                     h->comm.h_res, h->stream);
+    CU(h, cudaGetLastError());
+    h->result_pending = false;
+    h->comm.result_from_comm = true;
+  }
   for (int q = 0; q < 2; ++q) {
-    if ((st = wrap_dir(h, uvf[q], 1))) return st;
+    if (!comm && (st = wrap_dir(h, uvf[q], 1))) return st;
     double *a = (double *)h->buf[uvf[q]];
+    if (patch) { // ghost columns of the owned rows: they arrived from the x neighbours
+      for (int side = 0; side < 2; ++side) {
+        const long off = (long)wuv * rowUV + (side ? (long)(c.xm + wuv) * c.Mz : 0L);
+        CU(h, cudaMemcpy2DAsync(uvh[q] + off, (size_t)rowUV * sizeof(double), a + off, (size_t)rowUV * sizeof(double),
+                                (size_t)wuv * c.Mz * sizeof(double), (size_t)c.ym, cudaMemcpyDeviceToHost, h->stream));
+      }
+      h->bytes_d2h += 2 * (int64_t)wuv * c.Mz * 8 * c.ym;
+    }
     CU(h, cudaMemcpyAsync(uvh[q], a, (size_t)wuv * rowUV * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->bytes_d2h += 2 * (int64_t)wuv * rowUV * 8;
     const long off = (long)(wuv + c.ym) * rowUV;
@@ -1583,10 +1620,13 @@ int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b
   CU(h, cudaSetDevice(h->device));
   const siafd_b200_config &c = h->cfg;
   const bool whole = (c.xm == c.Mx && c.ym == c.My);
-  if (!whole) {
+  if (!whole && !h->comm.active) {
     return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT,
-                "siafd_b200_update is the single-rank form; a decomposed patch must use the split calls with ghost "
-                "exchanges at SIAFD.cc:498-499 and :946-947");
+                "siafd_b200_update on a patch of a decomposed domain needs a communicator (siafd_b200_comm_init), or "
+                "the split calls with ghost exchanges at SIAFD.cc:498-499 and :946-947");
+  }
+  if (!whole && !in->ghosts_valid && in->memory_space == 0) {
+    return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "host arrays of a patch must carry valid ghosts (PISM's always do)");
   }
   if (in->memory_space == 0 && out->memory_space == 0 && full_update && in->ghosts_valid && in->enthalpy && !in->age &&
       out->u && out->v && in->surface && in->thickness && in->mask && h->tuning.pipeline_host) {
@@ -1609,7 +1649,7 @@ int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b
     } else {
       if ((st = siafd_b200_bind(h, q.f, (void *)q.p))) return st;
     }
-    if (!in->ghosts_valid) {
+    if (!in->ghosts_valid && !h->comm.active) {
       if ((st = siafd_b200_wrap_ghosts(h, q.f))) return st;
     }
   }
@@ -1629,15 +1669,25 @@ int siafd_b200_update(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b
       if (q.p && (st = siafd_b200_bind(h, q.f, q.p))) return st;
     }
   }
-  if ((st = siafd_b200_compute_gradient(h))) return st;
-  if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
-    const int hxy[2] = {SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
-    if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
-  }
-  if ((st = siafd_b200_compute_flux_velocity(h, full_update, in->current_time))) return st;
-  if (full_update) { // sia/SIAFD.cc:946-947
-    const int uv[2] = {SIAFD_B200_F_U, SIAFD_B200_F_V};
-    if ((st = siafd_b200_wrap_ghosts_many(h, 2, uv))) return st;
+  if (h->comm.active) {
+    // one rank of a decomposed run (or a whole-domain handle with a one-rank communicator): every ghost update inside
+    if (out->memory_space != 0 || in->memory_space != 0) {
+      return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT,
+                  "with a communicator the fields must live in the handle's own storage: use host pointers here, or "
+                  "siafd_b200_device_ptr + siafd_b200_update_decomposed for device-resident fields");
+    }
+    if ((st = siafd_b200_update_decomposed(h, full_update, in->current_time, in->ghosts_valid ? 0 : 1))) return st;
+  } else {
+    if ((st = siafd_b200_compute_gradient(h))) return st;
+    if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
+      const int hxy[2] = {SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y};
+      if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
+    }
+    if ((st = siafd_b200_compute_flux_velocity(h, full_update, in->current_time))) return st;
+    if (full_update) { // sia/SIAFD.cc:946-947
+      const int uv[2] = {SIAFD_B200_F_U, SIAFD_B200_F_V};
+      if ((st = siafd_b200_wrap_ghosts_many(h, 2, uv))) return st;
+    }
   }
   if (out->memory_space == 0) {
     for (auto &q : outs) {
@@ -1679,6 +1729,7 @@ int siafd_b200_set_tuning(siafd_b200_handle *h, int rows_per_cta, int use_bulk_c
   if (rows_per_cta > 0) h->tuning.rows_per_cta = rows_per_cta;
   if (use_bulk_copy >= 0) h->tuning.use_bulk_copy = use_bulk_copy ? 1 : 0;
   if (skip_ice_free_rows >= 0) h->tuning.skip_ice_free = skip_ice_free_rows ? 1 : 0;
+  invalidate_graphs(h);
   return SIAFD_B200_OK;
 }
 

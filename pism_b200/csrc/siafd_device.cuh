@@ -14,7 +14,7 @@ enum : int { LAW_ISO = 0, LAW_PB = 1, LAW_GPBLD = 2, LAW_HOOKE = 3, LAW_ARR = 4,
 enum : int { GRAD_HASELOFF = 0, GRAD_MAHAFFY = 1, GRAD_ETA = 2 };
 
 // error bits raised by kernels (mapped to SIAFD_B200_ERR_* on the host)
-enum : unsigned { EB_NEG_THK = 1u, EB_OMEGA = 2u, EB_BELOW = 4u, EB_ABOVE = 8u };
+enum : unsigned { EB_NEG_THK = 1u, EB_OMEGA = 2u, EB_BELOW = 4u, EB_ABOVE = 8u, EB_COMM = 16u };
 
 // Passed by value to every kernel (__grid_constant__).
 struct DP {

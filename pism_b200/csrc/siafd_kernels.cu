@@ -187,7 +187,10 @@ __device__ __forceinline__ HasDirect haseloff_direct(double h0, double h1, int M
 __device__ __forceinline__ double inv_count(double W) {
   return W == 1.0 ? 1.0 : (W == 2.0 ? 0.5 : (W == 3.0 ? (1.0 / 3.0) : 0.25));
 }
-__global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F) {
+// PUSH: the ghost update of sia/SIAFD.cc:498-499 fused in -- an owned point on the rim of the patch is also stored into
+// the neighbours' ghost cells (PeerPush, siafd_kernels.cuh)
+template <bool PUSH>
+__global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
   const int nx = P.xm + 2;
   const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (long)nx * (P.ym + 2)) {
@@ -238,6 +241,7 @@ __global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F) {
     r = (W > 0) ? __dmul_rn(inv_count(W), (xm1.g + x01.g)) : 0.0;
   }
   F.h_x[s + 1] = r;
+  const double hx_cross = r;
   // y-derivative, i-offset (:469-495)
   if (x00.w > 0) {
     const double W = y00.w + y0m.w + y1m.w + y10.w;
@@ -250,6 +254,21 @@ __global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F) {
     r = (W > 0) ? __dmul_rn(inv_count(W), (y1m.g + y10.g)) : 0.0;
   }
   F.h_y[s + 0] = r;
+  if (PUSH) {
+    const int a = i - P.xs, b = j - P.ys;
+    const bool W_ = a < PP.w, E_ = a >= P.xm - PP.w, S_ = b < PP.w, N_ = b >= P.ym - PP.w;
+    if (W_ || E_ || S_ || N_) {
+      const double2 hx2 = make_double2(x00.g, hx_cross), hy2 = make_double2(r, y00.g);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        if (PP.a[d] != nullptr && peer_strip_member(d, W_, E_, S_, N_)) {
+          const long t = ((long)(b + P.wst + PP.dj[d]) * PP.rowc[d] + (a + P.wst + PP.di[d])) * 2;
+          *reinterpret_cast<double2 *>(PP.a[d] + t) = hx2;
+          *reinterpret_cast<double2 *>(PP.b[d] + t) = hy2;
+        }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -471,7 +490,7 @@ int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s) {
   return 1;
 }
 
-int launch_gradient(const DP &P, const Fields &F, cudaStream_t s) {
+int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push) {
   const long n1 = (long)(P.xm + 2) * (P.ym + 2);
   const long n2 = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
   switch (P.grad) { // sia/SIAFD.cc:197-220
@@ -483,7 +502,11 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s) {
     k_grad_eta<<<nblk(n1, 256), 256, 0, s>>>(P, F);
     return 2;
   default:
-    k_grad_haseloff<<<nblk(n1, 256), 256, 0, s>>>(P, F);
+    if (push != nullptr && push->on) {
+      k_grad_haseloff<true><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);
+    } else {
+      k_grad_haseloff<false><<<nblk(n1, 256), 256, 0, s>>>(P, F, PeerPush());
+    }
     return 1;
   }
 }

@@ -4,6 +4,8 @@
 
 namespace siafd {
 
+struct PeerPush;
+
 // Device pointers of one handle (PISM local ghosted layout, see include/siafd_b200.h).
 struct Fields {
   const double *h, *H, *mask, *bed, *E, *age, *sliding;
@@ -24,14 +26,15 @@ struct Tuning {
   int pipeline_host; // 1: siafd_b200_update with host arrays overlaps upload, kernel and download over row bands
   int pipeline_band; // row segments per band of that pipeline
   int sparse_host;   // 1: that pipeline moves only the parts of the 3D arrays that are within 3 cells of ice
+  int graph_step;    // 1: siafd_b200_update_decomposed replays a captured CUDA graph of the step
 };
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
 int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
-int launch_gradient(const DP &P, const Fields &F, cudaStream_t s);
+int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push = nullptr);
 // one launch covers the row segments [seg0, seg0 + nseg) of the extended patch (nseg < 0: all from seg0)
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz, int seg0,
-                int nseg, cudaStream_t s);
+                int nseg, cudaStream_t s, const PeerPush *push = nullptr);
 int slab_rows_per_segment(const Tuning &T);
 int slab_segments(const DP &P, const Tuning &T);
 size_t slab_smem_need(const DP &P, bool full, bool bulk); // shared memory of the smallest configuration
@@ -60,6 +63,54 @@ struct HaloSignal {
 int launch_halo_push(const HaloBatch &B, cudaStream_t s);
 int launch_halo_signal(const HaloSignal &S, cudaStream_t s);
 int launch_halo_wait(const unsigned long long *slots8, unsigned long long value, cudaStream_t s);
+
+// ---- communicator of a decomposed run (siafd_comm.cu): one process (or handle) per GPU of one node ---------------
+// Every rank owns a pad in device memory that all ranks map.  Ghost updates are direct stores into the neighbours'
+// arrays; the pad orders them (arrival counters, one row per phase) and carries the small all-rank reductions
+// (D_max, error bits, counters: SIAFD.cc:748-750; CFL: timestepping.cc).  The expected counter values live in the
+// pad itself, so a captured CUDA graph of a step replays unchanged.
+constexpr int COMM_MAXR = 32;   // ranks of one communicator
+constexpr int COMM_PHASES = 8;  // independent arrival-counter rows
+struct CommPad {
+  unsigned long long arrive[COMM_PHASES][8];   // [phase][direction the sender is seen in], written by the neighbours
+  unsigned long long red_flag[4][COMM_MAXR];   // [buffer][rank]
+  double red_val[4][COMM_MAXR][8];             // [buffer][rank][value]
+  // local bookkeeping, never written by a peer
+  unsigned long long step[COMM_PHASES], red_step[2];
+  unsigned int done[COMM_PHASES];
+  unsigned int timed_out; // a wait gave up (EB_COMM)
+};
+struct CommPeers { // device-resident, read-only after setup
+  CommPad *self;
+  CommPad *nb[8];          // the eight neighbours' pads (== self where the neighbour is this rank)
+  CommPad *all[COMM_MAXR]; // every rank's pad
+  int rank, size;
+};
+// Ghost update fused into the producing kernel: the owned cells within `w` of the patch edge are also stored into the
+// neighbours' ghost cells (peer memory; the own array where the neighbour is this rank: the periodic self-wrap).
+// Neighbour-local index of my local cell (il, jl): (jl + dj[d]) * rowc[d] + (il + di[d]).
+struct PeerPush {
+  double *a[8], *b[8];
+  long rowc[8];
+  int di[8], dj[8];
+  int w, on;
+};
+__host__ __device__ inline bool peer_strip_member(int d, bool W_, bool E_, bool S_, bool N_) {
+  // dir = 0..7 <-> (dx,dy) = (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1)
+  const int dx = (d == 0 || d == 3 || d == 5) ? -1 : ((d == 2 || d == 4 || d == 7) ? 1 : 0);
+  const int dy = (d < 3) ? -1 : (d > 4 ? 1 : 0);
+  return (dx == 0 || (dx < 0 ? W_ : E_)) && (dy == 0 || (dy < 0 ? S_ : N_));
+}
+// copy the strips of a phase, then (last CTA) signal the neighbours and wait for theirs
+int launch_halo_xchg(const HaloBatch &B, const CommPeers *cp, int phase, int signal, cudaStream_t s);
+// after a kernel with fused pushes: signal + wait of one phase
+int launch_comm_sync(const CommPeers *cp, int phase, cudaStream_t s);
+// end of an update: signal + wait of `phase` (u, v ghosts) and the all-rank reduction of {D_max, error bits,
+// high-diffusivity counter}; result {max, or, sum} to res_dev[0..2] (as 64-bit patterns) and, if given, res_host
+int launch_comm_final(const CommPeers *cp, int phase, unsigned long long *dmax, unsigned *err, int *hdc,
+                      unsigned long long *res_dev, unsigned long long *res_host, cudaStream_t s);
+// all-rank reduction of n <= 8 doubles (op 0: max, 1: min, 2: sum in rank order); vals_dev in/out
+int launch_comm_allreduce(const CommPeers *cp, double *vals_dev, double *vals_host, int n, int op, cudaStream_t s);
 
 // StressBalance::compute_vertical_velocity (stressbalance/StressBalance.cc:283-424)
 int launch_vertical_velocity(const DP &P, const double *mask, const double *u, const double *v, const double *bmr,

@@ -87,9 +87,121 @@ struct SlabArgs {
 // per-slot staging area of a row's 2D scalars (offsets in doubles)
 enum : int { AUX_TS = 0, AUX_TH = 18, AUX_HX = 36, AUX_HY = 68, AUX_N = 100 };
 
+// Stage B for one row of a strip on the rim of the patch: u, v of the regular columns (sia/SIAFD.cc:904-943) stored into
+// this rank's array AND, from the registers, into the ghost cell of the neighbour that faces the column -- the fused
+// ghost update of SIAFD.cc:946-947 (peer memory over NVLink, or this rank's own array: the periodic wrap).  The few
+// cells in the corners of the patch face three neighbours; push_rim_row serves the other two.
+struct RimTargets { // per pass: where the column's values also go (nullptr: nowhere), offset by the lane's first level
+  double *u2[4], *v2[4];
+};
+template <int NC, int NPASS, int LB, int LZ>
+__device__ __noinline__ void stage_b_rim(const int Mz, const int i_lo, const int i_hi, const long uv_row0, const RimTargets T,
+                                         double *u, double *v, const double *I0_s, const double *I1_s, const double *cf, int S,
+                                         int s_cur, bool south, bool any_valid, int ca, int qg, int lz, int lane, double svx,
+                                         double svy) {
+  // i_lo .. i_hi: the owned columns; uv_row0: offset (in doubles) of column i_lo of this row in the u / v arrays
+  const int s_nxt = s_cur ^ 1;
+  for (int p = 0; p < NPASS; ++p) {
+    const int qp = qg + p, i_p = ca + qp;
+    const int srcl = (lane & ~(LZ - 1)) + p * LB; // a lane whose own column (tid / LB) is qp
+    const double ub = __shfl_sync(FULLMASK, svx, srcl), vb = __shfl_sync(FULLMASK, svy, srcl);
+    if (qp >= 1 && i_p >= i_lo && i_p <= i_hi) {
+      const long uvo = uv_row0 + (long)(i_p - i_lo) * Mz + lz;
+      double *up = u + uvo, *vp = v + uvo;
+      double *up2 = T.u2[p], *vp2 = T.v2[p];
+      const bool dual = up2 != nullptr;
+      if (!any_valid) {
+        for (int k = lz; k < Mz; k += LZ, up += LZ, vp += LZ) {
+          *up = ub;
+          *vp = vb;
+          if (dual) *up2 = ub, *vp2 = vb, up2 += LZ, vp2 += LZ;
+        }
+      } else {
+        // the same expressions, in the same order, as the in-line stage B of the kernel: the values are bit-identical
+        const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
+        const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
+        const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
+        const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
+        const double *Ie = I0_s + qp * S + lz;
+        const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
+        int k = lz;
+        for (; k + 3 * LZ < Mz; k += 4 * LZ, up += 4 * LZ, vp += 4 * LZ, Ie += 4 * LZ, In += 4 * LZ, Is += 4 * LZ) {
+          double ie[4], iw[4], in[4], is[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LZ], iw[j] = (Ie - S)[j * LZ], in[j] = In[j * LZ], is[j] = Is[j * LZ];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double uu = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
+            const double vv = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
+            up[j * LZ] = uu;
+            vp[j * LZ] = vv;
+            if (dual) up2[j * LZ] = uu, vp2[j * LZ] = vv;
+          }
+          if (dual) up2 += 4 * LZ, vp2 += 4 * LZ;
+        }
+        for (; k < Mz; k += LZ, up += LZ, vp += LZ, Ie += LZ, In += LZ, Is += LZ) {
+          const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
+          const double uu = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
+          const double vv = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
+          *up = uu;
+          *vp = vv;
+          if (dual) *up2 = uu, *vp2 = vv, up2 += LZ, vp2 += LZ;
+        }
+      }
+    }
+  }
+}
+
+// Fused ghost update of u, v (SIAFD.cc:946-947), the part stage B does not do itself: a cell in a corner of the patch
+// faces three neighbours; stage B stores it into the first one's ghost cell, and here every thread copies the values
+// it has just stored (same column / level mapping as stage B) into the other two (peer memory over NVLink, or this
+// rank's own array: the periodic wrap).  Four cells per patch.
+template <int NPASS, int LB, int LZ>
+__device__ __noinline__ void push_rim_row(const DP &P, const PeerPush &PP, const double *u, const double *v, int r, int ca,
+                                          int qg, int lz) {
+  const int Mz = P.Mz;
+  const int b = r - P.ys;
+  const bool S_ = b < PP.w, N_ = b >= P.ym - PP.w;
+  for (int p = 0; p < NPASS; ++p) {
+    const int qp = qg + p, i_p = ca + qp;
+    if (qp >= 1 && i_p >= P.xs && i_p < P.xs + P.xm) {
+      const int a = i_p - P.xs;
+      const bool W_ = a < PP.w, E_ = a >= P.xm - PP.w;
+      if (W_ || E_ || S_ || N_) {
+        const long own = ((long)(b + P.wuv) * (P.xm + 2 * P.wuv) + (a + P.wuv)) * Mz;
+        // all loads first (eight levels per lane and trip), then the stores: the targets may alias the sources as far
+        // as the compiler knows, and one load per store would pay the L2 latency once per level
+        for (int kb = lz; kb < Mz; kb += 8 * LZ) {
+          double uu[8], vv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = min(kb + j * LZ, Mz - 1);
+            uu[j] = __ldcg(u + own + k), vv[j] = __ldcg(v + own + k);
+          }
+          bool first = true; // (stage B itself served the first neighbour that faces the cell)
+          for (int d = 0; d < 8; ++d) {
+            if (PP.a[d] != nullptr && peer_strip_member(d, W_, E_, S_, N_)) {
+              if (first) {
+                first = false;
+                continue;
+              }
+              const long t = ((long)(b + P.wuv + PP.dj[d]) * PP.rowc[d] + (a + P.wuv + PP.di[d])) * Mz;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int k = kb + j * LZ;
+                if (k < Mz) PP.a[d][t + k] = uu[j], PP.b[d][t + k] = vv[j];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int LAW, bool FULL, int NC, int WZ>
 __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
-    k_sia_slab(const __grid_constant__ DP P, const Fields F, const SlabArgs A) {
+    k_sia_slab(const __grid_constant__ DP P, const Fields F, const SlabArgs A, const __grid_constant__ PeerPush PP) {
   static_assert(NC <= 16, "AUX_* offsets and the partner shuffle assume at most 16 lane columns");
   extern __shared__ __align__(16) double sm[];
   constexpr int NT = 2 * NC * WZ;
@@ -117,12 +229,15 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   double2 *selAQ = (double2 *)(tab16 + 16);  // {ln A, Q / R} 16 / ln2 of the cold [0] and the warm [1] Paterson-Budd branch
   unsigned long long *bars = (unsigned long long *)(tab16 + 20);
 
-  const int ca = (P.xs - 1) + blockIdx.x * OWN;
+  // strips in the order last, 0, 1, ...: the two strips on the west / east rim of the patch (which also store into the
+  // neighbours' ghost cells) are the first of their grid row to start, never its tail
+  const int strip = (blockIdx.x == 0) ? (int)gridDim.x - 1 : (int)blockIdx.x - 1;
+  const int ca = (P.xs - 1) + strip * OWN;
   const int ilast = P.xs + P.xm; // last extended column
   const int i_c = ca + c;
   const bool col_ok = i_c <= ilast;
   const int iv = min(i_c, ilast);
-  const bool own_c = col_ok && (c >= 1 || blockIdx.x == 0); // this strip writes D, Q of the column
+  const bool own_c = col_ok && (c >= 1 || strip == 0); // this strip writes D, Q of the column
   const int ncolE = min(NC + 1, ilast + 2 - ca);            // enthalpy / thk_smooth columns ca .. ca + ncolE - 1
   const int ncolS = ncolE - 1;                              // valid lane columns
   const int seg = (int)blockIdx.y + A.seg0;
@@ -277,6 +392,14 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   };
   double2 sv_cur = make_double2(0.0, 0.0), sv_nxt = make_double2(0.0, 0.0), sv_nx2 = make_double2(0.0, 0.0);
   if (FULL) sv_cur = sliding_load(rbase + li), sv_nxt = sliding_load(rbase + LB + li), sv_nx2 = sliding_load(rbase + 2 * LB + li);
+
+  // fused ghost update of u, v (SIAFD.cc:946-947): does this strip hold owned columns within PP.w of the west / east
+  // edge of the patch (CTA-uniform)
+  bool strip_rim = false;
+  if (FULL && PP.on) {
+    const int i_first = max(ca + 1, P.xs), i_last = min(ca + NC - 1, P.xs + P.xm - 1);
+    strip_rim = (i_first < P.xs + PP.w) || (i_last >= P.xs + P.xm - PP.w);
+  }
 
   double dmax_local = 0.0;
   int hdc_local = 0;
@@ -581,7 +704,34 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       // everywhere in the strip: u = v = 0 on every level.  The owned columns of a row are contiguous in memory, so
       // each field's row leaves as ONE bulk store from a block of zeros (measured: 5.2 -> 5.9 TB/s in this regime).
       bool row_done = false;
-      if (A.use_bulk && !any_valid && r >= rbase && r < rend) { // CTA-uniform
+      // rows / strips on the rim of the patch (with a communicator): their u, v also go into the neighbours' ghost cells
+      const bool sn_row = (r - P.ys) < PP.w || (r - P.ys) >= P.ym - PP.w;
+      const bool rim_row = PP.on && r >= rbase && r < rend && (strip_rim || sn_row); // CTA-uniform
+      const bool corner_row = rim_row && strip_rim && sn_row; // holds a cell that faces three neighbours (push_rim_row)
+      // per pass of stage B: the ghost cell of the first neighbour that faces this thread's column (the neighbour table
+      // is read here, where it is a kernel parameter in the constant bank)
+      auto rim_targets = [&]() -> RimTargets {
+        RimTargets T;
+        const int b = r - P.ys;
+        const bool S_ = b < PP.w, N_ = b >= P.ym - PP.w;
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) {
+          const int qp = qg + p, a = ca + qp - P.xs;
+          const bool W_ = a < PP.w, E_ = a >= P.xm - PP.w;
+          T.u2[p] = nullptr, T.v2[p] = nullptr;
+          if (qp >= 1 && a >= 0 && a < P.xm) {
+            for (int d = 0; d < 8; ++d) {
+              if (PP.a[d] != nullptr && peer_strip_member(d, W_, E_, S_, N_)) {
+                const long t = ((long)(b + P.wuv + PP.dj[d]) * PP.rowc[d] + (a + P.wuv + PP.di[d])) * Mz + lz;
+                T.u2[p] = PP.a[d] + t, T.v2[p] = PP.b[d] + t;
+                break;
+              }
+            }
+          }
+        }
+        return T;
+      };
+      if (A.use_bulk && !any_valid && !corner_row && r >= rbase && r < rend) { // CTA-uniform
         if (__syncthreads_and(sv.x == 0.0 && sv.y == 0.0)) {
           if (!zero_ready) {
             for (int e = tid; e < NC * S; e += NT) I0_s[e] = 0.0;
@@ -604,54 +754,77 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
               }
             }
           }
+          if (rim_row) { // u = v = 0 on every level: the neighbours' ghost cells get the same
+            const RimTargets T = rim_targets();
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p) {
+              if (T.u2[p] != nullptr) {
+                for (int k = 0; lz + k < Mz; k += LZ) T.u2[p][k] = 0.0, T.v2[p][k] = 0.0;
+              }
+            }
+          }
           zero_inflight = true;
           row_done = true;
         }
       }
       if (!row_done && r >= rbase && r < rend) { // CTA-uniform
-        const bool south = (ivalid & (1u << s_nxt)) != 0;
+        if (rim_row) {
+          // rows / strips on the rim of the patch (with a communicator): out of line, so that the march stays lean
+          const RimTargets T = rim_targets();
+          stage_b_rim<NC, NPASS, LB, LZ>(Mz, P.xs, P.xs + P.xm - 1,
+                                         ((long)(r - (P.ys - P.wuv)) * (P.xm + 2 * P.wuv) + P.wuv) * Mz, T, F.u, F.v, I0_s, I1_s,
+                                         cf, S, s_cur, (ivalid & (1u << s_nxt)) != 0, any_valid, ca, qg, lz, lane, sv.x, sv.y);
+        } else {
+          const bool south = (ivalid & (1u << s_nxt)) != 0;
 #pragma unroll
-        for (int p = 0; p < NPASS; ++p) {
-          const int qp = qg + p, i_p = ca + qp;
-          const int srcl = (lane & ~(LZ - 1)) + p * LB; // a lane whose own column (tid / LB) is qp
-          const double ub = __shfl_sync(FULLMASK, sv.x, srcl), vb = __shfl_sync(FULLMASK, sv.y, srcl);
-          if (qp >= 1 && i_p >= P.xs && i_p < P.xs + P.xm) {
-            const long uvo = ((long)(r - (P.ys - P.wuv)) * (P.xm + 2 * P.wuv) + (i_p - P.xs + P.wuv)) * Mz + lz;
-            double *up = F.u + uvo, *vp = F.v + uvo;
-            if (!any_valid) {
-              // no ice at any staggered point of this and the previous row: I == 0, u = sliding velocity (G9)
-              for (int k = lz; k < Mz; k += LZ, up += LZ, vp += LZ) {
-                *up = ub;
-                *vp = vb;
-              }
-            } else {
-              // u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s): the factor -0.25 goes into the slopes
-              const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
-              const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
-              const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
-              const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
-              const double *Ie = I0_s + qp * S + lz;
-              const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
-              int k = lz;
-              for (; k + 3 * LZ < Mz; k += 4 * LZ, up += 4 * LZ, vp += 4 * LZ, Ie += 4 * LZ, In += 4 * LZ, Is += 4 * LZ) {
-                double ie[4], iw[4], in[4], is[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LZ], iw[j] = (Ie - S)[j * LZ], in[j] = In[j * LZ], is[j] = Is[j * LZ];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  up[j * LZ] = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
-                  vp[j * LZ] = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
+          for (int p = 0; p < NPASS; ++p) {
+            const int qp = qg + p, i_p = ca + qp;
+            const int srcl = (lane & ~(LZ - 1)) + p * LB; // a lane whose own column (tid / LB) is qp
+            const double ub = __shfl_sync(FULLMASK, sv.x, srcl), vb = __shfl_sync(FULLMASK, sv.y, srcl);
+            if (qp >= 1 && i_p >= P.xs && i_p < P.xs + P.xm) {
+              const long uvo = ((long)(r - (P.ys - P.wuv)) * (P.xm + 2 * P.wuv) + (i_p - P.xs + P.wuv)) * Mz + lz;
+              double *up = F.u + uvo, *vp = F.v + uvo;
+              if (!any_valid) {
+                // no ice at any staggered point of this and the previous row: I == 0, u = sliding velocity (G9)
+                for (int k = lz; k < Mz; k += LZ, up += LZ, vp += LZ) {
+                  *up = ub;
+                  *vp = vb;
                 }
-              }
-              for (; k < Mz; k += LZ, up += LZ, vp += LZ, Ie += LZ, In += LZ, Is += LZ) {
-                const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
-                *up = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
-                *vp = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
+              } else {
+                // u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s): the factor -0.25 goes into the slopes
+                const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
+                const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
+                const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
+                const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
+                const double *Ie = I0_s + qp * S + lz;
+                const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
+                int k = lz;
+                for (; k + 3 * LZ < Mz; k += 4 * LZ, up += 4 * LZ, vp += 4 * LZ, Ie += 4 * LZ, In += 4 * LZ, Is += 4 * LZ) {
+                  double ie[4], iw[4], in[4], is[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LZ], iw[j] = (Ie - S)[j * LZ], in[j] = In[j * LZ], is[j] = Is[j * LZ];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const double uu = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
+                    const double vv = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
+                    up[j * LZ] = uu;
+                    vp[j * LZ] = vv;
+                  }
+                }
+                for (; k < Mz; k += LZ, up += LZ, vp += LZ, Ie += LZ, In += LZ, Is += LZ) {
+                  const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
+                  const double uu = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
+                  const double vv = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
+                  *up = uu;
+                  *vp = vv;
+                }
               }
             }
           }
         }
       }
+      // (only where this strip holds a corner cell of the patch; out of line: keeps the march lean)
+      if (corner_row) push_rim_row<NPASS, LB, LZ>(P, PP, F.u, F.v, r, ca, qg, lz);
       if (any_valid) {
         // the zero-filled arrays now ARE valid zeros for the next row's "previous row" role
         ivalid |= (1u << s_cur);
@@ -704,7 +877,7 @@ static size_t slab_smem_bytes(const DP &P, bool full, int NC, int WZ, bool bulk)
 }
 
 template <int LAW, bool FULL, int NC, int WZ>
-static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaStream_t s) {
+static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaStream_t s, const PeerPush &PP) {
   const size_t smem = slab_smem_bytes(P, FULL, NC, WZ, A.use_bulk != 0);
   if (smem > (size_t)227 * 1024) return -1;
   static size_t configured[64] = {}; // per instantiation and per device (the attribute is a per-device setting)
@@ -719,38 +892,38 @@ static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaSt
     configured[slot] = smem;
   }
   dim3 grid((unsigned)((P.xm + 1 + (NC - 2)) / (NC - 1)), (unsigned)A.nseg);
-  k_sia_slab<LAW, FULL, NC, WZ><<<grid, 2 * NC * WZ, smem, s>>>(P, F, A);
+  k_sia_slab<LAW, FULL, NC, WZ><<<grid, 2 * NC * WZ, smem, s>>>(P, F, A, PP);
   return 1;
 }
 
 template <int LAW, bool FULL> static int launch_slab_l(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
-                                                       cudaStream_t s) {
+                                                       cudaStream_t s, const PeerPush &PP) {
   // 16 lane columns unless shared memory cannot hold them (very tall grids): then 8
   if (slab_smem_bytes(P, FULL, 16, 8, A.use_bulk != 0) <= (size_t)227 * 1024) {
-    if (T.wz == 4) return launch_slab_t<LAW, FULL, 16, 4>(P, F, A, s);
-    if (T.wz == 2) return launch_slab_t<LAW, FULL, 16, 2>(P, F, A, s);
-    return launch_slab_t<LAW, FULL, 16, 8>(P, F, A, s);
+    if (T.wz == 4) return launch_slab_t<LAW, FULL, 16, 4>(P, F, A, s, PP);
+    if (T.wz == 2) return launch_slab_t<LAW, FULL, 16, 2>(P, F, A, s, PP);
+    return launch_slab_t<LAW, FULL, 16, 8>(P, F, A, s, PP);
   }
-  return launch_slab_t<LAW, FULL, 8, 4>(P, F, A, s);
+  return launch_slab_t<LAW, FULL, 8, 4>(P, F, A, s, PP);
 }
 
 template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
-                                              cudaStream_t s) {
+                                              cudaStream_t s, const PeerPush &PP) {
   switch (P.law) {
   case LAW_ISO:
-    return launch_slab_l<LAW_ISO, FULL>(P, F, T, A, s);
+    return launch_slab_l<LAW_ISO, FULL>(P, F, T, A, s, PP);
   case LAW_PB:
-    return launch_slab_l<LAW_PB, FULL>(P, F, T, A, s);
+    return launch_slab_l<LAW_PB, FULL>(P, F, T, A, s, PP);
   case LAW_GPBLD:
-    return launch_slab_l<LAW_GPBLD, FULL>(P, F, T, A, s);
+    return launch_slab_l<LAW_GPBLD, FULL>(P, F, T, A, s, PP);
   case LAW_HOOKE:
-    return launch_slab_l<LAW_HOOKE, FULL>(P, F, T, A, s);
+    return launch_slab_l<LAW_HOOKE, FULL>(P, F, T, A, s, PP);
   case LAW_ARR:
-    return launch_slab_l<LAW_ARR, FULL>(P, F, T, A, s);
+    return launch_slab_l<LAW_ARR, FULL>(P, F, T, A, s, PP);
   case LAW_ARRWARM:
-    return launch_slab_l<LAW_ARRWARM, FULL>(P, F, T, A, s);
+    return launch_slab_l<LAW_ARRWARM, FULL>(P, F, T, A, s, PP);
   case LAW_GK:
-    return launch_slab_l<LAW_GK, FULL>(P, F, T, A, s);
+    return launch_slab_l<LAW_GK, FULL>(P, F, T, A, s, PP);
   default:
     return -1;
   }
@@ -765,7 +938,7 @@ int slab_segments(const DP &P, const Tuning &T) {
 }
 
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz, int seg0,
-                int nseg, cudaStream_t s) {
+                int nseg, cudaStream_t s, const PeerPush *push) {
   SlabArgs A;
   A.RS = slab_rows_per_segment(T); // the row flags of a CTA live in a 96-bit word
   A.seg0 = seg0;
@@ -775,7 +948,9 @@ int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long n
   A.nE = nE;
   A.n2 = n2;
   A.inv_dz = inv_dz;
-  return full ? launch_slab_f<true>(P, F, T, A, s) : launch_slab_f<false>(P, F, T, A, s);
+  PeerPush PP = PeerPush();
+  if (push != nullptr && push->on && full) PP = *push;
+  return full ? launch_slab_f<true>(P, F, T, A, s, PP) : launch_slab_f<false>(P, F, T, A, s, PP);
 }
 
 } // namespace siafd

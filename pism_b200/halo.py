@@ -108,62 +108,53 @@ def global_max(value, device, group=None):
     return float(t.item())
 
 
-DIRS = [(-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]  # siafd_b200.h: dir = 0..7
-
-
 class PeerHalo:
-    """Ghost exchange by direct stores into the neighbours' arrays (CUDA IPC peer memory over NVLink), the GPU
-    path of IceModelVec::update_ghosts for one process per GPU on one node.  Setup maps every neighbour's
-    arrays once (handles travel through torch.distributed); afterwards a phase is two stream-ordered calls,
-    `siafd_b200_halo_push` + `siafd_b200_halo_wait`: three small launches, no host synchronisation, BOX
-    corners included.  Fields must live in the handle's own storage (not bound tensors)."""
+    """Ghost exchange by direct stores into the neighbours' arrays (CUDA IPC peer memory over NVLink): a thin wrapper of
+    the library's own communicator (siafd_b200_comm_init / _comm_exchange / _comm_allreduce, include/siafd_b200.h), which
+    needs no torch.distributed: the IPC handles travel through files under `prefix`.  torch.distributed is only used here
+    to agree on a unique prefix when the caller gives none.  `names` are touched first so that optional fields take part.
+    A phase is ONE launch (strip copies, then the last CTA raises the neighbours' arrival counters and waits for this
+    rank's own); fields must live in the handle's own storage (not bound tensors)."""
 
-    def __init__(self, patch, patches, sia, names, group=None):
+    def __init__(self, patch, patches, sia, names=(), group=None, prefix=None):
         self.patch, self.sia = patch, sia
         h = sia.handle
-        mine = {}
-        for name in list(names) + [None]:
-            buf = (C.c_ubyte * 64)()
-            st = lib.siafd_b200_ipc_export(h, -1 if name is None else F[name], buf)
-            assert st == 0, lib.siafd_b200_last_error(h)
-            mine[name] = bytes(buf)
-        world = dist.get_world_size(group)
-        everyone = [None] * world
-        dist.all_gather_object(everyone, mine, group=group)
-        mapped = {}  # (rank, name) -> peer pointer: a handle is opened once per process
-        self.bytes_per_push = {}
-        for name in list(names) + [None]:
-            f = -1 if name is None else F[name]
-            for d, (dx, dy) in enumerate(DIRS):
-                nb = patch.neighbor(dx, dy)
-                if nb == patch.rank:
-                    ptr = None
-                else:
-                    if (nb, name) not in mapped:
-                        out = C.c_void_p()
-                        st = lib.siafd_b200_ipc_open(h, everyone[nb][name], C.byref(out))
-                        assert st == 0, lib.siafd_b200_last_error(h)
-                        mapped[(nb, name)] = out.value
-                    ptr = mapped[(nb, name)]
-                st = lib.siafd_b200_halo_attach(h, f, d, ptr, patches[nb].xm, patches[nb].ym)
-                assert st == 0, lib.siafd_b200_last_error(h)
-        dist.barrier(group=group)  # nobody pushes before everybody has mapped
+        for name in names:
+            assert lib.siafd_b200_device_ptr(h, F[name]), lib.siafd_b200_last_error(h)
+        if prefix is None:
+            box = [None]
+            if dist.get_rank(group) == 0:
+                import os
+                import uuid
+                d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+                box[0] = os.path.join(d, "siafd_b200_%s" % uuid.uuid4().hex)
+            dist.broadcast_object_list(box, src=0, group=group)
+            prefix = box[0]
+        st = lib.siafd_b200_comm_init(h, patch.rank, len(patches), prefix.encode(), 120.0)
+        if st != 0:
+            raise RuntimeError(lib.siafd_b200_last_error(h).decode())
         self.bytes_sent = 0
 
-    def exchange(self, names_widths, phase):
+    def exchange(self, names_widths, phase=None):
         """update_ghosts() of several fields at once: [(name, width), ...]."""
         n = len(names_widths)
         fa = (C.c_int * n)(*[F[nm] for nm, _ in names_widths])
         wa = (C.c_int * n)(*[w for _, w in names_widths])
         h = self.sia.handle
-        st = lib.siafd_b200_halo_push(h, n, fa, wa, phase)
-        assert st == 0, lib.siafd_b200_last_error(h)
-        st = lib.siafd_b200_halo_wait(h, phase)
+        st = lib.siafd_b200_comm_exchange(h, n, fa, wa)
         assert st == 0, lib.siafd_b200_last_error(h)
         p = self.patch
         for nm, w in names_widths:
             dof = lib.siafd_b200_field_dof(h, F[nm])
             self.bytes_sent += 8 * dof * (2 * w * p.ym + 2 * w * (p.xm + 2 * w))
+
+    def allreduce(self, values, op="max"):
+        """GlobalMax / GlobalMin / GlobalSum (util/pism_utilities.cc:140-167) of up to 8 doubles, through the pads."""
+        n = len(values)
+        v = (C.c_double * n)(*values)
+        st = lib.siafd_b200_comm_allreduce(self.sia.handle, {"max": 0, "min": 1, "sum": 2}[op], n, v)
+        assert st == 0, lib.siafd_b200_last_error(self.sia.handle)
+        return list(v)
 
 
 def device_view(sia, name, shape, device):

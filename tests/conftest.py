@@ -1,4 +1,8 @@
 import os
+
+# several handles of one process wait for each other inside kernels (tests/test_gpu_comm.py): their streams must not
+# share a hardware queue.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import sys
 
 import pytest

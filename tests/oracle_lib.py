@@ -101,6 +101,7 @@ def lib():
         L.orc_siafd_flux_velocity.argtypes = [PP, FP, C.c_int]
         L.orc_siafd_update_single.argtypes = [PP, FP, C.c_int]
         L.orc_siafd_update_many.argtypes = [C.c_int, PP, FP, C.c_int, C.c_int]
+        L.orc_siafd_update_decomposed.argtypes = [C.c_int, PP, FP, C.c_int, C.c_int]
         L.orc_vertical_velocity.argtypes = [PP, _pd, _pd, _pd, _pd, C.c_int, _pd]
         L.orc_value_at_height.restype = None
         L.orc_value_at_height.argtypes = [PP, _pd, C.c_int, _pd, C.c_int, _f64, _pd]

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(raw, s), "libsiafd_b200.so does not export %s" % s
     assert sorted(capi.EXPORTS) == syms, "pism_b200/capi.py and include/siafd_b200.h disagree"
-    assert capi.lib.siafd_b200_abi_version() == 1
+    assert capi.lib.siafd_b200_abi_version() == 2
 
 
 def test_field_ids_of_the_python_binding_match_the_header():
