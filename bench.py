@@ -62,6 +62,8 @@ def parse():
                          "radius 1.5 Lx, every column carries ice (diagnostics)")
     ap.add_argument("--no-input-exchange", action="store_true",
                     help="skip the per-step width-2 exchange of the inputs' ghosts (N > 1)")
+    ap.add_argument("--cost-ratio", type=float, default=2.7,
+                    help="cost of an icy column relative to an ice-free one, for the balanced ownership ranges")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of a CUDA graph")
     return ap.parse_args()
 
@@ -372,7 +374,9 @@ def main():
         g0 = G.Grid(M, M, Mz, Lh, Lh, 4000.0)
         icy = S.dome_2d(g0, capi.default_config(), torch.as_tensor(g0.x, dtype=torch.float64),
                         torch.as_tensor(g0.y, dtype=torch.float64))["thickness"] > 0
-        cost = np.where(icy.numpy(), 2.7, 1.0)  # cost of an icy column relative to an ice-free one
+        # cost of an icy column relative to an ice-free one (measured at 8 ranks: the ranges this gives are
+        # within 2 % of the point where the slowest central and the slowest outer rank take the same time)
+        cost = np.where(icy.numpy(), args.cost_ratio, 1.0)
         procs_x, procs_y = G.balanced_ownership_ranges(cost, Nx_, Ny_)
         del icy, cost
     uniform_x, uniform_y = G.ownership_ranges(M, Nx_), G.ownership_ranges(M, Ny_)
@@ -417,6 +421,8 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)), out
 
+    per_rank_kernel_ms = []
+
     def kernel_only_ms(Rk, steps, fullk=True):
         """CUDA events around the fused kernel alone, on its own stream (ungraphed launches of the same step)."""
         Rk.check(lib.siafd_b200_kernel_timing(Rk.sia.handle, 1))
@@ -427,7 +433,12 @@ def main():
         nk = C.c_int(0)
         kms = lib.siafd_b200_kernel_time_ms(Rk.sia.handle, C.byref(nk))
         Rk.check(lib.siafd_b200_kernel_timing(Rk.sia.handle, 0))
-        return max_over_ranks(kms / max(nk.value, 1))
+        mine = kms / max(nk.value, 1)
+        if multi:
+            t = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(N)]
+            dist.all_gather(t, torch.tensor([mine], dtype=torch.float64, device=dev))
+            per_rank_kernel_ms[:] = [float(x.item()) for x in t]
+        return max_over_ranks(mine)
 
     peak, peak_src = measured_peak()
 
@@ -449,6 +460,7 @@ def main():
     for _ in range(W):
         R.step(full)
     k_avg_ms = kernel_only_ms(R, min(args.steps, 10), full)
+    kernel_ms_by_rank = list(per_rank_kernel_ms)
     R.step(full)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = sia.launch_count()
@@ -478,7 +490,7 @@ def main():
                 "traffic": None, "dram_frac": None, "kernel": "k_sia_slab", "kernel_ms": k_avg_ms,
                 "peak_source": peak_src, "algorithmic_bytes_per_column": B, "columns_per_launch": patch.xm * patch.ym,
                 "whole_step_frac": B * cols_total / N / (ms / args.steps / 1e3) / 1e9 / peak,
-                "step_minus_kernel_ms": ms / args.steps - k_avg_ms}
+                "step_minus_kernel_ms": ms / args.steps - k_avg_ms, "kernel_ms_by_rank": kernel_ms_by_rank or None}
     tr = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tr) and N == 1 and full and args.regime == "dome":
         try:  # quoted only if it was captured (ncu --set full) on this very kernel source

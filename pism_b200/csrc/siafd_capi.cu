@@ -127,7 +127,8 @@ Fields fields_of(siafd_b200_handle *h) {
   F.E = D(SIAFD_B200_F_ENTHALPY);
   F.age = D(SIAFD_B200_F_AGE);
   F.sliding = D(SIAFD_B200_F_SLIDING);
-  F.topgsmooth = D(SIAFD_B200_F_TOPGSMOOTH);
+  // smoother off: topgsmooth is a ghosted copy of the bed (sia/BedSmoother.cc:101-109) -- read the bed itself
+  F.topgsmooth = (!(h->cfg.smoother_range > 0.0) && !h->smoother_set) ? D(SIAFD_B200_F_BED) : D(SIAFD_B200_F_TOPGSMOOTH);
   F.maxtl = D(SIAFD_B200_F_MAXTL);
   F.C2 = D(SIAFD_B200_F_C2);
   F.C3 = D(SIAFD_B200_F_C3);
@@ -566,7 +567,11 @@ int siafd_b200_download(siafd_b200_handle *h, int f, double *host) {
   int st = ensure(h, f);
   if (st) return st;
   const size_t bytes = (size_t)siafd_b200_field_size(h, f) * sizeof(double);
-  CU(h, cudaMemcpyAsync(host, h->buf[f], bytes, cudaMemcpyDeviceToHost, h->stream));
+  const void *src = h->buf[f];
+  if (f == SIAFD_B200_F_TOPGSMOOTH && !(h->cfg.smoother_range > 0.0) && !h->smoother_set && h->buf[SIAFD_B200_F_BED]) {
+    src = h->buf[SIAFD_B200_F_BED]; // smoother off: topgsmooth IS the bed (sia/BedSmoother.cc:101-109)
+  }
+  CU(h, cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   h->bytes_d2h += (int64_t)bytes;
   return SIAFD_B200_OK;
@@ -879,7 +884,7 @@ int siafd_b200_compute_gradient(siafd_b200_handle *h) {
 
 // checks, scratch fields and the 2D preparation of SIAFD::compute_diffusivity (SIAFD.cc:555-582)
 extern "C++" {
-int siafd_host::flux_velocity_prepare(siafd_b200_handle *h, int full_update, double current_time) {
+int siafd_host::flux_velocity_prepare(siafd_b200_handle *h, int full_update, double current_time, bool prep2d_done) {
   CU(h, cudaSetDevice(h->device));
   const siafd_b200_config &c = h->cfg;
   const int need[] = {SIAFD_B200_F_SURFACE,    SIAFD_B200_F_THICKNESS, SIAFD_B200_F_MASK,  SIAFD_B200_F_BED,
@@ -905,17 +910,13 @@ int siafd_host::flux_velocity_prepare(siafd_b200_handle *h, int full_update, dou
                 "bed smoother is on (range %.1f m): call siafd_b200_preprocess_bed or _set_smoothed_bed first",
                 c.smoother_range);
   }
-  if (!(c.smoother_range > 0.0) && !h->smoother_set) {
-    // sia/BedSmoother.cc:101-109: topgsmooth = ghosted copy of the bed; maxtl, C2..C4 stay zero
-    const size_t bytes = (size_t)siafd_b200_field_size(h, SIAFD_B200_F_BED) * sizeof(double);
-    CU(h, cudaMemcpyAsync(h->buf[SIAFD_B200_F_TOPGSMOOTH], h->buf[SIAFD_B200_F_BED], bytes, cudaMemcpyDeviceToDevice,
-                          h->stream));
-  }
+  // (smoother off: sia/BedSmoother.cc:101-109, topgsmooth = ghosted copy of the bed: fields_of() hands the bed to the
+  // kernels in its place; maxtl, C2..C4 stay zero)
   h->P.current_time = current_time;
   const Fields F = fields_of(h);
   CU(h, cudaMemsetAsync(h->d_dmax, 0, sizeof(unsigned long long), h->stream));
   CU(h, cudaMemsetAsync(h->d_hdc, 0, sizeof(int), h->stream));
-  h->launches += launch_prep2d(h->P, F, h->stream); // sia/SIAFD.cc:580-582
+  if (!prep2d_done) h->launches += launch_prep2d(h->P, F, h->stream); // sia/SIAFD.cc:580-582
   CU(h, cudaGetLastError());
   return SIAFD_B200_OK;
 }
@@ -1289,10 +1290,9 @@ static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E
         if (l0[r] <= h0[r]) lo = std::min(lo, l0[r]), hi = std::max(hi, h0[r]);
       }
       if (hi >= lo) {
-        lo = lo - wg - margin, hi = hi - wg + margin; // owned-column indices
-        if (lo < margin || hi > xm - 1 - margin) {
-          lo = -1, hi = xm; // ice near the edge of the patch: whole rows
-        }
+        // owned-column indices, clipped to the patch (the enthalpy upload widens a range that touches an edge of the
+        // patch to the ghost columns beyond it; the ghost columns of u, v come down separately)
+        lo = std::max(lo - wg - margin, 0), hi = std::min(hi - wg + margin, xm - 1);
         E.lo[j] = lo, E.hi[j] = hi;
       }
     }
@@ -1500,10 +1500,12 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
                             cudaMemcpyHostToDevice, h->s_up));
       h->bytes_h2d += (int64_t)(r1 - r0) * rowE * 8;
     } else {
-      h->bytes_h2d += (int64_t)(hi - lo + 1) * c.Mz * 8 * (r1 - r0);
-      const long off = r0 * rowE + (long)(lo + we) * c.Mz;
+      // local columns [c0, c1) of the enthalpy array; a patch: a range that touches an edge takes the ghost columns too
+      const int c0 = (patch && lo <= 0) ? 0 : lo + we, c1 = (patch && hi >= c.xm - 1) ? c.xm + 2 * we : hi + 1 + we;
+      h->bytes_h2d += (int64_t)(c1 - c0) * c.Mz * 8 * (r1 - r0);
+      const long off = r0 * rowE + (long)c0 * c.Mz;
       CU(h, cudaMemcpy2DAsync(E_dev + off, (size_t)rowE * sizeof(double), in->enthalpy + off, (size_t)rowE * sizeof(double),
-                              (size_t)(hi - lo + 1) * c.Mz * sizeof(double), (size_t)(r1 - r0), cudaMemcpyHostToDevice,
+                              (size_t)(c1 - c0) * c.Mz * sizeof(double), (size_t)(r1 - r0), cudaMemcpyHostToDevice,
                               h->s_up));
     }
     return SIAFD_B200_OK;

@@ -624,9 +624,11 @@ int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double c
     const Fields F = fields_of(h);
     PeerPush PPg;
     comm_make_push(h, SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y, h->cfg.w_stag, 1, PPg);
-    h->launches += launch_gradient(h->P, F, h->stream, haseloff ? &PPg : nullptr); // SIAFD.cc:137, :498-499
+    // gradient (SIAFD.cc:137, ghost update :498-499 fused) and, for haseloff, thk_smooth / theta (:580-582) in one pass
+    h->P.current_time = current_time;
+    h->launches += launch_gradient(h->P, F, h->stream, haseloff ? &PPg : nullptr, haseloff);
     CU(h, cudaGetLastError());
-    if ((st = flux_velocity_prepare(h, full_update, current_time))) return st; // thk_smooth, theta: SIAFD.cc:580-582
+    if ((st = flux_velocity_prepare(h, full_update, current_time, haseloff))) return st;
     if (haseloff && multi) h->launches += launch_comm_sync(C.d_peers, 2, h->stream);
     if (forked) CU(h, cudaStreamWaitEvent(h->stream, C.ev_join, 0));
     PeerPush PPu;

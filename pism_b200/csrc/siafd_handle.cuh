@@ -99,7 +99,7 @@ siafd::Fields fields_of(siafd_b200_handle *h);
 int status_from_bits(unsigned bits);
 int fetch_result(siafd_b200_handle *h);
 // checks, scratch fields and the 2D preparation of SIAFD::compute_diffusivity (SIAFD.cc:555-582); the fused kernel
-int flux_velocity_prepare(siafd_b200_handle *h, int full_update, double current_time);
+int flux_velocity_prepare(siafd_b200_handle *h, int full_update, double current_time, bool prep2d_done = false);
 int flux_velocity_launch(siafd_b200_handle *h, int full_update, int seg0, int nseg, const siafd::PeerPush *push = nullptr);
 // siafd_comm.cu: fused-push table of two same-shaped fields (h_x / h_y, u / v) with ghost width W, strips of width w
 void comm_make_push(const siafd_b200_handle *h, int fa, int fb, int W, int w, siafd::PeerPush &PP);

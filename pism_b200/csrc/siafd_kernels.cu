@@ -26,12 +26,7 @@ namespace siafd {
 // ---------------------------------------------------------------------------------------------
 // k_prep2d: thk_smooth and theta on owned + wg ghosts (no communication, like the reference)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_prep2d(const __grid_constant__ DP P, const Fields F) {
-  const long n = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
-  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) {
-    return;
-  }
+__device__ __forceinline__ void prep2d_point(const DP &P, const Fields &F, const long q) {
   // BedSmoother::smoothed_thk, sia/BedSmoother.cc:300-322
   const double thk = F.H[q];
   double ts;
@@ -75,6 +70,15 @@ __global__ void k_prep2d(const __grid_constant__ DP P, const Fields F) {
     th = fmin(fmax(P.theta_min, th), 1.0); // clip(), util/pism_utilities.hh:91-93
   }
   F.theta[q] = th;
+}
+
+__global__ void k_prep2d(const __grid_constant__ DP P, const Fields F) {
+  const long n = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) {
+    return;
+  }
+  prep2d_point(P, F, q);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -189,14 +193,23 @@ __device__ __forceinline__ double inv_count(double W) {
 }
 // PUSH: the ghost update of sia/SIAFD.cc:498-499 fused in -- an owned point on the rim of the patch is also stored into
 // the neighbours' ghost cells (PeerPush, siafd_kernels.cuh)
-template <bool PUSH>
+// PREP: thk_smooth and theta of SIAFD::compute_diffusivity (sia/SIAFD.cc:580-582; k_prep2d) in the same pass: the threads
+// then cover owned + wg ghosts, and those on owned + 1 go on to the gradient.
+template <bool PUSH, bool PREP>
 __global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
-  const int nx = P.xm + 2;
+  const int ring = PREP ? P.wg : 1;
+  const int nx = P.xm + 2 * ring;
   const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= (long)nx * (P.ym + 2)) {
+  if (q >= (long)nx * (P.ym + 2 * ring)) {
     return;
   }
-  const int i = P.xs - 1 + (int)(q % nx), j = P.ys - 1 + (int)(q / nx);
+  const int i = P.xs - ring + (int)(q % nx), j = P.ys - ring + (int)(q / nx);
+  if (PREP) {
+    prep2d_point(P, F, q); // (ring == wg: q is the point's index in a geometry-width array)
+    if (i < P.xs - 1 || i > P.xs + P.xm || j < P.ys - 1 || j > P.ys + P.ym) {
+      return;
+    }
+  }
   // the 3 x 3 cells around (i, j): c[b][a] = cell (i - 1 + a, j - 1 + b)
   double h[3][3];
   int M[3][3];
@@ -215,8 +228,7 @@ __global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, co
   const HasDirect y00 = haseloff_direct(h[1][1], h[2][1], M[1][1], M[2][1], P.dy, P.inv_dy); // h_y(i, j, 1), w_j(i, j)
   F.h_x[s + 0] = x00.g;
   F.h_y[s + 1] = y00.g;
-  F.w_i[idx2(P, i, j, P.wg)] = x00.w; // (kept: the reference leaves them in its work vectors)
-  F.w_j[idx2(P, i, j, P.wg)] = y00.w;
+  // (the weights w_i, w_j of the reference's work vectors are not stored: nothing reads them after this kernel)
   if (i < P.xs || i >= P.xs + P.xm || j < P.ys || j >= P.ys + P.ym) {
     return; // the second loop runs over owned points only; its ghosts come from the exchange (:498-499)
   }
@@ -490,7 +502,7 @@ int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s) {
   return 1;
 }
 
-int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push) {
+int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push, bool with_prep2d) {
   const long n1 = (long)(P.xm + 2) * (P.ym + 2);
   const long n2 = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
   switch (P.grad) { // sia/SIAFD.cc:197-220
@@ -502,10 +514,16 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush
     k_grad_eta<<<nblk(n1, 256), 256, 0, s>>>(P, F);
     return 2;
   default:
-    if (push != nullptr && push->on) {
-      k_grad_haseloff<true><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);
+    if (with_prep2d) {
+      if (push != nullptr && push->on) {
+        k_grad_haseloff<true, true><<<nblk(n2, 256), 256, 0, s>>>(P, F, *push);
+      } else {
+        k_grad_haseloff<false, true><<<nblk(n2, 256), 256, 0, s>>>(P, F, PeerPush());
+      }
+    } else if (push != nullptr && push->on) {
+      k_grad_haseloff<true, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);
     } else {
-      k_grad_haseloff<false><<<nblk(n1, 256), 256, 0, s>>>(P, F, PeerPush());
+      k_grad_haseloff<false, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, PeerPush());
     }
     return 1;
   }

@@ -31,7 +31,8 @@ struct Tuning {
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
 int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
-int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push = nullptr);
+// with_prep2d (haseloff only): thk_smooth / theta of launch_prep2d in the same pass; returns the launches made
+int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push = nullptr, bool with_prep2d = false);
 // one launch covers the row segments [seg0, seg0 + nseg) of the extended patch (nseg < 0: all from seg0)
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz, int seg0,
                 int nseg, cudaStream_t s, const PeerPush *push = nullptr);
