@@ -62,8 +62,9 @@ def parse():
                          "radius 1.5 Lx, every column carries ice (diagnostics)")
     ap.add_argument("--no-input-exchange", action="store_true",
                     help="skip the per-step width-2 exchange of the inputs' ghosts (N > 1)")
-    ap.add_argument("--cost-ratio", type=float, default=2.7,
-                    help="cost of an icy column relative to an ice-free one, for the balanced ownership ranges")
+    ap.add_argument("--cost-ratio", type=float, default=0.0,
+                    help="constant cost of an icy column relative to an ice-free one for the balanced ownership ranges "
+                         "(0: the thickness-proportional model)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of a CUDA graph")
     return ap.parse_args()
 
@@ -372,13 +373,19 @@ def main():
     if multi and not args.uniform and procs_x is None and procs_y is None and args.regime == "dome":
         Lh = (M - 1) / 2.0 * 5000.0
         g0 = G.Grid(M, M, Mz, Lh, Lh, 4000.0)
-        icy = S.dome_2d(g0, capi.default_config(), torch.as_tensor(g0.x, dtype=torch.float64),
-                        torch.as_tensor(g0.y, dtype=torch.float64))["thickness"] > 0
-        # cost of an icy column relative to an ice-free one (measured at 8 ranks: the ranges this gives are
-        # within 2 % of the point where the slowest central and the slowest outer rank take the same time)
-        cost = np.where(icy.numpy(), args.cost_ratio, 1.0)
+        H0 = S.dome_2d(g0, capi.default_config(), torch.as_tensor(g0.x, dtype=torch.float64),
+                       torch.as_tensor(g0.y, dtype=torch.float64))["thickness"].numpy()
+        # cost of a column relative to an ice-free one: the fused kernel streams ice-free columns at
+        # 3.65 G/s and integrates the dome's icy ones at 1.18 G/s on average (3.1 x), in proportion to the levels below
+        # the surface.  Measured at 8 ranks (profiles/): these ranges bring the central and the outer ranks of PISM's
+        # 2 x 4 grid to within 2 % of each other; a constant ratio (--cost-ratio 2.7: round 1) leaves the central ones
+        # 28 % slower.
+        if args.cost_ratio > 0:
+            cost = np.where(H0 > 0, args.cost_ratio, 1.0)
+        else:
+            cost = np.where(H0 > 0, 1.0 + 2.1 * H0 / H0[H0 > 0].mean(), 1.0)
         procs_x, procs_y = G.balanced_ownership_ranges(cost, Nx_, Ny_)
-        del icy, cost
+        del H0, cost
     uniform_x, uniform_y = G.ownership_ranges(M, Nx_), G.ownership_ranges(M, Ny_)
     if procs_x is not None or procs_y is not None:
         ranges_note = "PISM DMDA, -procs_x %s -procs_y %s" % (",".join(map(str, procs_x or uniform_x)),

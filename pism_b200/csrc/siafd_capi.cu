@@ -147,6 +147,8 @@ Fields fields_of(siafd_b200_handle *h) {
   F.err = h->d_err;
   F.dmax = h->d_dmax;
   F.hdc = h->d_hdc;
+  F.segw = h->d_segw;
+  F.segdone = h->d_segdone;
   return F;
 }
 
@@ -412,6 +414,8 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.pipeline_band = 1; // 4096^2, segments per band 1 / 2 / 4 / 8: 368 / 375 / 386 / 411 ms (tools/e2e_sweep.py)
   h->tuning.sparse_host = 1;
   h->tuning.graph_step = 1;
+  h->tuning.order_segments = 1;
+  if (const char *e = getenv("SIAFD_B200_ORDER")) h->tuning.order_segments = atoi(e);
   if (const char *e = getenv("SIAFD_B200_GRAPH")) h->tuning.graph_step = atoi(e);
   if (const char *e = getenv("SIAFD_B200_SPARSE")) h->tuning.sparse_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_FILL_THREADS")) h->fill_threads = std::max(1, atoi(e));
@@ -451,6 +455,10 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   CUC(cudaMalloc(&h->d_err, sizeof(unsigned)));
   CUC(cudaMalloc(&h->d_dmax, sizeof(unsigned long long)));
   CUC(cudaMalloc(&h->d_hdc, sizeof(int)));
+  CUC(cudaMalloc(&h->d_segw, 256 * sizeof(int)));
+  CUC(cudaMalloc(&h->d_segdone, sizeof(unsigned)));
+  CUC(cudaMemset(h->d_segw, 0, 256 * sizeof(int)));
+  CUC(cudaMemset(h->d_segdone, 0, sizeof(unsigned)));
   CUC(cudaMemset(h->d_err, 0, sizeof(unsigned)));
   CUC(cudaMemset(h->d_dmax, 0, sizeof(unsigned long long)));
   CUC(cudaMemset(h->d_hdc, 0, sizeof(int)));
@@ -478,6 +486,8 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   cudaFree(h->d_err);
   cudaFree(h->d_dmax);
   cudaFree(h->d_hdc);
+  cudaFree(h->d_segw);
+  cudaFree(h->d_segdone);
   cudaFree(h->d_cfl);
   if (h->h_cfl) cudaFreeHost(h->h_cfl);
   cudaFree(h->d_global_bed);

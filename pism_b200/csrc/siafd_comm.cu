@@ -624,8 +624,15 @@ int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double c
     const Fields F = fields_of(h);
     PeerPush PPg;
     comm_make_push(h, SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y, h->cfg.w_stag, 1, PPg);
-    // gradient (SIAFD.cc:137, ghost update :498-499 fused) and, for haseloff, thk_smooth / theta (:580-582) in one pass
+    // gradient (SIAFD.cc:137, ghost update :498-499 fused) and, for haseloff, thk_smooth / theta (:580-582) in one pass;
+    // the pass also weighs the fused kernel's row segments, and its last CTA sorts them, heaviest first
     h->P.current_time = current_time;
+    {
+      const int nseg_all = slab_segments(h->P, h->tuning);
+      const bool order = h->tuning.order_segments && nseg_all <= 128 && nseg_all > 1;
+      h->P.seg_rows = slab_rows_per_segment(h->tuning), h->P.seg_n = order ? nseg_all : 0;
+      if (order) CU(h, cudaMemsetAsync(h->d_segw, 0, 128 * sizeof(int), h->stream));
+    }
     h->launches += launch_gradient(h->P, F, h->stream, haseloff ? &PPg : nullptr, haseloff);
     CU(h, cudaGetLastError());
     if ((st = flux_velocity_prepare(h, full_update, current_time, haseloff))) return st;
@@ -639,7 +646,9 @@ int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double c
       if (timed) CU(h, cudaEventRecord(h->ev_start[h->ev_count], h->stream));
       const int n = launch_slab(h->P, F, full_update != 0, T, (long)siafd_b200_field_size(h, SIAFD_B200_F_ENTHALPY),
                                 (long)siafd_b200_field_size(h, SIAFD_B200_F_THK_SMOOTH), h->inv_dz, 0, -1, h->stream,
-                                (full_update && !getenv("SIAFD_B200_NOPUSH")) ? &PPu : nullptr);
+                                (full_update && !getenv("SIAFD_B200_NOPUSH")) ? &PPu : nullptr,
+                                h->P.seg_n > 0 ? h->d_segw + 128 : nullptr);
+      h->P.seg_n = 0; // (only this entry point sorts: the split calls and the banded host pipeline keep the plain order)
       if (timed) {
         CU(h, cudaEventRecord(h->ev_stop[h->ev_count], h->stream));
         h->ev_count += 1;

@@ -48,6 +48,9 @@ struct DP {
   // GeometryCalculator (util/Mask.hh:71-79)
   double gc_alpha, gc_icefree;
   int gc_dry, pad2;
+  // heaviest-first order of the fused kernel's row segments (siafd_slab.cu): rows per segment and number of segments
+  // the 2D pass weighs (0: off)
+  int seg_rows, seg_n;
 };
 
 // ---- local ghosted array indexing ([j][i][dof], util/IceModelVec_inline.hh:28-40) ----------

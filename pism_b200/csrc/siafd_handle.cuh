@@ -28,6 +28,8 @@ struct siafd_b200_handle {
   int vvel_kind = 0;       // 0: k_vvel_slab (shared memory, z sweep in registers); 1: k_vvel_march (lanes across z)
   int vvel_wz = 16;        // z ranges per column of k_vvel_slab
   int *d_hdc = nullptr;
+  int *d_segw = nullptr;          // [0, 128) weights of the fused kernel's row segments, [128, 256) their order
+  unsigned *d_segdone = nullptr;  // CTA counter of the 2D pass that sorts them
   // pinned host mirror of {err, hdc, dmax}
   struct Result {
     unsigned long long dmax;

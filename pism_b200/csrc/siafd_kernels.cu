@@ -26,7 +26,8 @@ namespace siafd {
 // ---------------------------------------------------------------------------------------------
 // k_prep2d: thk_smooth and theta on owned + wg ghosts (no communication, like the reference)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void prep2d_point(const DP &P, const Fields &F, const long q) {
+// returns the row segment of the fused kernel the point counts for (it holds ice), or -1
+__device__ __forceinline__ int prep2d_point(const DP &P, const Fields &F, const long q) {
   // BedSmoother::smoothed_thk, sia/BedSmoother.cc:300-322
   const double thk = F.H[q];
   double ts;
@@ -44,6 +45,11 @@ __device__ __forceinline__ void prep2d_point(const DP &P, const Fields &F, const
     ts = thk;
   }
   F.thk_smooth[q] = ts;
+  int seg = -1;
+  if (P.seg_n > 0 && ts > 0.0) {
+    const int j = (int)(q / (P.xm + 2 * P.wg)) - P.wg; // row relative to the first owned row
+    seg = min(max(j + 1, 0) / P.seg_rows, P.seg_n - 1);
+  }
 
   // BedSmoother::theta, sia/BedSmoother.cc:353-397
   double th;
@@ -70,15 +76,62 @@ __device__ __forceinline__ void prep2d_point(const DP &P, const Fields &F, const
     th = fmin(fmax(P.theta_min, th), 1.0); // clip(), util/pism_utilities.hh:91-93
   }
   F.theta[q] = th;
+  return seg;
+}
+
+// weight of the fused kernel's row segments = icy points per segment: counted per CTA in shared memory (a CTA's points
+// lie in a few consecutive rows), one global atomic per CTA and segment.  Called by every thread of the CTA.
+__device__ __forceinline__ void seg_weight_cta(const DP &P, const Fields &F, const int seg, const long q0) {
+  if (P.seg_n <= 0) return;
+  __shared__ int cnt[8];
+  const int j0 = (int)(q0 / (P.xm + 2 * P.wg)) - P.wg;
+  const int seg_lo = min(max(j0 + 1, 0) / P.seg_rows, P.seg_n - 1);
+  if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if (seg >= 0) {
+    const int d = seg - seg_lo;
+    if (d < 8) {
+      atomicAdd(&cnt[d], 1);
+    } else {
+      atomicAdd(F.segw + seg, 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && cnt[threadIdx.x] != 0) atomicAdd(F.segw + seg_lo + threadIdx.x, cnt[threadIdx.x]);
+  __syncthreads(); // (the counters are reused by the CTA's next batch of points)
+}
+
+// The last CTA of the 2D pass sorts the row segments of the fused kernel by weight, heaviest first (ties by index): the
+// expensive (icy) segments start first and the cheap ones fill the tail of the launch.
+__device__ __forceinline__ void seg_order_epilogue(const DP &P, const Fields &F) {
+  if (P.seg_n <= 0) return;
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    last = (atomicAdd(F.segdone, 1u) == gridDim.x - 1);
+    if (last) *F.segdone = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int s = threadIdx.x; s < P.seg_n; s += blockDim.x) {
+    const int ws = *(volatile int *)(F.segw + s);
+    int rank = 0;
+    for (int t = 0; t < P.seg_n; ++t) {
+      const int wt = *(volatile int *)(F.segw + t);
+      rank += (wt > ws) || (wt == ws && t < s);
+    }
+    F.segw[128 + rank] = s;
+  }
 }
 
 __global__ void k_prep2d(const __grid_constant__ DP P, const Fields F) {
   const long n = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
   const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) {
-    return;
-  }
-  prep2d_point(P, F, q);
+  const int seg = (q < n) ? prep2d_point(P, F, q) : -1;
+  seg_weight_cta(P, F, seg, (long)blockIdx.x * blockDim.x);
+  seg_order_epilogue(P, F);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -196,18 +249,18 @@ __device__ __forceinline__ double inv_count(double W) {
 // PREP: thk_smooth and theta of SIAFD::compute_diffusivity (sia/SIAFD.cc:580-582; k_prep2d) in the same pass: the threads
 // then cover owned + wg ghosts, and those on owned + 1 go on to the gradient.
 template <bool PUSH, bool PREP>
-__global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
+__device__ __forceinline__ int grad_haseloff_point(const DP &P, const Fields &F, const PeerPush &PP, const long q) {
   const int ring = PREP ? P.wg : 1;
   const int nx = P.xm + 2 * ring;
-  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int seg = -1;
   if (q >= (long)nx * (P.ym + 2 * ring)) {
-    return;
+    return seg;
   }
   const int i = P.xs - ring + (int)(q % nx), j = P.ys - ring + (int)(q / nx);
   if (PREP) {
-    prep2d_point(P, F, q); // (ring == wg: q is the point's index in a geometry-width array)
+    seg = prep2d_point(P, F, q); // (ring == wg: q is the point's index in a geometry-width array)
     if (i < P.xs - 1 || i > P.xs + P.xm || j < P.ys - 1 || j > P.ys + P.ym) {
-      return;
+      return seg;
     }
   }
   // the 3 x 3 cells around (i, j): c[b][a] = cell (i - 1 + a, j - 1 + b)
@@ -230,7 +283,7 @@ __global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, co
   F.h_y[s + 1] = y00.g;
   // (the weights w_i, w_j of the reference's work vectors are not stored: nothing reads them after this kernel)
   if (i < P.xs || i >= P.xs + P.xm || j < P.ys || j >= P.ys + P.ym) {
-    return; // the second loop runs over owned points only; its ghosts come from the exchange (:498-499)
+    return seg; // the second loop runs over owned points only; its ghosts come from the exchange (:498-499)
   }
   const bool icy = m_icy(M[1][1]);
   // neighbours of the second loop, each evaluated as the first loop evaluates it at its own point
@@ -281,6 +334,23 @@ __global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, co
       }
     }
   }
+  return seg;
+}
+
+template <bool PUSH, bool PREP>
+__global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
+  if (!PREP) {
+    grad_haseloff_point<PUSH, PREP>(P, F, PP, (long)blockIdx.x * blockDim.x + threadIdx.x);
+    return;
+  }
+  // PREP: a bounded grid strides over the points in batches of one CTA width (few CTAs: the sort below costs one
+  // atomic per CTA on a single counter)
+  const long n = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
+  for (long q0 = (long)blockIdx.x * blockDim.x; q0 < n; q0 += (long)gridDim.x * blockDim.x) {
+    const int seg = grad_haseloff_point<PUSH, PREP>(P, F, PP, q0 + threadIdx.x);
+    seg_weight_cta(P, F, seg, q0);
+  }
+  seg_order_epilogue(P, F);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -515,10 +585,11 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush
     return 2;
   default:
     if (with_prep2d) {
+      const unsigned nb = std::min(nblk(n2, 256), 148u * 16u);
       if (push != nullptr && push->on) {
-        k_grad_haseloff<true, true><<<nblk(n2, 256), 256, 0, s>>>(P, F, *push);
+        k_grad_haseloff<true, true><<<nb, 256, 0, s>>>(P, F, *push);
       } else {
-        k_grad_haseloff<false, true><<<nblk(n2, 256), 256, 0, s>>>(P, F, PeerPush());
+        k_grad_haseloff<false, true><<<nb, 256, 0, s>>>(P, F, PeerPush());
       }
     } else if (push != nullptr && push->on) {
       k_grad_haseloff<true, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);

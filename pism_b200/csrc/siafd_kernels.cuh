@@ -16,6 +16,8 @@ struct Fields {
   unsigned *err;             // error bits (EB_*)
   unsigned long long *dmax;  // bit pattern of max D (D >= 0, so unsigned order == double order)
   int *hdc;                  // high_diffusivity_counter
+  int *segw;                 // [0, 128): icy points per row segment; [128, 256): segments, heaviest first
+  unsigned *segdone;         // CTAs of the 2D pass that have finished (the last one sorts)
 };
 
 struct Tuning {
@@ -27,6 +29,7 @@ struct Tuning {
   int pipeline_band; // row segments per band of that pipeline
   int sparse_host;   // 1: that pipeline moves only the parts of the 3D arrays that are within 3 cells of ice
   int graph_step;    // 1: siafd_b200_update_decomposed replays a captured CUDA graph of the step
+  int order_segments; // 1: the fused kernel takes its row segments heaviest (most icy points) first: short tail
 };
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
@@ -34,8 +37,9 @@ int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
 // with_prep2d (haseloff only): thk_smooth / theta of launch_prep2d in the same pass; returns the launches made
 int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push = nullptr, bool with_prep2d = false);
 // one launch covers the row segments [seg0, seg0 + nseg) of the extended patch (nseg < 0: all from seg0)
+// seg_order: device array of nseg segment indices to take in blockIdx.y order (whole-patch launches only), or NULL
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz, int seg0,
-                int nseg, cudaStream_t s, const PeerPush *push = nullptr);
+                int nseg, cudaStream_t s, const PeerPush *push = nullptr, const int *seg_order = nullptr);
 int slab_rows_per_segment(const Tuning &T);
 int slab_segments(const DP &P, const Tuning &T);
 size_t slab_smem_need(const DP &P, bool full, bool bulk); // shared memory of the smallest configuration

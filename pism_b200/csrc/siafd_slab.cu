@@ -82,6 +82,7 @@ struct SlabArgs {
   double inv_dz; // (Mz - 1) / Lz if the levels are equally spaced, else 0
   int seg0;      // first row segment of this launch (a launch may cover a band of segments)
   int nseg;      // segments in this launch
+  const int *order; // segment to take for each blockIdx.y (heaviest first), or NULL: seg0 + blockIdx.y
 };
 
 // per-slot staging area of a row's 2D scalars (offsets in doubles)
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   const bool own_c = col_ok && (c >= 1 || strip == 0); // this strip writes D, Q of the column
   const int ncolE = min(NC + 1, ilast + 2 - ca);            // enthalpy / thk_smooth columns ca .. ca + ncolE - 1
   const int ncolS = ncolE - 1;                              // valid lane columns
-  const int seg = (int)blockIdx.y + A.seg0;
+  const int seg = (A.order != nullptr) ? A.order[blockIdx.y] : (int)blockIdx.y + A.seg0;
   const int ra = (P.ys - 1) + seg * A.RS;
   const int rb = min(ra + A.RS, P.ys + P.ym + 1);
   const int r0 = (FULL && seg > 0) ? ra - 1 : ra; // warm-up row: I1 of the row below the segment
@@ -938,11 +939,12 @@ int slab_segments(const DP &P, const Tuning &T) {
 }
 
 int launch_slab(const DP &P, const Fields &F, bool full, const Tuning &T, long nE, long n2, double inv_dz, int seg0,
-                int nseg, cudaStream_t s, const PeerPush *push) {
+                int nseg, cudaStream_t s, const PeerPush *push, const int *seg_order) {
   SlabArgs A;
   A.RS = slab_rows_per_segment(T); // the row flags of a CTA live in a 96-bit word
   A.seg0 = seg0;
   A.nseg = nseg < 0 ? slab_segments(P, T) - seg0 : nseg;
+  A.order = (seg0 == 0 && A.nseg == slab_segments(P, T)) ? seg_order : nullptr;
   A.use_bulk = (T.use_bulk_copy && (P.Mz & 1)) ? 1 : 0; // even Mz: padded columns, 8-byte cp.async
   A.skip_rows = T.skip_ice_free;
   A.nE = nE;
