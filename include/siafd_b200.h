@@ -263,9 +263,11 @@ int siafd_b200_halo_wait(siafd_b200_handle *h, int phase);
  *     (periodic in x and y); the decomposition must be a tensor product of 1D ranges, as PISM's is (IceGrid.cc:489-499).
  *     The prefix must be unique to this communicator; the files are removed by siafd_b200_destroy.
  *   comm_init_local: the same for `size` handles of ONE process (any devices with peer access; one device for tests).
- *   comm_exchange: update_ghosts of 1..6 fields at once, ONE launch: the eight strips of every field are stored straight
- *     into the neighbours' ghost cells (BOX corners included), the last CTA raises the neighbours' arrival counters and
- *     waits for this rank's own.  Stream-ordered, no host synchronisation.  Collective: all ranks make the same calls.
+ *   comm_exchange: update_ghosts of 1..6 fields at once: a "ready to receive" round (one single-CTA launch: a neighbour
+ *     stores into this rank's ghost cells only after everything this rank enqueued before the call has run, e.g. an
+ *     upload that rewrote the whole array), then ONE launch that stores the eight strips of every field straight into the
+ *     neighbours' ghost cells (BOX corners included); its last CTA raises the neighbours' arrival counters and waits for
+ *     this rank's own.  Stream-ordered, no host synchronisation.  Collective: all ranks make the same calls.
  *   comm_allreduce: max (op 0) / min (1) / sum in rank order (2) of 1..8 doubles over all ranks, through the pads;
  *     values in / out on the host; synchronises the stream. */
 int siafd_b200_comm_init(siafd_b200_handle *h, int rank, int size, const char *rendezvous_prefix, double timeout_seconds);
@@ -282,7 +284,11 @@ int siafd_b200_comm_allreduce(siafd_b200_handle *h, int op, int n, double *value
  * neighbours' u, v and reduces {D_max, error bits, high-diffusivity counter} over ALL ranks (:748-750) into pinned host
  * memory.  4-6 launches, captured once as a CUDA graph and replayed.  Asynchronous; siafd_b200_finish waits and returns
  * the status, which is the same on every rank (ParallelSection), as are siafd_b200_max_diffusivity and
- * _high_diffusivity_count afterwards.  Works with a communicator of one rank (periodic self-wrap). */
+ * _high_diffusivity_count afterwards.  Works with a communicator of one rank (periodic self-wrap).
+ * exchange_inputs = 1 has no "ready to receive" round (the step stays 4-6 launches): between two updates the caller must
+ * change the input fields through their OWNED cells only (kernels of its own, or siafd_b200_upload with ghosts_valid
+ * host arrays followed by exchange_inputs = 0) -- a neighbour that is already in its next update may be storing into
+ * this rank's ghost cells. */
 int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double current_time, int exchange_inputs);
 
 /* BedSmoother::preprocess_bed on the GLOBAL bed (Mx*My doubles, [j][i], no ghosts; host
@@ -378,6 +384,11 @@ int siafd_b200_geometry_compute(siafd_b200_handle *h, int64_t n, const double *s
 /* FlowLaw::flow for n points on device (rheology/FlowLaw.cc:97-105); known-answer tests. */
 int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev, const double *enthalpy_dev,
                       const double *pressure_dev, const double *grainsize_dev, double *result_dev);
+
+/* The same for HOST arrays (staged through the device): SSB_Modifier::flow_law()->flow(...) for host-side diagnostics
+ * (IceCompModel::reportErrors, verification/iceCompModel.cc:642).  grainsize may be NULL (the configured constant). */
+int siafd_b200_flow_host(siafd_b200_handle *h, int64_t n, const double *stress, const double *enthalpy,
+                         const double *pressure, const double *grainsize, double *result);
 
 /* Kernel tuning knobs, for benchmarking: rows_per_cta > 0 sets the row-segment length one CTA
  * marches over (0 keeps it); use_bulk_copy / skip_ice_free_rows: 0 or 1 sets, -1 keeps. */

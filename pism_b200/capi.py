@@ -118,6 +118,7 @@ def _load():
         "siafd_b200_update": (C.c_int, [vp, C.POINTER(Inputs), C.POINTER(Outputs), C.c_int]),
         "siafd_b200_geometry_compute": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
         "siafd_b200_flow_n": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
+        "siafd_b200_flow_host": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
         "siafd_b200_set_tuning": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "siafd_b200_launch_count": (i64, [vp]),
         "siafd_b200_transfer_bytes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),

@@ -299,9 +299,13 @@ int fetch_result(siafd_b200_handle *h) {
   }
   h->comm.result_from_comm = false;
   if (h->result_pending) {
-    CU(h, cudaMemcpyAsync(&h->h_res->dmax, h->d_dmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    // (several ranks: D_max and the counter of the last update stay the reduced, global ones; the device copies are
+    // this rank's own.  Only the error bits a later call raised are picked up here.)
+    if (!(h->comm.active && h->comm.size > 1)) {
+      CU(h, cudaMemcpyAsync(&h->h_res->dmax, h->d_dmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaMemcpyAsync(&h->h_res->hdc, h->d_hdc, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
     CU(h, cudaMemcpyAsync(&h->h_res->err, h->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(&h->h_res->hdc, h->d_hdc, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     // error bits are sticky on the device until they have been read: an error raised by a call that follows an
     // update (ensure_consistency, cfl) is reported by the next finish, not erased by the next update
     CU(h, cudaMemsetAsync(h->d_err, 0, sizeof(unsigned), h->stream));
@@ -1733,6 +1737,30 @@ int siafd_b200_flow_n(siafd_b200_handle *h, int64_t n, const double *stress_dev,
   h->launches += k;
   CU(h, cudaGetLastError());
   CU(h, cudaStreamSynchronize(h->stream));
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_flow_host(siafd_b200_handle *h, int64_t n, const double *stress, const double *enthalpy,
+                         const double *pressure, const double *grainsize, double *result) {
+  if (!h) return null_handle();
+  if (n < 1 || !stress || !enthalpy || !pressure || !result) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "flow_host: null argument");
+  CU(h, cudaSetDevice(h->device));
+  double *d = nullptr;
+  CU(h, cudaMalloc(&d, (size_t)n * 5 * sizeof(double)));
+  std::vector<double> gs((size_t)n, h->cfg.grain_size);
+  if (grainsize) gs.assign(grainsize, grainsize + n);
+  const double *src[4] = {stress, enthalpy, pressure, gs.data()};
+  cudaError_t e = cudaSuccess;
+  for (int q = 0; q < 4 && e == cudaSuccess; ++q) {
+    e = cudaMemcpyAsync(d + (size_t)q * n, src[q], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  }
+  if (e == cudaSuccess) {
+    h->launches += launch_flow_n(h->P, (long)n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, h->stream);
+    e = cudaMemcpyAsync(result, d + 4 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(h, SIAFD_B200_ERR_CUDA, "flow_host: %s", cudaGetErrorString(e));
   return SIAFD_B200_OK;
 }
 

@@ -333,6 +333,20 @@ int finish_setup(siafd_b200_handle *h, int rank, const std::vector<RankInfo> &R,
     CU(h, cudaMalloc(&C.d_red, 8 * sizeof(double)));
     CU(h, cudaMallocHost(&C.h_red, 8 * sizeof(double)));
   }
+  // everything the host-buffer pipeline (siafd_b200_update with host arrays) creates lazily: now, so that no rank makes
+  // a (possibly device-synchronising) allocation while its neighbours already wait for it inside a kernel
+  if (!h->s_up) {
+    CU(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    CU(h, cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking));
+  }
+  {
+    const int nseg = slab_segments(h->P, h->tuning);
+    while ((int)h->ev_pipe.size() < 2 * nseg + 4) {
+      cudaEvent_t e;
+      CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev_pipe.push_back(e);
+    }
+  }
   if (!C.s_aux) {
     CU(h, cudaStreamCreateWithFlags(&C.s_aux, cudaStreamNonBlocking));
     CU(h, cudaEventCreateWithFlags(&C.ev_fork, cudaEventDisableTiming));
@@ -542,9 +556,13 @@ int siafd_b200_comm_exchange(siafd_b200_handle *h, int n, const int *fields, con
     int st = strips_to_peers(h, fields[q], widths[q], B);
     if (st) return st;
   }
-  // phases 4..7 in turn: every rank makes the same sequence of calls, so the rows match up
-  const int phase = 4 + (int)(h->comm.xchg_calls++ & 3);
-  h->launches += launch_halo_xchg(B, h->comm.d_peers, phase, 1, h->stream);
+  // Two rounds.  (1) "ready to receive": a neighbour may only store into this rank's ghost cells once everything this
+  // rank enqueued before this call has run (e.g. an upload that rewrote the whole array, ghost cells included): phase 7.
+  // (2) the strips, then "delivered": phases 4..6 in turn; every rank makes the same sequence of calls, so the rows of
+  // counters match up.
+  if (h->comm.size > 1) h->launches += launch_comm_sync(h->comm.d_peers, 7, h->stream);
+  const int phase = 4 + (int)(h->comm.xchg_calls++ % 3);
+  h->launches += launch_halo_xchg(B, h->comm.d_peers, phase, h->comm.size > 1 ? 1 : 0, h->stream);
   h->cfl3_fresh = false;
   CU(h, cudaGetLastError());
   return SIAFD_B200_OK;

@@ -36,8 +36,8 @@ public:
   }
   // :347-350 (the area-specific volume only changes with part_grid)
   void apply_flux_divergence(Geometry &geometry) const {
-    for (int j = 0; j < m_grid->ym(); ++j)
-      for (int i = 0; i < m_grid->xm(); ++i) geometry.ice_thickness(i, j) = geometry.ice_thickness(i, j) + 1.0 * m_thickness_change(i, j);
+    for (int j = m_grid->ys(); j < m_grid->ys() + m_grid->ym(); ++j)
+      for (int i = m_grid->xs(); i < m_grid->xs() + m_grid->xm(); ++i) geometry.ice_thickness(i, j) = geometry.ice_thickness(i, j) + 1.0 * m_thickness_change(i, j);
   }
   // :327-343
   void source_term_step(const Geometry &geometry, double dt, const IceModelVec2Int *thickness_bc_mask,
@@ -54,8 +54,8 @@ public:
   }
   // :360-390: the same order of additions as the non-negativity code
   void apply_mass_fluxes(Geometry &geometry) const {
-    for (int j = 0; j < m_grid->ym(); ++j)
-      for (int i = 0; i < m_grid->xm(); ++i) {
+    for (int j = m_grid->ys(); j < m_grid->ys() + m_grid->ym(); ++j)
+      for (int i = m_grid->xs(); i < m_grid->xs() + m_grid->xm(); ++i) {
         const double H_new = (geometry.ice_thickness(i, j) + m_effective_SMB(i, j)) + m_effective_BMB(i, j);
         geometry.ice_thickness(i, j) = H_new;
       }

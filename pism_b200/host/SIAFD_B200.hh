@@ -5,10 +5,19 @@
 // Nothing here computes physics: update() marshals raw pointers of the (PISM-owned, host) ghosted arrays to
 // siafd_b200_update and converts the status code back into an exception.
 //
-// This header is written against pism_mirror.hh so that it compiles and is tested without PETSc/MPI; over
-// PISM's own headers the class body is the same ("The shim a PISM maintainer adds").
+// The host types (IceGrid, IceModelVec*, Geometry, Inputs, Config, RuntimeError) come from SIAFD_B200_HOST_TYPES: PISM's
+// own headers in a PISM build ("The shim a PISM maintainer adds"), or the PETSc-free mirror the tests
+// compile against (tests/host_cpp/pism_mirror.hh, on the include path of tests/host_cpp/Makefile).
+//
+// Decomposed runs (one process per GPU, PISM's DMDA patches): pass a rendezvous prefix to the constructor; the class
+// then forms the library's communicator (siafd_b200_comm_init: no MPI / NCCL underneath), update() runs every ghost
+// update of the reference between the GPUs, max_diffusivity() / high_diffusivity_counter() are global, and an error
+// on any rank throws on every rank (ParallelSection, util/error_handling.cc:189-214).
 #pragma once
-#include "pism_mirror.hh"
+#ifndef SIAFD_B200_HOST_TYPES
+#define SIAFD_B200_HOST_TYPES "pism_mirror.hh"
+#endif
+#include SIAFD_B200_HOST_TYPES
 
 #include "../../include/siafd_b200.h"
 
@@ -20,7 +29,8 @@ class SSB_Modifier {
 public:
   explicit SSB_Modifier(IceGrid::ConstPtr g)
       : m_grid(g), m_config(g->config()), m_D_max(0.0), m_diffusive_flux(g, "diffusive_flux", WITH_GHOSTS, 1),
-        m_u(g, "uvel", WITH_GHOSTS, 1), m_v(g, "vvel", WITH_GHOSTS, 1) {} // SSB_Modifier.cc:30-58
+        m_u(g, "uvel", WITH_GHOSTS, 1), m_v(g, "vvel", WITH_GHOSTS, 1), m_strain_heating(g, "strainheat", WITHOUT_GHOSTS) {
+  } // SSB_Modifier.cc:30-58
   virtual ~SSB_Modifier() {}
   virtual void init() {}
   virtual void update(const IceModelVec2V &sliding_velocity, const Inputs &inputs, bool full_update) = 0;
@@ -28,22 +38,79 @@ public:
   virtual double max_diffusivity() const { return m_D_max; }
   const IceModelVec3 &velocity_u() const { return m_u; }
   const IceModelVec3 &velocity_v() const { return m_v; }
+  // SSB_Modifier.cc:81-87: the modifier's own strain heating field (SIAFD leaves it at zero: the SIA's strain heating is
+  // StressBalance::compute_volumetric_strain_heating, StressBalance_B200 below) and an empty report
+  const IceModelVec3 &volumetric_strain_heating() const { return m_strain_heating; }
+  virtual std::string stdout_report() const { return ""; }
 
 protected:
   IceGrid::ConstPtr m_grid;
   Config::Ptr m_config;
   double m_D_max;
   IceModelVec2Stag m_diffusive_flux;
-  IceModelVec3 m_u, m_v;
+  IceModelVec3 m_u, m_v, m_strain_heating;
+};
+
+} // namespace stressbalance
+
+// rheology::FlowLaw as SSB_Modifier::flow_law() hands it out (rheology/FlowLaw.hh:70-116; used by
+// IceCompModel::reportErrors, iceCompModel.cc:642): name, exponent, enhancement factor and flow(), which evaluates the
+// library's own device implementation (siafd_b200_flow_host), so that host-side diagnostics see the same law
+namespace rheology {
+class FlowLaw_B200 {
+public:
+  FlowLaw_B200(siafd_b200_handle *h, const std::string &name, double n, double e) : m_h(h), m_name(name), m_n(n), m_e(e) {}
+  std::string name() const { return m_name; }
+  double exponent() const { return m_n; }
+  double enhancement_factor() const { return m_e; }
+  // FlowLaw::flow(stress, enthalpy, pressure, grainsize), FlowLaw.cc:97-105
+  double flow(double stress, double enthalpy, double pressure, double grainsize) const {
+    double result = 0.0;
+    const int status = siafd_b200_flow_host(m_h, 1, &stress, &enthalpy, &pressure, &grainsize, &result);
+    if (status != SIAFD_B200_OK) throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(m_h));
+    return result;
+  }
+
+private:
+  siafd_b200_handle *m_h;
+  std::string m_name;
+  double m_n, m_e;
+};
+} // namespace rheology
+
+namespace stressbalance {
+
+// BedSmoother as SIAFD::bed_smoother() hands it out (sia/BedSmoother.hh:70-110): the smoothed bed and the fields of the
+// last update, read back from the device on demand
+class BedSmoother_B200 {
+public:
+  BedSmoother_B200(IceGrid::ConstPtr g, siafd_b200_handle *h, int width)
+      : m_h(h), m_topgsmooth(g, "topgsmooth", WITH_GHOSTS, width), m_theta(g, "theta", WITH_GHOSTS, width),
+        m_thk_smooth(g, "thksmooth", WITH_GHOSTS, width) {}
+  const IceModelVec2S &smoothed_bed() const { return fetch(SIAFD_B200_F_TOPGSMOOTH, m_topgsmooth); } // BedSmoother.cc:155
+  const IceModelVec2S &theta() const { return fetch(SIAFD_B200_F_THETA, m_theta); }                   // :351-404
+  const IceModelVec2S &smoothed_thk() const { return fetch(SIAFD_B200_F_THK_SMOOTH, m_thk_smooth); }  // :284-327
+
+private:
+  const IceModelVec2S &fetch(int field, IceModelVec2S &v) const {
+    const int status = siafd_b200_download(m_h, field, v.get_array());
+    if (status != SIAFD_B200_OK) throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(m_h));
+    return v;
+  }
+  siafd_b200_handle *m_h;
+  mutable IceModelVec2S m_topgsmooth, m_theta, m_thk_smooth;
 };
 
 class SIAFD_B200 : public SSB_Modifier {
 public:
   // SIAFD::SIAFD, SIAFD.cc:42-91: everything the reference's constructor, FlowLaw (rheology/FlowLaw.cc:33-58) and
   // EnthalpyConverter (util/EnthalpyConverter.cc:55-69) read from Config goes into siafd_b200_config
-  explicit SIAFD_B200(IceGrid::ConstPtr g, int device = -1)
+  // comm_prefix (decomposed runs, g->size() > 1): a path prefix unique to this run that every rank can write to (e.g.
+  // "/dev/shm/pism_<jobid>"), the rendezvous of siafd_b200_comm_init
+  explicit SIAFD_B200(IceGrid::ConstPtr g, int device = -1, const char *comm_prefix = NULL)
       : SSB_Modifier(g), m_handle(NULL), m_stencil_width((int)m_config->get_number("grid.max_stencil_width")),
-        m_h_x(g, "h_x", WITH_GHOSTS, 1), m_h_y(g, "h_y", WITH_GHOSTS, 1), m_D(g, "diffusivity", WITH_GHOSTS, 1) {
+        m_h_x(g, "h_x", WITH_GHOSTS, 1), m_h_y(g, "h_y", WITH_GHOSTS, 1), m_D(g, "diffusivity", WITH_GHOSTS, 1),
+        m_high_diffusivity_counter(0) {
     siafd_b200_config c;
     siafd_b200_default_config(&c);
     c.Mx = (int)g->Mx(), c.My = (int)g->My(), c.Mz = (int)g->Mz();
@@ -100,10 +167,24 @@ public:
     c.sea_water_density = cf.get_number("constants.sea_water.density");
     c.ice_free_thickness = cf.get_number("geometry.ice_free_thickness_standard");
     c.dry_simulation = cf.get_flag("ocean.always_grounded") ? 1 : 0;
-    const int status = siafd_b200_create(&c, device, &m_handle);
+    int status = siafd_b200_create(&c, device, &m_handle);
     if (status != SIAFD_B200_OK) {
       throw RuntimeError::formatted(status, "%s", siafd_b200_last_error(NULL));
     }
+    if (g->size() > 1) {
+      if (comm_prefix == NULL) {
+        siafd_b200_destroy(m_handle);
+        throw RuntimeError::formatted(SIAFD_B200_ERR_BAD_ARGUMENT, "SIAFD_B200 on %d ranks needs a rendezvous prefix", g->size());
+      }
+      status = siafd_b200_comm_init(m_handle, g->rank(), g->size(), comm_prefix, 120.0);
+      if (status != SIAFD_B200_OK) {
+        const std::string why = siafd_b200_last_error(m_handle);
+        siafd_b200_destroy(m_handle);
+        throw RuntimeError::formatted(status, "%s", why.c_str());
+      }
+    }
+    m_flow_law.reset(new rheology::FlowLaw_B200(m_handle, cf.get_string("stress_balance.sia.flow_law"), c.fl_n, c.fl_e));
+    m_bed_smoother.reset(new BedSmoother_B200(g, m_handle, m_stencil_width));
   }
   virtual ~SIAFD_B200() { siafd_b200_destroy(m_handle); }
 
@@ -112,10 +193,15 @@ public:
   // SIAFD::update, SIAFD.cc:122-155.  `full_update == false` leaves m_u, m_v untouched (:149-154).
   virtual void update(const IceModelVec2V &sliding_velocity, const Inputs &inputs, bool full_update) {
     const Geometry &geometry = *inputs.geometry;
-    if (inputs.new_bed_elevation) { // :130-134 (BedSmoother::preprocess_bed on the owned part of the bed)
+    if (inputs.new_bed_elevation) { // :130-134 (BedSmoother::preprocess_bed)
+      if (m_grid->size() > 1 && m_config->get_number("stress_balance.sia.bed_smoother.range") > 0.0) {
+        // the reference gathers the bed on rank 0 (BedSmoother.cc:157-267); a decomposed PISM build hands the five
+        // fields its own BedSmoother computed to siafd_b200_set_smoothed_bed instead
+        throw RuntimeError::formatted(SIAFD_B200_ERR_BAD_CONFIG, "bed smoother on several ranks: use siafd_b200_set_smoothed_bed");
+      }
       std::vector<double> bed((size_t)m_grid->Mx() * m_grid->My());
-      for (int j = 0; j < m_grid->ym(); ++j)
-        for (int i = 0; i < m_grid->xm(); ++i) bed[(size_t)j * m_grid->Mx() + i] = geometry.bed_elevation(i, j);
+      for (int j = m_grid->ys(); j < m_grid->ys() + m_grid->ym(); ++j)
+        for (int i = m_grid->xs(); i < m_grid->xs() + m_grid->xm(); ++i) bed[(size_t)j * m_grid->Mx() + i] = geometry.bed_elevation(i, j);
       check(siafd_b200_preprocess_bed(m_handle, bed.data()));
     }
     siafd_b200_inputs in;
@@ -134,13 +220,19 @@ public:
     out.flux = m_diffusive_flux.get_array();
     out.u = m_u.get_array(), out.v = m_v.get_array();
     out.memory_space = 0, out.pad = 0;
+    // on several ranks the status is the same everywhere (the library reduces the error flags with D_max), so that
+    // every rank throws, as under ParallelSection (util/error_handling.cc:189-214)
     check(siafd_b200_update(m_handle, &in, &out, full_update ? 1 : 0));
-    m_D_max = siafd_b200_max_diffusivity(m_handle); // :748 (one rank: the local max is the global max)
+    m_D_max = siafd_b200_max_diffusivity(m_handle);                           // :748 GlobalMax
+    m_high_diffusivity_counter = siafd_b200_high_diffusivity_count(m_handle); // :750 GlobalSum
   }
 
   const IceModelVec2Stag &surface_gradient_x() const { return m_h_x; } // SIAFD.cc:963-973
   const IceModelVec2Stag &surface_gradient_y() const { return m_h_y; }
   const IceModelVec2Stag &diffusivity() const { return m_D; }
+  const BedSmoother_B200 &bed_smoother() const { return *m_bed_smoother; }                       // SIAFD.cc:975-977
+  std::shared_ptr<const rheology::FlowLaw_B200> flow_law() const { return m_flow_law; }           // SSB_Modifier.cc:89-91
+  int high_diffusivity_counter() const { return m_high_diffusivity_counter; }                    // SIAFD.cc:750, summed over ranks
   siafd_b200_handle *handle() { return m_handle; }
 
   // rheology/FlowLawFactory.cc:71-87
@@ -169,6 +261,9 @@ private:
   siafd_b200_handle *m_handle;
   const int m_stencil_width;
   IceModelVec2Stag m_h_x, m_h_y, m_D;
+  int m_high_diffusivity_counter;
+  std::shared_ptr<rheology::FlowLaw_B200> m_flow_law;
+  std::shared_ptr<BedSmoother_B200> m_bed_smoother;
 };
 
 // stressbalance/timestepping.hh: what max_timestep_cfl_2d / _3d return
@@ -219,6 +314,12 @@ public:
       double out[8];
       status = siafd_b200_cfl(h, cf.get_number("time_stepping.maximum_time_step") * seconds_per_year_udunits(),
                               full_update ? 1 : 0, out);
+      if (status == SIAFD_B200_OK && m_grid->size() > 1) { // GlobalMin / GlobalMax, timestepping.cc:85-99, :145-151
+        double dts[2] = {out[0], out[4]}, vel[6] = {out[1], out[2], out[3], out[5], out[6], 0.0};
+        status = siafd_b200_comm_allreduce(h, 1, 2, dts);
+        if (status == SIAFD_B200_OK) status = siafd_b200_comm_allreduce(h, 0, 6, vel);
+        out[0] = dts[0], out[4] = dts[1], out[1] = vel[0], out[2] = vel[1], out[3] = vel[2], out[5] = vel[3], out[6] = vel[4];
+      }
       if (status == SIAFD_B200_OK) {
         if (full_update) m_cfl_3d.dt_max = out[0], m_cfl_3d.u_max = out[1], m_cfl_3d.v_max = out[2], m_cfl_3d.w_max = out[3];
         m_cfl_2d.dt_max = out[4], m_cfl_2d.u_max = out[5], m_cfl_2d.v_max = out[6], m_cfl_2d.w_max = 0.0;

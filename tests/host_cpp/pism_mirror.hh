@@ -10,11 +10,14 @@
 //   pism::RuntimeError                 src/util/error_handling.hh:47-68
 //   pism::Config (only the parameters on the SIAFD path, defaults of src/pism_config.cdl)
 // Under real PISM these headers are NOT used: INTEGRATION.md shows the same class over PISM's own types.
-// Single rank: update_ghosts() is the periodic self-wrap a one-process DMDA performs (IceGrid.cc:870-872).
+// TEST SCAFFOLDING (it lives with the tests): one rank: update_ghosts() is the periodic self-wrap a one-process DMDA
+// performs (IceGrid.cc:870-872); several ranks (one process each, PISM's decomposition IceGrid.cc:443-499): the driver
+// installs a ghost exchanger on the grid, which stands for DMLocalToLocal over MPI.
 #pragma once
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -140,9 +143,11 @@ public:
     return z;
   }
 
-  // one rank owning the whole (non-periodic, cell-corner registered) domain: dx = 2 Lx / (Mx - 1), IceGrid.cc:545-560
-  IceGrid(Config::Ptr config, unsigned int Mx, unsigned int My, double Lx, double Ly, const std::vector<double> &z)
-      : m_config(config), m_Mx(Mx), m_My(My), m_Lx(Lx), m_Ly(Ly), m_z(z), m_time(0.0) {
+  // cell-corner registered domain, dx = 2 Lx / (Mx - 1) (IceGrid.cc:545-560), this rank's patch of PISM's DMDA
+  // decomposition: processor grid from compute_nprocs (IceGrid.cc:443-484), ownership ranges :489-499, rank = px + Nx py
+  IceGrid(Config::Ptr config, unsigned int Mx, unsigned int My, double Lx, double Ly, const std::vector<double> &z,
+          int rank = 0, int size = 1)
+      : m_config(config), m_Mx(Mx), m_My(My), m_Lx(Lx), m_Ly(Ly), m_z(z), m_time(0.0), m_rank(rank), m_size(size) {
     m_dx = 2.0 * Lx / (Mx - 1);
     m_dy = 2.0 * Ly / (My - 1);
     m_x.resize(Mx);
@@ -151,15 +156,55 @@ public:
     for (unsigned int j = 0; j < My; ++j) m_y[j] = -Ly + j * m_dy;
     m_x[Mx - 1] = Lx;
     m_y[My - 1] = Ly;
+    unsigned int Nx = 1, Ny = 1;
+    compute_nprocs(Mx, My, (unsigned int)size, Nx, Ny);
+    const std::vector<unsigned int> px = ownership_ranges(Mx, Nx), py = ownership_ranges(My, Ny);
+    const unsigned int ix = (unsigned int)rank % Nx, iy = (unsigned int)rank / Nx;
+    m_xs = m_ys = 0;
+    for (unsigned int k = 0; k < ix; ++k) m_xs += (int)px[k];
+    for (unsigned int k = 0; k < iy; ++k) m_ys += (int)py[k];
+    m_xm = (int)px[ix], m_ym = (int)py[iy];
+  }
+  // IceGrid.cc:443-484
+  static void compute_nprocs(unsigned int Mx, unsigned int My, unsigned int size, unsigned int &Nx, unsigned int &Ny) {
+    if (My <= 0) throw RuntimeError::formatted(-1, "'My' is invalid.");
+    Nx = (unsigned int)(0.5 + sqrt(((double)Mx) * ((double)size) / ((double)My)));
+    Ny = 0;
+    if (Nx == 0) Nx = 1;
+    while (Nx > 0) {
+      Ny = size / Nx;
+      if (Nx * Ny == size) break;
+      Nx--;
+    }
+    if (Mx > My and Nx < Ny) { // Swap Nx and Ny
+      unsigned int tmp = Nx;
+      Nx = Ny;
+      Ny = tmp;
+    }
+    if ((Mx / Nx) < 2) throw RuntimeError::formatted(-1, "Can't split %d grid points into %d parts (X-direction).", Mx, (int)Nx);
+    if ((My / Ny) < 2) throw RuntimeError::formatted(-1, "Can't split %d grid points into %d parts (Y-direction).", My, (int)Ny);
+  }
+  // IceGrid.cc:489-499
+  static std::vector<unsigned int> ownership_ranges(unsigned int Mx, unsigned int Nx) {
+    std::vector<unsigned int> result(Nx);
+    for (unsigned int i = 0; i < Nx; i++) result[i] = Mx / Nx + ((Mx % Nx) > i);
+    return result;
   }
   Config::Ptr config() const { return m_config; }
   unsigned int Mx() const { return m_Mx; }
   unsigned int My() const { return m_My; }
   unsigned int Mz() const { return (unsigned int)m_z.size(); }
-  int xs() const { return 0; }
-  int ys() const { return 0; }
-  int xm() const { return (int)m_Mx; }
-  int ym() const { return (int)m_My; }
+  int xs() const { return m_xs; }
+  int ys() const { return m_ys; }
+  int xm() const { return m_xm; }
+  int ym() const { return m_ym; }
+  int rank() const { return m_rank; }
+  int size() const { return m_size; }
+  // DMLocalToLocal between ranks (util/iceModelVec.cc:630-643): installed by the driver of a multi-process run;
+  // gets the vector's name, local array, ghost width and dof
+  typedef std::function<void(const std::string &, double *, int, unsigned int)> GhostExchanger;
+  void set_ghost_exchanger(GhostExchanger f) const { m_exchanger = f; }
+  const GhostExchanger &ghost_exchanger() const { return m_exchanger; }
   double dx() const { return m_dx; }
   double dy() const { return m_dy; }
   double Lx() const { return m_Lx; }
@@ -178,6 +223,8 @@ private:
   double m_Lx, m_Ly, m_dx, m_dy;
   std::vector<double> m_x, m_y, m_z;
   double m_time;
+  int m_rank, m_size, m_xs, m_xm, m_ys, m_ym;
+  mutable GhostExchanger m_exchanger;
 };
 
 inline double radius(const IceGrid &grid, int i, int j) { return sqrt(grid.x(i) * grid.x(i) + grid.y(j) * grid.y(j)); }
@@ -202,13 +249,20 @@ public:
   size_t size() const { return m_data.size(); }
   void set(double c) { std::fill(m_data.begin(), m_data.end(), c); }
   void copy_from(const IceModelVec &other) {
-    for (int j = 0; j < m_grid->ym(); ++j)
-      for (int i = 0; i < m_grid->xm(); ++i)
+    for (int j = m_grid->ys(); j < m_grid->ys() + m_grid->ym(); ++j)
+      for (int i = m_grid->xs(); i < m_grid->xs() + m_grid->xm(); ++i)
         for (unsigned int d = 0; d < m_dof; ++d) at(i, j, d) = other.at(i, j, d);
     update_ghosts();
   }
-  // DMLocalToLocal on one periodic rank (util/iceModelVec.cc:630-643, IceGrid.cc:870-872)
+  // DMLocalToLocal (util/iceModelVec.cc:630-643): the periodic self-wrap of a one-rank DMDA (IceGrid.cc:870-872), or
+  // the exchanger the driver of a multi-process run installed on the grid
   void update_ghosts() {
+    if (m_width == 0) return;
+    if (m_grid->size() > 1) {
+      if (!m_grid->ghost_exchanger()) throw RuntimeError::formatted(-1, "no ghost exchanger installed on a decomposed grid");
+      m_grid->ghost_exchanger()(m_name, m_data.data(), m_width, m_dof);
+      return;
+    }
     const int Mx = m_grid->xm(), My = m_grid->ym(), w = m_width;
     for (int j = -w; j < My + w; ++j)
       for (int i = -w; i < Mx + w; ++i) {
@@ -221,7 +275,10 @@ public:
   const double &at(int i, int j, unsigned int d) const { return m_data[index(i, j) * m_dof + d]; }
 
 protected:
-  size_t index(int i, int j) const { return (size_t)(j + m_width) * (m_grid->xm() + 2 * m_width) + (i + m_width); }
+  // (i, j) are GLOBAL grid indices, valid on [xs - w, xs + xm + w) x [ys - w, ys + ym + w), as in PISM
+  size_t index(int i, int j) const {
+    return (size_t)(j - m_grid->ys() + m_width) * (m_grid->xm() + 2 * m_width) + (i - m_grid->xs() + m_width);
+  }
   IceGrid::ConstPtr m_grid;
   std::string m_name;
   unsigned int m_dof;
@@ -317,8 +374,8 @@ public:
     const Config &config = *grid->config();
     const double alpha = 1 - config.get_number("constants.ice.density") / config.get_number("constants.sea_water.density");
     const bool is_dry_simulation = config.get_flag("ocean.always_grounded");
-    for (int j = 0; j < grid->ym(); ++j) {
-      for (int i = 0; i < grid->xm(); ++i) {
+    for (int j = grid->ys(); j < grid->ys() + grid->ym(); ++j) {
+      for (int i = grid->xs(); i < grid->xs() + grid->xm(); ++i) {
         const double thickness = ice_thickness(i, j);
         if (thickness < 0.0) {
           throw RuntimeError::formatted(1, "Thickness is negative at point i=%d, j=%d", i, j);

@@ -4,6 +4,12 @@
 // Prints the reference's report (src/verification/iceCompModel.cc:661-667), which test/regression/test_15.sh diffs
 // against its golden rows.  TEST CODE: the exact solution comes from the reference's own exactTestsABCD.c compiled
 // into oracle/_ref/libpism_exact.so.
+//
+// Several ranks: one PROCESS per rank (`-rank R -size S -prefix P`, P a path prefix every rank can write to), each with
+// its patch of PISM's decomposition; SIAFD_B200 forms the library's communicator, the host arrays' ghost updates
+// (DMLocalToLocal over MPI in PISM) go through siafd_b200_comm_exchange, and the report's sums / maxima through
+// siafd_b200_comm_allreduce.  `-poison_rank R` makes the thickness negative at one point owned by rank R before the
+// first update: every rank must fail with the reference's message (ParallelSection, util/error_handling.cc:189-214).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -23,7 +29,14 @@ int main(int argc, char *argv[]) {
   using namespace pism::stressbalance;
   int Mx = 31, My = 31, Mz = 31;
   double run_length_years = 5000.0;
+  int rank = 0, size = 1, poison_rank = -1, trace = 0;
+  std::string prefix;
   for (int a = 1; a + 1 < argc; a += 2) {
+    if (!strcmp(argv[a], "-rank")) rank = atoi(argv[a + 1]);
+    if (!strcmp(argv[a], "-size")) size = atoi(argv[a + 1]);
+    if (!strcmp(argv[a], "-prefix")) prefix = argv[a + 1];
+    if (!strcmp(argv[a], "-poison_rank")) poison_rank = atoi(argv[a + 1]);
+    if (!strcmp(argv[a], "-trace")) trace = atoi(argv[a + 1]);
     if (!strcmp(argv[a], "-Mx")) Mx = atoi(argv[a + 1]);
     if (!strcmp(argv[a], "-My")) My = atoi(argv[a + 1]);
     if (!strcmp(argv[a], "-Mz")) Mz = atoi(argv[a + 1]);
@@ -41,7 +54,7 @@ int main(int argc, char *argv[]) {
     config->set_flag("ocean.always_grounded", true);
     config->set_flag("enthalpy_converter.cold_mode", true); // pismv.cc:61
     // pismv_grid_defaults + vertical_grid_from_options: 2000 km x 2000 km x 4000 m, QUADRATIC levels (pismv.cc:96-102, :155)
-    IceGrid::Ptr grid(new IceGrid(config, Mx, My, 1000e3, 1000e3, IceGrid::compute_vertical_levels(4000.0, Mz, QUADRATIC)));
+    IceGrid::Ptr grid(new IceGrid(config, Mx, My, 1000e3, 1000e3, IceGrid::compute_vertical_levels(4000.0, Mz, QUADRATIC), rank, size));
     const int WIDE_STENCIL = (int)config->get_number("grid.max_stencil_width");
     const double ice_density = config->get_number("constants.ice.density");
     const double ice_free_thickness = config->get_number("geometry.ice_free_thickness_standard");
@@ -56,17 +69,30 @@ int main(int argc, char *argv[]) {
     double time = 0.0;
     const double run_end = run_length_years * year;
     // initTestABCDH, iceCompModel.cc:301-356
-    for (int j = 0; j < grid->ym(); ++j)
-      for (int i = 0; i < grid->xm(); ++i) {
+    for (int j = grid->ys(); j < grid->ys() + grid->ym(); ++j)
+      for (int i = grid->xs(); i < grid->xs() + grid->xm(); ++i) {
         double H, M;
         ref_exactC(time, radius(*grid, i, j), &H, &M);
         geometry.ice_thickness(i, j) = H;
       }
-    geometry.ice_thickness.update_ghosts();
-
-    StressBalance_B200 stress_balance(grid, new SIAFD_B200(grid));
+    int ndev = 1;
+    if (const char *e = getenv("PISMV_NDEV")) ndev = std::max(1, atoi(e)); // (GPUs to spread the ranks over; 1: share one)
+    StressBalance_B200 stress_balance(grid, new SIAFD_B200(grid, rank % ndev, size > 1 ? prefix.c_str() : NULL));
     stress_balance.init();
-    GeometryEvolution_B200 geometry_evolution(grid, stress_balance.modifier()->handle());
+    siafd_b200_handle *handle = stress_balance.modifier()->handle();
+    GeometryEvolution_B200 geometry_evolution(grid, handle);
+    if (size > 1) {
+      // IceModelVec::update_ghosts of the HOST arrays between processes: through the device and the communicator
+      grid->set_ghost_exchanger([handle](const std::string &name, double *a, int width, unsigned int) {
+        const int f = name == "thk" ? SIAFD_B200_F_THICKNESS : (name == "mask" ? SIAFD_B200_F_MASK : (name == "usurf" ? SIAFD_B200_F_SURFACE : -1));
+        if (f < 0) throw RuntimeError::formatted(-1, "no ghost exchange for '%s' in this driver", name.c_str());
+        int st = siafd_b200_upload(handle, f, a);
+        if (st == SIAFD_B200_OK) st = siafd_b200_comm_exchange(handle, 1, &f, &width);
+        if (st == SIAFD_B200_OK) st = siafd_b200_download(handle, f, a);
+        if (st != SIAFD_B200_OK) throw RuntimeError::formatted(st, "%s", siafd_b200_last_error(handle));
+      });
+    }
+    geometry.ice_thickness.update_ghosts();
 
     Inputs inputs;
     inputs.geometry = &geometry;
@@ -74,6 +100,9 @@ int main(int argc, char *argv[]) {
     inputs.new_bed_elevation = false;
 
     geometry.ensure_consistency(ice_free_thickness); // IceModel::run, IceModel.cc:763
+    if (poison_rank == rank) { // an owned point away from the patch edge: only this rank sees it
+      geometry.ice_thickness(grid->xs() + grid->xm() / 2, grid->ys() + grid->ym() / 2) = -1.0;
+    }
     const double max_dt = config->get_number("time_stepping.maximum_time_step") * year;
     int steps = 0;
     while (time < run_end) { // IceModel::run :790 / IceModel::step
@@ -99,8 +128,8 @@ int main(int argc, char *argv[]) {
       geometry_evolution.apply_flux_divergence(geometry);
       geometry.ensure_consistency(ice_free_thickness);
       // surface::Verification::update_ABCDH at the start-of-step time, PSVerification.cc:165-224
-      for (int j = 0; j < grid->ym(); ++j)
-        for (int i = 0; i < grid->xm(); ++i) {
+      for (int j = grid->ys(); j < grid->ys() + grid->ym(); ++j)
+        for (int i = grid->xs(); i < grid->xs() + grid->xm(); ++i) {
           double H, M;
           ref_exactC(time, radius(*grid, i, j), &H, &M);
           mass_flux(i, j) = M * ice_density;
@@ -108,6 +137,16 @@ int main(int argc, char *argv[]) {
       geometry_evolution.source_term_step(geometry, dt, NULL, mass_flux, NULL);
       geometry_evolution.apply_mass_fluxes(geometry);
       geometry.ensure_consistency(ice_free_thickness);
+      if (trace) { // per step: dt, D_max and the ice volume (decomposition-independence debugging)
+        double sH[1] = {0.0};
+        for (int j = grid->ys(); j < grid->ys() + grid->ym(); ++j)
+          for (int i = grid->xs(); i < grid->xs() + grid->xm(); ++i) sH[0] += geometry.ice_thickness(i, j);
+        if (size > 1) siafd_b200_comm_allreduce(handle, 2, 1, sH);
+        if (rank == 0) {
+          printf("trace step %d dt %.17g D_max %.17g cfl3 %.17g cfl2 %.17g sumH %.17g\n", steps, dt, D_max,
+                 stress_balance.max_timestep_cfl_3d().dt_max, stress_balance.max_timestep_cfl_2d().dt_max, sH[0]);
+        }
+      }
       time += dt; // Time::step, Time.cc:206-215
       if (run_end > time && run_end - time < 1e-3) time = run_end;
       steps += 1;
@@ -116,8 +155,8 @@ int main(int argc, char *argv[]) {
     // IceCompModel::computeGeometryErrors + reportErrors, iceCompModel.cc:442-583, :661-667
     const double a = grid->dx() * grid->dy() * 1e-3 * 1e-3, m = (2.0 * 3.0 + 2.0) / 3.0;
     double vol = 0, volexact = 0, Herr = 0, avHerr = 0, etaerr = 0, domeHexact = 0;
-    for (int j = 0; j < grid->ym(); ++j)
-      for (int i = 0; i < grid->xm(); ++i) {
+    for (int j = grid->ys(); j < grid->ys() + grid->ym(); ++j)
+      for (int i = grid->xs(); i < grid->xs() + grid->xm(); ++i) {
         double Hexact, M;
         ref_exactC(time, radius(*grid, i, j), &Hexact, &M);
         const double H = geometry.ice_thickness(i, j);
@@ -128,6 +167,17 @@ int main(int argc, char *argv[]) {
         etaerr = std::max(etaerr, fabs(pow(H, m) - pow(Hexact, m)));
         avHerr += fabs(H - Hexact);
       }
+    if (size > 1) { // GlobalSum / GlobalMax, iceCompModel.cc:540-560
+      double sums[3] = {vol, volexact, avHerr}, maxs[3] = {Herr, etaerr, domeHexact};
+      int st = siafd_b200_comm_allreduce(handle, 2, 3, sums);
+      if (st == SIAFD_B200_OK) st = siafd_b200_comm_allreduce(handle, 0, 3, maxs);
+      if (st != SIAFD_B200_OK) throw RuntimeError::formatted(st, "%s", siafd_b200_last_error(handle));
+      vol = sums[0], volexact = sums[1], avHerr = sums[2], Herr = maxs[0], etaerr = maxs[1], domeHexact = maxs[2];
+    }
+    if (rank != 0) {
+      printf("rank %d done, steps %d\n", rank, steps);
+      return 0;
+    }
     printf("NUMERICAL ERRORS evaluated at final time (relative to exact solution):\n");
     printf("geometry  :    prcntVOL        maxH         avH   relmaxETA\n");
     printf("           %12.6f%12.6f%12.6f%12.6f\n", 100 * fabs(vol - volexact) / volexact, Herr, avHerr / (grid->Mx() * grid->My()),
@@ -135,7 +185,7 @@ int main(int argc, char *argv[]) {
     printf("NUM ERRORS DONE\n");
     printf("steps %d\n", steps);
   } catch (RuntimeError &e) {
-    fprintf(stderr, "PISM ERROR: %s\n", e.what());
+    fprintf(stderr, "PISM ERROR (rank %d): %s\n", rank, e.what());
     return 1;
   }
   return 0;

@@ -45,8 +45,8 @@ void setInitStateF(const IceGrid &grid, IceModelVec2S &bed, IceModelVec2CellType
   bed.set(0.0);
   mask.set(MASK_GROUNDED);
   std::vector<double> T(grid.Mz());
-  for (int j = 0; j < grid.ym(); ++j) {
-    for (int i = 0; i < grid.xm(); ++i) {
+  for (int j = grid.ys(); j < grid.ys() + grid.ym(); ++j) {
+    for (int i = grid.xs(); i < grid.xs() + grid.xm(); ++i) {
       const double r = std::max(radius(grid, i, j), 1.0), Ts = Tmin + ST * r;
       if (r > LforFG - 1.0) {
         thickness(i, j) = 0.0;
@@ -70,8 +70,8 @@ void computeSurfaceVelocityErrors(const IceGrid &grid, const IceModelVec2S &ice_
                                   double &gmaxWerr, double &gavWerr) {
   double maxUerr = 0.0, avUerr = 0.0, maxWerr = 0.0, avWerr = 0.0;
   const double LforFG = 750000;
-  for (int j = 0; j < grid.ym(); ++j) {
-    for (int i = 0; i < grid.xm(); ++i) {
+  for (int j = grid.ys(); j < grid.ys() + grid.ym(); ++j) {
+    for (int i = grid.xs(); i < grid.xs() + grid.xm(); ++i) {
       const double xx = grid.x(i), yy = grid.y(j), r = sqrt(xx * xx + yy * yy);
       if ((r >= 1.0) && (r <= LforFG - 1.0)) {
         const double H = ice_thickness(i, j);
@@ -130,8 +130,8 @@ int main(int argc, char *argv[]) {
     // Geometry::ensure_consistency (Geometry.cc:121-187) with bed = 0, sea level 0, all cells grounded: ice-free
     // cells become ice-free bedrock, the surface is bed + thickness
     const double H_min = config->get_number("geometry.ice_free_thickness_standard");
-    for (int j = 0; j < grid->ym(); ++j)
-      for (int i = 0; i < grid->xm(); ++i)
+    for (int j = grid->ys(); j < grid->ys() + grid->ym(); ++j)
+      for (int i = grid->xs(); i < grid->xs() + grid->xm(); ++i)
         geometry.cell_type(i, j) = geometry.ice_thickness(i, j) > H_min ? MASK_GROUNDED : MASK_ICE_FREE_BEDROCK;
     geometry.cell_type.update_ghosts();
 
@@ -150,8 +150,8 @@ int main(int argc, char *argv[]) {
     printf("surf vels :     maxUvec      avUvec        maxW         avW\n");
     printf("           %12.6f%12.6f%12.6f%12.6f\n", maxUerr * secpera, avUerr * secpera, maxWerr * secpera, avWerr * secpera);
     double sumD = 0.0, sumQ = 0.0, sumU = 0.0;
-    for (int j = 0; j < grid->ym(); ++j)
-      for (int i = 0; i < grid->xm(); ++i) {
+    for (int j = grid->ys(); j < grid->ys() + grid->ym(); ++j)
+      for (int i = grid->xs(); i < grid->xs() + grid->xm(); ++i) {
         sumD += sia.diffusivity()(i, j, 0) + sia.diffusivity()(i, j, 1);
         sumQ += fabs(sia.diffusive_flux()(i, j, 0)) + fabs(sia.diffusive_flux()(i, j, 1));
         sumU += fabs(sia.velocity_u().get_column(i, j)[Mz / 2]);

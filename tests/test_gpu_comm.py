@@ -172,3 +172,77 @@ def test_generic_exchange_and_allreduce():
         s01 += 0.1 * (q + 1)
     for q in range(n):
         assert out[q] == ([float(n), 0.0, 0.5 * n], [n * (n + 1) / 2.0, s01], [1.0]), out[q]
+
+
+@pytest.mark.parametrize("name,decomp,full", [
+    ("dome_64_21", dict(size=4), True),
+    ("C4s_nosmooth", dict(size=6, Nx=2, Ny=3, procs_x=[40, 21], procs_y=[50, 13, 50]), True),
+    ("C1", dict(size=2), True),
+    ("dome_64_21", dict(size=2), False),
+])
+def test_host_arrays_through_update_on_every_rank(name, decomp, full):
+    """siafd_b200_update with HOST arrays (valid ghosts, as PISM's are) on every rank of a decomposed run: the drop-in call
+    of a multi-rank PISM.  One host thread per rank (a rank's call returns when its neighbours have delivered their
+    ghosts).  Every output array must equal the single-rank call's, ghosts included."""
+    import threading
+    import torch
+    from pism_b200.sia import Geometry, Inputs
+
+    def pinned(a):
+        # page-locked host arrays: a blocking copy from pageable memory holds a per-process staging lock, which would
+        # serialise the ranks of this ONE-process test against each other (separate processes, as under MPI, do not share it)
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+
+    grid, cfg, inputs, gb = cases.case(name)
+    cfg.w_sliding = 1
+    inputs = dict(inputs)
+    inputs["sliding"] = np.zeros((grid.My + 2, grid.Mx + 2, 2))
+    glob = _global(grid, inputs)
+    one = U.make_sia(grid, cfg, None)
+    U.gpu_update(one, inputs, full)
+    names = ("h_x", "h_y", "D", "flux") + (("u", "v") if full else ())
+    ref = {k: one.download(k) for k in names}
+    size = decomp.pop("size")
+    patches = G.decompose(grid.Mx, grid.My, size, **decomp)
+    sias = [U.make_sia(grid, cfg, None, patch=pt) for pt in patches]
+    hs = (C.c_void_p * size)(*[s.handle for s in sias])
+    assert lib.siafd_b200_comm_init_local(hs, size) == 0
+    errs = [None] * size
+    keep = []
+    locs = []
+    for s, pt in zip(sias, patches):
+        loc = {}
+        for k in INPUTS:
+            loc[k], t = pinned(G.global_to_local(glob[k], pt, lib.siafd_b200_field_width(s.handle, F[k])))
+            keep.append(t)
+        for k in ("h_x", "h_y", "D", "flux", "u", "v"):
+            s._host_out[k], t = pinned(np.zeros(s.field_shape(k)))
+            keep.append(t)
+        locs.append(loc)
+
+    def work(q):
+        try:
+            s, loc = sias[q], locs[q]
+            for rep in range(2):
+                s.update(loc["sliding"], Inputs(Geometry(loc["bed"], loc["thickness"], loc["surface"], loc["mask"]), loc["enthalpy"]),
+                         full)
+        except Exception as e:  # noqa: BLE001
+            errs[q] = e
+
+    ts = [threading.Thread(target=work, args=(q,)) for q in range(size)]
+    [t.start() for t in ts]
+    [t.join(120) for t in ts]
+    assert errs == [None] * size, errs
+    for s, pt in zip(sias, patches):
+        assert s.max_diffusivity() == one.max_diffusivity()
+        got = {"h_x": s.surface_gradient_x(), "h_y": s.surface_gradient_y(), "D": s.diffusivity(), "flux": s.diffusive_flux()}
+        if full:
+            got["u"], got["v"] = s.velocity_u(), s.velocity_v()
+        for k in names:
+            w = lib.siafd_b200_field_width(s.handle, F[k])
+            want = _local(np.ascontiguousarray(cases.interior(ref[k], w)), pt, w)
+            if k in ("D", "flux"):
+                assert np.array_equal(cases.interior(got[k], w), cases.interior(want, w)), (k, pt)
+            else:
+                assert np.array_equal(got[k], want), (k, pt)

@@ -86,3 +86,55 @@ def test_pismv_test_C_cpp_fails_loudly_without_a_gpu():
         pytest.skip("a GPU is present; covered by the gpu test")
     r = subprocess.run([os.path.join(DIR, "pismv_test_C")], capture_output=True, text=True)
     assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def _run_ranks(size, extra, timeout=600):
+    """`size` processes of pismv_test_C, one per rank, as mpiexec would start them; they share GPU 0 unless the box has
+    more (CUDA IPC works between processes on one device too).  Returns the CompletedProcess of every rank."""
+    import tempfile
+    import torch
+    import uuid
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    prefix = os.path.join(d, "siafd_b200_test_%s" % uuid.uuid4().hex)
+    env = dict(os.environ, PISMV_NDEV=str(max(1, min(size, torch.cuda.device_count()))))
+    procs = [subprocess.Popen([os.path.join(DIR, "pismv_test_C"), "-rank", str(r), "-size", str(size), "-prefix", prefix] + extra,
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for r in range(size)]
+    out = []
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        out.append(subprocess.CompletedProcess(p.args, p.returncode, o, e))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [2, 4])
+def test_pismv_test_C_on_several_ranks_in_cpp_reproduces_test_15(size):
+    """The same C++ driver as one process per rank (PISM's decomposition of the 31 x 31 grid): SIAFD_B200::update on
+    every rank's host arrays, the library's communicator underneath (no MPI, no torch), ghost updates and reductions of
+    the host side through it.  Rank 0 prints the golden row of test/regression/test_15.sh."""
+    build()
+    import pismv_oracle as PO
+    res = _run_ranks(size, ["-Mx", "31", "-My", "31"])
+    for r in res:
+        assert r.returncode == 0, (r.stdout, r.stderr)
+    lines = res[0].stdout.splitlines()
+    assert lines[2] == "           " + PO.TEST_15_GOLDEN[31], (lines, PO.TEST_15_GOLDEN[31])
+    assert lines[4] == "steps 84"
+    for q in range(1, size):
+        assert res[q].stdout.strip() == "rank %d done, steps 84" % q
+
+
+@pytest.mark.gpu
+def test_an_error_on_one_rank_raises_on_every_rank_in_cpp():
+    """A negative thickness at one point owned by rank 1: BOTH processes must throw the reference's RuntimeError
+    (sia/BedSmoother.cc:303-305 under ParallelSection, util/error_handling.cc:189-214)."""
+    build()
+    res = _run_ranks(2, ["-Mx", "31", "-My", "31", "-poison_rank", "1"], timeout=300)
+    for q, r in enumerate(res):
+        assert r.returncode == 1, (q, r.stdout, r.stderr)
+        assert "PISM ERROR (rank %d)" % q in r.stderr and "negative original thickness" in r.stderr, r.stderr
