@@ -39,7 +39,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // bounded spin (a few seconds): a peer that never arrives raises EB_COMM instead of hanging the GPU
 __device__ __forceinline__ void wait_at_least(const unsigned long long *p, unsigned long long v, CommPad *self) {
   for (long it = 0; ld_acquire_sys(p) < v; ++it) {
-    __nanosleep(it < 64 ? 32 : 256);
+    if (it >= 128) __nanosleep(it < 1024 ? 32 : 256); // (the first polls back to back: a neighbour is rarely far behind)
     if (it > (8L << 20)) {
       self->timed_out = 1u;
       return;
@@ -140,7 +140,12 @@ __global__ void k_comm_final(const CommPeers *cp, int phase, unsigned long long 
   mine[1] = __longlong_as_double((long long)e);
   mine[2] = (double)*hdc;
   bool have;
-  publish_and_collect(cp, 0, mine, 3, got, have);
+  if (cp->size == 1) { // one rank: nothing to exchange
+    have = lane == 0;
+    got[0] = mine[0], got[1] = mine[1], got[2] = mine[2];
+  } else {
+    publish_and_collect(cp, 0, mine, 3, got, have);
+  }
   double m = have ? got[0] : 0.0;
   unsigned long long bits = have ? (unsigned long long)__double_as_longlong(got[1]) : 0ull;
   double cnt = have ? got[2] : 0.0;

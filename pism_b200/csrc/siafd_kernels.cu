@@ -338,7 +338,8 @@ __device__ __forceinline__ int grad_haseloff_point(const DP &P, const Fields &F,
 }
 
 template <bool PUSH, bool PREP>
-__global__ void k_grad_haseloff(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
+__global__ void __launch_bounds__(256, 6)
+    k_grad_haseloff(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
   if (!PREP) {
     grad_haseloff_point<PUSH, PREP>(P, F, PP, (long)blockIdx.x * blockDim.x + threadIdx.x);
     return;
