@@ -81,19 +81,19 @@ __device__ __forceinline__ int prep2d_point(const DP &P, const Fields &F, const 
 
 // weight of the fused kernel's row segments = icy points per segment: counted per CTA in shared memory (a CTA's points
 // lie in a few consecutive rows), one global atomic per CTA and segment.  Called by every thread of the CTA.
-__device__ __forceinline__ void seg_weight_cta(const DP &P, const Fields &F, const int seg, const long q0) {
+// j0: the row (relative to the first owned row) of the CTA's first point; n: icy points this thread adds to `seg`
+__device__ __forceinline__ void seg_weight_cta(const DP &P, const Fields &F, const int seg, const int j0, const int n = 1) {
   if (P.seg_n <= 0) return;
   __shared__ int cnt[8];
-  const int j0 = (int)(q0 / (P.xm + 2 * P.wg)) - P.wg;
   const int seg_lo = min(max(j0 + 1, 0) / P.seg_rows, P.seg_n - 1);
   if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
   __syncthreads();
-  if (seg >= 0) {
+  if (seg >= 0 && n > 0) {
     const int d = seg - seg_lo;
     if (d < 8) {
-      atomicAdd(&cnt[d], 1);
+      atomicAdd(&cnt[d], n);
     } else {
-      atomicAdd(F.segw + seg, 1);
+      atomicAdd(F.segw + seg, n);
     }
   }
   __syncthreads();
@@ -130,7 +130,7 @@ __global__ void k_prep2d(const __grid_constant__ DP P, const Fields F) {
   const long n = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
   const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int seg = (q < n) ? prep2d_point(P, F, q) : -1;
-  seg_weight_cta(P, F, seg, (long)blockIdx.x * blockDim.x);
+  seg_weight_cta(P, F, seg, (int)(((long)blockIdx.x * blockDim.x) / (P.xm + 2 * P.wg)) - P.wg);
   seg_order_epilogue(P, F);
 }
 
@@ -349,7 +349,124 @@ __global__ void __launch_bounds__(256, 6)
   const long n = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
   for (long q0 = (long)blockIdx.x * blockDim.x; q0 < n; q0 += (long)gridDim.x * blockDim.x) {
     const int seg = grad_haseloff_point<PUSH, PREP>(P, F, PP, q0 + threadIdx.x);
-    seg_weight_cta(P, F, seg, q0);
+    seg_weight_cta(P, F, seg, (int)(q0 / (P.xm + 2 * P.wg)) - P.wg);
+  }
+  seg_order_epilogue(P, F);
+}
+
+// The same pass (PREP = true) with FOUR adjacent points of a row per thread.  The 3 x 3 neighbourhoods of the four points
+// overlap: one thread loads 3 x 6 cells and evaluates 20 direct components where four single-point threads load 36 cells
+// and evaluate 32, and the index arithmetic is shared.  Every value is produced by the same expression as in
+// grad_haseloff_point (the tests pin the gradients bit for bit).  The single-point kernel was bound by instruction
+// issue (profiles/ncu_r02_k_grad_haseloff_4096_summary.txt: 20 warp instructions per point, DRAM at 30 %).
+template <bool PUSH>
+__global__ void __launch_bounds__(128)
+    k_grad_haseloff_quad(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
+  const int wg = P.wg;
+  const int nx = P.xm + 2 * wg, ny = P.ym + 2 * wg;
+  const int nqx = (nx + 3) >> 2;
+  const long nq = (long)nqx * ny;
+  for (long Q0 = (long)blockIdx.x * blockDim.x; Q0 < nq; Q0 += (long)gridDim.x * blockDim.x) {
+    const long Q = Q0 + threadIdx.x;
+    int seg = -1, icy_points = 0;
+    if (Q < nq) {
+      const int jy = (int)(Q / nqx), c0 = 4 * (int)(Q - (long)jy * nqx); // row / first column in the geometry-width array
+      const int j = P.ys - wg + jy;
+      const long rowq = (long)jy * nx;
+      // thk_smooth, theta (k_prep2d) of the four points
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (c0 + p < nx) {
+          const int sp = prep2d_point(P, F, rowq + c0 + p);
+          if (sp >= 0) seg = sp, icy_points += 1;
+        }
+      }
+      // gradient on owned + 1: rows ys - 1 .. ys + ym, columns xs - 1 .. xs + xm
+      const int ia = P.xs - wg + c0; // column of point 0
+      if (j >= P.ys - 1 && j <= P.ys + P.ym && ia + 3 >= P.xs - 1 && ia <= P.xs + P.xm) {
+        // cells: column index a = 0..5 <-> column ia - 1 + a, row index b = 0..2 <-> row j - 1 + b (clamped to the array:
+        // a clamped cell is only ever read by a point outside owned + 1, which is not stored)
+        double h[3][6];
+        int M[3][6];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const int rb = min(max(jy - 1 + b, 0), ny - 1);
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            const int ca = min(max(c0 - 1 + a, 0), nx - 1);
+            const long g = (long)rb * nx + ca;
+            h[b][a] = F.h[g];
+            M[b][a] = mask_int(F.mask[g]);
+          }
+        }
+        // direct components: X[b][a] at the i-offset point of cell (a, b + 1), Y[b][a] at the j-offset point of cell (a + 1, b)
+        HasDirect X[2][5], Y[2][5];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+          for (int a = 0; a < 5; ++a) {
+            X[b][a] = haseloff_direct(h[b + 1][a], h[b + 1][a + 1], M[b + 1][a], M[b + 1][a + 1], P.dx, P.inv_dx);
+            Y[b][a] = haseloff_direct(h[b][a + 1], h[b + 1][a + 1], M[b][a + 1], M[b + 1][a + 1], P.dy, P.inv_dy);
+          }
+        }
+        const bool row_owned = j >= P.ys && j < P.ys + P.ym;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int i = ia + p;
+          if (i < P.xs - 1 || i > P.xs + P.xm) continue;
+          const HasDirect x00 = X[0][p + 1], y00 = Y[1][p]; // h_x(i, j, 0), w_i(i, j); h_y(i, j, 1), w_j(i, j)
+          const long s2 = idx2(P, i, j, P.wst) * 2;
+          if (!row_owned || i < P.xs || i >= P.xs + P.xm) {
+            F.h_x[s2 + 0] = x00.g; // the second loop runs over owned points only; its ghosts come from the exchange
+            F.h_y[s2 + 1] = y00.g;
+            continue;
+          }
+          const bool icy = m_icy(M[1][p + 1]);
+          const HasDirect xm0 = X[0][p], xm1 = X[1][p], x01 = X[1][p + 1];         // (i-1, j), (i-1, j+1), (i, j+1)
+          const HasDirect y0m = Y[0][p], y1m = Y[0][p + 1], y10 = Y[1][p + 1];     // (i, j-1), (i+1, j-1), (i+1, j)
+          double r;
+          if (y00.w > 0) { // x-derivative, j-offset (:441-467)
+            const double W = x00.w + xm0.w + xm1.w + x01.w;
+            r = (W > 0) ? __dmul_rn(inv_count(W), (x00.g + xm0.g + xm1.g + x01.g)) : 0.0;
+          } else if (icy) {
+            const double W = x00.w + xm0.w;
+            r = (W > 0) ? __dmul_rn(inv_count(W), (x00.g + xm0.g)) : 0.0;
+          } else {
+            const double W = x01.w + xm1.w;
+            r = (W > 0) ? __dmul_rn(inv_count(W), (xm1.g + x01.g)) : 0.0;
+          }
+          const double hx_cross = r;
+          if (x00.w > 0) { // y-derivative, i-offset (:469-495)
+            const double W = y00.w + y0m.w + y1m.w + y10.w;
+            r = (W > 0) ? __dmul_rn(inv_count(W), (y00.g + y0m.g + y1m.g + y10.g)) : 0.0;
+          } else if (icy) {
+            const double W = y00.w + y0m.w;
+            r = (W > 0) ? __dmul_rn(inv_count(W), (y00.g + y0m.g)) : 0.0;
+          } else {
+            const double W = y1m.w + y10.w;
+            r = (W > 0) ? __dmul_rn(inv_count(W), (y1m.g + y10.g)) : 0.0;
+          }
+          const double2 hx2 = make_double2(x00.g, hx_cross), hy2 = make_double2(r, y00.g);
+          *reinterpret_cast<double2 *>(F.h_x + s2) = hx2; // (a staggered pair starts on a 16-byte boundary)
+          *reinterpret_cast<double2 *>(F.h_y + s2) = hy2;
+          if (PUSH) {
+            const int a = i - P.xs, b = j - P.ys;
+            const bool W_ = a < PP.w, E_ = a >= P.xm - PP.w, S_ = b < PP.w, N_ = b >= P.ym - PP.w;
+            if (W_ || E_ || S_ || N_) {
+#pragma unroll
+              for (int d = 0; d < 8; ++d) {
+                if (PP.a[d] != nullptr && peer_strip_member(d, W_, E_, S_, N_)) {
+                  const long t = ((long)(b + P.wst + PP.dj[d]) * PP.rowc[d] + (a + P.wst + PP.di[d])) * 2;
+                  *reinterpret_cast<double2 *>(PP.a[d] + t) = hx2;
+                  *reinterpret_cast<double2 *>(PP.b[d] + t) = hy2;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    seg_weight_cta(P, F, seg, (int)(Q0 / nqx) - wg, icy_points);
   }
   seg_order_epilogue(P, F);
 }
@@ -586,11 +703,12 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush
     return 2;
   default:
     if (with_prep2d) {
-      const unsigned nb = std::min(nblk(n2, 256), 148u * 16u);
+      const long nq = (long)((P.xm + 2 * P.wg + 3) / 4) * (P.ym + 2 * P.wg); // four points of a row per thread
+      const unsigned nb = std::min(nblk(nq, 128), 148u * 16u);
       if (push != nullptr && push->on) {
-        k_grad_haseloff<true, true><<<nb, 256, 0, s>>>(P, F, *push);
+        k_grad_haseloff_quad<true><<<nb, 128, 0, s>>>(P, F, *push);
       } else {
-        k_grad_haseloff<false, true><<<nb, 256, 0, s>>>(P, F, PeerPush());
+        k_grad_haseloff_quad<false><<<nb, 128, 0, s>>>(P, F, PeerPush());
       }
     } else if (push != nullptr && push->on) {
       k_grad_haseloff<true, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);

@@ -44,6 +44,11 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_u32(unsigned smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // shared -> global bulk store (a row leaves through the copy engine), its group bookkeeping, and the fence that makes
 // this thread's generic-proxy writes to shared memory visible to the copy engine
 __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes) {

@@ -32,10 +32,14 @@
 // Newton reciprocal; sums over z are taken per z range and then added.
 #include "siafd_math.cuh"
 
+#include <atomic>
 #include <type_traits>
 
 #ifndef SLAB_LZ
 #define SLAB_LZ 16 // lanes across z in stage B
+#endif
+#ifndef SLAB_MINB
+#define SLAB_MINB 3 // CTAs per SM the register allocation aims at (128-thread CTAs)
 #endif
 #ifndef SLAB_NL
 #define SLAB_NL 3 // levels per trip of the Arrhenius loop
@@ -85,6 +89,15 @@ struct SlabArgs {
   const int *order; // segment to take for each blockIdx.y (heaviest first), or NULL: seg0 + blockIdx.y
 };
 
+// one bulk copy of the row loader: source array, offset of the CTA's first row (doubles), row stride, array size,
+// doubles per row; destination in slot 0 (shared-memory address) and the distance between the two slots (bytes)
+struct RowCopy {
+  const double *base;
+  long off0, stride, lim;
+  int cnt, dslot;
+  unsigned dst, pad;
+};
+
 // per-slot staging area of a row's 2D scalars (offsets in doubles)
 enum : int { AUX_TS = 0, AUX_TH = 18, AUX_HX = 36, AUX_HY = 68, AUX_N = 100 };
 
@@ -120,9 +133,9 @@ __device__ __noinline__ void stage_b_rim(const int Mz, const int i_lo, const int
       } else {
         // the same expressions, in the same order, as the in-line stage B of the kernel: the values are bit-identical
         const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
-        const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
-        const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
-        const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
+        const double hxe = cE[0], hye = cE[1], hxn = cE[2], hyn = cE[3]; // (-0.25 h_x, -0.25 h_y: scaled by the writer)
+        const double hxw = cW[0], hyw = cW[1];
+        const double hxs = south ? cS[2] : 0.0, hys = south ? cS[3] : 0.0;
         const double *Ie = I0_s + qp * S + lz;
         const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
         int k = lz;
@@ -200,8 +213,8 @@ __device__ __noinline__ void push_rim_row(const DP &P, const PeerPush &PP, const
   }
 }
 
-template <int LAW, bool FULL, int NC, int WZ>
-__global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
+template <int LAW, bool FULL, int NC, int WZ, bool BULK>
+__global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB : 1)
     k_sia_slab(const __grid_constant__ DP P, const Fields F, const SlabArgs A, const __grid_constant__ PeerPush PP) {
   static_assert(NC <= 16, "AUX_* offsets and the partner shuffle assume at most 16 lane columns");
   extern __shared__ __align__(16) double sm[];
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   const int c = tid % NC, pt = (tid / NC) & 1, w = tid / (2 * NC); // stage A role
   const int lane = tid & 31;
   const int Mz = P.Mz;
-  const int S = A.use_bulk ? Mz : (Mz | 1); // shared-memory column stride
+  const int S = BULK ? Mz : (Mz | 1); // shared-memory column stride
 
   // ---- shared memory carve-up (offsets in doubles; every region 16-byte aligned) ----
   const int slotE = ((NC + 1) * S + 2 + 1) & ~1; // +2: a bulk copy may start one double early / end one late
@@ -225,10 +238,11 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   double *I1_s = I0_s + (FULL ? colI : 0);
   double *sL = I1_s + (FULL ? 2 * colI : 0); // [2][WZ][NC] delta at the last level of a range; then D of a range
   double *sT = sL + 2 * WZ * NC;             // [2][WZ][NC] I increment over a range
-  double *cf = sT + 2 * WZ * NC;             // [2][NC][4]  h_x, h_y of the o = 0 and o = 1 points, by row parity
+  double *cf = sT + 2 * WZ * NC;             // [2][NC][4]  -0.25 h_x, -0.25 h_y of the o = 0 and o = 1 points, by row parity
   double *tab16 = cf + 2 * NC * 4;           // 2^(j/16), for exp_tab
   double2 *selAQ = (double2 *)(tab16 + 16);  // {ln A, Q / R} 16 / ln2 of the cold [0] and the warm [1] Paterson-Budd branch
   unsigned long long *bars = (unsigned long long *)(tab16 + 20);
+  RowCopy *cpt = (RowCopy *)(tab16 + 22); // [6]
 
   // strips in the order last, 0, 1, ...: the two strips on the west / east rim of the patch (which also store into the
   // neighbours' ghost cells) are the first of their grid row to start, never its tail
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   }
   if (tid < 16) tab16[tid] = EXPT[tid];
   if (tid == 16) selAQ[0] = make_double2(P.lnA2_cold, P.QoR2_cold), selAQ[1] = make_double2(P.lnA2_warm, P.QoR2_warm);
-  if (A.use_bulk && tid == 0) {
+  if (BULK && tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     fence_mbar_init();
@@ -295,39 +309,55 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   const long g2off0 = (long)(r0 - row_lo) * wgx + cb2; // thk_smooth / theta, row r0
   const long sst = 2L * (P.xm + 2 * P.wst);
   const long gsoff0 = idx2(P, ca, r0, P.wst) * 2; // h_x / h_y, row r0 (even: always 16-byte aligned)
+  // Bulk mode: one copy per lane of warp 0 (lane 0 enthalpy, 1 age, 2 thk_smooth, 3 theta, 4 h_x, 5 h_y), all issued by
+  // one instruction stream: source offset of row r0 (in doubles), row stride, doubles per row, array size (a copy is
+  // clamped to it), destination in slot 0 and the distance between the two slots.  A row starts on any 8-byte boundary
+  // and a bulk copy on a 16-byte one: the copy starts one double early / ends one late where it has to, and the
+  // readers add the parity of the row's offset (shc, sh2c below).
+  // (the six descriptors live in shared memory: registers are what limits the CTAs per SM)
+  if (BULK && tid < 6) {
+    RowCopy d;
+    d.base = nullptr, d.dst = 0, d.off0 = 0, d.stride = 0, d.lim = 0, d.cnt = 0, d.dslot = 0;
+    switch (tid) {
+    case 0: d.base = F.E, d.dst = smem_u32(E_s), d.off0 = goff0, d.stride = gstride, d.lim = A.nE, d.cnt = rowcount, d.dslot = slotE * 8; break;
+    case 1: if (P.use_age) d.base = F.age, d.dst = smem_u32(A_s), d.off0 = goff0, d.stride = gstride, d.lim = A.nE, d.cnt = rowcount, d.dslot = slotE * 8; break;
+    case 2: d.base = F.thk_smooth, d.dst = smem_u32(aux + AUX_TS), d.off0 = g2off0, d.stride = wgx, d.lim = A.n2, d.cnt = ncolE, d.dslot = AUX_N * 8; break;
+    case 3: d.base = F.theta, d.dst = smem_u32(aux + AUX_TH), d.off0 = g2off0, d.stride = wgx, d.lim = A.n2, d.cnt = ncolE, d.dslot = AUX_N * 8; break;
+    case 4: d.base = F.h_x, d.dst = smem_u32(aux + AUX_HX), d.off0 = gsoff0, d.stride = sst, d.lim = 1L << 60, d.cnt = 2 * ncolS, d.dslot = AUX_N * 8; break;
+    default: d.base = F.h_y, d.dst = smem_u32(aux + AUX_HY), d.off0 = gsoff0, d.stride = sst, d.lim = 1L << 60, d.cnt = 2 * ncolS, d.dslot = AUX_N * 8; break;
+    }
+    cpt[tid] = d;
+  }
   auto issue_row = [&](int it_row, int slot) {    // it_row = r - r0
     const long goff = goff0 + (long)it_row * gstride;
     const long g2 = g2off0 + (long)it_row * wgx;
     const long gs = gsoff0 + (long)it_row * sst;
     const bool stag_row = (r0 + it_row) <= P.ys + P.ym; // row rb is only ever a "north" row
     double *ax = aux + slot * AUX_N;
-    if (A.use_bulk) {
-      if (tid == 0) {
-        const long a0 = goff & ~1L;
-        long a1 = (goff + rowcount + 1) & ~1L;
-        if (a1 > A.nE) { // last row of the array and an odd end: fetch the last double separately
-          a1 -= 2;
-          E_s[slot * slotE + (goff - a0) + rowcount - 1] = F.E[goff + rowcount - 1];
-          if (P.use_age) A_s[slot * slotE + (goff - a0) + rowcount - 1] = F.age[goff + rowcount - 1];
+    if (BULK) {
+      if (tid < 32) { // (warp 0, converged)
+        unsigned bytes = 0, dst = 0;
+        const double *src = nullptr;
+        if (lane < 6 && (lane < 4 || stag_row)) {
+          const RowCopy d = cpt[lane];
+          if (d.cnt > 0) {
+            const long g = d.off0 + (long)it_row * d.stride;
+            const long a0 = g & ~1L;
+            long a1 = (g + d.cnt + 1) & ~1L;
+            dst = d.dst + (unsigned)(slot * d.dslot);
+            if (a1 > d.lim) { // last row of the array and an odd end: fetch the last double separately
+              a1 -= 2;
+              const double last = d.base[g + d.cnt - 1];
+              asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + 8u * (unsigned)((g - a0) + d.cnt - 1)), "d"(last) : "memory");
+            }
+            bytes = (unsigned)((a1 - a0) * 8);
+            src = d.base + a0;
+          }
         }
-        const long b0 = g2 & ~1L;
-        long b1 = (g2 + ncolE + 1) & ~1L;
-        if (b1 > A.n2) {
-          b1 -= 2;
-          ax[AUX_TS + (g2 - b0) + ncolE - 1] = F.thk_smooth[g2 + ncolE - 1];
-          ax[AUX_TH + (g2 - b0) + ncolE - 1] = F.theta[g2 + ncolE - 1];
-        }
-        const unsigned bytesE = (unsigned)((a1 - a0) * 8), bytes2 = (unsigned)((b1 - b0) * 8);
-        const unsigned bytesS = stag_row ? (unsigned)(ncolS * 16) : 0u;
-        mbar_expect_tx(&bars[slot], (P.use_age ? 2 * bytesE : bytesE) + 2 * bytes2 + 2 * bytesS);
-        bulk_g2s(E_s + slot * slotE, F.E + a0, bytesE, &bars[slot]);
-        if (P.use_age) bulk_g2s(A_s + slot * slotE, F.age + a0, bytesE, &bars[slot]);
-        bulk_g2s(ax + AUX_TS, F.thk_smooth + b0, bytes2, &bars[slot]);
-        bulk_g2s(ax + AUX_TH, F.theta + b0, bytes2, &bars[slot]);
-        if (stag_row) {
-          bulk_g2s(ax + AUX_HX, F.h_x + gs, bytesS, &bars[slot]);
-          bulk_g2s(ax + AUX_HY, F.h_y + gs, bytesS, &bars[slot]);
-        }
+        const unsigned total = __reduce_add_sync(FULLMASK, bytes);
+        if (lane == 0) mbar_expect_tx(&bars[slot], total);
+        __syncwarp();
+        if (bytes) bulk_g2s_u32(dst, src, bytes, &bars[slot]);
       }
     } else {
       const unsigned dst = smem_u32(E_s + slot * slotE);
@@ -379,6 +409,15 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   // adjacent columns one after the other (LB >= 16: one column per LB lanes)
   constexpr int LZW = SLAB_LZ, LZ = (LB >= LZW) ? LB : LZW, NPASS = (LB >= LZW) ? 1 : LZW / LB;
   const int qg = (tid / LZ) * NPASS, lz = tid % LZ;
+  // stage B's stores: offset of (row, column ca + qg, level lz) in u / v, advanced row by row; bit p of pass_ok: column
+  // ca + qg + p is an owned column of this strip
+  long uvo_run = ((long)(max(ra, P.ys) - (P.ys - P.wuv)) * (P.xm + 2 * P.wuv) + (ca + qg - P.xs + P.wuv)) * Mz + lz;
+  unsigned pass_ok = 0;
+#pragma unroll
+  for (int p = 0; p < NPASS; ++p) {
+    const int qp = qg + p, i_p = ca + qp;
+    if (qp >= 1 && i_p >= P.xs && i_p < P.xs + P.xm) pass_ok |= 1u << p;
+  }
   const double *sl_p =
       (FULL && uv_col && F.sliding != nullptr) ? F.sliding + idx2(P, i_q, P.ys - P.wsl, P.wsl) * 2 : nullptr;
   const long ssl = 2L * (P.xm + 2 * P.wsl);
@@ -411,7 +450,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
   // stores as whole rows of u and v; zero_inflight = such a store may still be reading I0_s
   bool zero_ready = false, zero_inflight = false;
 
-  for (int r = r0; r < rb; ++r) {
+  for (int r = r0; r < rb; ++r, DQ_D += sst, DQ_Q += sst) {
     const int it = r - r0;
     const int s_cur = it & 1, s_nxt = s_cur ^ 1;
     const bool row_active = (rf & 6u) != 0;                    // rowts(r) | rowts(r + 1)
@@ -441,7 +480,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       zero_ready = false;
       // ---------------- stage A: integrate z range w of staggered point pt of lane column c ------------
       if (pending) { // CTA-uniform
-        if (A.use_bulk) {
+        if (BULK) {
           if (pending & 1u) { mbar_wait(&bars[0], bar_phase & 1u); bar_phase ^= 1u; }
           if (pending & 2u) { mbar_wait(&bars[1], (bar_phase >> 1) & 1u); bar_phase ^= 2u; }
         } else {
@@ -452,8 +491,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       }
       const int cc = min(c, ncolS - 1); // (lanes past the patch read a clamped column; results masked)
       const double *axc = aux + s_cur * AUX_N, *axn = aux + s_nxt * AUX_N;
-      const int sh2c = A.use_bulk ? (int)((g2off0 + ro * wgx) & 1) : 0;
-      const int sh2n = A.use_bulk ? (int)((g2off0 + (ro + 1) * wgx) & 1) : 0;
+      const int sh2c = BULK ? (int)((g2off0 + ro * wgx) & 1) : 0;
+      const int sh2n = BULK ? (int)((g2off0 + (ro + 1) * wgx) & 1) : 0;
       const double tsC = axc[AUX_TS + sh2c + cc], thC = axc[AUX_TH + sh2c + cc];
       const double ts2 = pt ? axn[AUX_TS + sh2n + cc] : axc[AUX_TS + sh2c + cc + 1];
       const double th2 = pt ? axn[AUX_TH + sh2n + cc] : axc[AUX_TH + sh2c + cc + 1];
@@ -474,8 +513,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       const double theta = 0.5 * (thC + th2);
       const double c2c = P.e * theta * 2.0; // e_factor * theta_local * 2.0
 
-      const int shc = A.use_bulk ? (int)((goff0 + ro * gstride) & 1) : 0;
-      const int shn = A.use_bulk ? (int)((goff0 + (ro + 1) * gstride) & 1) : 0;
+      const int shc = BULK ? (int)((goff0 + ro * gstride) & 1) : 0;
+      const int shn = BULK ? (int)((goff0 + (ro + 1) * gstride) & 1) : 0;
       const int o1 = s_cur * slotE + shc + cc * S;                                        // column (i, r)
       const int o2 = pt ? (s_nxt * slotE + shn + cc * S) : (s_cur * slotE + shc + (cc + 1) * S); // (i, r+1) or (i+1, r)
       const double *E1 = E_s + o1, *E2 = E_s + o2;
@@ -666,7 +705,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
     if (w == 0) {
       if (FULL) {
         double *cfr = cf + (s_cur * NC + c) * 4 + 2 * pt;
-        cfr[0] = hx, cfr[1] = hy; // (rows without ice: 0, multiplied by I = 0 in stage B)
+        cfr[0] = -0.25 * hx, cfr[1] = -0.25 * hy; // the factor of sia/SIAFD.cc:928-931, exact (rows without ice: 0)
       }
       if (own_c && r >= ra) {
         const bool edge = (i_c < 0 || i_c >= P.Mx - 1 || r < 0 || r >= P.My - 1);
@@ -680,8 +719,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
           }
           dmax_local = fmax(dmax_local, D);
         }
-        DQ_D[ro * sst] = D;
-        DQ_Q[ro * sst] = -D * hq;
+        *DQ_D = D;
+        *DQ_Q = -D * hq;
       }
     }
 
@@ -732,7 +771,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
         }
         return T;
       };
-      if (A.use_bulk && !any_valid && !corner_row && r >= rbase && r < rend) { // CTA-uniform
+      if (BULK && !any_valid && !corner_row && r >= rbase && r < rend) { // CTA-uniform
         if (__syncthreads_and(sv.x == 0.0 && sv.y == 0.0)) {
           if (!zero_ready) {
             for (int e = tid; e < NC * S; e += NT) I0_s[e] = 0.0;
@@ -779,11 +818,11 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
           const bool south = (ivalid & (1u << s_nxt)) != 0;
 #pragma unroll
           for (int p = 0; p < NPASS; ++p) {
-            const int qp = qg + p, i_p = ca + qp;
+            const int qp = qg + p;
             const int srcl = (lane & ~(LZ - 1)) + p * LB; // a lane whose own column (tid / LB) is qp
             const double ub = __shfl_sync(FULLMASK, sv.x, srcl), vb = __shfl_sync(FULLMASK, sv.y, srcl);
-            if (qp >= 1 && i_p >= P.xs && i_p < P.xs + P.xm) {
-              const long uvo = ((long)(r - (P.ys - P.wuv)) * (P.xm + 2 * P.wuv) + (i_p - P.xs + P.wuv)) * Mz + lz;
+            if (pass_ok & (1u << p)) {
+              const long uvo = uvo_run + p * Mz;
               double *up = F.u + uvo, *vp = F.v + uvo;
               if (!any_valid) {
                 // no ice at any staggered point of this and the previous row: I == 0, u = sliding velocity (G9)
@@ -794,9 +833,9 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
               } else {
                 // u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s): the factor -0.25 goes into the slopes
                 const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
-                const double hxe = -0.25 * cE[0], hye = -0.25 * cE[1], hxn = -0.25 * cE[2], hyn = -0.25 * cE[3];
-                const double hxw = -0.25 * cW[0], hyw = -0.25 * cW[1];
-                const double hxs = south ? -0.25 * cS[2] : 0.0, hys = south ? -0.25 * cS[3] : 0.0;
+                const double hxe = cE[0], hye = cE[1], hxn = cE[2], hyn = cE[3];
+                const double hxw = cW[0], hyw = cW[1];
+                const double hxs = south ? cS[2] : 0.0, hys = south ? cS[3] : 0.0;
                 const double *Ie = I0_s + qp * S + lz;
                 const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
                 int k = lz;
@@ -826,6 +865,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? 3 : 1)
       }
       // (only where this strip holds a corner cell of the patch; out of line: keeps the march lean)
       if (corner_row) push_rim_row<NPASS, LB, LZ>(P, PP, F.u, F.v, r, ca, qg, lz);
+      if (r >= rbase && r < rend) uvo_run += uv_row;
       if (any_valid) {
         // the zero-filled arrays now ARE valid zeros for the next row's "previous row" role
         ivalid |= (1u << s_cur);
@@ -874,42 +914,60 @@ static size_t slab_smem_bytes(const DP &P, bool full, int NC, int WZ, bool bulk)
   const long colI = (NC * S + 1) & ~1L;
   long d = 2 * Mz + 2 * slotE + (P.use_age ? 2 * slotE : 0) + 2 * AUX_N + (full ? 3 * colI : 0) + 2 * 2 * WZ * NC +
            2 * NC * 4 + 16 + 4;
-  return (size_t)d * 8 + 2 * 8 /* mbarriers */ + 16;
+  return (size_t)d * 8 + 2 * 8 /* mbarriers */ + 6 * sizeof(RowCopy) + 16;
 }
 
-template <int LAW, bool FULL, int NC, int WZ>
+template <int LAW, bool FULL, int NC, int WZ, bool BULK>
 static int launch_slab_t(const DP &P, const Fields &F, const SlabArgs &A, cudaStream_t s, const PeerPush &PP) {
-  const size_t smem = slab_smem_bytes(P, FULL, NC, WZ, A.use_bulk != 0);
+  const size_t smem = slab_smem_bytes(P, FULL, NC, WZ, BULK);
   if (smem > (size_t)227 * 1024) return -1;
-  static size_t configured[64] = {}; // per instantiation and per device (the attribute is a per-device setting)
+  // per instantiation and per device (the attribute is a per-device setting); handles on different host threads may
+  // arrive here together
+  static std::atomic<size_t> configured[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
   const int slot = dev & 63;
-  if (smem > configured[slot]) {
-    if (cudaFuncSetAttribute(k_sia_slab<LAW, FULL, NC, WZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+  if (smem > configured[slot].load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(k_sia_slab<LAW, FULL, NC, WZ, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess) {
       return -1;
     }
-    configured[slot] = smem;
+    size_t seen = configured[slot].load(std::memory_order_relaxed);
+    while (seen < smem && !configured[slot].compare_exchange_weak(seen, smem, std::memory_order_release)) {
+    }
   }
   dim3 grid((unsigned)((P.xm + 1 + (NC - 2)) / (NC - 1)), (unsigned)A.nseg);
-  k_sia_slab<LAW, FULL, NC, WZ><<<grid, 2 * NC * WZ, smem, s>>>(P, F, A, PP);
+  k_sia_slab<LAW, FULL, NC, WZ, BULK><<<grid, 2 * NC * WZ, smem, s>>>(P, F, A, PP);
   return 1;
 }
 
+#ifndef SLAB_DEV
 template <int LAW, bool FULL> static int launch_slab_l(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
                                                        cudaStream_t s, const PeerPush &PP) {
-  // 16 lane columns unless shared memory cannot hold them (very tall grids): then 8
-  if (slab_smem_bytes(P, FULL, 16, 8, A.use_bulk != 0) <= (size_t)227 * 1024) {
-    if (T.wz == 4) return launch_slab_t<LAW, FULL, 16, 4>(P, F, A, s, PP);
-    if (T.wz == 2) return launch_slab_t<LAW, FULL, 16, 2>(P, F, A, s, PP);
-    return launch_slab_t<LAW, FULL, 16, 8>(P, F, A, s, PP);
+  // 16 lane columns unless shared memory cannot hold them (very tall grids): then 8.  Rows arrive by bulk copy (odd Mz:
+  // columns are an odd number of doubles apart as they lie in memory) or by 8-byte cp.async into padded columns.
+  const bool bulk = A.use_bulk != 0;
+#ifdef SLAB_WZ_VARIANTS // z ranges per column other than 4 (tuning experiments; SIAFD_B200_WZ)
+  if (slab_smem_bytes(P, FULL, 16, 8, bulk) <= (size_t)227 * 1024 && T.wz != 4 && bulk) {
+    if (T.wz == 2) return launch_slab_t<LAW, FULL, 16, 2, true>(P, F, A, s, PP);
+    return launch_slab_t<LAW, FULL, 16, 8, true>(P, F, A, s, PP);
   }
-  return launch_slab_t<LAW, FULL, 8, 4>(P, F, A, s, PP);
+#endif
+  (void)T;
+  if (slab_smem_bytes(P, FULL, 16, 4, bulk) <= (size_t)227 * 1024) {
+    return bulk ? launch_slab_t<LAW, FULL, 16, 4, true>(P, F, A, s, PP) : launch_slab_t<LAW, FULL, 16, 4, false>(P, F, A, s, PP);
+  }
+  return bulk ? launch_slab_t<LAW, FULL, 8, 4, true>(P, F, A, s, PP) : launch_slab_t<LAW, FULL, 8, 4, false>(P, F, A, s, PP);
 }
+
+#endif
 
 template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, const Tuning &T, const SlabArgs &A,
                                               cudaStream_t s, const PeerPush &PP) {
+#ifdef SLAB_DEV // development builds: one instantiation (gpbld, 16 lane columns, 4 z ranges) compiles in seconds
+  (void)T;
+  return (P.law == LAW_GPBLD && A.use_bulk) ? launch_slab_t<LAW_GPBLD, FULL, 16, 4, true>(P, F, A, s, PP) : -1;
+#else
   switch (P.law) {
   case LAW_ISO:
     return launch_slab_l<LAW_ISO, FULL>(P, F, T, A, s, PP);
@@ -928,6 +986,7 @@ template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, cons
   default:
     return -1;
   }
+#endif
 }
 
 size_t slab_smem_need(const DP &P, bool full, bool bulk) { return slab_smem_bytes(P, full, 8, 4, bulk); }
