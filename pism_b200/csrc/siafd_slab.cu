@@ -60,7 +60,11 @@ __device__ __forceinline__ int k_below_height2(const double2 *zz, int Mz, double
     return 0;
   }
   if (inv_dz > 0.0) {
+    // the guess is nearly always the answer: both neighbours are read at once (one shared-memory latency instead of
+    // two); otherwise the exact search from there
     int k = min(max((int)(height * inv_dz), 0), Mz - 2);
+    const double za = zz[k].x, zb = zz[k + 1].x;
+    if (za <= height && height < zb) return k;
     while (k < Mz - 2 && zz[k + 1].x <= height) ++k;
     while (k > 0 && zz[k].x > height) --k;
     return k;
@@ -101,6 +105,55 @@ struct RowCopy {
 // per-slot staging area of a row's 2D scalars (offsets in doubles)
 enum : int { AUX_TS = 0, AUX_TH = 18, AUX_HX = 36, AUX_HY = 68, AUX_N = 100 };
 
+// u, v of one regular column on every level, u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s) and the same
+// for v (sia/SIAFD.cc:904-943): LZ lanes across z, this lane takes levels lz, lz + LZ, ...  c? = {-0.25 h_x, -0.25 h_y} of
+// the four staggered points around the column, I? their integrals at this lane's first level (the west point is one
+// shared-memory column, S doubles, before the east one).  DUAL: the values also go to up2 / vp2 (a neighbour's ghost
+// column).  Four levels per trip, then ONE predicated block for the up to three levels that are left (a loop over single
+// levels cost 2.3 times as many instructions per level, profiles/).
+template <int LZ, bool DUAL>
+__device__ __forceinline__ void uv_column(const int Mz, const int lz, const int S, const double ub, const double vb,
+                                          const double2 ce, const double2 cw, const double2 cn, const double2 cs,
+                                          const double *Ie, const double *In, const double *Is, double *up, double *vp,
+                                          double *up2, double *vp2) {
+  const double hxe = ce.x, hye = ce.y, hxw = cw.x, hyw = cw.y, hxn = cn.x, hyn = cn.y, hxs = cs.x, hys = cs.y;
+  int k = lz;
+  for (; k + 3 * LZ < Mz; k += 4 * LZ, up += 4 * LZ, vp += 4 * LZ, Ie += 4 * LZ, In += 4 * LZ, Is += 4 * LZ) {
+    double ie[4], iw[4], in[4], is[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LZ], iw[j] = (Ie - S)[j * LZ], in[j] = In[j * LZ], is[j] = Is[j * LZ];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double uu = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
+      const double vv = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
+      up[j * LZ] = uu;
+      vp[j * LZ] = vv;
+      if (DUAL) up2[j * LZ] = uu, vp2[j * LZ] = vv;
+    }
+    if (DUAL) up2 += 4 * LZ, vp2 += 4 * LZ;
+  }
+  if (k < Mz) {
+    double ie[3], iw[3], in[3], is[3];
+    bool ok[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      ok[j] = k + j * LZ < Mz;
+      const int o = ok[j] ? j * LZ : 0; // (a level past the top re-reads the first one; its result is not stored)
+      ie[j] = Ie[o], iw[j] = (Ie - S)[o], in[j] = In[o], is[j] = Is[o];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double uu = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
+      const double vv = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
+      if (ok[j]) {
+        up[j * LZ] = uu;
+        vp[j * LZ] = vv;
+        if (DUAL) up2[j * LZ] = uu, vp2[j * LZ] = vv;
+      }
+    }
+  }
+}
+
 // Stage B for one row of a strip on the rim of the patch: u, v of the regular columns (sia/SIAFD.cc:904-943) stored into
 // this rank's array AND, from the registers, into the ghost cell of the neighbour that faces the column -- the fused
 // ghost update of SIAFD.cc:946-947 (peer memory over NVLink, or this rank's own array: the periodic wrap).  The few
@@ -131,35 +184,16 @@ __device__ __noinline__ void stage_b_rim(const int Mz, const int i_lo, const int
           if (dual) *up2 = ub, *vp2 = vb, up2 += LZ, vp2 += LZ;
         }
       } else {
-        // the same expressions, in the same order, as the in-line stage B of the kernel: the values are bit-identical
-        const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
-        const double hxe = cE[0], hye = cE[1], hxn = cE[2], hyn = cE[3]; // (-0.25 h_x, -0.25 h_y: scaled by the writer)
-        const double hxw = cW[0], hyw = cW[1];
-        const double hxs = south ? cS[2] : 0.0, hys = south ? cS[3] : 0.0;
+        // (the same routine as the in-line stage B of the kernel: the values are bit-identical)
+        const double2 *c2 = reinterpret_cast<const double2 *>(cf);
+        const double2 ce = c2[(s_cur * NC + qp) * 2], cw = c2[(s_cur * NC + qp - 1) * 2], cn = c2[(s_cur * NC + qp) * 2 + 1];
+        const double2 cs = south ? c2[(s_nxt * NC + qp) * 2 + 1] : make_double2(0.0, 0.0);
         const double *Ie = I0_s + qp * S + lz;
         const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
-        int k = lz;
-        for (; k + 3 * LZ < Mz; k += 4 * LZ, up += 4 * LZ, vp += 4 * LZ, Ie += 4 * LZ, In += 4 * LZ, Is += 4 * LZ) {
-          double ie[4], iw[4], in[4], is[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LZ], iw[j] = (Ie - S)[j * LZ], in[j] = In[j * LZ], is[j] = Is[j * LZ];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double uu = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
-            const double vv = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
-            up[j * LZ] = uu;
-            vp[j * LZ] = vv;
-            if (dual) up2[j * LZ] = uu, vp2[j * LZ] = vv;
-          }
-          if (dual) up2 += 4 * LZ, vp2 += 4 * LZ;
-        }
-        for (; k < Mz; k += LZ, up += LZ, vp += LZ, Ie += LZ, In += LZ, Is += LZ) {
-          const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
-          const double uu = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
-          const double vv = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
-          *up = uu;
-          *vp = vv;
-          if (dual) *up2 = uu, *vp2 = vv, up2 += LZ, vp2 += LZ;
+        if (dual) {
+          uv_column<LZ, true>(Mz, lz, S, ub, vb, ce, cw, cn, cs, Ie, In, Is, up, vp, up2, vp2);
+        } else {
+          uv_column<LZ, false>(Mz, lz, S, ub, vb, ce, cw, cn, cs, Ie, In, Is, up, vp, nullptr, nullptr);
         }
       }
     }
@@ -236,9 +270,8 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
   double *aux = A_s + (P.use_age ? 2 * slotE : 0);
   double *I0_s = aux + 2 * AUX_N;
   double *I1_s = I0_s + (FULL ? colI : 0);
-  double *sL = I1_s + (FULL ? 2 * colI : 0); // [2][WZ][NC] delta at the last level of a range; then D of a range
-  double *sT = sL + 2 * WZ * NC;             // [2][WZ][NC] I increment over a range
-  double *cf = sT + 2 * WZ * NC;             // [2][NC][4]  -0.25 h_x, -0.25 h_y of the o = 0 and o = 1 points, by row parity
+  double *sX = I1_s + (FULL ? 2 * colI : 0); // [2][WZ][NC][4] per range: last delta, first delta, I sum, D sum
+  double *cf = sX + 2 * WZ * NC * 4;             // [2][NC][4]  -0.25 h_x, -0.25 h_y of the o = 0 and o = 1 points, by row parity
   double *tab16 = cf + 2 * NC * 4;           // 2^(j/16), for exp_tab
   double2 *selAQ = (double2 *)(tab16 + 16);  // {ln A, Q / R} 16 / ln2 of the cold [0] and the warm [1] Paterson-Budd branch
   unsigned long long *bars = (unsigned long long *)(tab16 + 20);
@@ -655,42 +688,60 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
         const double depk = thk - zz[ks].x;
         dp = fma(0.5 * depk * depk, prev, dp);
       }
-      sL[(pt * WZ + w) * NC + c] = prev;
-      __syncthreads(); // #1: last deltas visible; every read of row r's slot is done
+      // what the ranges of a column exchange: {last delta, first delta} and {I sum, D sum} of each range
+      {
+        double2 *px = reinterpret_cast<double2 *>(sX) + (pt * WZ + w) * NC + c; // (two planes: 16 lanes, 16 contiguous entries)
+        px[0] = make_double2(prev, first);
+        px[2 * WZ * NC] = make_double2(run, dp);
+      }
+      __syncthreads(); // #1: the ranges' sums visible; every read of row r's slot is done
       if (prefetch) {
         issue_row(it + 2, s_cur);
         pending |= (1u << s_cur);
       }
-      // trapezoid across the lower boundary of this range (the range below ends at k0 - 1)
-      double bI = 0.0, bD = 0.0;
-      if (w > 0 && ke >= k0) {
-        const double2 zh = zz[k0];
-        const double dl = sL[(pt * WZ + w - 1) * NC + c], depF = thk - zh.x;
-        bI = zh.y * (dl + first);
-        bD = zh.y * fma(depF + (zh.y + zh.y), dl, depF * first);
-      }
-      sT[(pt * WZ + w) * NC + c] = run + bI; // empty range: 0
-      // D of this range goes where the last delta of the range below was: only this thread reads that entry
-      sL[(pt * WZ + ((w + WZ - 1) % WZ)) * NC + c] = dp + bD;
-      __syncthreads(); // #2
-      if (FULL) {
-        double off = 0.0, tot = 0.0;
+      // The trapezoid across the lower boundary of a range (the range below ends at its first level - 1) belongs to that
+      // range.  Every thread of a column evaluates the boundaries of all its ranges itself -- a few operations -- instead
+      // of a second exchange through shared memory with its own barrier.  Same expressions, same order of the sums as
+      // ever: I offset = sum over the ranges below in ascending order; D = ranges 1, 2, ..., WZ - 1, then range 0.
+      if (FULL || w == 0) {
+        const double2 *px = reinterpret_cast<const double2 *>(sX) + pt * WZ * NC + c;
+        double off = 0.0, tot = 0.0, bI = 0.0, D0 = 0.0, dl = 0.0;
 #pragma unroll
         for (int ww = 0; ww < WZ; ++ww) {
-          const double t = sT[(pt * WZ + ww) * NC + c];
+          const double2 pf = px[ww * NC], rd = px[ww * NC + 2 * WZ * NC]; // {last, first delta}, {I sum, D sum} of range ww
+          double bIw = 0.0, bDw = 0.0;
+          if (ww > 0 && ks >= ww * Lc) { // the range is not empty
+            const double2 zh = zz[ww * Lc];
+            const double depF = thk - zh.x;
+            bIw = zh.y * (dl + pf.y);
+            bDw = zh.y * fma(depF + (zh.y + zh.y), dl, depF * pf.y);
+          }
+          const double t = rd.x + bIw; // empty range: 0
           off += (ww < w) ? t : 0.0;
           tot += t;
+          if (ww == 0) {
+            D0 = rd.y + bDw;
+          } else {
+            Dsum += rd.y + bDw;
+          }
+          bI = (ww == w) ? bIw : bI;
+          dl = pf.x;
         }
-        if (w > 0) {
-          const double add = off + bI;
-          for (int k = k0; k <= ke; ++k) Ic[k] += add;
+        Dsum += D0;
+        if (FULL) {
+          if (w > 0 && ke >= k0) {
+            const double add = off + bI;
+            double *icp = Ic + k0;
+            int n = ke - k0 + 1;
+            for (; n >= 4; n -= 4, icp += 4) {
+              const double a0 = icp[0], a1 = icp[1], a2 = icp[2], a3 = icp[3];
+              icp[0] = a0 + add, icp[1] = a1 + add, icp[2] = a2 + add, icp[3] = a3 + add;
+            }
+            for (; n > 0; --n, ++icp) *icp += add;
+          }
+          // above the ice I keeps its last value (:861-863); ice-free points (ks = -1): I = 0 everywhere
+          for (int k = ks + 1 + w; k < Mz; k += WZ) Ic[k] = tot;
         }
-        // above the ice I keeps its last value (:861-863); ice-free points (ks = -1): I = 0 everywhere
-        for (int k = ks + 1 + w; k < Mz; k += WZ) Ic[k] = tot;
-      }
-      if (w == 0) {
-#pragma unroll
-        for (int ww = 0; ww < WZ; ++ww) Dsum += sL[(pt * WZ + ww) * NC + c];
       }
       if (FULL) ivalid |= 4u | (1u << s_cur);
     } else {
@@ -831,33 +882,12 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
                   *vp = vb;
                 }
               } else {
-                // u = u_b - 0.25 (I_e h_x_e + I_w h_x_w + I_n h_x_n + I_s h_x_s): the factor -0.25 goes into the slopes
-                const double *cE = cf + (s_cur * NC + qp) * 4, *cW = cE - 4, *cS = cf + (s_nxt * NC + qp) * 4;
-                const double hxe = cE[0], hye = cE[1], hxn = cE[2], hyn = cE[3];
-                const double hxw = cW[0], hyw = cW[1];
-                const double hxs = south ? cS[2] : 0.0, hys = south ? cS[3] : 0.0;
+                const double2 *c2 = reinterpret_cast<const double2 *>(cf);
+                const double2 ce = c2[(s_cur * NC + qp) * 2], cw = c2[(s_cur * NC + qp - 1) * 2], cn = c2[(s_cur * NC + qp) * 2 + 1];
+                const double2 cs = south ? c2[(s_nxt * NC + qp) * 2 + 1] : make_double2(0.0, 0.0);
                 const double *Ie = I0_s + qp * S + lz;
                 const double *In = I1_s + (s_cur * NC + qp) * S + lz, *Is = I1_s + (s_nxt * NC + qp) * S + lz;
-                int k = lz;
-                for (; k + 3 * LZ < Mz; k += 4 * LZ, up += 4 * LZ, vp += 4 * LZ, Ie += 4 * LZ, In += 4 * LZ, Is += 4 * LZ) {
-                  double ie[4], iw[4], in[4], is[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) ie[j] = Ie[j * LZ], iw[j] = (Ie - S)[j * LZ], in[j] = In[j * LZ], is[j] = Is[j * LZ];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const double uu = fma(is[j], hxs, fma(in[j], hxn, fma(iw[j], hxw, fma(ie[j], hxe, ub))));
-                    const double vv = fma(is[j], hys, fma(in[j], hyn, fma(iw[j], hyw, fma(ie[j], hye, vb))));
-                    up[j * LZ] = uu;
-                    vp[j * LZ] = vv;
-                  }
-                }
-                for (; k < Mz; k += LZ, up += LZ, vp += LZ, Ie += LZ, In += LZ, Is += LZ) {
-                  const double ie = *Ie, iw = *(Ie - S), in = *In, is = *Is;
-                  const double uu = fma(is, hxs, fma(in, hxn, fma(iw, hxw, fma(ie, hxe, ub))));
-                  const double vv = fma(is, hys, fma(in, hyn, fma(iw, hyw, fma(ie, hye, vb))));
-                  *up = uu;
-                  *vp = vv;
-                }
+                uv_column<LZ, false>(Mz, lz, S, ub, vb, ce, cw, cn, cs, Ie, In, Is, up, vp, nullptr, nullptr);
               }
             }
           }
@@ -885,9 +915,9 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
       m = (o > m) ? o : m;
       cnt += __shfl_xor_sync(FULLMASK, cnt, d);
     }
-    __syncthreads(); // sT is free
-    unsigned long long *wm = (unsigned long long *)sT;
-    int *wc = (int *)(sT + 32);
+    __syncthreads(); // sX is free
+    unsigned long long *wm = (unsigned long long *)sX;
+    int *wc = (int *)(sX + 32);
     if ((tid & 31) == 0) {
       wm[tid >> 5] = m;
       wc[tid >> 5] = cnt;
@@ -912,7 +942,7 @@ static size_t slab_smem_bytes(const DP &P, bool full, int NC, int WZ, bool bulk)
   const long Mz = P.Mz, S = bulk ? Mz : (Mz | 1);
   const long slotE = ((NC + 1) * S + 2 + 1) & ~1L;
   const long colI = (NC * S + 1) & ~1L;
-  long d = 2 * Mz + 2 * slotE + (P.use_age ? 2 * slotE : 0) + 2 * AUX_N + (full ? 3 * colI : 0) + 2 * 2 * WZ * NC +
+  long d = 2 * Mz + 2 * slotE + (P.use_age ? 2 * slotE : 0) + 2 * AUX_N + (full ? 3 * colI : 0) + 2 * WZ * NC * 4 +
            2 * NC * 4 + 16 + 4;
   return (size_t)d * 8 + 2 * 8 /* mbarriers */ + 6 * sizeof(RowCopy) + 16;
 }
