@@ -429,6 +429,7 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1)), out
 
     per_rank_kernel_ms = []
+    step_breakdown = {}
 
     def kernel_only_ms(Rk, steps, fullk=True):
         """CUDA events around the fused kernel alone, on its own stream (ungraphed launches of the same step)."""
@@ -439,8 +440,17 @@ def main():
         barrier()
         nk = C.c_int(0)
         kms = lib.siafd_b200_kernel_time_ms(Rk.sia.handle, C.byref(nk))
+        sec, ns = (C.c_double * 5)(), C.c_int(0)
+        Rk.check(lib.siafd_b200_step_breakdown_ms(Rk.sia.handle, sec, C.byref(ns)))
         Rk.check(lib.siafd_b200_kernel_timing(Rk.sia.handle, 0))
         mine = kms / max(nk.value, 1)
+        # the sections of an (ungraphed) step, per rank; reported as the maximum over the ranks of each section
+        names = ("input_ghosts_2d", "gradient_pass", "wait_before_fused_kernel", "fused_kernel", "uv_arrival_and_reduction")
+        vals = torch.tensor(list(sec), dtype=torch.float64, device=dev)
+        if multi:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        step_breakdown.clear()
+        step_breakdown.update({n: float(v) for n, v in zip(names, vals.tolist())})
         if multi:
             t = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(N)]
             dist.all_gather(t, torch.tensor([mine], dtype=torch.float64, device=dev))
@@ -468,6 +478,7 @@ def main():
         R.step(full)
     k_avg_ms = kernel_only_ms(R, min(args.steps, 10), full)
     kernel_ms_by_rank = list(per_rank_kernel_ms)
+    breakdown = dict(step_breakdown)
     R.step(full)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = sia.launch_count()
@@ -497,7 +508,10 @@ def main():
                 "traffic": None, "dram_frac": None, "kernel": "k_sia_slab", "kernel_ms": k_avg_ms,
                 "peak_source": peak_src, "algorithmic_bytes_per_column": B, "columns_per_launch": patch.xm * patch.ym,
                 "whole_step_frac": B * cols_total / N / (ms / args.steps / 1e3) / 1e9 / peak,
-                "step_minus_kernel_ms": ms / args.steps - k_avg_ms, "kernel_ms_by_rank": kernel_ms_by_rank or None}
+                "step_minus_kernel_ms": ms / args.steps - k_avg_ms, "kernel_ms_by_rank": kernel_ms_by_rank or None,
+                "step_breakdown_ms": breakdown or None,
+                "step_breakdown_note": "CUDA events between the launches of an ungraphed step (max over ranks per "
+                                       "section); the timed region replays the same launches as one CUDA graph"}
     tr = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tr) and N == 1 and full and args.regime == "dome":
         try:  # quoted only if it was captured (ncu --set full) on this very kernel source

@@ -404,6 +404,11 @@ int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t 
  * enable, run updates (<= 256), then read the accumulated milliseconds and launch count. */
 int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable);
 double siafd_b200_kernel_time_ms(siafd_b200_handle *h, int *launches_out);
+/* In the same mode siafd_b200_update_decomposed also times its sections (ungraphed launches, up to 64 steps): average
+ * milliseconds of {ghosts of the 2D inputs, gradient + thk_smooth/theta pass, wait before the fused kernel (ghosts of
+ * the 3D inputs on their side stream; the gradient's ghost update where it is not computed locally), fused kernel,
+ * arrival of u, v + all-rank reduction of D_max / status / counter} -- what bench.py reports as "step_breakdown_ms". */
+int siafd_b200_step_breakdown_ms(siafd_b200_handle *h, double *out5, int *steps_out);
 
 #ifdef __cplusplus
 }

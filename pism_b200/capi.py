@@ -120,6 +120,7 @@ def _load():
         "siafd_b200_flow_n": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
         "siafd_b200_flow_host": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
         "siafd_b200_set_tuning": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+        "siafd_b200_step_breakdown_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
         "siafd_b200_launch_count": (i64, [vp]),
         "siafd_b200_transfer_bytes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "siafd_b200_kernel_timing": (C.c_int, [vp, C.c_int]),

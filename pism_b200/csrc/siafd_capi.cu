@@ -504,6 +504,7 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   for (cudaEvent_t e : h->ev_pipe) cudaEventDestroy(e);
   if (h->s_up) cudaStreamDestroy(h->s_up);
   if (h->s_dn) cudaStreamDestroy(h->s_dn);
+  for (auto &e : h->ev_sec) cudaEventDestroy(e);
   for (size_t q = 0; q < h->ev_start.size(); ++q) {
     cudaEventDestroy(h->ev_start[q]);
     cudaEventDestroy(h->ev_stop[q]);
@@ -1533,6 +1534,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   }
   // gradient and 2D preparation while the first band is in flight
   PeerPush PPu = PeerPush();
+  bool prep_done = false;
   if (comm) {
     const int more[] = {SIAFD_B200_F_W_I, SIAFD_B200_F_W_J};
     for (int f : more) {
@@ -1542,9 +1544,15 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     comm_make_push(h, SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y, c.w_stag, 1, PPg);
     comm_make_push(h, SIAFD_B200_F_U, SIAFD_B200_F_V, c.w_uv, 1, PPu);
     const bool haseloff = c.gradient_method == SIAFD_B200_GRAD_HASELOFF;
-    h->launches += launch_gradient(h->P, fields_of(h), h->stream, haseloff ? &PPg : nullptr); // SIAFD.cc:137, :498-499
+    // SIAFD.cc:137, :498-499; haseloff: thk_smooth / theta in the same pass (no row-segment weights: the bands keep
+    // the plain order)
+    h->P.seg_n = 0;
+    h->launches += launch_gradient(h->P, fields_of(h), h->stream, haseloff ? &PPg : nullptr, haseloff);
     CU(h, cudaGetLastError());
-    if (haseloff && h->comm.size > 1) h->launches += launch_comm_sync(h->comm.d_peers, 2, h->stream);
+    if (haseloff && h->comm.size > 1 && !gradient_ring_is_local(h->P)) {
+      h->launches += launch_comm_sync(h->comm.d_peers, 2, h->stream);
+    }
+    prep_done = haseloff;
   } else {
     if ((st = siafd_b200_compute_gradient(h))) return st;
     if (c.gradient_method == SIAFD_B200_GRAD_HASELOFF) { // sia/SIAFD.cc:498-499
@@ -1552,7 +1560,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
       if ((st = siafd_b200_wrap_ghosts_many(h, 2, hxy))) return st;
     }
   }
-  if ((st = flux_velocity_prepare(h, 1, in->current_time))) return st;
+  if ((st = flux_velocity_prepare(h, 1, in->current_time, prep_done))) return st;
   const int uvf[2] = {SIAFD_B200_F_U, SIAFD_B200_F_V};
   double *uvh[2] = {out->u, out->v};
   for (int b = 0; b < NB; ++b) {
@@ -1794,8 +1802,32 @@ int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable) {
       CU(h, cudaEventCreate(&h->ev_stop[q]));
     }
   }
+  if (enable && h->ev_sec.empty()) {
+    h->ev_sec.resize(6 * 64);
+    for (auto &e : h->ev_sec) CU(h, cudaEventCreate(&e));
+  }
   h->timing = enable != 0;
   h->ev_count = 0;
+  h->sec_count = 0;
+  return SIAFD_B200_OK;
+}
+
+int siafd_b200_step_breakdown_ms(siafd_b200_handle *h, double *out5, int *steps_out) {
+  if (!h) return null_handle();
+  if (!out5) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "null argument");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < 5; ++q) out5[q] = 0.0;
+  for (int n = 0; n < h->sec_count; ++n) {
+    for (int q = 0; q < 5; ++q) {
+      float ms = 0.f;
+      CU(h, cudaEventElapsedTime(&ms, h->ev_sec[6 * n + q], h->ev_sec[6 * n + q + 1]));
+      out5[q] += ms;
+    }
+  }
+  for (int q = 0; q < 5 && h->sec_count > 0; ++q) out5[q] /= h->sec_count;
+  if (steps_out) *steps_out = h->sec_count;
+  h->sec_count = 0;
   return SIAFD_B200_OK;
 }
 

@@ -624,6 +624,12 @@ int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double c
     const int64_t l0 = h->launches;
     int st;
     bool forked = false;
+    // (timing mode, ungraphed: an event after every section of the step, see siafd_b200_step_breakdown_ms)
+    const bool sec = h->timing && !h->ev_sec.empty() && h->sec_count < (int)h->ev_sec.size() / 6;
+    auto mark = [&](int q) {
+      if (sec) cudaEventRecord(h->ev_sec[6 * h->sec_count + q], h->stream);
+    };
+    mark(0);
     if (exchange_inputs) {
       // the inputs' ghosts (device-resident callers; under PISM the host arrays already carry them): the 2D fields on
       // the main stream, the enthalpy beside them on a second one, joined before the fused kernel
@@ -644,6 +650,7 @@ int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double c
       CU(h, cudaEventRecord(C.ev_join, C.s_aux));
       forked = true;
     }
+    mark(1);
     const Fields F = fields_of(h);
     PeerPush PPg;
     comm_make_push(h, SIAFD_B200_F_H_X, SIAFD_B200_F_H_Y, h->cfg.w_stag, 1, PPg);
@@ -659,8 +666,12 @@ int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double c
     h->launches += launch_gradient(h->P, F, h->stream, haseloff ? &PPg : nullptr, haseloff);
     CU(h, cudaGetLastError());
     if ((st = flux_velocity_prepare(h, full_update, current_time, haseloff))) return st;
-    if (haseloff && multi) h->launches += launch_comm_sync(C.d_peers, 2, h->stream);
+    mark(2);
+    // (haseloff with geometry ghosts two cells wide: the pass evaluates the ring of ghost points itself, bit for bit
+    // what the neighbours hold -- no exchange, no synchronisation of the ranks in the middle of the step)
+    if (haseloff && multi && !gradient_ring_is_local(h->P)) h->launches += launch_comm_sync(C.d_peers, 2, h->stream);
     if (forked) CU(h, cudaStreamWaitEvent(h->stream, C.ev_join, 0));
+    mark(3);
     PeerPush PPu;
     comm_make_push(h, SIAFD_B200_F_U, SIAFD_B200_F_V, h->cfg.w_uv, 1, PPu);
     {
@@ -679,10 +690,13 @@ int siafd_b200_update_decomposed(siafd_b200_handle *h, int full_update, double c
       if (n < 0) return fail(h, SIAFD_B200_ERR_CUDA, "could not configure the fused kernel");
       h->launches += n;
     }
+    mark(4);
     // u, v arrival + {D_max, error bits, counter} over all ranks (SIAFD.cc:748-750), straight into pinned host memory
     h->launches += launch_comm_final(C.d_peers, (full_update && multi) ? 3 : -1, h->d_dmax, h->d_err, h->d_hdc, C.d_res,
                                      C.h_res, h->stream);
     CU(h, cudaGetLastError());
+    mark(5);
+    if (sec) h->sec_count += 1;
     C.graph_launches[key] = (int)(h->launches - l0);
     return SIAFD_B200_OK;
   };

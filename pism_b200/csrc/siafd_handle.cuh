@@ -81,6 +81,11 @@ struct siafd_b200_handle {
   std::vector<cudaEvent_t> ev_start, ev_stop;
   int ev_count = 0;
   bool timing = false;
+  // ... and, in the same mode, six events per step of siafd_b200_update_decomposed: start | inputs' ghosts (2D) |
+  // gradient pass | synchronisation before the fused kernel (+ the 3D ghosts' side stream) | fused kernel | final
+  // signal / wait / reduction (siafd_b200_step_breakdown_ms)
+  std::vector<cudaEvent_t> ev_sec;
+  int sec_count = 0;
   std::string err;
 };
 

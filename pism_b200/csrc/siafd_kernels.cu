@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256, 6)
 // and evaluate 32, and the index arithmetic is shared.  Every value is produced by the same expression as in
 // grad_haseloff_point (the tests pin the gradients bit for bit).  The single-point kernel was bound by instruction
 // issue (profiles/ncu_r02_k_grad_haseloff_4096_summary.txt: 20 warp instructions per point, DRAM at 30 %).
-template <bool PUSH>
+template <bool PUSH, bool LOCAL_RING>
 __global__ void __launch_bounds__(128)
     k_grad_haseloff_quad(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
   const int wg = P.wg;
@@ -409,6 +409,11 @@ __global__ void __launch_bounds__(128)
             Y[b][a] = haseloff_direct(h[b][a + 1], h[b + 1][a + 1], M[b][a + 1], M[b + 1][a + 1], P.dy, P.inv_dy);
           }
         }
+        // The reference's second loop runs over the owned points and a ghost update (sia/SIAFD.cc:498-499) brings the
+        // cross components of the ring around them.  With geometry ghosts two cells wide (PISM's WIDE_STENCIL; the
+        // kernel's precondition) a point of that ring has its whole 3 x 3 neighbourhood in this rank's arrays, and the
+        // owner's value is the same expression of the same cells: it is evaluated here, bit for bit, and the exchange --
+        // a synchronisation of all ranks in the middle of the step -- is not needed.
         const bool row_owned = j >= P.ys && j < P.ys + P.ym;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -416,8 +421,8 @@ __global__ void __launch_bounds__(128)
           if (i < P.xs - 1 || i > P.xs + P.xm) continue;
           const HasDirect x00 = X[0][p + 1], y00 = Y[1][p]; // h_x(i, j, 0), w_i(i, j); h_y(i, j, 1), w_j(i, j)
           const long s2 = idx2(P, i, j, P.wst) * 2;
-          if (!row_owned || i < P.xs || i >= P.xs + P.xm) {
-            F.h_x[s2 + 0] = x00.g; // the second loop runs over owned points only; its ghosts come from the exchange
+          if (!LOCAL_RING && (!row_owned || i < P.xs || i >= P.xs + P.xm)) {
+            F.h_x[s2 + 0] = x00.g; // (geometry ghosts one cell wide: the ring's cross components come from an exchange)
             F.h_y[s2 + 1] = y00.g;
             continue;
           }
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(128)
           const double2 hx2 = make_double2(x00.g, hx_cross), hy2 = make_double2(r, y00.g);
           *reinterpret_cast<double2 *>(F.h_x + s2) = hx2; // (a staggered pair starts on a 16-byte boundary)
           *reinterpret_cast<double2 *>(F.h_y + s2) = hy2;
-          if (PUSH) {
+          if (PUSH && !LOCAL_RING) {
             const int a = i - P.xs, b = j - P.ys;
             const bool W_ = a < PP.w, E_ = a >= P.xm - PP.w, S_ = b < PP.w, N_ = b >= P.ym - PP.w;
             if (W_ || E_ || S_ || N_) {
@@ -705,10 +710,12 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush
     if (with_prep2d) {
       const long nq = (long)((P.xm + 2 * P.wg + 3) / 4) * (P.ym + 2 * P.wg); // four points of a row per thread
       const unsigned nb = std::min(nblk(nq, 128), 148u * 16u);
-      if (push != nullptr && push->on) {
-        k_grad_haseloff_quad<true><<<nb, 128, 0, s>>>(P, F, *push);
+      if (gradient_ring_is_local(P)) {
+        k_grad_haseloff_quad<false, true><<<nb, 128, 0, s>>>(P, F, PeerPush());
+      } else if (push != nullptr && push->on) {
+        k_grad_haseloff_quad<true, false><<<nb, 128, 0, s>>>(P, F, *push);
       } else {
-        k_grad_haseloff_quad<false><<<nb, 128, 0, s>>>(P, F, PeerPush());
+        k_grad_haseloff_quad<false, false><<<nb, 128, 0, s>>>(P, F, PeerPush());
       }
     } else if (push != nullptr && push->on) {
       k_grad_haseloff<true, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);

@@ -34,7 +34,10 @@ struct Tuning {
 
 // number of kernel launches each call makes is returned (for gpu_launches accounting)
 int launch_prep2d(const DP &P, const Fields &F, cudaStream_t s);
-// with_prep2d (haseloff only): thk_smooth / theta of launch_prep2d in the same pass; returns the launches made
+// with_prep2d (haseloff only): thk_smooth / theta of launch_prep2d in the same pass; returns the launches made.
+// gradient_ring_is_local: that pass also evaluates the cross components on the ring of ghost points around the patch
+// (geometry ghosts two cells wide), so that the ghost update of sia/SIAFD.cc:498-499 has nothing left to bring
+inline bool gradient_ring_is_local(const DP &P) { return P.grad == GRAD_HASELOFF && P.wg >= 2 && P.wst == 1; }
 int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush *push = nullptr, bool with_prep2d = false);
 // one launch covers the row segments [seg0, seg0 + nseg) of the extended patch (nseg < 0: all from seg0)
 // seg_order: device array of nseg segment indices to take in blockIdx.y order (whole-patch launches only), or NULL

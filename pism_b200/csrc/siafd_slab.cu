@@ -455,16 +455,31 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
       (FULL && uv_col && F.sliding != nullptr) ? F.sliding + idx2(P, i_q, P.ys - P.wsl, P.wsl) * 2 : nullptr;
   const long ssl = 2L * (P.xm + 2 * P.wsl);
 
-  // Sliding velocity of stage B's column: the LB lanes that share a column hold the values of LB consecutive
-  // rows (lane li: row rbase + block * LB + li) and hand them out by shuffle; blocks are loaded two blocks
-  // ahead, so that rows without ice never wait on a load.
+  // Sliding velocity of stage B's column.  Which rows of the strip have a sliding velocity other than zero at all is
+  // found up front, by every warp for itself like the ice flags (lane = row, one ballot per 32 rows; bit j of
+  // sw2:sw1:sw0 = row r0 - 1 + j): the march over rows without ice and without sliding -- the write-only regime, where
+  // the memory system is saturated with stores and a load takes many microseconds -- then never waits on one, and a
+  // row that does slide fetches its values at the top of the row, long before stage B uses them.
   const int rbase = max(ra, P.ys), rend = min(rb, P.ys + P.ym); // stage B rows [rbase, rend)
-  auto sliding_load = [&](int rho) -> double2 {
-    return (sl_p != nullptr && rho < rend) ? __ldg(reinterpret_cast<const double2 *>(sl_p + (long)(rho - (P.ys - P.wsl)) * ssl))
-                                           : make_double2(0.0, 0.0);
-  };
-  double2 sv_cur = make_double2(0.0, 0.0), sv_nxt = make_double2(0.0, 0.0), sv_nx2 = make_double2(0.0, 0.0);
-  if (FULL) sv_cur = sliding_load(rbase + li), sv_nxt = sliding_load(rbase + LB + li), sv_nx2 = sliding_load(rbase + 2 * LB + li);
+  unsigned sw0 = 0u, sw1 = 0u, sw2 = 0u;
+  if (FULL && F.sliding != nullptr) {
+    const int i_first = max(ca + 1, P.xs), i_last = min(ca + NC - 1, P.xs + P.xm - 1);
+    unsigned sw[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int rho = r0 - 1 + 32 * b + lane;
+      bool nz = false;
+      if (rho >= rbase && rho < rend) {
+        const double2 *sr = reinterpret_cast<const double2 *>(F.sliding + idx2(P, i_first, rho, P.wsl) * 2);
+        for (int e = 0; e <= i_last - i_first; ++e) {
+          const double2 sl = __ldg(sr + e);
+          nz |= !(sl.x == 0.0 && sl.y == 0.0);
+        }
+      }
+      sw[b] = __ballot_sync(FULLMASK, nz);
+    }
+    sw0 = sw[0], sw1 = sw[1], sw2 = sw[2];
+  }
 
   // fused ghost update of u, v (SIAFD.cc:946-947): does this strip hold owned columns within PP.w of the west / east
   // edge of the patch (CTA-uniform)
@@ -491,15 +506,11 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
     rf = row_flags(it + 1);
     const long ro = (long)it; // row offset from r0
     double2 sv = make_double2(0.0, 0.0);
-    if (FULL && r >= rbase && r < rend) { // CTA-uniform
-      const int j = (r - rbase) % LB;
-      if (j == 0 && r > rbase) {
-        sv_cur = sv_nxt, sv_nxt = sv_nx2;
-        sv_nx2 = sliding_load(r + 2 * LB + li); // two blocks ahead: rows without ice pass in well under 100 cycles
-      }
-      const int src = (lane & ~(LB - 1)) | j;
-      sv.x = __shfl_sync(FULLMASK, sv_cur.x, src);
-      sv.y = __shfl_sync(FULLMASK, sv_cur.y, src);
+    bool slide = false; // CTA-uniform: some column of the strip slides in this row
+    if (FULL && r >= rbase && r < rend) {
+      const unsigned wsel = (it + 1 < 32) ? sw0 : ((it + 1 < 64) ? sw1 : sw2);
+      slide = ((wsel >> ((it + 1) & 31)) & 1u) != 0u;
+      if (slide && sl_p != nullptr) sv = __ldg(reinterpret_cast<const double2 *>(sl_p + (long)(r - (P.ys - P.wsl)) * ssl));
     }
 
     double Dsum = 0.0, hx = 0.0, hy = 0.0;
@@ -823,7 +834,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
         return T;
       };
       if (BULK && !any_valid && !corner_row && r >= rbase && r < rend) { // CTA-uniform
-        if (__syncthreads_and(sv.x == 0.0 && sv.y == 0.0)) {
+        if (!slide) {
           if (!zero_ready) {
             for (int e = tid; e < NC * S; e += NT) I0_s[e] = 0.0;
             fence_proxy_async();
