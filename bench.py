@@ -375,15 +375,15 @@ def main():
         g0 = G.Grid(M, M, Mz, Lh, Lh, 4000.0)
         H0 = S.dome_2d(g0, capi.default_config(), torch.as_tensor(g0.x, dtype=torch.float64),
                        torch.as_tensor(g0.y, dtype=torch.float64))["thickness"].numpy()
-        # cost of a column relative to an ice-free one: the fused kernel streams ice-free columns at
-        # 3.65 G/s and integrates the dome's icy ones at 1.18 G/s on average (3.1 x), in proportion to the levels below
-        # the surface.  Measured at 8 ranks (profiles/): these ranges bring the central and the outer ranks of PISM's
-        # 2 x 4 grid to within 2 % of each other; a constant ratio (--cost-ratio 2.7: round 1) leaves the central ones
-        # 28 % slower.
+        # cost of a column relative to an ice-free one: fitted to the per-rank times of the fused kernel
+        # measured at 8 ranks (profiles/scale8_variants_r02.json: 1.045 ms on the outer, 1.333 ms on the central patches
+        # of -procs_y 1238,810,810,1238): an ice-free column 0.274 ns, an icy one 0.299 ns + 0.639 ns x H / mean(H), in
+        # proportion to the levels below the surface.  A constant ratio (--cost-ratio 2.7: round 1) leaves the central
+        # ranks 28 % slower than the outer ones.
         if args.cost_ratio > 0:
             cost = np.where(H0 > 0, args.cost_ratio, 1.0)
         else:
-            cost = np.where(H0 > 0, 1.0 + 2.1 * H0 / H0[H0 > 0].mean(), 1.0)
+            cost = np.where(H0 > 0, 1.09 + 2.34 * H0 / H0[H0 > 0].mean(), 1.0)
         procs_x, procs_y = G.balanced_ownership_ranges(cost, Nx_, Ny_)
         del H0, cost
     uniform_x, uniform_y = G.ownership_ranges(M, Nx_), G.ownership_ranges(M, Ny_)

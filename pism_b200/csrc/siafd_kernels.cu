@@ -354,59 +354,80 @@ __global__ void __launch_bounds__(256, 6)
   seg_order_epilogue(P, F);
 }
 
-// The same pass (PREP = true) with FOUR adjacent points of a row per thread.  The 3 x 3 neighbourhoods of the four points
-// overlap: one thread loads 3 x 6 cells and evaluates 20 direct components where four single-point threads load 36 cells
-// and evaluate 32, and the index arithmetic is shared.  Every value is produced by the same expression as in
-// grad_haseloff_point (the tests pin the gradients bit for bit).  The single-point kernel was bound by instruction
-// issue (profiles/ncu_r02_k_grad_haseloff_4096_summary.txt: 20 warp instructions per point, DRAM at 30 %).
+// The same pass (PREP = true) with GQ_ROWS points per thread: a column of rows, the lanes of a warp across x.  The
+// 3 x 3 neighbourhoods of vertically adjacent points overlap: with two rows a thread loads 3 x 4 cells and evaluates 12
+// direct components where two single-point threads load 18 cells and evaluate 16, the index arithmetic is shared, and
+// every load and store of a warp is a contiguous run of 8- or 16-byte items.  Every value is produced by the same
+// expression as in grad_haseloff_point (the tests pin the gradients bit for bit).  The pass is bound by the latency of
+// its chains of predicated selects, not by DRAM (profiles/ncu_r02_k_grad_haseloff_4096_summary.txt: DRAM at 30 %):
+// what counts is warps per SM times work shared per thread, hence two rows at 64 registers (8 CTAs per SM).
+#ifndef GQ_ROWS
+#define GQ_ROWS 2 // points (rows) per thread (measured at 4096^2, B200: 1 / 2 / 4 rows at 8 / 8 / 4 CTAs per SM: 0.54 / 0.47 / 0.65 ms)
+#endif
+#ifndef GQ_MINB
+#define GQ_MINB 8 // CTAs per SM the register allocation aims at (the pass is bound by latency: warps count)
+#endif
+constexpr int GQ_T = 128;    // threads per CTA = columns per tile; a tile is GQ_T columns x GQ_R rows
+constexpr int GQ_R = GQ_ROWS;
 template <bool PUSH, bool LOCAL_RING>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(GQ_T, GQ_MINB)
     k_grad_haseloff_quad(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
   const int wg = P.wg;
   const int nx = P.xm + 2 * wg, ny = P.ym + 2 * wg;
-  const int nqx = (nx + 3) >> 2;
-  const long nq = (long)nqx * ny;
-  for (long Q0 = (long)blockIdx.x * blockDim.x; Q0 < nq; Q0 += (long)gridDim.x * blockDim.x) {
-    const long Q = Q0 + threadIdx.x;
-    int seg = -1, icy_points = 0;
-    if (Q < nq) {
-      const int jy = (int)(Q / nqx), c0 = 4 * (int)(Q - (long)jy * nqx); // row / first column in the geometry-width array
-      const int j = P.ys - wg + jy;
-      const long rowq = (long)jy * nx;
+  const int ntx = (nx + GQ_T - 1) / GQ_T, nty = (ny + GQ_R - 1) / GQ_R;
+  const long nt = (long)ntx * nty;
+  __shared__ int cnt[8];
+  for (long t = blockIdx.x; t < nt; t += gridDim.x) {
+    const int ty = (int)(t / ntx), tx = (int)(t - (long)ty * ntx);
+    const int c0 = tx * GQ_T + threadIdx.x, jy0 = GQ_R * ty; // column / first row in the geometry-width array
+    // weights of the fused kernel's row segments: icy points per segment, counted per CTA in shared memory
+    const int seg_lo = (P.seg_n > 0) ? min(max(jy0 - wg + 1, 0) / P.seg_rows, P.seg_n - 1) : 0;
+    if (P.seg_n > 0) {
+      if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+      __syncthreads();
+    }
+    if (c0 < nx) {
       // thk_smooth, theta (k_prep2d) of the four points
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        if (c0 + p < nx) {
-          const int sp = prep2d_point(P, F, rowq + c0 + p);
-          if (sp >= 0) seg = sp, icy_points += 1;
+      for (int p = 0; p < GQ_R; ++p) {
+        if (jy0 + p < ny) {
+          const int sp = prep2d_point(P, F, (long)(jy0 + p) * nx + c0);
+          if (sp >= 0) {
+            const int d = sp - seg_lo;
+            if (d < 8) {
+              atomicAdd(&cnt[d], 1);
+            } else {
+              atomicAdd(F.segw + sp, 1);
+            }
+          }
         }
       }
       // gradient on owned + 1: rows ys - 1 .. ys + ym, columns xs - 1 .. xs + xm
-      const int ia = P.xs - wg + c0; // column of point 0
-      if (j >= P.ys - 1 && j <= P.ys + P.ym && ia + 3 >= P.xs - 1 && ia <= P.xs + P.xm) {
-        // cells: column index a = 0..5 <-> column ia - 1 + a, row index b = 0..2 <-> row j - 1 + b (clamped to the array:
+      const int i = P.xs - wg + c0, ja = P.ys - wg + jy0; // column, row of point 0
+      if (i >= P.xs - 1 && i <= P.xs + P.xm && ja + GQ_R - 1 >= P.ys - 1 && ja <= P.ys + P.ym) {
+        // cells: column index a = 0..2 <-> column i - 1 + a, row index b = 0..5 <-> row ja - 1 + b (clamped to the array:
         // a clamped cell is only ever read by a point outside owned + 1, which is not stored)
-        double h[3][6];
-        int M[3][6];
+        double h[GQ_R + 2][3];
+        int M[GQ_R + 2][3];
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
-          const int rb = min(max(jy - 1 + b, 0), ny - 1);
+        for (int b = 0; b < GQ_R + 2; ++b) {
+          const int rb = min(max(jy0 - 1 + b, 0), ny - 1);
 #pragma unroll
-          for (int a = 0; a < 6; ++a) {
+          for (int a = 0; a < 3; ++a) {
             const int ca = min(max(c0 - 1 + a, 0), nx - 1);
             const long g = (long)rb * nx + ca;
             h[b][a] = F.h[g];
             M[b][a] = mask_int(F.mask[g]);
           }
         }
-        // direct components: X[b][a] at the i-offset point of cell (a, b + 1), Y[b][a] at the j-offset point of cell (a + 1, b)
-        HasDirect X[2][5], Y[2][5];
+        // direct components: X[a][b] at the i-offset point of cell (a, b + 1), Y[a][b] at the j-offset point of cell (a + 1, b)
+        HasDirect X[2][GQ_R + 1], Y[2][GQ_R + 1];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
+        for (int a = 0; a < 2; ++a) {
 #pragma unroll
-          for (int a = 0; a < 5; ++a) {
-            X[b][a] = haseloff_direct(h[b + 1][a], h[b + 1][a + 1], M[b + 1][a], M[b + 1][a + 1], P.dx, P.inv_dx);
-            Y[b][a] = haseloff_direct(h[b][a + 1], h[b + 1][a + 1], M[b][a + 1], M[b + 1][a + 1], P.dy, P.inv_dy);
+          for (int b = 0; b < GQ_R + 1; ++b) {
+            X[a][b] = haseloff_direct(h[b + 1][a], h[b + 1][a + 1], M[b + 1][a], M[b + 1][a + 1], P.dx, P.inv_dx);
+            Y[a][b] = haseloff_direct(h[b][a + 1], h[b + 1][a + 1], M[b][a + 1], M[b + 1][a + 1], P.dy, P.inv_dy);
           }
         }
         // The reference's second loop runs over the owned points and a ghost update (sia/SIAFD.cc:498-499) brings the
@@ -414,21 +435,21 @@ __global__ void __launch_bounds__(128)
         // kernel's precondition) a point of that ring has its whole 3 x 3 neighbourhood in this rank's arrays, and the
         // owner's value is the same expression of the same cells: it is evaluated here, bit for bit, and the exchange --
         // a synchronisation of all ranks in the middle of the step -- is not needed.
-        const bool row_owned = j >= P.ys && j < P.ys + P.ym;
+        const bool col_owned = i >= P.xs && i < P.xs + P.xm;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int i = ia + p;
-          if (i < P.xs - 1 || i > P.xs + P.xm) continue;
-          const HasDirect x00 = X[0][p + 1], y00 = Y[1][p]; // h_x(i, j, 0), w_i(i, j); h_y(i, j, 1), w_j(i, j)
+        for (int p = 0; p < GQ_R; ++p) {
+          const int j = ja + p;
+          if (j < P.ys - 1 || j > P.ys + P.ym) continue;
+          const HasDirect x00 = X[1][p], y00 = Y[0][p + 1]; // h_x(i, j, 0), w_i(i, j); h_y(i, j, 1), w_j(i, j)
           const long s2 = idx2(P, i, j, P.wst) * 2;
-          if (!LOCAL_RING && (!row_owned || i < P.xs || i >= P.xs + P.xm)) {
+          if (!LOCAL_RING && (!col_owned || j < P.ys || j >= P.ys + P.ym)) {
             F.h_x[s2 + 0] = x00.g; // (geometry ghosts one cell wide: the ring's cross components come from an exchange)
             F.h_y[s2 + 1] = y00.g;
             continue;
           }
-          const bool icy = m_icy(M[1][p + 1]);
-          const HasDirect xm0 = X[0][p], xm1 = X[1][p], x01 = X[1][p + 1];         // (i-1, j), (i-1, j+1), (i, j+1)
-          const HasDirect y0m = Y[0][p], y1m = Y[0][p + 1], y10 = Y[1][p + 1];     // (i, j-1), (i+1, j-1), (i+1, j)
+          const bool icy = m_icy(M[p + 1][1]);
+          const HasDirect xm0 = X[0][p], xm1 = X[0][p + 1], x01 = X[1][p + 1]; // (i-1, j), (i-1, j+1), (i, j+1)
+          const HasDirect y0m = Y[0][p], y1m = Y[1][p], y10 = Y[1][p + 1];     // (i, j-1), (i+1, j-1), (i+1, j)
           double r;
           if (y00.w > 0) { // x-derivative, j-offset (:441-467)
             const double W = x00.w + xm0.w + xm1.w + x01.w;
@@ -461,9 +482,9 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
               for (int d = 0; d < 8; ++d) {
                 if (PP.a[d] != nullptr && peer_strip_member(d, W_, E_, S_, N_)) {
-                  const long t = ((long)(b + P.wst + PP.dj[d]) * PP.rowc[d] + (a + P.wst + PP.di[d])) * 2;
-                  *reinterpret_cast<double2 *>(PP.a[d] + t) = hx2;
-                  *reinterpret_cast<double2 *>(PP.b[d] + t) = hy2;
+                  const long tt = ((long)(b + P.wst + PP.dj[d]) * PP.rowc[d] + (a + P.wst + PP.di[d])) * 2;
+                  *reinterpret_cast<double2 *>(PP.a[d] + tt) = hx2;
+                  *reinterpret_cast<double2 *>(PP.b[d] + tt) = hy2;
                 }
               }
             }
@@ -471,7 +492,11 @@ __global__ void __launch_bounds__(128)
         }
       }
     }
-    seg_weight_cta(P, F, seg, (int)(Q0 / nqx) - wg, icy_points);
+    if (P.seg_n > 0) {
+      __syncthreads();
+      if (threadIdx.x < 8 && cnt[threadIdx.x] != 0) atomicAdd(F.segw + seg_lo + threadIdx.x, cnt[threadIdx.x]);
+      __syncthreads(); // (the counters are reused by the CTA's next tile)
+    }
   }
   seg_order_epilogue(P, F);
 }
@@ -708,14 +733,15 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush
     return 2;
   default:
     if (with_prep2d) {
-      const long nq = (long)((P.xm + 2 * P.wg + 3) / 4) * (P.ym + 2 * P.wg); // four points of a row per thread
-      const unsigned nb = std::min(nblk(nq, 128), 148u * 16u);
+      // tiles of GQ_T columns x GQ_R rows, one thread per column of a tile
+      const long ntiles = (long)((P.xm + 2 * P.wg + GQ_T - 1) / GQ_T) * ((P.ym + 2 * P.wg + GQ_R - 1) / GQ_R);
+      const unsigned nb = (unsigned)std::min<long>(ntiles, 148L * 4L * GQ_MINB);
       if (gradient_ring_is_local(P)) {
-        k_grad_haseloff_quad<false, true><<<nb, 128, 0, s>>>(P, F, PeerPush());
+        k_grad_haseloff_quad<false, true><<<nb, GQ_T, 0, s>>>(P, F, PeerPush());
       } else if (push != nullptr && push->on) {
-        k_grad_haseloff_quad<true, false><<<nb, 128, 0, s>>>(P, F, *push);
+        k_grad_haseloff_quad<true, false><<<nb, GQ_T, 0, s>>>(P, F, *push);
       } else {
-        k_grad_haseloff_quad<false, false><<<nb, 128, 0, s>>>(P, F, PeerPush());
+        k_grad_haseloff_quad<false, false><<<nb, GQ_T, 0, s>>>(P, F, PeerPush());
       }
     } else if (push != nullptr && push->on) {
       k_grad_haseloff<true, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);

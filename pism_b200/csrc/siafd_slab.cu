@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
       double m = 0.0;
       if (rho >= row_lo && rho < row_hi && rho <= rb + 3) {
         const double *tsr = F.thk_smooth + (long)(rho - row_lo) * wgx + cb2;
+#ifndef SLAB_DIAG_NOFLAGS // (diagnostic builds: no ice anywhere, nothing read)
         for (int e = 0; e < ncolE; ++e) m = fmax(m, __ldg(tsr + e));
+#endif
       }
       fw[b] = __ballot_sync(FULLMASK, m > 0.0);
     }
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
     const unsigned lo = it < 32 ? fw0 : (it < 64 ? fw1 : fw2), hi = it < 32 ? fw1 : (it < 64 ? fw2 : 0u);
     return __funnelshift_r(lo, hi, it & 31) & 31u;
   };
-  unsigned rf = row_flags(0);
+  unsigned rf = row_flags(0); // bits 0..4 = rowts(r - 1 .. r + 3) of the current row (prologue: row r0)
 
   // ---- row loader: enthalpy (and age) columns [ca, ca + ncolE) and the 2D scalars of row r -> slot ----
   const int rowcount = ncolE * Mz;
@@ -500,10 +502,10 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
 
   for (int r = r0; r < rb; ++r, DQ_D += sst, DQ_Q += sst) {
     const int it = r - r0;
+    rf = row_flags(it);
     const int s_cur = it & 1, s_nxt = s_cur ^ 1;
     const bool row_active = (rf & 6u) != 0;                    // rowts(r) | rowts(r + 1)
     const bool prefetch = (r + 2 <= rb) && ((rf & 28u) != 0); // rowts(r+1) | (r+2) | (r+3)
-    rf = row_flags(it + 1);
     const long ro = (long)it; // row offset from r0
     double2 sv = make_double2(0.0, 0.0);
     bool slide = false; // CTA-uniform: some column of the strip slides in this row
@@ -781,8 +783,13 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
           }
           dmax_local = fmax(dmax_local, D);
         }
-        *DQ_D = D;
-        *DQ_Q = -D * hq;
+#ifdef SLAB_DIAG_NODQ // (diagnostic builds: D, Q of rows without ice are not written)
+        if (row_active)
+#endif
+        {
+          *DQ_D = D;
+          *DQ_Q = -D * hq;
+        }
       }
     }
 
@@ -805,6 +812,9 @@ __global__ void __launch_bounds__(2 * NC *WZ, (2 * NC * WZ <= 256) ? SLAB_MINB :
       // Write-only rows (no ice at any staggered point of this and the previous row, G9) whose sliding velocity is zero
       // everywhere in the strip: u = v = 0 on every level.  The owned columns of a row are contiguous in memory, so
       // each field's row leaves as ONE bulk store from a block of zeros (measured: 5.2 -> 5.9 TB/s in this regime).
+      // (Tried in round 2: thread t storing row r + t of a whole run of such rows at once.  Slower, 4.75 -> 4.90 ms in the
+      // ice-free regime at 4096^2: the DRAM takes few concurrent store streams best -- tools/store_pattern.cu, 6.0 TB/s
+      // with 16 CTAs per SM writing against 7.0 with 3 -- and sixty rows per CTA in flight scatter the writes.)
       bool row_done = false;
       // rows / strips on the rim of the patch (with a communicator): their u, v also go into the neighbours' ghost cells
       const bool sn_row = (r - P.ys) < PP.w || (r - P.ys) >= P.ym - PP.w;
