@@ -583,7 +583,7 @@ def main():
                                         "algorithmic_bytes_per_column": bh,
                                         "achieved_GBps": bh * cols_total / (ms_h / args.steps / 1e3) / 1e9,
                                         "frac": bh * cols_total / (ms_h / args.steps / 1e3) / 1e9 / peak,
-                                        "note": "FP64-bound where there is ice (exp + 2 cbrt per level), "
+                                        "note": "FP64-bound where there is ice (one exp, one cbrt per level), "
                                                 "write-bound elsewhere"},
                      "mass_continuity_step_ms": ms_m / args.steps,
                      "mass_continuity_launches": 8,
