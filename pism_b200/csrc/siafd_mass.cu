@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(256, 4) k_strain_heating(const __grid_constant
         const double hard = hardness_eval<LAW>(P, e_p[k], pr, A.n, A.inv_n, A.iso_hardness, s_tab16);
         double dpow;
         if (n3) {
-          const double cr = cbrt(d2);
+          const double cr = cbrt(d2); // (a single-precision seed + two Newton steps instead: no faster, 12.3 ms either way)
           dpow = cr * cr;
         } else {
           dpow = pow(d2, exponent);

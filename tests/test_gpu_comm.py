@@ -246,3 +246,31 @@ def test_host_arrays_through_update_on_every_rank(name, decomp, full):
                 assert np.array_equal(cases.interior(got[k], w), cases.interior(want, w)), (k, pt)
             else:
                 assert np.array_equal(got[k], want), (k, pt)
+
+
+def test_step_breakdown_times_the_sections_of_a_step():
+    """siafd_b200_step_breakdown_ms (bench.py's roofline.step_breakdown_ms): in kernel-timing mode every ungraphed step of
+    siafd_b200_update_decomposed leaves five section times; the fused kernel's section agrees with
+    siafd_b200_kernel_time_ms, and reading the breakdown resets it."""
+    grid, cfg, inputs, gb = cases.case("dome_64_21")
+    glob = _global(grid, dict(inputs))
+    patches = G.decompose(grid.Mx, grid.My, 2)
+    sias = _handles(grid, cfg, patches, glob, poison_ghosts=False)
+    for s in sias:
+        s._check(lib.siafd_b200_kernel_timing(s.handle, 1))
+    for rep in range(3):
+        for s in sias:
+            s._check(lib.siafd_b200_update_decomposed(s.handle, 1, 0.0, 1))
+        for s in sias:
+            s._check(lib.siafd_b200_finish(s.handle))
+    for s in sias:
+        sec, n = (C.c_double * 5)(), C.c_int(0)
+        s._check(lib.siafd_b200_step_breakdown_ms(s.handle, sec, C.byref(n)))
+        nk = C.c_int(0)
+        k_ms = lib.siafd_b200_kernel_time_ms(s.handle, C.byref(nk))
+        assert n.value == 3 and nk.value == 3
+        assert all(v >= 0.0 for v in sec) and sec[3] > 0.0
+        assert abs(sec[3] - k_ms / 3) <= 0.5 * sec[3] + 0.05  # the same kernel between neighbouring events
+        s._check(lib.siafd_b200_step_breakdown_ms(s.handle, sec, C.byref(n)))
+        assert n.value == 0
+        s._check(lib.siafd_b200_kernel_timing(s.handle, 0))
