@@ -245,24 +245,15 @@ __device__ __forceinline__ double inv_count(double W) {
   return W == 1.0 ? 1.0 : (W == 2.0 ? 0.5 : (W == 3.0 ? (1.0 / 3.0) : 0.25));
 }
 // PUSH: the ghost update of sia/SIAFD.cc:498-499 fused in -- an owned point on the rim of the patch is also stored into
-// the neighbours' ghost cells (PeerPush, siafd_kernels.cuh)
-// PREP: thk_smooth and theta of SIAFD::compute_diffusivity (sia/SIAFD.cc:580-582; k_prep2d) in the same pass: the threads
-// then cover owned + wg ghosts, and those on owned + 1 go on to the gradient.
-template <bool PUSH, bool PREP>
-__device__ __forceinline__ int grad_haseloff_point(const DP &P, const Fields &F, const PeerPush &PP, const long q) {
-  const int ring = PREP ? P.wg : 1;
-  const int nx = P.xm + 2 * ring;
-  int seg = -1;
-  if (q >= (long)nx * (P.ym + 2 * ring)) {
-    return seg;
+// the neighbours' ghost cells (PeerPush, siafd_kernels.cuh).  One point per thread, on owned + 1: the kernel of the
+// split calls (siafd_b200_compute_gradient); the whole-step entry points take k_grad_haseloff_quad below.
+template <bool PUSH>
+__device__ __forceinline__ void grad_haseloff_point(const DP &P, const Fields &F, const PeerPush &PP, const long q) {
+  const int nx = P.xm + 2;
+  if (q >= (long)nx * (P.ym + 2)) {
+    return;
   }
-  const int i = P.xs - ring + (int)(q % nx), j = P.ys - ring + (int)(q / nx);
-  if (PREP) {
-    seg = prep2d_point(P, F, q); // (ring == wg: q is the point's index in a geometry-width array)
-    if (i < P.xs - 1 || i > P.xs + P.xm || j < P.ys - 1 || j > P.ys + P.ym) {
-      return seg;
-    }
-  }
+  const int i = P.xs - 1 + (int)(q % nx), j = P.ys - 1 + (int)(q / nx);
   // the 3 x 3 cells around (i, j): c[b][a] = cell (i - 1 + a, j - 1 + b)
   double h[3][3];
   int M[3][3];
@@ -283,7 +274,7 @@ __device__ __forceinline__ int grad_haseloff_point(const DP &P, const Fields &F,
   F.h_y[s + 1] = y00.g;
   // (the weights w_i, w_j of the reference's work vectors are not stored: nothing reads them after this kernel)
   if (i < P.xs || i >= P.xs + P.xm || j < P.ys || j >= P.ys + P.ym) {
-    return seg; // the second loop runs over owned points only; its ghosts come from the exchange (:498-499)
+    return; // the second loop runs over owned points only; its ghosts come from the exchange (:498-499)
   }
   const bool icy = m_icy(M[1][1]);
   // neighbours of the second loop, each evaluated as the first loop evaluates it at its own point
@@ -334,27 +325,17 @@ __device__ __forceinline__ int grad_haseloff_point(const DP &P, const Fields &F,
       }
     }
   }
-  return seg;
+  return;
 }
 
-template <bool PUSH, bool PREP>
+template <bool PUSH>
 __global__ void __launch_bounds__(256, 6)
     k_grad_haseloff(const __grid_constant__ DP P, const Fields F, const __grid_constant__ PeerPush PP) {
-  if (!PREP) {
-    grad_haseloff_point<PUSH, PREP>(P, F, PP, (long)blockIdx.x * blockDim.x + threadIdx.x);
-    return;
-  }
-  // PREP: a bounded grid strides over the points in batches of one CTA width (few CTAs: the sort below costs one
-  // atomic per CTA on a single counter)
-  const long n = (long)(P.xm + 2 * P.wg) * (P.ym + 2 * P.wg);
-  for (long q0 = (long)blockIdx.x * blockDim.x; q0 < n; q0 += (long)gridDim.x * blockDim.x) {
-    const int seg = grad_haseloff_point<PUSH, PREP>(P, F, PP, q0 + threadIdx.x);
-    seg_weight_cta(P, F, seg, (int)(q0 / (P.xm + 2 * P.wg)) - P.wg);
-  }
-  seg_order_epilogue(P, F);
+  grad_haseloff_point<PUSH>(P, F, PP, (long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-// The same pass (PREP = true) with GQ_ROWS points per thread: a column of rows, the lanes of a warp across x.  The
+// Gradient AND thk_smooth / theta (k_prep2d) in one pass, GQ_ROWS points per thread: a column of rows, the lanes of a
+// warp across x; the threads cover owned + wg ghosts, those on owned + 1 go on to the gradient.  The
 // 3 x 3 neighbourhoods of vertically adjacent points overlap: with two rows a thread loads 3 x 4 cells and evaluates 12
 // direct components where two single-point threads load 18 cells and evaluate 16, the index arithmetic is shared, and
 // every load and store of a warp is a contiguous run of 8- or 16-byte items.  Every value is produced by the same
@@ -744,9 +725,9 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush
         k_grad_haseloff_quad<false, false><<<nb, GQ_T, 0, s>>>(P, F, PeerPush());
       }
     } else if (push != nullptr && push->on) {
-      k_grad_haseloff<true, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);
+      k_grad_haseloff<true><<<nblk(n1, 256), 256, 0, s>>>(P, F, *push);
     } else {
-      k_grad_haseloff<false, false><<<nblk(n1, 256), 256, 0, s>>>(P, F, PeerPush());
+      k_grad_haseloff<false><<<nblk(n1, 256), 256, 0, s>>>(P, F, PeerPush());
     }
     return 1;
   }

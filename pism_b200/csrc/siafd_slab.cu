@@ -1017,7 +1017,11 @@ template <bool FULL> static int launch_slab_f(const DP &P, const Fields &F, cons
                                               cudaStream_t s, const PeerPush &PP) {
 #ifdef SLAB_DEV // development builds: one instantiation (gpbld, 16 lane columns, 4 z ranges) compiles in seconds
   (void)T;
+#ifdef SLAB_DEV_WZ8 // (experiment: 8 z ranges per column, 256 threads per CTA; build with -DSLAB_MINB=2)
+  return (P.law == LAW_GPBLD && A.use_bulk) ? launch_slab_t<LAW_GPBLD, FULL, 16, 8, true>(P, F, A, s, PP) : -1;
+#else
   return (P.law == LAW_GPBLD && A.use_bulk) ? launch_slab_t<LAW_GPBLD, FULL, 16, 4, true>(P, F, A, s, PP) : -1;
+#endif
 #else
   switch (P.law) {
   case LAW_ISO:
