@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--mz", type=int, default=101)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--settings", default="8:4,16:4,32:4,16:2,16:8", help="fill_threads:band, comma-separated")
+    ap.add_argument("--comm", action="store_true", help="with a one-rank communicator (what bench.py's e2e does at N = 1)")
     args = ap.parse_args()
 
     import torch
@@ -65,6 +66,9 @@ def main():
         os.environ["SIAFD_B200_FILL_THREADS"] = ft
         os.environ["SIAFD_B200_BAND"] = band
         sia = SIAFD(grid, config=cfg, device=0)
+        if args.comm:
+            hs = (C.c_void_p * 1)(sia.handle)
+            assert lib.siafd_b200_comm_init_local(hs, 1) == 0
         ms = []
         for it in range(args.steps + 1):
             t0 = time.perf_counter()
@@ -76,7 +80,7 @@ def main():
                 ms.append((t1 - t0) * 1e3)
         b = (C.c_int64(), C.c_int64())
         lib.siafd_b200_transfer_bytes(sia.handle, C.byref(b[0]), C.byref(b[1]))
-        results.append({"fill_threads": int(ft), "band": int(band), "ms": ms, "best_ms": min(ms), "D_max": dmax,
+        results.append({"comm": bool(args.comm), "fill_threads": int(ft), "band": int(band), "ms": ms, "best_ms": min(ms), "D_max": dmax,
                         "h2d_bytes_per_step": b[0].value // (args.steps + 1),
                         "d2h_bytes_per_step": b[1].value // (args.steps + 1),
                         "sum_abs_u_row_2048": float(host["u"][M // 2].abs().sum())})

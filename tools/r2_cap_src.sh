@@ -1,0 +1,8 @@
+#!/bin/bash
+# ncu --set full of one kernel with the source page: tools/r2_cap_src.sh TAG KERNEL_REGEX bench-args...
+mkdir -p gpurun_out
+TAG=$1; K=$2; shift 2
+ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -o /tmp/$TAG -f python bench.py "$@" > gpurun_out/ncu_$TAG.log 2>&1
+python tools/ncu_summary.py /tmp/$TAG.ncu-rep 80 > gpurun_out/ncu_r02_${TAG}_summary.txt 2>&1
+ncu -i /tmp/$TAG.ncu-rep --page source --csv > gpurun_out/ncu_r02_${TAG}_source.csv 2>/dev/null
+ls -la gpurun_out/ncu_r02_${TAG}_*
