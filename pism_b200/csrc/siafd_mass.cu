@@ -500,7 +500,13 @@ __global__ void __launch_bounds__(256, (NCH <= 4) ? 2 : 1)
 // Two barriers per row.  Shared memory 112 KB at Mz = 101: 2 CTAs per SM.  HBM-bound: 24 Mz bytes per column.
 // Needs an odd Mz (bank layout) -- otherwise the caller falls back to k_vvel_march.
 // ---------------------------------------------------------------------------------------------
-constexpr int VNC = 16;
+#ifndef VVEL_NC
+#define VVEL_NC 16 // columns per strip of k_vvel_slab
+#endif
+#ifndef VVEL_MINB
+#define VVEL_MINB 2 // CTAs per SM its register allocation aims at
+#endif
+constexpr int VNC = VVEL_NC;
 
 struct VvelArgs {
   const double *mask, *thk, *u, *v, *bmr, *z;
@@ -549,7 +555,7 @@ __device__ __forceinline__ int k_below_height_s(const double *zz, int Mz, double
   return ilo;
 }
 
-__global__ void __launch_bounds__(256, 2) k_vvel_slab(const __grid_constant__ DP P, const VvelArgs A) {
+__global__ void __launch_bounds__(VNC * 16, VVEL_MINB) k_vvel_slab(const __grid_constant__ DP P, const VvelArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int Mz = P.Mz, WZ = A.WZ, Lq = A.Lq, T = blockDim.x, tid = threadIdx.x;
   const int SU = vvel_su(Mz), SV = vvel_sv(Mz), SW = vvel_sw(Mz), MzE = (Mz + 1) & ~1;
