@@ -574,6 +574,12 @@ __global__ void __launch_bounds__(VNC * 16, VVEL_MINB) k_vvel_slab(const __grid_
   const int i0 = P.xs + blockIdx.x * VNC, ncol = min(VNC, P.xs + P.xm - i0);
   const int j0 = P.ys + blockIdx.y * A.RS, nrows = min(A.RS, P.ys + P.ym - j0);
   const int c = tid % VNC, q = tid / VNC; // q < WZ
+  // The chores of a row -- issuing the bulk copies and stores, fetching the next row's per-column scalars -- go to the
+  // threads of the LAST z range: it holds the fewest levels (none when WZ Lq >= Mz + Lq), whereas the first range's warp
+  // also takes the CFL maxima; with the chores on warp 0 the other warps waited for it at every barrier (31 % of the
+  // stall samples, profiles/ncu_r02_k_vvel_slab_2048_summary.txt)
+  const int q_io = WZ - 1;
+  const bool is_io = tid == q_io * VNC;
   const long rowuv = (long)(P.xm + 2 * P.wuv) * Mz, rowg = P.xm + 2 * P.wg, roww = (long)P.xm * Mz;
   const long gu0 = idx2(P, i0 - 1, j0, P.wuv) * Mz, gv0 = idx2(P, i0, j0, P.wuv) * Mz;
   const long gw0 = ((long)(j0 - P.ys) * P.xm + (i0 - P.xs)) * Mz;
@@ -623,14 +629,14 @@ __global__ void __launch_bounds__(VNC * 16, VVEL_MINB) k_vvel_slab(const __grid_
     }
     bulk_g2s(slot, base + a0, (unsigned)((a1 - a0) * 8), bar);
   };
-  if (tid == 0) { // rows j0 - 1, j0, j0 + 1 of v and row j0 of u: the group of row r = 0
+  if (is_io) { // rows j0 - 1, j0, j0 + 1 of v and row j0 of u: the group of row r = 0
     unsigned bytes = copy_bytes(gu0, nu);
     for (int rv = -1; rv <= 1; ++rv) bytes += copy_bytes(gv0 + rv * rowuv, nv);
     mbar_expect_tx(&bars[0], bytes);
     copy_issue(A.u, gu0, nu, su, &bars[0]);
     for (int rv = -1; rv <= 1; ++rv) copy_issue(A.v, gv0 + rv * rowuv, nv, sv + ((rv + 1) & 3) * SV, &bars[0]);
   }
-  if (q == 0 && c < ncol) {
+  if (q == q_io && c < ncol) {
     int M[5];
     double H, B;
     load_scalars(j0, M, H, B);
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(VNC * 16, VVEL_MINB) k_vvel_slab(const __grid_
     const int j = j0 + r, sl = r & 1;
     const bool more = r + 1 < nrows;
     // ---- issue the loads of row r + 1: u row r + 1 and v row r + 2 -------------------------------------------------
-    if (tid == 0 && more) {
+    if (is_io && more) {
       const long gu = gu0 + (long)(r + 1) * rowuv, gv = gv0 + (long)(r + 2) * rowuv;
       unsigned long long *bar = &bars[(r + 1) & 1];
       mbar_expect_tx(bar, copy_bytes(gu, nu) + copy_bytes(gv, nv));
@@ -652,7 +658,7 @@ __global__ void __launch_bounds__(VNC * 16, VVEL_MINB) k_vvel_slab(const __grid_
     }
     int Mnext[5];
     double Hnext = 0.0, Bnext = 0.0;
-    const bool pre = more && q == 0 && c < ncol;
+    const bool pre = more && q == q_io && c < ncol;
     if (pre) load_scalars(j + 1, Mnext, Hnext, Bnext);
     mbar_wait(&bars[sl], (r >> 1) & 1);
     // ---- sweep: range-local running integral -----------------------------------------------------------------------
@@ -731,9 +737,9 @@ __global__ void __launch_bounds__(VNC * 16, VVEL_MINB) k_vvel_slab(const __grid_
       }
     }
     fence_proxy_async();                // this thread's shared-memory writes, for the bulk-copy engine
-    if (tid == 0) bulk_wait_read0();    // the store of row r - 1 has read its slot: the next sweep may overwrite it
+    if (is_io) bulk_wait_read0();       // the store of row r - 1 has read its slot: the next sweep may overwrite it
     __syncthreads();
-    if (tid == 0) {
+    if (is_io) {
       const int n = ncol * Mz;
       const long a0 = (gw + 1) & ~1L, a1 = (gw + n) & ~1L; // the 16-byte aligned middle
       const double *src = sw + sl * SW + (gw & 1);
@@ -745,7 +751,7 @@ __global__ void __launch_bounds__(VNC * 16, VVEL_MINB) k_vvel_slab(const __grid_
       }
     }
   }
-  if (tid == 0) bulk_wait_read0();
+  if (is_io) bulk_wait_read0();
   if (docfl) {
     dmax = warp_max(dmax), umax = warp_max(umax), vmax = warp_max(vmax), wmax = warp_max(wmax);
     __syncthreads();
