@@ -461,6 +461,7 @@ def main():
 
     def measure(Rk, steps, fullk=True):
         """Whole-step time (max over ranks) and the fused kernel's own time for one Rank."""
+        barrier()
         for _ in range(3):
             Rk.step(fullk)
         k_ms = kernel_only_ms(Rk, min(steps, 10), fullk)
@@ -622,6 +623,7 @@ def main():
             return lib.siafd_b200_max_diffusivity(sia.handle)
 
         b0, b1 = (C.c_int64(), C.c_int64()), (C.c_int64(), C.c_int64())
+        barrier()   # (pinning gigabytes of host memory takes the ranks of one host seconds apart)
         step_e2e()  # (warm-up, before the byte counters are read)
         lib.siafd_b200_transfer_bytes(sia.handle, C.byref(b0[0]), C.byref(b0[1]))
         ms_e, dmax_e = timed(step_e2e, args.e2e_steps, 0)

@@ -36,13 +36,27 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// bounded spin (a few seconds): a peer that never arrives raises EB_COMM instead of hanging the GPU
+// bounded spin: a peer that never arrives raises EB_COMM instead of hanging the GPU.  The bound is on elapsed time
+// (about half a minute of the global nanosecond timer), not on iterations: ranks legitimately reach a ghost update
+// seconds apart -- e.g. when the hosts of some are still pinning gigabytes of memory (an iteration bound of ~2.5 s made
+// the first host-buffer call of an 8-rank run fail on a busy host).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void wait_at_least(const unsigned long long *p, unsigned long long v, CommPad *self) {
+  unsigned long long t0 = 0ull;
   for (long it = 0; ld_acquire_sys(p) < v; ++it) {
-    if (it >= 128) __nanosleep(it < 1024 ? 32 : 256); // (the first polls back to back: a neighbour is rarely far behind)
-    if (it > (8L << 20)) {
-      self->timed_out = 1u;
-      return;
+    if (it >= 128) __nanosleep(it < 1024 ? 32 : 512); // (the first polls back to back: a neighbour is rarely far behind)
+    if ((it & 0xffff) == 0xffff) { // every ~30 ms: look at the clock
+      const unsigned long long t = globaltimer_ns();
+      if (t0 == 0ull) {
+        t0 = t;
+      } else if (t - t0 > 30ull * 1000000000ull) {
+        self->timed_out = 1u;
+        return;
+      }
     }
   }
 }
