@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full of one kernel of a bench.py run, summarised on the box: tools/r2_cap.sh TAG KERNEL_REGEX BLOCK bench-args...
+# ncu --set full of one kernel of a bench.py run, summarised on the box: tools/ncu_capture.sh TAG KERNEL_REGEX BLOCK bench-args...
 mkdir -p gpurun_out
 TAG=$1; K=$2; BLK=$3; shift 3
 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -o /tmp/$TAG -f python bench.py "$@" > gpurun_out/ncu_$TAG.log 2>&1

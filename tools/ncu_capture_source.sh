@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full of one kernel with the source page: tools/r2_cap_src.sh TAG KERNEL_REGEX bench-args...
+# ncu --set full of one kernel with the source page: tools/ncu_capture_source.sh TAG KERNEL_REGEX bench-args...
 mkdir -p gpurun_out
 TAG=$1; K=$2; shift 2
 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -o /tmp/$TAG -f python bench.py "$@" > gpurun_out/ncu_$TAG.log 2>&1
