@@ -4,7 +4,8 @@
 //   compute_diffusivity            :543-770   (delta column, D, D_max, diffusivity cap, edge override)
 //   compute_diffusive_flux         :772-793
 //   compute_I                      :807-870
-//   compute_3d_horizontal_velocity :890-948   (the ghost exchange at :946-947 stays outside)
+//   compute_3d_horizontal_velocity :890-948   (with a communicator the ghost update of :946-947 too: rim rows store
+//                                              into the neighbours' ghost cells, stage_b_rim / push_rim_row)
 // delta never leaves registers and I only lives in shared memory: HBM sees one read of the enthalpy
 // and one write of u, v.
 //
@@ -18,18 +19,20 @@
 //             (odd) doubles apart, so the column-strided reads of the enthalpy and writes of I are bank-
 //             conflict free, and every per-column scalar (thickness, k_s, slope, theta) is per lane -- no
 //             scans.  The thread integrates levels [w Lc, (w+1) Lc) of its point serially in registers;
-//             Lc = ceil((ks + 1) / WZ) per column.  The WZ partial sums of a column are stitched through
-//             shared memory (two barriers).
+//             Lc = ceil((ks + 1) / WZ) per column (rounded up to whole trips of the level loop).  The WZ ranges of a
+//             column exchange {last delta, first delta, I sum, D sum} through shared memory once (one barrier); every
+//             thread then evaluates the trapezoids across the range boundaries of its column itself.
 //   stage B : thread (q, li): column q, 2 WZ lanes li across z: u, v of the regular column from
 //             I_e, I_w (I0 of lane columns q, q - 1), I_n, I_s (I1 of this and the previous row).
-//   One mbarrier-tracked group of cp.async.bulk copies per row brings the enthalpy row AND the row's 2D
-//   scalars (thk_smooth, theta, h_x, h_y) into shared memory, issued one row ahead of use into the slot
-//   the previous row just vacated; rows no staggered point needs are never loaded, and rows of a strip
-//   without ice skip stage A altogether (u, v = sliding velocity, SIAFD.cc:631-637).
+//   One mbarrier-tracked group of cp.async.bulk copies per row (six copies, issued by six lanes of warp 0 from
+//   descriptors in shared memory) brings the enthalpy row AND the row's 2D scalars (thk_smooth, theta, h_x, h_y) into
+//   shared memory, one row ahead of use into the slot the previous row just vacated; rows no staggered point needs are
+//   never loaded, and rows of a strip without ice skip stage A altogether (u, v = sliding velocity, SIAFD.cc:631-637).
+//   Three barriers per row where there is ice; none of them in rows without.
 //
 // Arithmetic deviations from the reference's glibc build, all far inside the 1e-10 bar:
-// FMA contraction; exp() and the division inside the Arrhenius factor use an inlined 1-ulp exp and a
-// Newton reciprocal; sums over z are taken per z range and then added.
+// FMA contraction; exp() and the division inside the Arrhenius factor use an inlined table-based 2^(y/16) (~2 ulp) and
+// a cubic-step reciprocal (2^-60); sums over z are taken per z range and then added in a fixed order.
 #include "siafd_math.cuh"
 
 #include <atomic>
