@@ -400,6 +400,28 @@ int64_t siafd_b200_launch_count(const siafd_b200_handle *h);
  * and u = v = sliding velocity elsewhere, SIAFD.cc:631-637, :935-942: those parts of u, v are filled on the host);
  * afterwards the DEVICE copy of the enthalpy is only current in those parts. */
 int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t *d2h);
+/* The level cut of that call (single rank, bed smoother off): of a column near ice only the levels [0, n) cross PCIe,
+ * n = siafd_b200_host_levels_needed(z, Mz, T) with T the largest thk_smooth (BedSmoother.cc:306-320 with the
+ * smoother off: 0 without ice, max(H, usurf - topg) where grounded, H where floating) over the column and the columns
+ * next to it.  A staggered point reads the enthalpy on the levels k <= ks = kBelowHeight(thk) only
+ * (SIAFD.cc:613-627, IceGrid.cc:427-440) and I is constant above ks (SIAFD.cc:857-859), so u and v (SIAFD.cc:935-942)
+ * are constant from level n - 1 up: the host replicates that value, and the host arrays are bit-identical to a full
+ * transfer.  Pure host arithmetic (no GPU needed): returns Mz when nothing can be cut.  Environment:
+ * SIAFD_B200_LEVEL_CUT = 0 (off) / 1 (default: single rank) / 2 (also with several ranks),
+ * SIAFD_B200_CUT_COLS (columns that share one n, default 128), SIAFD_B200_REPL_THREADS (default 4). */
+int siafd_b200_host_levels_needed(const double *z, int Mz, double max_thickness);
+/* Dry run of what siafd_b200_update with host arrays moves and fills, on HOST arrays only (no GPU; for tests of the
+ * host logic): the same plan (pism_b200/csrc/siafd_hostplan.hh) -- row bands of `band` segments of rows_per_segment
+ * rows, sparse rectangles, level cut with cut_cols columns per chunk, patch = 1 for one patch of a decomposed domain
+ * -- executed with memcpy.  enthalpy_dev (in/out) stands for the device copy of the enthalpy: it receives what would be
+ * uploaded and nothing else; u_dev, v_dev stand for the device's result (ghosts valid); u, v receive what the call would
+ * leave in the host arrays (downloaded pieces, host fills from `sliding` (may be NULL = zero), values replicated above
+ * the cut, ghost rows / columns).  All arrays in the local ghosted layout of cfg.  h2d / d2h (may be NULL): bytes of the
+ * 3D arrays that would cross PCIe. */
+int siafd_b200_host_plan_emulate(const siafd_b200_config *cfg, int rows_per_segment, int band, int sparse, int level_cut,
+                                 int cut_cols, int patch, const double *thickness, const double *surface, const double *bed,
+                                 const double *mask, const double *sliding, const double *enthalpy, double *enthalpy_dev,
+                                 const double *u_dev, const double *v_dev, double *u, double *v, int64_t *h2d, int64_t *d2h);
 /* CUDA-event timing of the fused kernel alone, on the handle's stream (bench.py's roofline):
  * enable, run updates (<= 256), then read the accumulated milliseconds and launch count. */
 int siafd_b200_kernel_timing(siafd_b200_handle *h, int enable);

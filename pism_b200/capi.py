@@ -123,6 +123,8 @@ def _load():
         "siafd_b200_step_breakdown_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
         "siafd_b200_launch_count": (i64, [vp]),
         "siafd_b200_transfer_bytes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "siafd_b200_host_levels_needed": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_double]),
+        "siafd_b200_host_plan_emulate": (C.c_int, [C.POINTER(Config)] + [C.c_int] * 6 + [vp] * 11 + [C.POINTER(i64)] * 2),
         "siafd_b200_kernel_timing": (C.c_int, [vp, C.c_int]),
         "siafd_b200_kernel_time_ms": (C.c_double, [vp, C.POINTER(C.c_int)]),
     }

@@ -7,6 +7,8 @@
 #include "siafd_handle.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -417,12 +419,17 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.pipeline_host = 1;
   h->tuning.pipeline_band = 1; // 4096^2, segments per band 1 / 2 / 4 / 8: 368 / 375 / 386 / 411 ms (tools/e2e_sweep.py)
   h->tuning.sparse_host = 1;
+  h->tuning.level_cut = 1;
+  h->tuning.cut_cols = 128;
   h->tuning.graph_step = 1;
   h->tuning.order_segments = 1;
   if (const char *e = getenv("SIAFD_B200_ORDER")) h->tuning.order_segments = atoi(e);
   if (const char *e = getenv("SIAFD_B200_GRAPH")) h->tuning.graph_step = atoi(e);
   if (const char *e = getenv("SIAFD_B200_SPARSE")) h->tuning.sparse_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_FILL_THREADS")) h->fill_threads = std::max(1, atoi(e));
+  if (const char *e = getenv("SIAFD_B200_LEVEL_CUT")) h->tuning.level_cut = atoi(e);
+  if (const char *e = getenv("SIAFD_B200_CUT_COLS")) h->tuning.cut_cols = std::max(8, atoi(e));
+  if (const char *e = getenv("SIAFD_B200_REPL_THREADS")) h->repl_threads = std::max(1, atoi(e));
   if (const char *e = getenv("SIAFD_B200_PIPELINE")) h->tuning.pipeline_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_BAND")) h->tuning.pipeline_band = atoi(e);
   if (const char *e = getenv("SIAFD_B200_WZ")) h->tuning.wz = atoi(e);
@@ -1270,143 +1277,115 @@ int siafd_b200_high_diffusivity_count(siafd_b200_handle *h) {
   return h->h_res->hdc;
 }
 
-// siafd_b200_update with host arrays, full update: the three legs of the drop-in call -- host->device copy of the
-// enthalpy, the fused kernel, device->host copy of u and v -- run as a pipeline over bands of rows on three streams
-// (PCIe is full duplex), instead of one after the other.  The bands are whole row segments of the fused kernel, and
-// every array is contiguous in rows, so each leg of a band is one cudaMemcpyAsync / one launch.
-// Where there is no ice the fused kernel reads no enthalpy and writes u = v = sliding velocity on every level
-// (SIAFD.cc:631-637, :935-942), so those parts of the 3D arrays need not cross PCIe: per band of rows only the
-// rectangle of columns within 3 cells of ice goes up (enthalpy) and comes down (u, v); the rest of u, v is filled in
-// place on the host by a few threads while the copies run.  The host arrays end up bit-identical to a full transfer.
-struct IceExtent {
-  std::vector<int> lo, hi; // per owned row: columns [lo, hi] to transfer (lo > hi: none; lo < 0: the whole row)
-};
+// The plan of the call -- which pieces of the 3D arrays cross PCIe, what the host fills in itself -- is plain C++ in
+// siafd_hostplan.hh (checked without a GPU through siafd_b200_host_plan_emulate); this file executes it.
+#include "siafd_hostplan.hh"
+using namespace siafd_hostplan;
 
-static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E, bool patch_mode) {
-  const int xm = c.xm, ym = c.ym, wg = c.w_geom;
-  const long pitch = xm + 2 * wg;
-  if (patch_mode) {
-    // one patch of a decomposed domain: the ghost cells (width wg >= 2) are the neighbours' thickness, no wrap.  A
-    // column matters when there is ice within one cell of it (the staggered points around it); two cells are taken.
-    const int margin = 2, R = ym + 2 * wg;
-    std::vector<int> l0(R), h0(R); // per local row (ghost rows included): local columns [l0, h0] with ice, ghosts included
-    for (int r = 0; r < R; ++r) {
-      const double *row = H + (long)r * pitch;
-      int a = 0, b = (int)pitch - 1;
-      while (a < pitch && row[a] == 0.0) ++a;
-      while (b >= a && row[b] == 0.0) --b;
-      l0[r] = a, h0[r] = b;
-    }
-    E.lo.assign(ym, xm), E.hi.assign(ym, -1);
-    for (int j = 0; j < ym; ++j) {
-      int lo = 1 << 30, hi = -1;
-      for (int d = -margin; d <= margin; ++d) {
-        const int r = j + wg + d; // wg >= margin: always a row of the array
-        if (l0[r] <= h0[r]) lo = std::min(lo, l0[r]), hi = std::max(hi, h0[r]);
-      }
-      if (hi >= lo) {
-        // owned-column indices, clipped to the patch (the enthalpy upload widens a range that touches an edge of the
-        // patch to the ghost columns beyond it; the ghost columns of u, v come down separately)
-        lo = std::max(lo - wg - margin, 0), hi = std::min(hi - wg + margin, xm - 1);
-        E.lo[j] = lo, E.hi[j] = hi;
-      }
-    }
-    return;
-  }
-  const int margin = 3;
-  std::vector<int> l0(ym), h0(ym);
-  for (int j = 0; j < ym; ++j) {
-    const double *row = H + (long)(j + wg) * pitch + wg;
-    int a = 0, b = xm - 1;
-    while (a < xm && row[a] == 0.0) ++a;
-    while (b >= a && row[b] == 0.0) --b;
-    l0[j] = a, h0[j] = b; // a > b: no ice in this row
-  }
-  E.lo.assign(ym, xm), E.hi.assign(ym, -1);
-  for (int j = 0; j < ym; ++j) {
-    int lo = xm, hi = -1;
-    for (int d = -margin; d <= margin; ++d) { // rows wrap periodically, like the ghosts
-      const int jj = ((j + d) % ym + ym) % ym;
-      if (l0[jj] <= h0[jj]) lo = std::min(lo, l0[jj]), hi = std::max(hi, h0[jj]);
-    }
-    if (hi >= lo) {
-      lo -= margin, hi += margin;
-      if (lo < margin || hi > xm - 1 - margin) lo = -1, hi = xm; // ice near the edge of the domain: whole rows
-    }
-    E.lo[j] = lo, E.hi[j] = hi;
-  }
+int siafd_b200_host_levels_needed(const double *z, int Mz, double max_thickness) {
+  return host_levels_needed(z, Mz, max_thickness);
 }
 
-// rectangle of the owned rows [j0, j1) (wrapped into [0, ym)): returns false when there is nothing to transfer
-static bool band_extent(const IceExtent &E, int ym, int j0, int j1, int *lo, int *hi, bool *whole, bool patch_mode = false) {
-  int a = 1 << 30, b = -1;
-  *whole = false;
-  for (int j = j0; j < j1; ++j) {
-    // (a patch: the ghost rows take the extent of the nearest owned row, which already looks two rows past the edge)
-    const int jj = patch_mode ? std::min(std::max(j, 0), ym - 1) : ((j % ym) + ym) % ym;
-    if (E.hi[jj] < E.lo[jj]) continue;
-    if (E.lo[jj] < 0) *whole = true;
-    a = std::min(a, E.lo[jj]), b = std::max(b, E.hi[jj]);
+int siafd_b200_host_plan_emulate(const siafd_b200_config *cfg, int rows_per_segment, int band, int sparse, int level_cut,
+                                 int cut_cols, int patch, const double *thickness, const double *surface, const double *bed,
+                                 const double *mask, const double *sliding, const double *enthalpy, double *enthalpy_dev,
+                                 const double *u_dev, const double *v_dev, double *u, double *v, int64_t *h2d, int64_t *d2h) {
+  if (!cfg || !cfg->z || rows_per_segment < 1 || !thickness || !surface || !mask || !enthalpy || !enthalpy_dev || !u_dev ||
+      !v_dev || !u || !v || (level_cut && !bed)) {
+    return SIAFD_B200_ERR_BAD_ARGUMENT;
   }
-  *lo = a, *hi = b;
-  return b >= a || *whole;
-}
-
-// n doubles starting at p set to `value` with non-temporal stores where the ISA has them: the filled parts of u, v
-// (gigabytes) are not read again by this call, and a regular store would first read every cache line it overwrites,
-// doubling the DRAM traffic that competes with the PCIe copies landing in the same arrays
-static void fill_stream(double *p, size_t n, double value) {
-#if defined(__x86_64__) || defined(_M_X64)
-  size_t k = 0;
-  while (k < n && (reinterpret_cast<uintptr_t>(p + k) & 15u)) p[k++] = value;
-  const __m128d v = _mm_set1_pd(value);
-  for (; k + 8 <= n; k += 8) {
-    _mm_stream_pd(p + k, v);
-    _mm_stream_pd(p + k + 2, v);
-    _mm_stream_pd(p + k + 4, v);
-    _mm_stream_pd(p + k + 6, v);
+  const siafd_b200_config &c = *cfg;
+  HostPlan P;
+  plan_host_update(c, rows_per_segment, band, sparse != 0, level_cut != 0, patch != 0, cut_cols, 2, thickness, surface, bed, mask,
+                   P);
+  const int we = c.w_3d_in, wuv = c.w_uv, Mz = c.Mz;
+  const long cellsE = c.xm + 2 * we, cellsUV = c.xm + 2 * wuv, rowUV = cellsUV * Mz;
+  int64_t up = 0, dn = 0;
+  for (const Piece &p : P.up_pieces) copy_piece_host(enthalpy_dev, enthalpy, cellsE, Mz, p), up += piece_bytes(p);
+  if (!P.fills.empty()) fill_rows(c, sliding, u, v, P.fills.data(), P.fills.size(), 0, 1);
+  for (const Piece &p : P.down_pieces) {
+    copy_piece_host(u, u_dev, cellsUV, Mz, p), copy_piece_host(v, v_dev, cellsUV, Mz, p);
+    dn += 2 * piece_bytes(p);
   }
-  for (; k + 2 <= n; k += 2) _mm_stream_pd(p + k, v);
-  for (; k < n; ++k) p[k] = value;
-#else
-  std::fill(p, p + n, value);
-#endif
-}
-
-struct FillTask {
-  int j, c0, c1; // owned row, local columns [c0, c1) of the u / v arrays (ghost columns included)
-};
-
-// u, v of ice-free columns: the sliding velocity on every level (zero when there is no sliding field)
-static void fill_rows(const siafd_b200_config &c, const double *sliding, double *u, double *v, const FillTask *tasks,
-                      size_t n, size_t first, size_t stride) {
-  const int wuv = c.w_uv, wsl = c.w_sliding, Mz = c.Mz, xm = c.xm;
-  const long rowUV = (long)(xm + 2 * wuv) * Mz, pitchS = (long)(xm + 2 * wsl) * 2;
-  for (size_t t = first; t < n; t += stride) {
-    const FillTask &T = tasks[t];
-    double *ur = u + (long)(T.j + wuv) * rowUV, *vr = v + (long)(T.j + wuv) * rowUV;
-    bool zero = true;
-    if (sliding) {
-      const double *sr = sliding + (long)(T.j + wsl) * pitchS + 2L * wsl;
-      for (int cc = T.c0; cc < T.c1 && zero; ++cc) {
-        const int i = ((cc - wuv) % xm + xm) % xm; // ghost columns wrap periodically
-        zero = (sr[2L * i] == 0.0 && sr[2L * i + 1] == 0.0);
-      }
-      if (!zero) {
-        for (int cc = T.c0; cc < T.c1; ++cc) {
-          const int i = ((cc - wuv) % xm + xm) % xm;
-          fill_stream(ur + (long)cc * Mz, (size_t)Mz, sr[2L * i]);
-          fill_stream(vr + (long)cc * Mz, (size_t)Mz, sr[2L * i + 1]);
+  for (const ReplTask &T : P.repl) replicate_piece(T.p, u, v, cellsUV, Mz);
+  // the end of update_host_pipelined: ghost rows, and the ghost columns of a patch's owned rows
+  const double *src[2] = {u_dev, v_dev};
+  double *dst[2] = {u, v};
+  for (int q = 0; q < 2; ++q) {
+    if (patch) {
+      for (int j = wuv; j < c.ym + wuv; ++j) {
+        for (int side = 0; side < 2; ++side) {
+          const long off = (long)j * rowUV + (side ? (long)(c.xm + wuv) * Mz : 0L);
+          std::memcpy(dst[q] + off, src[q] + off, (size_t)wuv * Mz * sizeof(double));
         }
       }
+      dn += 2 * (int64_t)wuv * Mz * 8 * c.ym;
     }
-    if (zero) {
-      fill_stream(ur + (long)T.c0 * Mz, (size_t)(T.c1 - T.c0) * Mz, 0.0);
-      fill_stream(vr + (long)T.c0 * Mz, (size_t)(T.c1 - T.c0) * Mz, 0.0);
+    std::memcpy(dst[q], src[q], (size_t)wuv * rowUV * sizeof(double));
+    const long off = (long)(wuv + c.ym) * rowUV;
+    std::memcpy(dst[q] + off, src[q] + off, (size_t)wuv * rowUV * sizeof(double));
+    dn += 2 * (int64_t)wuv * rowUV * 8;
+  }
+  if (h2d) *h2d = up;
+  if (d2h) *d2h = dn;
+  return SIAFD_B200_OK;
+}
+
+// one piece between a host and a device array of rows of `row_cells` columns (same local layout on both sides)
+static cudaError_t copy_piece(double *dst, const double *src, long row_cells, int Mz, const Piece &p, cudaMemcpyKind kind,
+                              cudaStream_t s) {
+  const size_t colB = (size_t)Mz * sizeof(double);
+  if (p.n >= Mz) {
+    const long off = (long)p.r0 * row_cells * Mz + (long)p.c0 * Mz;
+    if (p.c1 - p.c0 == row_cells) {
+      return cudaMemcpyAsync(dst + off, src + off, (size_t)(p.r1 - p.r0) * row_cells * colB, kind, s);
     }
+    return cudaMemcpy2DAsync(dst + off, (size_t)row_cells * colB, src + off, (size_t)row_cells * colB,
+                             (size_t)(p.c1 - p.c0) * colB, (size_t)(p.r1 - p.r0), kind, s);
+  }
+  cudaMemcpy3DParms q;
+  memset(&q, 0, sizeof(q));
+  q.srcPtr = make_cudaPitchedPtr(const_cast<double *>(src), colB, colB, (size_t)row_cells);
+  q.dstPtr = make_cudaPitchedPtr(dst, colB, colB, (size_t)row_cells);
+  q.srcPos = make_cudaPos(0, (size_t)p.c0, (size_t)p.r0);
+  q.dstPos = q.srcPos;
+  q.extent = make_cudaExtent((size_t)p.n * sizeof(double), (size_t)(p.c1 - p.c0), (size_t)(p.r1 - p.r0));
+  q.kind = kind;
+  return cudaMemcpy3DAsync(&q, s);
+}
+
+// The host threads that replicate above the cut: the tasks of a band may start once its copies have finished (the
+// band's event), which the issuing thread announces through `recorded` after it has recorded that event.
+struct ReplShared {
+  std::atomic<int> recorded{0}; // bands whose download event has been recorded
+  std::atomic<bool> abort{false};
+  std::atomic<int> failed{0};
+};
+
+static void replicate_pieces(int device, const cudaEvent_t *done, ReplShared *S, const ReplTask *tasks, size_t n, size_t first,
+                             size_t stride, double *u, double *v, long row_cells, int Mz) {
+  if (cudaSetDevice(device) != cudaSuccess) {
+    S->failed = 1;
+    return;
+  }
+  int synced = -1;
+  for (size_t t = first; t < n; t += stride) {
+    const ReplTask &T = tasks[t];
+    if (T.band != synced) {
+      while (S->recorded.load(std::memory_order_acquire) <= T.band) {
+        if (S->abort.load(std::memory_order_acquire)) return;
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+      }
+      if (cudaEventSynchronize(done[T.band]) != cudaSuccess) {
+        S->failed = 1;
+        return;
+      }
+      synced = T.band;
+    }
+    replicate_piece(T.p, u, v, row_cells, Mz);
   }
 #if defined(__x86_64__) || defined(_M_X64)
-  _mm_sfence(); // the streamed stores are globally visible before the thread is joined
+  _mm_sfence();
 #endif
 }
 
@@ -1417,10 +1396,24 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     CU(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
     CU(h, cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking));
   }
-  const int RS = slab_rows_per_segment(h->tuning), nseg = slab_segments(h->P, h->tuning);
-  const int band = std::max(1, h->tuning.pipeline_band);
-  const int NB = (nseg + band - 1) / band;
-  while ((int)h->ev_pipe.size() < 2 * NB + 4) {
+  // With a communicator (siafd_b200_comm_init*, one rank or many) the ghost updates of h_x, h_y and u, v are stores by
+  // the producing kernels into the neighbours' arrays (this rank's own where it is its own periodic neighbour), and the
+  // status / D_max are reduced over all ranks.  patch: the neighbours in x are other ranks, so the ghost columns of
+  // u, v arrive from them and are downloaded at the end, with the ghost rows.
+  const bool comm = h->comm.active;
+  const bool patch = comm && (c.xm != c.Mx || c.ym != c.My);
+  // which parts of the 3D arrays have to move at all (sparse = 0 moves everything); the level cut: bed smoother off,
+  // the bed given with this call; several ranks per host only when asked for (level_cut = 2) -- there the call is bound
+  // by the host's memory system, which the cut does not relieve
+  const bool sparse = h->tuning.sparse_host != 0;
+  const bool cut = sparse && in->bed && !(c.smoother_range > 0.0) && !h->smoother_set &&
+                   (h->tuning.level_cut >= 2 || (h->tuning.level_cut == 1 && (!comm || h->comm.size == 1)));
+  HostPlan plan;
+  plan_host_update(c, slab_rows_per_segment(h->tuning), h->tuning.pipeline_band, sparse, cut, patch, h->tuning.cut_cols,
+                   h->fill_threads, in->thickness, in->surface, in->bed, in->mask, plan);
+  const int NB = plan.NB, band = plan.band, nseg = plan.nseg;
+  if (nseg != slab_segments(h->P, h->tuning)) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "host plan and kernel disagree on the row segments");
+  while ((int)h->ev_pipe.size() < 3 * NB + 4) {
     cudaEvent_t e;
     CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->ev_pipe.push_back(e);
@@ -1431,64 +1424,42 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     if ((st = ensure(h, f))) return st;
   }
   const int we = c.w_3d_in, wuv = c.w_uv;
-  const long rowsE = c.ym + 2 * we, rowE = (long)(c.xm + 2 * we) * c.Mz;
   const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
-  // ---- which parts of the 3D arrays have to move at all (sparse = 0 moves everything) ----
-  const bool sparse = h->tuning.sparse_host != 0;
-  // With a communicator (siafd_b200_comm_init*, one rank or many) the ghost updates of h_x, h_y and u, v are stores by
-  // the producing kernels into the neighbours' arrays (this rank's own where it is its own periodic neighbour), and the
-  // status / D_max are reduced over all ranks.  patch: the neighbours in x are other ranks, so the ghost columns of
-  // u, v arrive from them and are downloaded at the end, with the ghost rows.
-  const bool comm = h->comm.active;
-  const bool patch = comm && (c.xm != c.Mx || c.ym != c.My);
-  IceExtent ext;
-  if (sparse) ice_extent(c, in->thickness, ext, patch);
-  // the host fills what is not downloaded; the tasks are known up front, so the threads start before the copies
-  std::vector<FillTask> fills;
+  // the host's own work is known up front, so its threads start before the copies: the fills at once, the tasks above
+  // the cut as their bands come down
   std::vector<std::thread> workers;
-  struct Rect {
-    int o0, o1, c0, c1; // owned rows [o0, o1), local columns [c0, c1) of u / v to download (c0 >= c1: none)
-  };
-  std::vector<Rect> down(NB);
-  for (int b = 0; b < NB; ++b) {
-    const int s0 = b * band, s1 = std::min(nseg, (b + 1) * band);
-    // (a patch: owned columns only -- the ghost columns are the neighbours' to fill and come down at the end)
-    Rect R{std::max(0, s0 * RS - 1), std::min(c.ym, s1 * RS - 1), patch ? wuv : 0, patch ? c.xm + wuv : c.xm + 2 * wuv};
-    if (sparse && R.o1 > R.o0) {
-      int lo, hi;
-      bool whole;
-      const bool any = band_extent(ext, c.ym, R.o0, R.o1, &lo, &hi, &whole, patch);
-      if (!any) {
-        R.c0 = R.c1 = 0;
-      } else if (!whole) {
-        R.c0 = lo + wuv, R.c1 = hi + 1 + wuv;
-      }
-      // (a patch: the host fills owned columns only; the ghost columns come down from the device at the end)
-      const int f0 = patch ? wuv : 0, f1 = patch ? c.xm + wuv : c.xm + 2 * wuv;
-      for (int j = R.o0; j < R.o1; ++j) {
-        if (R.c0 >= R.c1) {
-          fills.push_back({j, f0, f1});
-        } else {
-          if (R.c0 > f0) fills.push_back({j, f0, R.c0});
-          if (R.c1 < f1) fills.push_back({j, R.c1, f1});
-        }
-      }
-    }
-    down[b] = R;
-  }
+  ReplShared repl_state;
+  const std::vector<FillTask> &fills = plan.fills;
+  const std::vector<ReplTask> &repl = plan.repl;
+  const std::vector<Piece> &pieces = plan.down_pieces;
+  const std::vector<size_t> &piece0 = plan.down0;
   if (!fills.empty()) {
     const size_t nt = std::min<size_t>(std::max(1u, std::min((unsigned)h->fill_threads, std::thread::hardware_concurrency())), fills.size());
     for (size_t t = 0; t < nt; ++t) {
       workers.emplace_back(fill_rows, std::cref(c), in->sliding, out->u, out->v, fills.data(), fills.size(), t, nt);
     }
   }
+  const cudaEvent_t *ev_down = h->ev_pipe.data() + 2 * NB + 4; // band b's copies of u, v have finished
+  if (!repl.empty()) {
+    const size_t nt = std::min<size_t>(std::max(1u, std::min((unsigned)h->repl_threads, std::thread::hardware_concurrency())), repl.size());
+    for (size_t t = 0; t < nt; ++t) {
+      workers.emplace_back(replicate_pieces, h->device, ev_down, &repl_state, repl.data(), repl.size(), t, nt, out->u, out->v,
+                           (long)(c.xm + 2 * wuv), c.Mz);
+    }
+  }
   struct Joiner { // the workers are joined on every way out of this function
     std::vector<std::thread> &w;
-    ~Joiner() {
+    ReplShared &S;
+    bool released = false;
+    void join() {
       for (auto &t : w)
         if (t.joinable()) t.join();
     }
-  } joiner{workers};
+    ~Joiner() {
+      if (!released) S.abort = true; // an early return: tasks that still wait for their band give up
+      join();
+    }
+  } joiner{workers, repl_state};
 
   cudaEvent_t ev_start = h->ev_pipe[2 * NB];
   CU(h, cudaEventRecord(ev_start, h->stream)); // earlier work on the handle's stream (fresh buffers' zero-fill)
@@ -1503,33 +1474,13 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   for (auto &q : small) {
     if (q.p && (st = siafd_b200_upload(h, q.f, q.p))) return st;
   }
-  // enthalpy bands on the upload stream: band b reads local rows below (b + 1) band RS + w_3d_in (+1 of slack)
+  // enthalpy bands on the upload stream
   double *E_dev = (double *)h->buf[SIAFD_B200_F_ENTHALPY];
-  auto upload_rows = [&](long r0, long r1) -> int { // local rows [r0, r1) of the enthalpy array
-    if (r1 <= r0) return SIAFD_B200_OK;
-    int lo = 0, hi = 0;
-    bool whole = true;
-    if (sparse && !band_extent(ext, c.ym, (int)r0 - we, (int)r1 - we, &lo, &hi, &whole, patch)) return SIAFD_B200_OK; // no ice
-    if (!sparse || whole) {
-      CU(h, cudaMemcpyAsync(E_dev + r0 * rowE, in->enthalpy + r0 * rowE, (size_t)(r1 - r0) * rowE * sizeof(double),
-                            cudaMemcpyHostToDevice, h->s_up));
-      h->bytes_h2d += (int64_t)(r1 - r0) * rowE * 8;
-    } else {
-      // local columns [c0, c1) of the enthalpy array; a patch: a range that touches an edge takes the ghost columns too
-      const int c0 = (patch && lo <= 0) ? 0 : lo + we, c1 = (patch && hi >= c.xm - 1) ? c.xm + 2 * we : hi + 1 + we;
-      h->bytes_h2d += (int64_t)(c1 - c0) * c.Mz * 8 * (r1 - r0);
-      const long off = r0 * rowE + (long)c0 * c.Mz;
-      CU(h, cudaMemcpy2DAsync(E_dev + off, (size_t)rowE * sizeof(double), in->enthalpy + off, (size_t)rowE * sizeof(double),
-                              (size_t)(c1 - c0) * c.Mz * sizeof(double), (size_t)(r1 - r0), cudaMemcpyHostToDevice,
-                              h->s_up));
-    }
-    return SIAFD_B200_OK;
-  };
-  long up0 = 0;
   for (int b = 0; b < NB; ++b) {
-    const long up1 = (b == NB - 1) ? rowsE : std::min<long>(rowsE, (long)std::min(nseg, (b + 1) * band) * RS + we + 1);
-    if ((st = upload_rows(up0, up1))) return st;
-    up0 = std::max(up0, up1);
+    for (size_t t = plan.up0[b]; t < plan.up0[b + 1]; ++t) {
+      CU(h, copy_piece(E_dev, in->enthalpy, c.xm + 2 * we, c.Mz, plan.up_pieces[t], cudaMemcpyHostToDevice, h->s_up));
+      h->bytes_h2d += piece_bytes(plan.up_pieces[t]);
+    }
     CU(h, cudaEventRecord(h->ev_pipe[b], h->s_up));
   }
   // gradient and 2D preparation while the first band is in flight
@@ -1568,7 +1519,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_pipe[b], 0));
     if ((st = flux_velocity_launch(h, 1, s0, s1 - s0, comm ? &PPu : nullptr))) return st;
     // owned rows of this band (extended row e = ys - 1 + s RS ... ; owned rows are ys .. ys + ym - 1)
-    const Rect &R = down[b];
+    const HostPlan::Rect &R = plan.down[b];
     const int o0 = R.o0, o1 = R.o1;
     if (o1 > o0) {
       for (int q = 0; q < 2 && !comm; ++q) { // periodic wrap in x of the band's rows (SIAFD.cc:946-947), then download
@@ -1580,18 +1531,17 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
       }
       CU(h, cudaEventRecord(h->ev_pipe[NB + b], h->stream));
       CU(h, cudaStreamWaitEvent(h->s_dn, h->ev_pipe[NB + b], 0));
-      for (int q = 0; q < 2 && R.c1 > R.c0; ++q) {
-        const long off = (long)(wuv + o0) * rowUV + (long)R.c0 * c.Mz;
-        h->bytes_d2h += (int64_t)(R.c1 - R.c0) * c.Mz * 8 * (o1 - o0);
-        if (R.c0 == 0 && R.c1 == c.xm + 2 * wuv) {
-          CU(h, cudaMemcpyAsync(uvh[q] + off, (double *)h->buf[uvf[q]] + off, (size_t)(o1 - o0) * rowUV * sizeof(double),
-                                cudaMemcpyDeviceToHost, h->s_dn));
-        } else {
-          CU(h, cudaMemcpy2DAsync(uvh[q] + off, (size_t)rowUV * sizeof(double), (double *)h->buf[uvf[q]] + off,
-                                  (size_t)rowUV * sizeof(double), (size_t)(R.c1 - R.c0) * c.Mz * sizeof(double),
-                                  (size_t)(o1 - o0), cudaMemcpyDeviceToHost, h->s_dn));
+      for (size_t t = piece0[b]; t < piece0[b + 1]; ++t) {
+        const Piece &p = pieces[t];
+        for (int q = 0; q < 2; ++q) {
+          CU(h, copy_piece(uvh[q], (const double *)h->buf[uvf[q]], c.xm + 2 * wuv, c.Mz, p, cudaMemcpyDeviceToHost, h->s_dn));
+          h->bytes_d2h += piece_bytes(p);
         }
       }
+    }
+    if (!repl.empty()) { // (also for a band without copies: the counter is the number of bands issued)
+      CU(h, cudaEventRecord(ev_down[b], h->s_dn));
+      repl_state.recorded.store(b + 1, std::memory_order_release);
     }
   }
   // ghost rows of u, v (periodic wrap in y / the neighbours' stores), the 2D outputs, D_max and the error flags
@@ -1632,6 +1582,9 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   st = siafd_b200_finish(h);
   CU(h, cudaStreamSynchronize(h->s_dn));
   CU(h, cudaStreamSynchronize(h->s_up));
+  joiner.released = true;
+  joiner.join();
+  if (repl_state.failed.load()) return fail(h, SIAFD_B200_ERR_CUDA, "a host thread of the level cut could not wait for its band");
   return st;
 }
 

@@ -28,6 +28,9 @@ struct Tuning {
   int pipeline_host; // 1: siafd_b200_update with host arrays overlaps upload, kernel and download over row bands
   int pipeline_band; // row segments per band of that pipeline
   int sparse_host;   // 1: that pipeline moves only the parts of the 3D arrays that are within 3 cells of ice
+  int level_cut;     // 1: ... and of those columns only the levels up to the thickest ice nearby (u, v are constant
+                     // above the surface, the enthalpy is not read there); the host replicates the top value
+  int cut_cols;      // columns per chunk of a band that share one cut level
   int graph_step;    // 1: siafd_b200_update_decomposed replays a captured CUDA graph of the step
   int order_segments; // 1: the fused kernel takes its row segments heaviest (most icy points) first: short tail
 };

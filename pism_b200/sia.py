@@ -174,6 +174,12 @@ class SIAFD(SSB_Modifier):
     def launch_count(self):
         return lib.siafd_b200_launch_count(self._h)
 
+    def transfer_bytes(self):
+        """(host -> device, device -> host) bytes the host-array calls of this solver have moved since it was made."""
+        up, dn = C.c_int64(0), C.c_int64(0)
+        self._check(lib.siafd_b200_transfer_bytes(self._h, C.byref(up), C.byref(dn)))
+        return up.value, dn.value
+
     def set_tuning(self, rows_per_cta=0, use_bulk_copy=-1, skip_ice_free_rows=-1):
         self._check(lib.siafd_b200_set_tuning(self._h, rows_per_cta, use_bulk_copy, skip_ice_free_rows))
 

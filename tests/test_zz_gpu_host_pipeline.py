@@ -14,7 +14,8 @@ import gpu_util as U
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ("SIAFD_B200_PIPELINE", "SIAFD_B200_BAND", "SIAFD_B200_ROWS", "SIAFD_B200_SPARSE")
+KNOBS = ("SIAFD_B200_PIPELINE", "SIAFD_B200_BAND", "SIAFD_B200_ROWS", "SIAFD_B200_SPARSE", "SIAFD_B200_LEVEL_CUT",
+         "SIAFD_B200_CUT_COLS", "SIAFD_B200_REPL_THREADS", "SIAFD_B200_FILL_THREADS")
 
 
 @pytest.fixture
@@ -28,17 +29,30 @@ def knobs():
             os.environ[k] = v
 
 
-def _run(name, **env):
+def _sliding(grid, cfg, inputs):
+    """A sliding velocity that is nonzero under the ice and over part of the ice-free ground (periodic in x, y)."""
+    w = cfg.w_sliding
+    jj, ii = np.meshgrid(np.arange(-w, grid.My + w) % grid.My, np.arange(-w, grid.Mx + w) % grid.Mx, indexing="ij")
+    s = np.zeros(inputs["sliding"].shape)
+    s[..., 0] = 3e-7 * np.sin(2 * np.pi * ii / grid.Mx) * (jj > grid.My // 3)
+    s[..., 1] = -2e-7 * np.cos(2 * np.pi * jj / grid.My) * (ii < 2 * grid.Mx // 3)
+    return s
+
+
+def _run(name, sliding=False, **env):
     for k in KNOBS:
         os.environ.pop(k, None)
     for k, v in env.items():
         os.environ["SIAFD_B200_" + k] = str(v)
     grid, cfg, inputs, gb = cases.case(name)
+    if sliding:
+        inputs["sliding"] = _sliding(grid, cfg, inputs)
     sia = U.make_sia(grid, cfg, gb)
     U.gpu_update(sia, inputs, True)
     out = {k: np.array(v, copy=True) for k, v in (("u", sia.velocity_u()), ("v", sia.velocity_v()),
                                                   ("D", sia.diffusivity()), ("Q", sia.diffusive_flux()))}
     out["D_max"] = sia.max_diffusivity()
+    out["bytes"] = sia.transfer_bytes()
     return out
 
 
@@ -52,3 +66,30 @@ def test_pipelined_host_update_equals_plain(name, knobs):
         for k in ("u", "v", "D", "Q"):
             assert np.array_equal(got[k], plain[k]), (name, env, k)
         assert got["D_max"] == plain["D_max"], (name, env)
+
+
+@pytest.mark.parametrize("name", ["Fs", "dome_96_31", "dome_96_31_rough", "dome_64_31_quadratic", "C4s_nosmooth"])
+def test_level_cut_of_the_sparse_host_update_is_bit_identical(name, knobs):
+    """The level cut (include/siafd_b200.h, siafd_b200_host_levels_needed): only the levels up to the thickest ice
+    next to a column cross PCIe, the host replicates the top value of u, v.  Same bits as the plain form and as the
+    pipeline without the cut, with and without sliding, for several chunk widths; and it does move fewer bytes."""
+    for sliding in (False, True):
+        plain = _run(name, sliding, PIPELINE=0)
+        uncut = _run(name, sliding, PIPELINE=1, ROWS=16, LEVEL_CUT=0)
+        settings = [dict(ROWS=16), dict(ROWS=16, CUT_COLS=8, REPL_THREADS=1), dict(ROWS=8, BAND=2, CUT_COLS=16, REPL_THREADS=3),
+                    dict(ROWS=32, CUT_COLS=1000), dict(ROWS=16, LEVEL_CUT=2, FILL_THREADS=1)]
+        for env in settings:
+            got = _run(name, sliding, PIPELINE=1, **env)
+            for k in ("u", "v", "D", "Q"):
+                assert np.array_equal(got[k], plain[k]), (name, sliding, env, k)
+            assert got["D_max"] == plain["D_max"], (name, env)
+            assert got["bytes"][0] < uncut["bytes"][0] and got["bytes"][1] < uncut["bytes"][1], (name, env, got["bytes"], uncut["bytes"])
+
+
+def test_level_cut_is_off_with_the_bed_smoother(knobs):
+    """thk_smooth = usurf - topgsmooth can exceed H by the roughness of the bed (BedSmoother.cc:306-320): no cut."""
+    a = _run("C4s", PIPELINE=1, ROWS=16, LEVEL_CUT=1)
+    b = _run("C4s", PIPELINE=1, ROWS=16, LEVEL_CUT=0)
+    assert a["bytes"] == b["bytes"]
+    for k in ("u", "v", "D", "Q"):
+        assert np.array_equal(a[k], b[k])

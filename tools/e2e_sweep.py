@@ -1,6 +1,9 @@
 """Sweep of the host-side knobs of the pipelined host-buffer update (siafd_b200_update with pinned HOST arrays,
-bench.py's `e2e`): number of host fill threads and row segments per band.  One process, one set of pinned
-buffers, one fresh handle per setting (the knobs are read from the environment at siafd_b200_create).
+bench.py's `e2e`): host fill / replicate threads, row segments per band, level cut and its chunk width.  One process,
+one set of pinned buffers, one fresh handle per setting (the knobs are read from the environment at
+siafd_b200_create).  A setting is "KNOB=value;KNOB=value" with the SIAFD_B200_ prefix left off ("" = the defaults);
+the old "fill_threads:band" form still works.  Before every setting the host's u, v are overwritten with NaN, and a
+checksum of a sample of their rows (bit patterns) must agree between all settings.
 Usage (GPU box): python tools/e2e_sweep.py [--size 4096] [--steps 2] > gpurun_out/e2e_sweep.json"""
 import argparse
 import ctypes as C
@@ -17,7 +20,8 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--mz", type=int, default=101)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--settings", default="8:4,16:4,32:4,16:2,16:8", help="fill_threads:band, comma-separated")
+    ap.add_argument("--settings", default="LEVEL_CUT=0,,CUT_COLS=64,CUT_COLS=256,REPL_THREADS=2,REPL_THREADS=8",
+                    help="comma-separated settings, each KNOB=value;KNOB=value (or fill_threads:band)")
     ap.add_argument("--comm", action="store_true", help="with a one-rank communicator (what bench.py's e2e does at N = 1)")
     args = ap.parse_args()
 
@@ -61,10 +65,22 @@ def main():
     cout.memory_space = 0
 
     results = []
+    knobs = ("FILL_THREADS", "BAND", "LEVEL_CUT", "CUT_COLS", "REPL_THREADS", "SPARSE", "ROWS", "PIPELINE")
+    sums = []
     for s in args.settings.split(","):
-        ft, band = s.split(":")
-        os.environ["SIAFD_B200_FILL_THREADS"] = ft
-        os.environ["SIAFD_B200_BAND"] = band
+        for k in knobs:
+            os.environ.pop("SIAFD_B200_" + k, None)
+        env = {}
+        if ":" in s:
+            ft, band = s.split(":")
+            env = {"FILL_THREADS": ft, "BAND": band}
+        elif s:
+            env = dict(kv.split("=") for kv in s.split(";"))
+        for k, v in env.items():
+            assert k in knobs, k
+            os.environ["SIAFD_B200_" + k] = v
+        host["u"].fill_(float("nan"))
+        host["v"].fill_(float("nan"))
         sia = SIAFD(grid, config=cfg, device=0)
         if args.comm:
             hs = (C.c_void_p * 1)(sia.handle)
@@ -80,10 +96,13 @@ def main():
                 ms.append((t1 - t0) * 1e3)
         b = (C.c_int64(), C.c_int64())
         lib.siafd_b200_transfer_bytes(sia.handle, C.byref(b[0]), C.byref(b[1]))
-        results.append({"comm": bool(args.comm), "fill_threads": int(ft), "band": int(band), "ms": ms, "best_ms": min(ms), "D_max": dmax,
+        rows = slice(0, None, 5)
+        chk = [int(host[n][rows].view(torch.int64).sum().item()) for n in ("u", "v")]
+        sums.append(chk)
+        results.append({"comm": bool(args.comm), "setting": s, "ms": ms, "best_ms": min(ms), "D_max": dmax,
                         "h2d_bytes_per_step": b[0].value // (args.steps + 1),
                         "d2h_bytes_per_step": b[1].value // (args.steps + 1),
-                        "sum_abs_u_row_2048": float(host["u"][M // 2].abs().sum())})
+                        "checksum_u_v_every_5th_row": chk, "same_bits_as_first_setting": chk == sums[0]})
         print(json.dumps(results[-1]), flush=True)
         del sia
     print(json.dumps({"size": M, "mz": Mz, "cpu_count": os.cpu_count(), "results": results}))
