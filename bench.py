@@ -640,7 +640,8 @@ def main():
                "dense_h2d_bytes_per_step": int(h2d * N), "dense_d2h_bytes_per_step": int(d2h * N),
                "ms_per_step": ms_e / args.e2e_steps, "steps": args.e2e_steps,
                "api": "siafd_b200_update(host pointers), one call per rank: every rank streams its own patch over its "
-                      "own PCIe link (row bands, only the parts near ice), ghost updates between the GPUs",
+                      "own PCIe link (row bands, only the parts near ice; on one rank only the levels up to the thickest "
+                      "ice nearby, the host replicates u, v above), ghost updates between the GPUs",
                "host_memory": "pinned"}
         assert dmax_e == dmax, (dmax_e, dmax)
         if full:  # the host arrays are the device-resident result, bit for bit (ghosts included)

@@ -398,7 +398,9 @@ int64_t siafd_b200_launch_count(const siafd_b200_handle *h);
 /* Bytes the host-pointer calls (upload / download / update with host arrays) have moved over PCIe since create.
  * siafd_b200_update with host arrays moves only the parts of the 3D arrays within 3 cells of ice (no enthalpy is read
  * and u = v = sliding velocity elsewhere, SIAFD.cc:631-637, :935-942: those parts of u, v are filled on the host);
- * afterwards the DEVICE copy of the enthalpy is only current in those parts. */
+ * afterwards the DEVICE copy of the enthalpy is only current in those parts (with the level cut below: on the levels
+ * up to the cut), which is all that the path and its device-resident consumers read (strain heating stops at the
+ * surface); a caller that wants the whole field on the device uploads it (siafd_b200_upload). */
 int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t *d2h);
 /* The level cut of that call (single rank, bed smoother off): of a column near ice only the levels [0, n) cross PCIe,
  * n = siafd_b200_host_levels_needed(z, Mz, T) with T the largest thk_smooth (BedSmoother.cc:306-320 with the
@@ -408,7 +410,7 @@ int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t 
  * are constant from level n - 1 up: the host replicates that value, and the host arrays are bit-identical to a full
  * transfer.  Pure host arithmetic (no GPU needed): returns Mz when nothing can be cut.  Environment:
  * SIAFD_B200_LEVEL_CUT = 0 (off) / 1 (default: single rank) / 2 (also with several ranks),
- * SIAFD_B200_CUT_COLS (columns that share one n, default 128), SIAFD_B200_REPL_THREADS (default 4). */
+ * SIAFD_B200_CUT_COLS (columns that share one n, default 256), SIAFD_B200_REPL_THREADS (default 8). */
 int siafd_b200_host_levels_needed(const double *z, int Mz, double max_thickness);
 /* Dry run of what siafd_b200_update with host arrays moves and fills, on HOST arrays only (no GPU; for tests of the
  * host logic): the same plan (pism_b200/csrc/siafd_hostplan.hh) -- row bands of `band` segments of rows_per_segment

@@ -419,8 +419,10 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.pipeline_host = 1;
   h->tuning.pipeline_band = 1; // 4096^2, segments per band 1 / 2 / 4 / 8: 368 / 375 / 386 / 411 ms (tools/e2e_sweep.py)
   h->tuning.sparse_host = 1;
+  // 4096^2 dome, one rank, 16 host cores (tools/e2e_sweep.py, profiles/e2e_sweep_r02.json): no cut 363 ms; cut with 4 / 8 /
+  // 11 replicating threads 357 / 357 / 359 ms, with 8 threads and chunks of 256 columns 350 ms
   h->tuning.level_cut = 1;
-  h->tuning.cut_cols = 128;
+  h->tuning.cut_cols = 256;
   h->tuning.graph_step = 1;
   h->tuning.order_segments = 1;
   if (const char *e = getenv("SIAFD_B200_ORDER")) h->tuning.order_segments = atoi(e);

@@ -83,7 +83,8 @@ def test_level_cut_of_the_sparse_host_update_is_bit_identical(name, knobs):
             for k in ("u", "v", "D", "Q"):
                 assert np.array_equal(got[k], plain[k]), (name, sliding, env, k)
             assert got["D_max"] == plain["D_max"], (name, env)
-            assert got["bytes"][0] < uncut["bytes"][0] and got["bytes"][1] < uncut["bytes"][1], (name, env, got["bytes"], uncut["bytes"])
+            if env.get("ROWS") == 16 and "BAND" not in env:  # (the same bands as `uncut`)
+                assert got["bytes"][0] < uncut["bytes"][0] and got["bytes"][1] < uncut["bytes"][1], (name, env, got["bytes"], uncut["bytes"])
 
 
 def test_level_cut_is_off_with_the_bed_smoother(knobs):
