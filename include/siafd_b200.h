@@ -410,11 +410,13 @@ int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t 
  * are constant from level n - 1 up: the host replicates that value, and the host arrays are bit-identical to a full
  * transfer.  Pure host arithmetic (no GPU needed): returns Mz when nothing can be cut.  Environment:
  * SIAFD_B200_LEVEL_CUT = 0 (off) / 1 (default: single rank) / 2 (also with several ranks),
- * SIAFD_B200_CUT_COLS (columns that share one n, default 256), SIAFD_B200_REPL_THREADS (default 8). */
+ * SIAFD_B200_CUT_COLS (columns that share one n, default 256), SIAFD_B200_CUT_ROWS (rows that share one n, default 0
+ * = the rows of a band), SIAFD_B200_REPL_THREADS (default 8); SIAFD_B200_TRACE=1 prints the timeline of each call. */
 int siafd_b200_host_levels_needed(const double *z, int Mz, double max_thickness);
 /* Dry run of what siafd_b200_update with host arrays moves and fills, on HOST arrays only (no GPU; for tests of the
  * host logic): the same plan (pism_b200/csrc/siafd_hostplan.hh) -- row bands of `band` segments of rows_per_segment
- * rows, sparse rectangles, level cut with cut_cols columns per chunk, patch = 1 for one patch of a decomposed domain
+ * rows, sparse rectangles, level cut (level_cut = 1; 1 + k: chunks of k rows) with cut_cols columns per chunk, patch = 1
+ * for one patch of a decomposed domain
  * -- executed with memcpy.  enthalpy_dev (in/out) stands for the device copy of the enthalpy: it receives what would be
  * uploaded and nothing else; u_dev, v_dev stand for the device's result (ghosts valid); u, v receive what the call would
  * leave in the host arrays (downloaded pieces, host fills from `sliding` (may be NULL = zero), values replicated above

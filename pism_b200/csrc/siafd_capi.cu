@@ -423,6 +423,7 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   // 11 replicating threads 357 / 357 / 359 ms, with 8 threads and chunks of 256 columns 350 ms
   h->tuning.level_cut = 1;
   h->tuning.cut_cols = 256;
+  h->tuning.cut_rows = 0;
   h->tuning.graph_step = 1;
   h->tuning.order_segments = 1;
   if (const char *e = getenv("SIAFD_B200_ORDER")) h->tuning.order_segments = atoi(e);
@@ -431,6 +432,7 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   if (const char *e = getenv("SIAFD_B200_FILL_THREADS")) h->fill_threads = std::max(1, atoi(e));
   if (const char *e = getenv("SIAFD_B200_LEVEL_CUT")) h->tuning.level_cut = atoi(e);
   if (const char *e = getenv("SIAFD_B200_CUT_COLS")) h->tuning.cut_cols = std::max(8, atoi(e));
+  if (const char *e = getenv("SIAFD_B200_CUT_ROWS")) h->tuning.cut_rows = std::max(0, atoi(e));
   if (const char *e = getenv("SIAFD_B200_REPL_THREADS")) h->repl_threads = std::max(1, atoi(e));
   if (const char *e = getenv("SIAFD_B200_PIPELINE")) h->tuning.pipeline_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_BAND")) h->tuning.pipeline_band = atoi(e);
@@ -1298,7 +1300,7 @@ int siafd_b200_host_plan_emulate(const siafd_b200_config *cfg, int rows_per_segm
   }
   const siafd_b200_config &c = *cfg;
   HostPlan P;
-  plan_host_update(c, rows_per_segment, band, sparse != 0, level_cut != 0, patch != 0, cut_cols, 2, thickness, surface, bed, mask,
+  plan_host_update(c, rows_per_segment, band, sparse != 0, level_cut != 0, patch != 0, cut_cols, level_cut > 1 ? level_cut - 1 : 0, 2, thickness, surface, bed, mask,
                    P);
   const int we = c.w_3d_in, wuv = c.w_uv, Mz = c.Mz;
   const long cellsE = c.xm + 2 * we, cellsUV = c.xm + 2 * wuv, rowUV = cellsUV * Mz;
@@ -1344,6 +1346,14 @@ static cudaError_t copy_piece(double *dst, const double *src, long row_cells, in
     }
     return cudaMemcpy2DAsync(dst + off, (size_t)row_cells * colB, src + off, (size_t)row_cells * colB,
                              (size_t)(p.c1 - p.c0) * colB, (size_t)(p.r1 - p.r0), kind, s);
+  }
+  // a cut piece: lines of n levels at the pitch of a column.  Measured at 4096^2 (profiles/e2e_sweep_r02.json): one 3D
+  // copy per piece of 64 rows x 256 / 1024 / 4096 columns: 350 / 392 / 425 ms per step; one 2D copy per row of 512 /
+  // 1024 / 2048 columns: 465 / 440 / 418 ms -- although plain 2D copies of 65 k such lines run at 46 GB/s on their own
+  // (tools/memcpy2d_bw.cu).  Small 3D pieces are the best of these.
+  if (p.r1 - p.r0 == 1) {
+    const long off = ((long)p.r0 * row_cells + p.c0) * Mz;
+    return cudaMemcpy2DAsync(dst + off, colB, src + off, colB, (size_t)p.n * sizeof(double), (size_t)(p.c1 - p.c0), kind, s);
   }
   cudaMemcpy3DParms q;
   memset(&q, 0, sizeof(q));
@@ -1391,9 +1401,38 @@ static void replicate_pieces(int device, const cudaEvent_t *done, ReplShared *S,
 #endif
 }
 
+static double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// SIAFD_B200_TRACE=1: host-clock timeline of one call on stderr (when each band's enthalpy was up, when its u, v were
+// down, when the host threads were done) -- tools/e2e_sweep.py --trace
+struct PipeTrace {
+  bool on = false;
+  double t0 = 0;
+  std::vector<double> up, down, workers;
+  std::atomic<int> up_recorded{0};
+};
+
+static void trace_watch(int device, const cudaEvent_t *ev, std::atomic<int> *recorded, std::atomic<bool> *abort, int n, double t0,
+                        double *out) {
+  if (cudaSetDevice(device) != cudaSuccess) return;
+  for (int b = 0; b < n; ++b) {
+    while (recorded->load(std::memory_order_acquire) <= b) {
+      if (abort->load(std::memory_order_acquire)) return;
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    if (cudaEventSynchronize(ev[b]) != cudaSuccess) return;
+    out[b] = wall_ms() - t0;
+  }
+}
+
 static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *in, siafd_b200_outputs *out) {
   const siafd_b200_config &c = h->cfg;
   int st;
+  PipeTrace tr;
+  tr.on = getenv("SIAFD_B200_TRACE") != nullptr;
+  tr.t0 = wall_ms();
   if (!h->s_up) {
     CU(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
     CU(h, cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking));
@@ -1410,11 +1449,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   const bool sparse = h->tuning.sparse_host != 0;
   const bool cut = sparse && in->bed && !(c.smoother_range > 0.0) && !h->smoother_set &&
                    (h->tuning.level_cut >= 2 || (h->tuning.level_cut == 1 && (!comm || h->comm.size == 1)));
-  HostPlan plan;
-  plan_host_update(c, slab_rows_per_segment(h->tuning), h->tuning.pipeline_band, sparse, cut, patch, h->tuning.cut_cols,
-                   h->fill_threads, in->thickness, in->surface, in->bed, in->mask, plan);
-  const int NB = plan.NB, band = plan.band, nseg = plan.nseg;
-  if (nseg != slab_segments(h->P, h->tuning)) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "host plan and kernel disagree on the row segments");
+  const int nseg = slab_segments(h->P, h->tuning), band = std::max(1, h->tuning.pipeline_band), NB = (nseg + band - 1) / band;
   while ((int)h->ev_pipe.size() < 3 * NB + 4) {
     cudaEvent_t e;
     CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1425,6 +1460,24 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   for (int f : outs_f) {
     if ((st = ensure(h, f))) return st;
   }
+  cudaEvent_t ev_start = h->ev_pipe[2 * NB];
+  CU(h, cudaEventRecord(ev_start, h->stream)); // earlier work on the handle's stream (fresh buffers' zero-fill)
+  CU(h, cudaStreamWaitEvent(h->s_up, ev_start, 0));
+  CU(h, cudaStreamWaitEvent(h->s_dn, ev_start, 0));
+  // 2D inputs on the main stream (the gradient needs them first); they travel while the host makes its plan
+  struct {
+    int f;
+    const double *p;
+  } small[] = {{SIAFD_B200_F_SURFACE, in->surface}, {SIAFD_B200_F_THICKNESS, in->thickness}, {SIAFD_B200_F_MASK, in->mask},
+               {SIAFD_B200_F_BED, in->bed}, {SIAFD_B200_F_SLIDING, in->sliding}};
+  for (auto &q : small) {
+    if (q.p && (st = siafd_b200_upload(h, q.f, q.p))) return st;
+  }
+  HostPlan plan;
+  plan_host_update(c, slab_rows_per_segment(h->tuning), band, sparse, cut, patch, h->tuning.cut_cols, h->tuning.cut_rows, h->fill_threads, in->thickness,
+                   in->surface, in->bed, in->mask, plan);
+  const double t_plan = wall_ms() - tr.t0;
+  if (plan.nseg != nseg || plan.NB != NB) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "host plan and kernel disagree on the row segments");
   const int we = c.w_3d_in, wuv = c.w_uv;
   const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
   // the host's own work is known up front, so its threads start before the copies: the fills at once, the tasks above
@@ -1437,8 +1490,16 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   const std::vector<size_t> &piece0 = plan.down0;
   if (!fills.empty()) {
     const size_t nt = std::min<size_t>(std::max(1u, std::min((unsigned)h->fill_threads, std::thread::hardware_concurrency())), fills.size());
+    if (tr.on) tr.workers.assign(nt + 64, 0.0);
     for (size_t t = 0; t < nt; ++t) {
-      workers.emplace_back(fill_rows, std::cref(c), in->sliding, out->u, out->v, fills.data(), fills.size(), t, nt);
+      if (tr.on) {
+        workers.emplace_back([&, t, nt] {
+          fill_rows(c, in->sliding, out->u, out->v, fills.data(), fills.size(), t, nt);
+          tr.workers[t] = wall_ms() - tr.t0;
+        });
+      } else {
+        workers.emplace_back(fill_rows, std::cref(c), in->sliding, out->u, out->v, fills.data(), fills.size(), t, nt);
+      }
     }
   }
   const cudaEvent_t *ev_down = h->ev_pipe.data() + 2 * NB + 4; // band b's copies of u, v have finished
@@ -1448,6 +1509,11 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
       workers.emplace_back(replicate_pieces, h->device, ev_down, &repl_state, repl.data(), repl.size(), t, nt, out->u, out->v,
                            (long)(c.xm + 2 * wuv), c.Mz);
     }
+  }
+  if (tr.on) { // two watchers: when was band b's enthalpy up, when were its u, v down
+    tr.up.assign(NB, 0.0), tr.down.assign(NB, 0.0);
+    workers.emplace_back(trace_watch, h->device, h->ev_pipe.data(), &tr.up_recorded, &repl_state.abort, NB, tr.t0, tr.up.data());
+    workers.emplace_back(trace_watch, h->device, ev_down, &repl_state.recorded, &repl_state.abort, NB, tr.t0, tr.down.data());
   }
   struct Joiner { // the workers are joined on every way out of this function
     std::vector<std::thread> &w;
@@ -1463,28 +1529,24 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     }
   } joiner{workers, repl_state};
 
-  cudaEvent_t ev_start = h->ev_pipe[2 * NB];
-  CU(h, cudaEventRecord(ev_start, h->stream)); // earlier work on the handle's stream (fresh buffers' zero-fill)
-  CU(h, cudaStreamWaitEvent(h->s_up, ev_start, 0));
-  CU(h, cudaStreamWaitEvent(h->s_dn, ev_start, 0));
-  // 2D inputs on the main stream (the gradient needs them first)
-  struct {
-    int f;
-    const double *p;
-  } small[] = {{SIAFD_B200_F_SURFACE, in->surface}, {SIAFD_B200_F_THICKNESS, in->thickness}, {SIAFD_B200_F_MASK, in->mask},
-               {SIAFD_B200_F_BED, in->bed}, {SIAFD_B200_F_SLIDING, in->sliding}};
-  for (auto &q : small) {
-    if (q.p && (st = siafd_b200_upload(h, q.f, q.p))) return st;
-  }
-  // enthalpy bands on the upload stream
+  // enthalpy bands on the upload stream, issued a few bands ahead of the kernel that reads them (with the level cut a
+  // band is hundreds of copies: issuing them all up front would hold the first kernel back)
   double *E_dev = (double *)h->buf[SIAFD_B200_F_ENTHALPY];
-  for (int b = 0; b < NB; ++b) {
-    for (size_t t = plan.up0[b]; t < plan.up0[b + 1]; ++t) {
-      CU(h, copy_piece(E_dev, in->enthalpy, c.xm + 2 * we, c.Mz, plan.up_pieces[t], cudaMemcpyHostToDevice, h->s_up));
-      h->bytes_h2d += piece_bytes(plan.up_pieces[t]);
+  int up_issued = 0;
+  auto issue_uploads = [&](int upto) -> int { // bands [up_issued, upto)
+    for (; up_issued < std::min(upto, NB); ++up_issued) {
+      const int b = up_issued;
+      for (size_t t = plan.up0[b]; t < plan.up0[b + 1]; ++t) {
+        CU(h, copy_piece(E_dev, in->enthalpy, c.xm + 2 * we, c.Mz, plan.up_pieces[t], cudaMemcpyHostToDevice, h->s_up));
+        h->bytes_h2d += piece_bytes(plan.up_pieces[t]);
+      }
+      CU(h, cudaEventRecord(h->ev_pipe[b], h->s_up));
+      tr.up_recorded.store(b + 1, std::memory_order_release);
     }
-    CU(h, cudaEventRecord(h->ev_pipe[b], h->s_up));
-  }
+    return SIAFD_B200_OK;
+  };
+  if ((st = issue_uploads(plan.up_pieces.size() > 4 * (size_t)NB ? 3 : NB))) return st;
+  const double t_up_issued = wall_ms() - tr.t0;
   // gradient and 2D preparation while the first band is in flight
   PeerPush PPu = PeerPush();
   bool prep_done = false;
@@ -1518,6 +1580,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   double *uvh[2] = {out->u, out->v};
   for (int b = 0; b < NB; ++b) {
     const int s0 = b * band, s1 = std::min(nseg, (b + 1) * band);
+    if ((st = issue_uploads(b + 4))) return st;
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_pipe[b], 0));
     if ((st = flux_velocity_launch(h, 1, s0, s1 - s0, comm ? &PPu : nullptr))) return st;
     // owned rows of this band (extended row e = ys - 1 + s RS ... ; owned rows are ys .. ys + ym - 1)
@@ -1541,7 +1604,7 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
         }
       }
     }
-    if (!repl.empty()) { // (also for a band without copies: the counter is the number of bands issued)
+    if (!repl.empty() || tr.on) { // (also for a band without copies: the counter is the number of bands issued)
       CU(h, cudaEventRecord(ev_down[b], h->s_dn));
       repl_state.recorded.store(b + 1, std::memory_order_release);
     }
@@ -1581,11 +1644,28 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
                           h->stream));
     h->bytes_d2h += (int64_t)siafd_b200_field_size(h, q.f) * 8;
   }
+  const double t_issued = wall_ms() - tr.t0;
   st = siafd_b200_finish(h);
+  const double t_finish = wall_ms() - tr.t0;
   CU(h, cudaStreamSynchronize(h->s_dn));
   CU(h, cudaStreamSynchronize(h->s_up));
+  const double t_streams = wall_ms() - tr.t0;
   joiner.released = true;
   joiner.join();
+  if (tr.on) {
+    double wmax = 0;
+    for (double w : tr.workers) wmax = std::max(wmax, w);
+    fprintf(stderr, "siafd_b200 trace [ms]: plan %.1f, uploads issued %.1f, all issued %.1f, main stream done %.1f, copy streams done %.1f, "
+                    "host threads joined %.1f (fill threads done %.1f); bands %d, pieces up %zu down %zu\n",
+            t_plan, t_up_issued, t_issued, t_finish, t_streams, wall_ms() - tr.t0, wmax, NB, plan.up_pieces.size(), plan.down_pieces.size());
+    fprintf(stderr, "  band:       ");
+    for (int b = 0; b < NB; b += std::max(1, NB / 16)) fprintf(stderr, "%7d", b);
+    fprintf(stderr, "\n  E up at:    ");
+    for (int b = 0; b < NB; b += std::max(1, NB / 16)) fprintf(stderr, "%7.1f", tr.up[b]);
+    fprintf(stderr, "\n  u, v down at:");
+    for (int b = 0; b < NB; b += std::max(1, NB / 16)) fprintf(stderr, "%7.1f", tr.down[b]);
+    fprintf(stderr, "  last %.1f\n", tr.down[NB - 1]);
+  }
   if (repl_state.failed.load()) return fail(h, SIAFD_B200_ERR_CUDA, "a host thread of the level cut could not wait for its band");
   return st;
 }

@@ -318,7 +318,7 @@ struct HostPlan {
 };
 
 static void plan_host_update(const siafd_b200_config &c, int RS, int band, bool sparse, bool cut, bool patch, int cut_cols,
-                             int threads, const double *H, const double *surface, const double *bed, const double *mask,
+                             int cut_rows, int threads, const double *H, const double *surface, const double *bed, const double *mask,
                              HostPlan &P) {
   P.RS = RS, P.nseg = (c.ym + 2 + RS - 1) / RS, P.band = std::max(1, band), P.NB = (P.nseg + P.band - 1) / P.band;
   P.sparse = sparse, P.cut = sparse && cut, P.patch = patch;
@@ -356,7 +356,12 @@ static void plan_host_update(const siafd_b200_config &c, int RS, int band, bool 
     }
     P.down[b] = R;
     const size_t first = P.down_pieces.size();
-    cut_pieces(c, M, cut_cols, wuv, wuv + R.o0, wuv + R.o1, R.c0, R.c1, P.down_pieces);
+    // (cut_rows > 0: chunks of that many rows instead of the band's -- a row's own maximum cuts lower, but the copies
+    // get smaller; one row = a plain 2D copy)
+    const int step = (M && cut_rows > 0) ? cut_rows : std::max(1, R.o1 - R.o0);
+    for (int r = R.o0; r < R.o1; r += step) {
+      cut_pieces(c, M, cut_cols, wuv, wuv + r, wuv + std::min(R.o1, r + step), R.c0, R.c1, P.down_pieces);
+    }
     P.down0[b + 1] = P.down_pieces.size();
     for (size_t q = first; q < P.down_pieces.size(); ++q) {
       const Piece &D = P.down_pieces[q];
@@ -383,7 +388,10 @@ static void plan_host_update(const siafd_b200_config &c, int RS, int band, bool 
         // local columns [c0, c1) of the enthalpy array; a patch: a range that touches an edge takes the ghost columns too
         int c0 = 0, c1 = c.xm + 2 * we;
         if (sparse && !whole) c0 = (patch && lo <= 0) ? 0 : lo + we, c1 = (patch && hi >= c.xm - 1) ? c.xm + 2 * we : hi + 1 + we;
-        cut_pieces(c, M, cut_cols, we, (int)up0, (int)up1, c0, c1, P.up_pieces);
+        const int step = (M && cut_rows > 0) ? cut_rows : (int)(up1 - up0);
+        for (int r = (int)up0; r < (int)up1; r += step) {
+          cut_pieces(c, M, cut_cols, we, r, std::min((int)up1, r + step), c0, c1, P.up_pieces);
+        }
       }
     }
     up0 = std::max(up0, up1);

@@ -31,6 +31,7 @@ struct Tuning {
   int level_cut;     // 1: ... and of those columns only the levels up to the thickest ice nearby (u, v are constant
                      // above the surface, the enthalpy is not read there); the host replicates the top value
   int cut_cols;      // columns per chunk of a band that share one cut level
+  int cut_rows;      // rows per chunk (0: the rows of the band)
   int graph_step;    // 1: siafd_b200_update_decomposed replays a captured CUDA graph of the step
   int order_segments; // 1: the fused kernel takes its row segments heaviest (most icy points) first: short tail
 };

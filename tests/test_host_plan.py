@@ -44,9 +44,10 @@ def emulate(c, inputs, u_dev, v_dev, rows, band, sparse, cut, cut_cols, patch):
     return E_dev, u, v, up.value, dn.value
 
 
-SETTINGS = [  # rows per segment, segments per band, sparse, level cut, columns per chunk
+SETTINGS = [  # rows per segment, segments per band, sparse, level cut (1 + k: k rows per chunk), columns per chunk
     (16, 1, 1, 1, 128), (16, 1, 1, 1, 8), (8, 2, 1, 1, 16), (32, 1, 1, 1, 24), (64, 100, 1, 1, 9), (5, 3, 1, 1, 40),
     (16, 1, 1, 0, 128), (8, 3, 0, 0, 128), (88, 1, 1, 1, 32),
+    (16, 1, 1, 2, 16), (32, 2, 1, 5, 64),  # level cut 1 + k: chunks of k rows (k = 1: plain 2D copies)
 ]
 
 

@@ -15,7 +15,7 @@ import gpu_util as U
 pytestmark = pytest.mark.gpu
 
 KNOBS = ("SIAFD_B200_PIPELINE", "SIAFD_B200_BAND", "SIAFD_B200_ROWS", "SIAFD_B200_SPARSE", "SIAFD_B200_LEVEL_CUT",
-         "SIAFD_B200_CUT_COLS", "SIAFD_B200_REPL_THREADS", "SIAFD_B200_FILL_THREADS")
+         "SIAFD_B200_CUT_COLS", "SIAFD_B200_CUT_ROWS", "SIAFD_B200_REPL_THREADS", "SIAFD_B200_FILL_THREADS")
 
 
 @pytest.fixture
@@ -77,7 +77,8 @@ def test_level_cut_of_the_sparse_host_update_is_bit_identical(name, knobs):
         plain = _run(name, sliding, PIPELINE=0)
         uncut = _run(name, sliding, PIPELINE=1, ROWS=16, LEVEL_CUT=0)
         settings = [dict(ROWS=16), dict(ROWS=16, CUT_COLS=8, REPL_THREADS=1), dict(ROWS=8, BAND=2, CUT_COLS=16, REPL_THREADS=3),
-                    dict(ROWS=32, CUT_COLS=1000), dict(ROWS=16, LEVEL_CUT=2, FILL_THREADS=1)]
+                    dict(ROWS=32, CUT_COLS=1000), dict(ROWS=16, LEVEL_CUT=2, FILL_THREADS=1), dict(ROWS=16, CUT_ROWS=1, CUT_COLS=16),
+                    dict(ROWS=32, CUT_ROWS=5, CUT_COLS=32)]
         for env in settings:
             got = _run(name, sliding, PIPELINE=1, **env)
             for k in ("u", "v", "D", "Q"):
