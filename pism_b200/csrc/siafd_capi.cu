@@ -420,7 +420,8 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   h->tuning.pipeline_band = 1; // 4096^2, segments per band 1 / 2 / 4 / 8: 368 / 375 / 386 / 411 ms (tools/e2e_sweep.py)
   h->tuning.sparse_host = 1;
   // 4096^2 dome, one rank, 16 host cores (tools/e2e_sweep.py, profiles/e2e_sweep_r02.json): no cut 363 ms; cut with 4 / 8 /
-  // 11 replicating threads 357 / 357 / 359 ms, with 8 threads and chunks of 256 columns 350 ms
+  // 11 replicating threads 357 / 357 / 359 ms, with 8 threads and chunks of 256 columns 350 ms (wider chunks and
+  // row-by-row 2D copies are slower: copy_piece)
   h->tuning.level_cut = 1;
   h->tuning.cut_cols = 256;
   h->tuning.cut_rows = 0;
@@ -1444,8 +1445,8 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   const bool comm = h->comm.active;
   const bool patch = comm && (c.xm != c.Mx || c.ym != c.My);
   // which parts of the 3D arrays have to move at all (sparse = 0 moves everything); the level cut: bed smoother off,
-  // the bed given with this call; several ranks per host only when asked for (level_cut = 2) -- there the call is bound
-  // by the host's memory system, which the cut does not relieve
+  // the bed given with this call; several ranks per host only when asked for (level_cut = 2) -- each link then carries
+  // a fraction of the bytes and PCIe is not what bounds the call; not measured there
   const bool sparse = h->tuning.sparse_host != 0;
   const bool cut = sparse && in->bed && !(c.smoother_range > 0.0) && !h->smoother_set &&
                    (h->tuning.level_cut >= 2 || (h->tuning.level_cut == 1 && (!comm || h->comm.size == 1)));

@@ -22,7 +22,8 @@ struct siafd_b200_handle {
   unsigned long long *d_cfl = nullptr, *h_cfl = nullptr; // 8 maxima of siafd_b200_cfl and their pinned mirror
   bool cfl3_fresh = false; // slots 0..3 hold the maxima the last vertical-velocity launch took on the current fields
   int fill_threads = 4;    // host threads that fill the ice-free parts of u, v in the sparse host path (more of them
-                           // only compete with the PCIe copies for host DRAM: 4096^2, 4 / 8 threads: 362 / 368 ms)
+                           // do not help: 4096^2, 4 / 8 threads: 362 / 368 ms; while they run the copy engine's
+                           // device-to-host rate drops from 48 to 27 GB/s, profiles/e2e_trace_r02.txt)
   int repl_threads = 8;    // host threads that replicate the top value of u, v above the cut level (level_cut); a
                            // band of 64 rows is four tasks of 16 rows per chunk: 4 or 8 threads keep each thread in
                            // its own rows (6 threads measured 424 ms against 357 ms for 4 or 8)
