@@ -434,6 +434,7 @@ int siafd_b200_create(const siafd_b200_config *cfg, int device, siafd_b200_handl
   if (const char *e = getenv("SIAFD_B200_LEVEL_CUT")) h->tuning.level_cut = atoi(e);
   if (const char *e = getenv("SIAFD_B200_CUT_COLS")) h->tuning.cut_cols = std::max(8, atoi(e));
   if (const char *e = getenv("SIAFD_B200_CUT_ROWS")) h->tuning.cut_rows = std::max(0, atoi(e));
+  if (const char *e = getenv("SIAFD_B200_ZERO_COPY")) h->zero_copy = atoi(e);
   if (const char *e = getenv("SIAFD_B200_REPL_THREADS")) h->repl_threads = std::max(1, atoi(e));
   if (const char *e = getenv("SIAFD_B200_PIPELINE")) h->tuning.pipeline_host = atoi(e);
   if (const char *e = getenv("SIAFD_B200_BAND")) h->tuning.pipeline_band = atoi(e);
@@ -503,6 +504,7 @@ void siafd_b200_destroy(siafd_b200_handle *h) {
   cudaFree(h->d_dmax);
   cudaFree(h->d_hdc);
   cudaFree(h->d_segw);
+  cudaFree(h->d_pieces);
   cudaFree(h->d_segdone);
   cudaFree(h->d_cfl);
   if (h->h_cfl) cudaFreeHost(h->h_cfl);
@@ -1436,7 +1438,9 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   tr.t0 = wall_ms();
   if (!h->s_up) {
     CU(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
-    CU(h, cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking));
+    int lo_prio = 0, hi_prio = 0; // (the store kernel of the zero-copy path shares the SMs with the fused kernel)
+    CU(h, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CU(h, cudaStreamCreateWithPriority(&h->s_dn, cudaStreamNonBlocking, hi_prio));
   }
   // With a communicator (siafd_b200_comm_init*, one rank or many) the ghost updates of h_x, h_y and u, v are stores by
   // the producing kernels into the neighbours' arrays (this rank's own where it is its own periodic neighbour), and the
@@ -1481,6 +1485,33 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
   if (plan.nseg != nseg || plan.NB != NB) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "host plan and kernel disagree on the row segments");
   const int we = c.w_3d_in, wuv = c.w_uv;
   const long rowUV = (long)(c.xm + 2 * wuv) * c.Mz;
+  // zero copy: the caller's u, v are pinned and mapped into the device's address space (cudaHostAlloc / cudaHostRegister
+  // under unified addressing): a kernel stores the pieces there itself, whole aligned lines over PCIe, instead of the
+  // copy engine's strided lines
+  double *zc_uv[2] = {nullptr, nullptr};
+  if (h->zero_copy && !plan.down_pieces.empty()) {
+    double *hp[2] = {out->u, out->v};
+    for (int q = 0; q < 2; ++q) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, hp[q]) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer != nullptr) {
+        zc_uv[q] = (double *)a.devicePointer;
+      } else {
+        cudaGetLastError(); // (pageable memory: not an error of this call)
+      }
+    }
+    if (!zc_uv[0] || !zc_uv[1]) zc_uv[0] = zc_uv[1] = nullptr;
+  }
+  static_assert(sizeof(StorePiece) == sizeof(Piece), "the device's view of a piece is the plan's");
+  if (zc_uv[0]) {
+    const size_t need = plan.down_pieces.size() * sizeof(Piece);
+    if (need > h->d_pieces_bytes) {
+      cudaFree(h->d_pieces);
+      h->d_pieces = nullptr, h->d_pieces_bytes = 0;
+      CU(h, cudaMalloc(&h->d_pieces, need * 2));
+      h->d_pieces_bytes = need * 2;
+    }
+    CU(h, cudaMemcpyAsync(h->d_pieces, plan.down_pieces.data(), need, cudaMemcpyHostToDevice, h->s_dn));
+  }
   // the host's own work is known up front, so its threads start before the copies: the fills at once, the tasks above
   // the cut as their bands come down
   std::vector<std::thread> workers;
@@ -1597,11 +1628,19 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
       }
       CU(h, cudaEventRecord(h->ev_pipe[NB + b], h->stream));
       CU(h, cudaStreamWaitEvent(h->s_dn, h->ev_pipe[NB + b], 0));
-      for (size_t t = piece0[b]; t < piece0[b + 1]; ++t) {
-        const Piece &p = pieces[t];
-        for (int q = 0; q < 2; ++q) {
-          CU(h, copy_piece(uvh[q], (const double *)h->buf[uvf[q]], c.xm + 2 * wuv, c.Mz, p, cudaMemcpyDeviceToHost, h->s_dn));
-          h->bytes_d2h += piece_bytes(p);
+      if (zc_uv[0]) {
+        h->launches += launch_store_pieces((const double *)h->buf[uvf[0]], (const double *)h->buf[uvf[1]], zc_uv[0], zc_uv[1],
+                                           (const StorePiece *)h->d_pieces, (int)piece0[b], (int)piece0[b + 1], c.xm + 2 * wuv, c.Mz,
+                                           h->s_dn);
+        CU(h, cudaGetLastError());
+        for (size_t t = piece0[b]; t < piece0[b + 1]; ++t) h->bytes_d2h += 2 * piece_bytes(pieces[t]);
+      } else {
+        for (size_t t = piece0[b]; t < piece0[b + 1]; ++t) {
+          const Piece &p = pieces[t];
+          for (int q = 0; q < 2; ++q) {
+            CU(h, copy_piece(uvh[q], (const double *)h->buf[uvf[q]], c.xm + 2 * wuv, c.Mz, p, cudaMemcpyDeviceToHost, h->s_dn));
+            h->bytes_d2h += piece_bytes(p);
+          }
         }
       }
     }

@@ -45,6 +45,9 @@ struct siafd_b200_handle {
   int bedNx = -1, bedNy = -1;
   double *d_global_bed = nullptr;
   cudaStream_t s_up = nullptr, s_dn = nullptr; // upload / download legs of the pipelined host update
+  void *d_pieces = nullptr;                    // the call's download pieces on the device (zero_copy)
+  size_t d_pieces_bytes = 0;
+  int zero_copy = 0; // 1: u, v go into mapped pinned host arrays by stores of a kernel instead of strided copies
   std::vector<cudaEvent_t> ev_pipe;
   // peer halo exchange: per field and neighbour direction the mapped base of the neighbour's array (nullptr =
   // this rank) and its patch size; the arrival-counter pad [4 phases][8 dirs] and the neighbours' pads

@@ -733,6 +733,37 @@ int launch_gradient(const DP &P, const Fields &F, cudaStream_t s, const PeerPush
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// u, v of the pieces [p0, p1) into mapped host memory.  A row of a piece is one run of elements [base, base + len) of
+// which the levels k < n of every column are wanted: the threads sweep the run in windows that start on a 256-byte
+// boundary of the array, element e by the thread e mod window, so that a warp's stores are whole aligned lines except
+// where a column's cut begins or ends (PCIe write packets as large as the hardware makes them).  blockIdx.y strides
+// over the pieces, the blockIdx.x CTAs of a piece share each of its rows.
+constexpr int SP_T = 128, SP_X = 4, SP_Y = 32;
+__global__ void __launch_bounds__(SP_T) k_store_pieces(const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ hu,
+                                                       double *__restrict__ hv, const StorePiece *__restrict__ pieces, int p0, int p1,
+                                                       long row_cells, int Mz) {
+  for (int p = p0 + blockIdx.y; p < p1; p += gridDim.y) {
+    const StorePiece P = pieces[p];
+    for (int r = P.r0; r < P.r1; ++r) {
+      const long base = ((long)r * row_cells + P.c0) * Mz, end = base + (long)(P.c1 - P.c0) * Mz;
+      for (long e = (base & ~31L) + (long)blockIdx.x * SP_T + threadIdx.x; e < end; e += (long)gridDim.x * SP_T) {
+        if (e >= base && (int)(e - base) % Mz < P.n) { // (a row of a piece is far below 2^31 elements)
+          hu[e] = u[e];
+          hv[e] = v[e];
+        }
+      }
+    }
+  }
+}
+
+int launch_store_pieces(const double *u, const double *v, double *host_u, double *host_v, const StorePiece *pieces_dev, int p0,
+                        int p1, long row_cells, int Mz, cudaStream_t s) {
+  if (p1 <= p0) return 0;
+  k_store_pieces<<<dim3(SP_X, std::min(SP_Y, p1 - p0)), SP_T, 0, s>>>(u, v, host_u, host_v, pieces_dev, p0, p1, row_cells, Mz);
+  return 1;
+}
+
 int launch_copy_region(double *dst, long dst_row_cells, int dst_i0, int dst_j0, const double *src, long src_row_cells,
                        int src_i0, int src_j0, int wc, int hc, int dof, cudaStream_t s) {
   const long n = (long)wc * hc * dof;

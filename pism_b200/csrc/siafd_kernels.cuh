@@ -55,6 +55,15 @@ size_t slab_smem_need(const DP &P, bool full, bool bulk); // shared memory of th
 int launch_copy_region(double *dst, long dst_row_cells, int dst_i0, int dst_j0, const double *src, long src_row_cells,
                        int src_i0, int src_j0, int width_cells, int height_cells, int dof, cudaStream_t s);
 
+// Pieces of u and v stored straight into the caller's mapped pinned HOST arrays (same local layout as the device's):
+// rows [r0, r1) x columns [c0, c1) x levels [0, n) of each piece.  The host-array update's alternative to asking the
+// copy engine for strided lines (siafd_capi.cu::copy_piece).
+struct StorePiece {
+  int r0, r1, c0, c1, n;
+};
+int launch_store_pieces(const double *u, const double *v, double *host_u, double *host_v, const StorePiece *pieces_dev, int p0,
+                        int p1, long row_cells, int Mz, cudaStream_t s);
+
 // Peer halo exchange (CUDA IPC mapped neighbour arrays): one kernel copies every strip of a phase straight into
 // the neighbours' ghost cells over NVLink, a second one raises the neighbours' arrival counters, a third waits
 // for this rank's own counters.

@@ -15,7 +15,8 @@ import gpu_util as U
 pytestmark = pytest.mark.gpu
 
 KNOBS = ("SIAFD_B200_PIPELINE", "SIAFD_B200_BAND", "SIAFD_B200_ROWS", "SIAFD_B200_SPARSE", "SIAFD_B200_LEVEL_CUT",
-         "SIAFD_B200_CUT_COLS", "SIAFD_B200_CUT_ROWS", "SIAFD_B200_REPL_THREADS", "SIAFD_B200_FILL_THREADS")
+         "SIAFD_B200_CUT_COLS", "SIAFD_B200_CUT_ROWS", "SIAFD_B200_REPL_THREADS", "SIAFD_B200_FILL_THREADS",
+         "SIAFD_B200_ZERO_COPY")
 
 
 @pytest.fixture
@@ -39,7 +40,7 @@ def _sliding(grid, cfg, inputs):
     return s
 
 
-def _run(name, sliding=False, **env):
+def _run(name, sliding=False, pinned=False, **env):
     for k in KNOBS:
         os.environ.pop(k, None)
     for k, v in env.items():
@@ -48,11 +49,19 @@ def _run(name, sliding=False, **env):
     if sliding:
         inputs["sliding"] = _sliding(grid, cfg, inputs)
     sia = U.make_sia(grid, cfg, gb)
+    keep = []
+    if pinned:  # u, v in pinned (hence device-mapped) host memory, poisoned: every cell has to be written by the call
+        import torch
+        for n in ("u", "v"):
+            t = torch.full(sia.field_shape(n), float("nan"), dtype=torch.float64).pin_memory()
+            keep.append(t)
+            sia._host_out[n] = t.numpy()
     U.gpu_update(sia, inputs, True)
     out = {k: np.array(v, copy=True) for k, v in (("u", sia.velocity_u()), ("v", sia.velocity_v()),
                                                   ("D", sia.diffusivity()), ("Q", sia.diffusive_flux()))}
     out["D_max"] = sia.max_diffusivity()
     out["bytes"] = sia.transfer_bytes()
+    out["launches"] = sia.launch_count()
     return out
 
 
@@ -95,3 +104,26 @@ def test_level_cut_is_off_with_the_bed_smoother(knobs):
     assert a["bytes"] == b["bytes"]
     for k in ("u", "v", "D", "Q"):
         assert np.array_equal(a[k], b[k])
+
+
+@pytest.mark.parametrize("name", ["Fs", "dome_96_31_rough", "C4s_nosmooth", "C4s"])
+def test_zero_copy_stores_into_pinned_host_arrays_are_bit_identical(name, knobs):
+    """SIAFD_B200_ZERO_COPY=1: with u, v in pinned host memory a kernel stores the pieces there itself (k_store_pieces)
+    instead of the copy engine's strided copies -- same bits, with and without the level cut, for coarse and fine pieces;
+    pageable arrays keep the copies."""
+    for sliding in (False, True):
+        plain = _run(name, sliding, PIPELINE=0)
+        copies = _run(name, sliding, pinned=True, ROWS=16)
+        settings = [dict(ROWS=16), dict(ROWS=16, LEVEL_CUT=0), dict(ROWS=16, CUT_COLS=8, CUT_ROWS=1), dict(ROWS=8, BAND=2, CUT_COLS=24, CUT_ROWS=3),
+                    dict(ROWS=32, SPARSE=0)]
+        for env in settings:
+            got = _run(name, sliding, pinned=True, ZERO_COPY=1, **env)
+            for k in ("u", "v", "D", "Q"):
+                assert np.array_equal(got[k], plain[k]), (name, sliding, env, k)
+            assert got["D_max"] == plain["D_max"], (name, env)
+        zc = _run(name, sliding, pinned=True, ZERO_COPY=1, ROWS=16)
+        assert zc["launches"] > copies["launches"] and zc["bytes"] == copies["bytes"]
+        pageable = _run(name, sliding, ZERO_COPY=1, ROWS=16)  # numpy arrays: the copy engine
+        assert pageable["launches"] == copies["launches"]
+        for k in ("u", "v"):
+            assert np.array_equal(pageable[k], plain[k])
