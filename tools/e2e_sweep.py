@@ -65,7 +65,7 @@ def main():
     cout.memory_space = 0
 
     results = []
-    knobs = ("FILL_THREADS", "BAND", "LEVEL_CUT", "CUT_COLS", "CUT_ROWS", "REPL_THREADS", "SPARSE", "ROWS", "PIPELINE", "TRACE")
+    knobs = ("FILL_THREADS", "BAND", "LEVEL_CUT", "CUT_COLS", "CUT_ROWS", "REPL_THREADS", "SPARSE", "ROWS", "PIPELINE", "TRACE", "ZERO_COPY")
     sums = []
     for s in args.settings.split(","):
         for k in knobs:
