@@ -411,7 +411,9 @@ int siafd_b200_transfer_bytes(const siafd_b200_handle *h, int64_t *h2d, int64_t 
  * transfer.  Pure host arithmetic (no GPU needed): returns Mz when nothing can be cut.  Environment:
  * SIAFD_B200_LEVEL_CUT = 0 (off) / 1 (default: single rank) / 2 (also with several ranks),
  * SIAFD_B200_CUT_COLS (columns that share one n, default 256), SIAFD_B200_CUT_ROWS (rows that share one n, default 0
- * = the rows of a band), SIAFD_B200_REPL_THREADS (default 8); SIAFD_B200_TRACE=1 prints the timeline of each call. */
+ * = the rows of a band), SIAFD_B200_REPL_THREADS (default 8); SIAFD_B200_TRACE=1 prints the timeline of each call;
+ * SIAFD_B200_ZERO_COPY=1 (default 0): with u, v in pinned host memory a kernel stores the pieces there itself instead of
+ * the copy engine (same bits, measured slower: DESIGN.md section 7). */
 int siafd_b200_host_levels_needed(const double *z, int Mz, double max_thickness);
 /* Dry run of what siafd_b200_update with host arrays moves and fills, on HOST arrays only (no GPU; for tests of the
  * host logic): the same plan (pism_b200/csrc/siafd_hostplan.hh) -- row bands of `band` segments of rows_per_segment
