@@ -80,3 +80,46 @@ def test_random_geometry(seed):
             else:
                 full_bytes = (up, dn)
     assert cut_bytes[0] <= full_bytes[0] and cut_bytes[1] <= full_bytes[1]
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_random_geometry_on_patches(seed):
+    """The same on the patches of a decomposed domain (what every rank of a multi-GPU run plans for its own patch):
+    rectangles clipped at the patch edges, ghost columns from the neighbours, unequal ownership ranges."""
+    import oracle_lib as O
+    grid, cfg, inputs = random_case(seed)
+    rng = np.random.default_rng(seed)
+    one = cases.oracle_run(grid, cfg, inputs)
+    assert one.status == 0
+    Nx, Ny = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    if Nx * Ny == 1:
+        Nx = 2
+
+    def ranges(M, n):  # unequal ownership ranges, every one at least 4 wide
+        cuts = np.sort(rng.choice(np.arange(1, M // 4), size=n - 1, replace=False)) * 4 if n > 1 else np.array([], dtype=int)
+        edges = np.concatenate(([0], cuts, [M]))
+        return [int(b - a) for a, b in zip(edges[:-1], edges[1:])]
+
+    patches = G.decompose(grid.Mx, grid.My, Nx * Ny, Nx=Nx, Ny=Ny, procs_x=ranges(grid.Mx, Nx), procs_y=ranges(grid.My, Ny))
+    glob = {k: np.ascontiguousarray(cases.interior(np.asarray(v), (v.shape[0] - grid.My) // 2)) for k, v in inputs.items()}
+    widths = dict(enthalpy=cfg.w_3d_in, sliding=cfg.w_sliding)
+    for rows, band, cut, cols in ((8, 1, 1, 8), (16, 2, 2, 16), (8, 1, 0, 64)):
+        runs = []
+        for pt in patches:
+            c = capi_config(grid, cfg, pt)
+            loc = {k: G.global_to_local(glob[k], pt, widths.get(k, cfg.w_geom)) for k in glob}
+            want = {k: G.global_to_local(np.ascontiguousarray(cases.interior(one.a[k], 1)), pt, 1) for k in ("u", "v")}
+            E_dev, u, v, up, dn = emulate(c, loc, want["u"], want["v"], rows, band, 1, cut, cols, True)
+            assert np.array_equal(u, want["u"]) and np.array_equal(v, want["v"]), (seed, pt, rows, band, cut, cols)
+            runs.append(O.Run(cfg.oracle_params(grid, pt), dict(loc, enthalpy=E_dev)))
+        size = len(patches)
+        P = (O.Params * size)(*[r.p for r in runs])
+        Fa = (O.Fields * size)(*[r.f for r in runs])
+        assert O.lib().orc_siafd_update_decomposed(size, P, Fa, 1, 4) == 0
+        for q, (r, pt) in enumerate(zip(runs, patches)):
+            assert Fa[q].D_max == one.D_max
+            for k in ("u", "v"):
+                assert np.array_equal(r.a[k], G.global_to_local(np.ascontiguousarray(cases.interior(one.a[k], 1)), pt, 1)), (seed, k, q)
+            for k in ("D", "Q"):
+                want = G.global_to_local(np.ascontiguousarray(cases.interior(one.a[k], 1)), pt, 1)
+                assert np.array_equal(cases.interior(r.a[k], 1), cases.interior(want, 1)), (seed, k, q)
