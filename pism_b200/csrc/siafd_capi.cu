@@ -1479,8 +1479,10 @@ static int update_host_pipelined(siafd_b200_handle *h, const siafd_b200_inputs *
     if (q.p && (st = siafd_b200_upload(h, q.f, q.p))) return st;
   }
   HostPlan plan;
-  plan_host_update(c, slab_rows_per_segment(h->tuning), band, sparse, cut, patch, h->tuning.cut_cols, h->tuning.cut_rows, h->fill_threads, in->thickness,
-                   in->surface, in->bed, in->mask, plan);
+  // (the scans of the plan run before the fill / replication threads start: up to 8 threads for a few milliseconds)
+  const int plan_threads = std::max(h->fill_threads, (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
+  plan_host_update(c, slab_rows_per_segment(h->tuning), band, sparse, cut, patch, h->tuning.cut_cols, h->tuning.cut_rows, plan_threads,
+                   in->thickness, in->surface, in->bed, in->mask, plan);
   const double t_plan = wall_ms() - tr.t0;
   if (plan.nseg != nseg || plan.NB != NB) return fail(h, SIAFD_B200_ERR_BAD_ARGUMENT, "host plan and kernel disagree on the row segments");
   const int we = c.w_3d_in, wuv = c.w_uv;

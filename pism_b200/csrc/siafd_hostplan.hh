@@ -30,7 +30,26 @@ struct IceExtent {
   std::vector<int> lo, hi; // per owned row: columns [lo, hi] to transfer (lo > hi: none; lo < 0: the whole row)
 };
 
-static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E, bool patch_mode) {
+// per row of `rows` rows of `pitch` cells starting at H: the first and last of the cells [0, n) that hold ice (first >
+// last: none); rows shared between `threads` threads (134 MB of thickness at 4096^2: 17 ms on one thread)
+static void row_ice_bounds(const double *H, int rows, long pitch, int n, int *l0, int *h0, int threads) {
+  auto work = [=](int first, int stride) {
+    for (int r = first; r < rows; r += stride) {
+      const double *row = H + (long)r * pitch;
+      int a = 0, b = n - 1;
+      while (a < n && row[a] == 0.0) ++a;
+      while (b >= a && row[b] == 0.0) --b;
+      l0[r] = a, h0[r] = b;
+    }
+  };
+  const int nt = std::max(1, std::min(threads, rows / 64));
+  std::vector<std::thread> w;
+  for (int t = 1; t < nt; ++t) w.emplace_back(work, t, nt);
+  work(0, nt);
+  for (auto &t : w) t.join();
+}
+
+static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E, bool patch_mode, int threads = 1) {
   const int xm = c.xm, ym = c.ym, wg = c.w_geom;
   const long pitch = xm + 2 * wg;
   if (patch_mode) {
@@ -38,13 +57,7 @@ static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E
     // column matters when there is ice within one cell of it (the staggered points around it); two cells are taken.
     const int margin = 2, R = ym + 2 * wg;
     std::vector<int> l0(R), h0(R); // per local row (ghost rows included): local columns [l0, h0] with ice, ghosts included
-    for (int r = 0; r < R; ++r) {
-      const double *row = H + (long)r * pitch;
-      int a = 0, b = (int)pitch - 1;
-      while (a < pitch && row[a] == 0.0) ++a;
-      while (b >= a && row[b] == 0.0) --b;
-      l0[r] = a, h0[r] = b;
-    }
+    row_ice_bounds(H, R, pitch, (int)pitch, l0.data(), h0.data(), threads);
     E.lo.assign(ym, xm), E.hi.assign(ym, -1);
     for (int j = 0; j < ym; ++j) {
       int lo = 1 << 30, hi = -1;
@@ -62,14 +75,8 @@ static void ice_extent(const siafd_b200_config &c, const double *H, IceExtent &E
     return;
   }
   const int margin = 3;
-  std::vector<int> l0(ym), h0(ym);
-  for (int j = 0; j < ym; ++j) {
-    const double *row = H + (long)(j + wg) * pitch + wg;
-    int a = 0, b = xm - 1;
-    while (a < xm && row[a] == 0.0) ++a;
-    while (b >= a && row[b] == 0.0) --b;
-    l0[j] = a, h0[j] = b; // a > b: no ice in this row
-  }
+  std::vector<int> l0(ym), h0(ym); // (first > last: no ice in this row)
+  row_ice_bounds(H + (long)wg * pitch + wg, ym, pitch, xm, l0.data(), h0.data(), threads);
   E.lo.assign(ym, xm), E.hi.assign(ym, -1);
   for (int j = 0; j < ym; ++j) {
     int lo = xm, hi = -1;
@@ -198,7 +205,12 @@ static void thk_map_rows(const double *H, const double *surface, const double *b
     for (int b = 0; b < M->blocks; ++b) {
       const int c1 = std::min(M->pitch, (b + 1) * ThkMap::kBlock);
       double m = 0.0;
-      bool bad = false;
+      bool bad = false, any = false;
+      for (int cc = b * ThkMap::kBlock; cc < c1; ++cc) any |= (hr[cc] != 0.0); // (a NaN counts as ice)
+      if (!any) { // no ice in the block: thk_smooth = 0 whatever the other fields say, and they need not be read
+        q[b] = 0.0;
+        continue;
+      }
       for (int cc = b * ThkMap::kBlock; cc < c1; ++cc) {
         // thk_smooth with the smoother off (BedSmoother.cc:306-320; maxtl = 0): 0 where H = 0, usurf - topg where the
         // mask says grounded (Mask.hh:37-66: not ocean, i.e. below 3 after rounding), H where it floats
@@ -324,7 +336,7 @@ static void plan_host_update(const siafd_b200_config &c, int RS, int band, bool 
   P.sparse = sparse, P.cut = sparse && cut, P.patch = patch;
   const int NB = P.NB, nseg = P.nseg, we = c.w_3d_in, wuv = c.w_uv;
   IceExtent ext;
-  if (sparse) ice_extent(c, H, ext, patch);
+  if (sparse) ice_extent(c, H, ext, patch, threads);
   if (P.cut) thk_map_build(c, H, surface, bed, mask, P.tmap, threads);
   const ThkMap *M = P.cut ? &P.tmap : nullptr;
   // ---- u, v: per band the rectangle that comes down, the rest of the band's rows is the host's to fill ----

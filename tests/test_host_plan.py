@@ -51,7 +51,8 @@ SETTINGS = [  # rows per segment, segments per band, sparse, level cut (1 + k: k
 ]
 
 
-@pytest.mark.parametrize("name", ["Fs", "dome_96_31_rough", "dome_64_31_quadratic", "C4s_nosmooth", "C1_31", "dome_40_21_big"])
+@pytest.mark.parametrize("name", ["Fs", "dome_96_31_rough", "dome_64_31_quadratic", "C4s_nosmooth", "C1_31", "dome_40_21_big",
+                                  "dome_160_11_rough"])  # (160 rows: the scans of the plan run on two threads)
 def test_whole_domain_plan_leaves_the_full_result_on_the_host(name):
     big = name.endswith("_big")  # ice up to the edge of the domain: whole rows, ghost columns included
     grid, cfg, inputs, gb = cases.case(name[:-4] if big else name)
