@@ -418,8 +418,8 @@ int siafd_b200_host_levels_needed(const double *z, int Mz, double max_thickness)
 /* Dry run of what siafd_b200_update with host arrays moves and fills, on HOST arrays only (no GPU; for tests of the
  * host logic): the same plan (pism_b200/csrc/siafd_hostplan.hh) -- row bands of `band` segments of rows_per_segment
  * rows, sparse rectangles, level cut (level_cut = 1; 1 + k: chunks of k rows) with cut_cols columns per chunk, patch = 1
- * for one patch of a decomposed domain
- * -- executed with memcpy.  enthalpy_dev (in/out) stands for the device copy of the enthalpy: it receives what would be
+ * for one patch of a decomposed domain -- executed with memcpy.  It computes nothing of the update (this is not a CPU
+ * path: the "device" arrays are the caller's).  enthalpy_dev (in/out) stands for the device copy of the enthalpy: it receives what would be
  * uploaded and nothing else; u_dev, v_dev stand for the device's result (ghosts valid); u, v receive what the call would
  * leave in the host arrays (downloaded pieces, host fills from `sliding` (may be NULL = zero), values replicated above
  * the cut, ghost rows / columns).  All arrays in the local ghosted layout of cfg.  h2d / d2h (may be NULL): bytes of the
